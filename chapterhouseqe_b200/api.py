@@ -1,0 +1,446 @@
+"""ctypes binding of include/chdb_gpu.h + the reference-shaped Python entry points."""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from dataclasses import dataclass
+
+import pyarrow as pa
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class ChdbError(RuntimeError):
+    """An error returned through the C ABI. `.kind` is the reference's enum variant name
+    (e.g. "ArithmeticOverflow", "ColumnNotFound"); `.code` the chdb_code."""
+
+    def __init__(self, code: int, kind: str, message: str):
+        super().__init__(f"{kind}: {message}")
+        self.code, self.kind, self.message = code, kind, message
+
+
+class _Status(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int32), ("message", ctypes.c_char * 508)]
+
+
+class _ArrowSchema(ctypes.Structure):
+    pass
+
+
+class _ArrowArray(ctypes.Structure):
+    pass
+
+
+_ArrowSchema._fields_ = [("format", ctypes.c_char_p), ("name", ctypes.c_char_p), ("metadata", ctypes.c_char_p),
+                         ("flags", ctypes.c_int64), ("n_children", ctypes.c_int64),
+                         ("children", ctypes.POINTER(ctypes.POINTER(_ArrowSchema))),
+                         ("dictionary", ctypes.POINTER(_ArrowSchema)),
+                         ("release", ctypes.CFUNCTYPE(None, ctypes.POINTER(_ArrowSchema))),
+                         ("private_data", ctypes.c_void_p)]
+_ArrowArray._fields_ = [("length", ctypes.c_int64), ("null_count", ctypes.c_int64), ("offset", ctypes.c_int64),
+                        ("n_buffers", ctypes.c_int64), ("n_children", ctypes.c_int64),
+                        ("buffers", ctypes.POINTER(ctypes.c_void_p)),
+                        ("children", ctypes.POINTER(ctypes.POINTER(_ArrowArray))),
+                        ("dictionary", ctypes.POINTER(_ArrowArray)),
+                        ("release", ctypes.CFUNCTYPE(None, ctypes.POINTER(_ArrowArray))),
+                        ("private_data", ctypes.c_void_p)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libchdb_gpu.so")
+
+
+def load_library():
+    """Loads libchdb_gpu.so. Raises if it has not been built (python -m chapterhouseqe_b200.build):
+    there is deliberately no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m chapterhouseqe_b200.build` "
+                          "(nvcc, sm_100a). chapterhouseqe_b200 has no CPU fallback.")
+    L = ctypes.CDLL(path)
+    vp, cp, i32, i64 = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int64
+    stp = ctypes.POINTER(_Status)
+    pvp = ctypes.POINTER(ctypes.c_void_p)
+
+    def sig(name, restype, *argtypes):
+        f = getattr(L, name)
+        f.restype, f.argtypes = restype, list(argtypes)
+
+    sig("chdb_code_name", cp, i32)
+    sig("chdb_version", cp)
+    sig("chdb_compiled_arch", cp)
+    sig("chdb_ctx_create", i32, i32, pvp, stp)
+    sig("chdb_ctx_destroy", None, vp)
+    sig("chdb_ctx_stream", vp, vp)
+    sig("chdb_ctx_device", i32, vp)
+    sig("chdb_ctx_synchronize", i32, vp, stp)
+    sig("chdb_ctx_launch_count", i64, vp)
+    sig("chdb_program_compile_filter", i32, cp, vp, cp, pvp, stp)
+    sig("chdb_program_compile_project", i32, cp, vp, cp, pvp, stp)
+    sig("chdb_program_compile_filter_project", i32, cp, cp, vp, cp, pvp, stp)
+    sig("chdb_program_release", None, vp)
+    sig("chdb_program_disassemble", ctypes.c_size_t, vp, ctypes.c_char_p, ctypes.c_size_t)
+    sig("chdb_program_num_instructions", i32, vp)
+    sig("chdb_filter_record", i32, vp, vp, vp, vp, vp, vp, stp)
+    sig("chdb_project_record", i32, vp, vp, vp, vp, vp, vp, stp)
+    sig("chdb_filter_record_expr", i32, vp, vp, vp, cp, cp, vp, vp, stp)
+    sig("chdb_project_record_items", i32, vp, cp, vp, vp, cp, vp, vp, stp)
+    sig("chdb_compute_value", i32, vp, vp, vp, cp, cp, vp, vp, ctypes.POINTER(i32), stp)
+    sig("chdb_upload", i32, vp, vp, vp, pvp, stp)
+    sig("chdb_device_batch_wrap", i32, vp, vp, i64, pvp, pvp, pvp, pvp, stp)
+    sig("chdb_run_device", i32, vp, vp, vp, pvp, stp)
+    sig("chdb_device_batch_status", i32, vp, vp, stp)
+    sig("chdb_device_batch_num_rows", i64, vp, vp, stp)
+    sig("chdb_device_batch_num_columns", i32, vp)
+    sig("chdb_device_batch_nbytes", i64, vp, vp, stp)
+    sig("chdb_download", i32, vp, vp, vp, vp, stp)
+    sig("chdb_peer_copy", i32, vp, vp, vp, pvp, stp)
+    sig("chdb_device_batch_release", None, vp)
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "chdb_code_name", "chdb_version", "chdb_compiled_arch", "chdb_ctx_create", "chdb_ctx_destroy", "chdb_ctx_stream",
+    "chdb_ctx_device", "chdb_ctx_synchronize", "chdb_ctx_launch_count", "chdb_program_compile_filter",
+    "chdb_program_compile_project", "chdb_program_compile_filter_project", "chdb_program_release",
+    "chdb_program_disassemble", "chdb_program_num_instructions", "chdb_filter_record", "chdb_project_record",
+    "chdb_filter_record_expr", "chdb_project_record_items", "chdb_compute_value", "chdb_upload",
+    "chdb_device_batch_wrap", "chdb_run_device", "chdb_device_batch_status", "chdb_device_batch_num_rows",
+    "chdb_device_batch_num_columns", "chdb_device_batch_nbytes", "chdb_download", "chdb_peer_copy",
+    "chdb_device_batch_release",
+]
+
+
+def _check(rc: int, st: _Status):
+    if rc != 0:
+        L = load_library()
+        raise ChdbError(rc, L.chdb_code_name(rc).decode(), st.message.decode(errors="replace"))
+
+
+def _json(x) -> bytes | None:
+    if x is None:
+        return None
+    if isinstance(x, bytes):
+        return x
+    if isinstance(x, str):
+        return x.encode()
+    return json.dumps(x, separators=(",", ":")).encode()
+
+
+def _export_schema(schema: pa.Schema) -> _ArrowSchema:
+    c = _ArrowSchema()
+    schema._export_to_c(ctypes.addressof(c))
+    return c
+
+
+def _release_schema(c: _ArrowSchema):
+    if c.release:
+        c.release(ctypes.byref(c))
+
+
+def _export_batch(rb: pa.RecordBatch):
+    a, s = _ArrowArray(), _ArrowSchema()
+    rb._export_to_c(ctypes.addressof(a), ctypes.addressof(s))
+    return a, s
+
+
+def _import_batch(a: _ArrowArray, s: _ArrowSchema) -> pa.RecordBatch:
+    return pa.RecordBatch._import_from_c(ctypes.addressof(a), ctypes.addressof(s))
+
+
+# ---------------------------------------------------------------------------------------------
+class Context:
+    """One operator instance's GPU context (one device, one stream)."""
+
+    def __init__(self, device: int = 0):
+        L = load_library()
+        h, st = ctypes.c_void_p(), _Status()
+        _check(L.chdb_ctx_create(device, ctypes.byref(h), ctypes.byref(st)), st)
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().chdb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t as an integer (wrap with torch.cuda.ExternalStream to record events)."""
+        return int(load_library().chdb_ctx_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(load_library().chdb_ctx_launch_count(self._h))
+
+    def synchronize(self):
+        st = _Status()
+        _check(load_library().chdb_ctx_synchronize(self._h, ctypes.byref(st)), st)
+
+
+_DEFAULT_CTX: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _DEFAULT_CTX:
+        _DEFAULT_CTX[device] = Context(device)
+    return _DEFAULT_CTX[device]
+
+
+class Program:
+    """An expression tree lowered to bytecode for one input schema (no GPU needed to compile)."""
+
+    def __init__(self, handle, mode: str):
+        self._h, self.mode = handle, mode
+
+    @staticmethod
+    def _compile(mode, expr, items, schema: pa.Schema, table_aliases) -> "Program":
+        L = load_library()
+        cs = _export_schema(schema)
+        # a RecordBatch schema crosses as a struct-typed ArrowSchema
+        h, st = ctypes.c_void_p(), _Status()
+        try:
+            al = _json(table_aliases)
+            if mode == "filter":
+                rc = L.chdb_program_compile_filter(_json(expr), ctypes.addressof(cs), al, ctypes.byref(h), ctypes.byref(st))
+            elif mode == "project":
+                rc = L.chdb_program_compile_project(_json(items), ctypes.addressof(cs), al, ctypes.byref(h), ctypes.byref(st))
+            else:
+                rc = L.chdb_program_compile_filter_project(_json(expr), _json(items), ctypes.addressof(cs), al,
+                                                           ctypes.byref(h), ctypes.byref(st))
+        finally:
+            _release_schema(cs)
+        _check(rc, st)
+        return Program(h, mode)
+
+    @staticmethod
+    def compile_filter(expr, schema: pa.Schema, table_aliases=None) -> "Program":
+        return Program._compile("filter", expr, None, schema, table_aliases)
+
+    @staticmethod
+    def compile_project(select_items, schema: pa.Schema, table_aliases=None) -> "Program":
+        return Program._compile("project", None, select_items, schema, table_aliases)
+
+    @staticmethod
+    def compile_filter_project(expr, select_items, schema: pa.Schema, table_aliases=None) -> "Program":
+        return Program._compile("filter_project", expr, select_items, schema, table_aliases)
+
+    def disassemble(self) -> str:
+        L = load_library()
+        n = L.chdb_program_disassemble(self._h, None, 0)
+        buf = ctypes.create_string_buffer(n + 1)
+        L.chdb_program_disassemble(self._h, buf, n + 1)
+        return buf.value.decode()
+
+    @property
+    def num_instructions(self) -> int:
+        return int(load_library().chdb_program_num_instructions(self._h))
+
+    def run(self, rb: pa.RecordBatch, ctx: Context | None = None) -> pa.RecordBatch:
+        """Host batch in, host batch out (upload -> fused kernel -> download)."""
+        L = load_library()
+        ctx = ctx or default_context()
+        a, s = _export_batch(rb)
+        oa, os_, st = _ArrowArray(), _ArrowSchema(), _Status()
+        try:
+            rc = L.chdb_filter_record(ctx._h, self._h, ctypes.addressof(a), ctypes.addressof(s), ctypes.addressof(oa),
+                                      ctypes.addressof(os_), ctypes.byref(st))
+        finally:
+            if a.release:
+                a.release(ctypes.byref(a))
+            _release_schema(s)
+        _check(rc, st)
+        return _import_batch(oa, os_)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().chdb_program_release(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class DeviceBatch:
+    """A device-resident RecordBatch: what the exchanges carry between read_files, filter and
+    materialize in the GPU build."""
+
+    def __init__(self, handle, ctx: Context, keepalive=None):
+        self._h, self.ctx, self._keepalive = handle, ctx, keepalive
+
+    @staticmethod
+    def upload(rb: pa.RecordBatch, ctx: Context | None = None) -> "DeviceBatch":
+        L = load_library()
+        ctx = ctx or default_context()
+        a, s = _export_batch(rb)
+        h, st = ctypes.c_void_p(), _Status()
+        try:
+            rc = L.chdb_upload(ctx._h, ctypes.addressof(a), ctypes.addressof(s), ctypes.byref(h), ctypes.byref(st))
+        finally:
+            if a.release:
+                a.release(ctypes.byref(a))
+            _release_schema(s)
+        _check(rc, st)
+        return DeviceBatch(h, ctx)
+
+    @staticmethod
+    def wrap(schema: pa.Schema, num_rows: int, values, validity=None, offsets=None, ctx: Context | None = None,
+             keepalive=None) -> "DeviceBatch":
+        """Wrap device pointers (ints) the caller owns, e.g. torch tensors' data_ptr(). No copy."""
+        L = load_library()
+        ctx = ctx or default_context()
+        n = len(schema)
+        arr = ctypes.c_void_p * n
+        vals = arr(*[ctypes.c_void_p(v) for v in values])
+        vald = arr(*[ctypes.c_void_p(v or None) for v in (validity or [None] * n)])
+        offs = arr(*[ctypes.c_void_p(v or None) for v in (offsets or [None] * n)])
+        cs = _export_schema(schema)
+        h, st = ctypes.c_void_p(), _Status()
+        try:
+            rc = L.chdb_device_batch_wrap(ctx._h, ctypes.addressof(cs), num_rows, vals, vald, offs, ctypes.byref(h),
+                                          ctypes.byref(st))
+        finally:
+            _release_schema(cs)
+        _check(rc, st)
+        return DeviceBatch(h, ctx, keepalive)
+
+    def run(self, prog: Program) -> "DeviceBatch":
+        """Asynchronous on the ctx stream."""
+        L = load_library()
+        h, st = ctypes.c_void_p(), _Status()
+        _check(L.chdb_run_device(self.ctx._h, prog._h, self._h, ctypes.byref(h), ctypes.byref(st)), st)
+        return DeviceBatch(h, self.ctx, (self, self._keepalive))
+
+    def check(self):
+        st = _Status()
+        _check(load_library().chdb_device_batch_status(self.ctx._h, self._h, ctypes.byref(st)), st)
+
+    @property
+    def num_rows(self) -> int:
+        st = _Status()
+        n = load_library().chdb_device_batch_num_rows(self.ctx._h, self._h, ctypes.byref(st))
+        _check(st.code, st)
+        return int(n)
+
+    @property
+    def num_columns(self) -> int:
+        return int(load_library().chdb_device_batch_num_columns(self._h))
+
+    @property
+    def nbytes(self) -> int:
+        st = _Status()
+        n = load_library().chdb_device_batch_nbytes(self.ctx._h, self._h, ctypes.byref(st))
+        _check(st.code, st)
+        return int(n)
+
+    def download(self) -> pa.RecordBatch:
+        L = load_library()
+        oa, os_, st = _ArrowArray(), _ArrowSchema(), _Status()
+        _check(L.chdb_download(self.ctx._h, self._h, ctypes.addressof(oa), ctypes.addressof(os_), ctypes.byref(st)), st)
+        return _import_batch(oa, os_)
+
+    def peer_copy(self, dst_ctx: Context) -> "DeviceBatch":
+        L = load_library()
+        h, st = ctypes.c_void_p(), _Status()
+        _check(L.chdb_peer_copy(dst_ctx._h, self.ctx._h, self._h, ctypes.byref(h), ctypes.byref(st)), st)
+        return DeviceBatch(h, dst_ctx)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().chdb_device_batch_release(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's three functions
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ArrayDatum:
+    """compute_value.rs:34-55"""
+    array: pa.Array
+    is_scalar: bool
+
+
+def _host_call(fn_name: str, rb: pa.RecordBatch, ctx: Context | None, *mid_args):
+    L = load_library()
+    ctx = ctx or default_context()
+    a, s = _export_batch(rb)
+    oa, os_, st = _ArrowArray(), _ArrowSchema(), _Status()
+    try:
+        yield_args = (ctx, a, s, oa, os_, st)
+        rc = mid_args[0](L, *yield_args)
+    finally:
+        if a.release:
+            a.release(ctypes.byref(a))
+        _release_schema(s)
+    _check(rc, st)
+    return _import_batch(oa, os_)
+
+
+def filter_record(rec: pa.RecordBatch, table_aliases, expr, ctx: Context | None = None) -> pa.RecordBatch:
+    """filter_record.rs:21-39 -- `expr` is the serde-JSON form of sqlparser's Expr (dict or str)."""
+    def call(L, ctx, a, s, oa, os_, st):
+        return L.chdb_filter_record_expr(ctx._h, ctypes.addressof(a), ctypes.addressof(s), _json(table_aliases), _json(expr),
+                                         ctypes.addressof(oa), ctypes.addressof(os_), ctypes.byref(st))
+    return _host_call("filter", rec, ctx, call)
+
+
+def project_record(fields, record: pa.RecordBatch, table_aliases, ctx: Context | None = None) -> pa.RecordBatch:
+    """record_projection.rs:16-76 -- `fields` is the serde-JSON form of Vec<SelectItem>."""
+    def call(L, ctx, a, s, oa, os_, st):
+        return L.chdb_project_record_items(ctx._h, _json(fields), ctypes.addressof(a), ctypes.addressof(s),
+                                           _json(table_aliases), ctypes.addressof(oa), ctypes.addressof(os_),
+                                           ctypes.byref(st))
+    return _host_call("project", record, ctx, call)
+
+
+def compute_value(rec: pa.RecordBatch, table_aliases, expr, ctx: Context | None = None) -> ArrayDatum:
+    """compute_value.rs:57-344"""
+    flag = ctypes.c_int32(0)
+
+    def call(L, ctx, a, s, oa, os_, st):
+        return L.chdb_compute_value(ctx._h, ctypes.addressof(a), ctypes.addressof(s), _json(table_aliases), _json(expr),
+                                    ctypes.addressof(oa), ctypes.addressof(os_), ctypes.byref(flag), ctypes.byref(st))
+    out = _host_call("value", rec, ctx, call)
+    return ArrayDatum(out.column(0), bool(flag.value))
+
+
+def filter_project_record(expr, fields, rec: pa.RecordBatch, table_aliases, ctx: Context | None = None) -> pa.RecordBatch:
+    """project_record(fields, filter_record(rec, aliases, expr), aliases) as ONE fused pass."""
+    prog = Program.compile_filter_project(expr, fields, rec.schema, table_aliases)
+    try:
+        return prog.run(rec, ctx)
+    finally:
+        prog.close()
+
+
+def get_record_table_aliases(op_type: dict, record: pa.RecordBatch) -> list[list[str]]:
+    """record_aliases.rs:12-59 -- op_type is the serde form of planner::OperatorType."""
+    (_, body), = op_type.items()
+    (task_name, task), = body["task"].items()
+    if task_name not in ("TableFunc", "Table"):
+        raise ChdbError(11, "OperatorTaskTypeDoesNotHaveAnAliasField",
+                        f"operator task type does not have an alias field: OperatorTask::{task_name}")
+    alias = task.get("alias")
+    return [[alias] if alias is not None else [] for _ in range(record.num_columns)]

@@ -1,0 +1,204 @@
+/*
+ * chdb_gpu.h -- C ABI of the B200-native filter / projection / compaction path of
+ * ChapterhouseDB (alekLukanen/ChapterhouseQE).
+ *
+ * Drop-in boundary.  The reference's filter and materialize producer tasks call two pure,
+ * synchronous functions (paths relative to the reference's
+ * src/handlers/operator_handler/operators/):
+ *
+ *   record_utils/filter_record.rs:21-25
+ *       filter_record(rec: Arc<RecordBatch>, table_aliases: &Vec<Vec<String>>, expr: &Expr)
+ *           -> anyhow::Result<RecordBatch>               called at filter_tasks/filter_task.rs:99-103
+ *   record_utils/record_projection.rs:16-20
+ *       project_record(fields: &Vec<SelectItem>, record: Arc<RecordBatch>, table_aliases)
+ *           -> anyhow::Result<RecordBatch>               called at materialize_tasks/materialize_files_task.rs:110-114
+ *   record_utils/compute_value.rs:57-61
+ *       compute_value(rec, table_aliases, expr) -> Result<ArrayDatum>   (the evaluator under both)
+ *
+ * A Rust `chdb-gpu` crate binds exactly the functions below (see INTEGRATION.md for the
+ * extern "C" block and the TaskBuilder that replaces filter_task.rs:99).  Conventions:
+ *
+ *   - Batches cross as the Arrow C Data Interface (struct-typed ArrowArray + ArrowSchema:
+ *     arrow-rs 53 `arrow::ffi::{to_ffi, from_ffi}` on a StructArray, pyarrow `_export_to_c`).
+ *   - Expression trees cross as the serde-JSON of sqlparser 0.52 `Expr` / `Vec<SelectItem>`,
+ *     i.e. `serde_json::to_string(&filter_config.expr)`; the planner is unchanged.
+ *   - table_aliases crosses as JSON `[["alias"], [], ...]` (one list per input column), or NULL.
+ *   - Every fallible call returns a chdb_code (0 = ok) and fills the optional chdb_status;
+ *     codes mirror the reference's error enums (compute_value.rs:12-32, filter_record.rs:11-15,
+ *     record_projection.rs:10-14) and the ArrowError variants its arrow calls can raise.
+ *   - No thread-local state.  A chdb_ctx is single-owner (one operator instance = one GPU +
+ *     one stream) but may be used from any OS thread (tokio tasks migrate between threads);
+ *     different ctxs are independent.  Programs are immutable and shareable between ctxs of
+ *     any device.
+ *   - Inputs are borrowed for the duration of the call.  Outputs are owned by the caller and
+ *     freed through ArrowArray.release / chdb_device_batch_release.
+ *   - There is no CPU fallback: without a CUDA device every ctx call fails with CHDB_ERR_CUDA.
+ */
+#ifndef CHDB_GPU_H
+#define CHDB_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+
+/* ---- status ---- */
+typedef enum chdb_code {
+  CHDB_OK = 0,
+  /* ComputeValueError (compute_value.rs:12-32) */
+  CHDB_ERR_VALUE_TYPE_NOT_IMPLEMENTED = 1,
+  CHDB_ERR_EXPRESSION_TYPE_NOT_IMPLEMENTED = 2,
+  CHDB_ERR_BINARY_OPERATOR_NOT_IMPLEMENTED = 3,
+  CHDB_ERR_BINARY_OPERATION_CAST_FAILED = 4,
+  CHDB_ERR_FAILED_TO_PARSE_AS_AN_INTEGER = 5,
+  CHDB_ERR_FAILED_TO_PARSE_AS_A_FLOAT = 6,
+  CHDB_ERR_COLUMN_NOT_FOUND = 7,
+  CHDB_ERR_IDENTIFIER_NOT_FOUND = 8,
+  CHDB_ERR_UNSUPPORTED_TYPE_COERSION = 9,
+  /* FilterRecordError (filter_record.rs:11-15) */
+  CHDB_ERR_CAST_TO_BOOLEAN_ARRAY_FAILED = 10,
+  /* ProjectRecordError (record_projection.rs:10-14) and unsupported inputs of this library */
+  CHDB_ERR_NOT_IMPLEMENTED = 11,
+  /* ArrowError variants raised by the arrow kernels on this path */
+  CHDB_ERR_ARITHMETIC_OVERFLOW = 12,
+  CHDB_ERR_DIVIDE_BY_ZERO = 13,
+  CHDB_ERR_COMPUTE_ERROR = 14,
+  CHDB_ERR_INVALID_ARGUMENT = 15,
+  /* this library */
+  CHDB_ERR_CUDA = 16,
+  CHDB_ERR_BAD_JSON = 17,
+  CHDB_ERR_PANIC = 18 /* the reference would hit an .expect() (compute_value.rs:293) */
+} chdb_code;
+
+typedef struct chdb_status {
+  int32_t code;
+  char message[508];
+} chdb_status;
+
+/* Name of a code as the reference spells the enum variant, e.g. "ArithmeticOverflow". */
+const char* chdb_code_name(int32_t code);
+/* Library version string, and the SM architecture the kernels were compiled for ("sm_100a"). */
+const char* chdb_version(void);
+const char* chdb_compiled_arch(void);
+
+/* ---- context: one per operator instance (one GPU, one stream) ---- */
+typedef struct chdb_ctx chdb_ctx;
+int32_t chdb_ctx_create(int32_t device, chdb_ctx** out, chdb_status* st);
+void chdb_ctx_destroy(chdb_ctx* ctx);
+/* cudaStream_t the ctx launches on (for callers that record their own CUDA events). */
+void* chdb_ctx_stream(chdb_ctx* ctx);
+int32_t chdb_ctx_device(chdb_ctx* ctx);
+int32_t chdb_ctx_synchronize(chdb_ctx* ctx, chdb_status* st);
+/* Number of kernel launches issued by this ctx so far (bench.py's gpu_launches). */
+int64_t chdb_ctx_launch_count(chdb_ctx* ctx);
+
+/* ---- programs: an expression tree lowered to register bytecode for one input schema ----
+ * compile_filter  : predicate = `expr`,  outputs = every input column       (filter_record)
+ * compile_project : no predicate,        outputs = `select_items`           (project_record)
+ * compile_filter_project : both fused in one pass; identical results to
+ *                   project_record(filter_record(rec)) incl. "errors only on surviving rows".
+ * Compilation never touches the GPU. */
+typedef struct chdb_program chdb_program;
+int32_t chdb_program_compile_filter(const char* expr_json, const struct ArrowSchema* in_schema,
+                                    const char* table_aliases_json, chdb_program** out, chdb_status* st);
+int32_t chdb_program_compile_project(const char* select_items_json, const struct ArrowSchema* in_schema,
+                                     const char* table_aliases_json, chdb_program** out, chdb_status* st);
+int32_t chdb_program_compile_filter_project(const char* expr_json, const char* select_items_json,
+                                            const struct ArrowSchema* in_schema,
+                                            const char* table_aliases_json, chdb_program** out,
+                                            chdb_status* st);
+void chdb_program_release(chdb_program* prog);
+/* Human-readable bytecode listing; returns the number of bytes needed (excluding NUL). */
+size_t chdb_program_disassemble(const chdb_program* prog, char* buf, size_t cap);
+/* Algorithmic bytes per input row read by the program (sum over referenced columns of value
+ * width + validity/8; Utf8 counts its 4-byte offset only) -- used for roofline accounting. */
+int32_t chdb_program_num_instructions(const chdb_program* prog);
+
+/* ---- host batches: same contract as the reference's functions ----
+ * `in` / `in_schema`: a struct array whose children are the batch columns.
+ * `out` / `out_schema`: filled with a new struct array (caller releases both). */
+int32_t chdb_filter_record(chdb_ctx* ctx, const chdb_program* prog, const struct ArrowArray* in,
+                           const struct ArrowSchema* in_schema, struct ArrowArray* out,
+                           struct ArrowSchema* out_schema, chdb_status* st);
+int32_t chdb_project_record(chdb_ctx* ctx, const chdb_program* prog, const struct ArrowArray* in,
+                            const struct ArrowSchema* in_schema, struct ArrowArray* out,
+                            struct ArrowSchema* out_schema, chdb_status* st);
+/* One-shot forms taking the expression each call (exactly the reference signatures). */
+int32_t chdb_filter_record_expr(chdb_ctx* ctx, const struct ArrowArray* in, const struct ArrowSchema* in_schema,
+                                const char* table_aliases_json, const char* expr_json,
+                                struct ArrowArray* out, struct ArrowSchema* out_schema, chdb_status* st);
+int32_t chdb_project_record_items(chdb_ctx* ctx, const char* select_items_json, const struct ArrowArray* in,
+                                  const struct ArrowSchema* in_schema, const char* table_aliases_json,
+                                  struct ArrowArray* out, struct ArrowSchema* out_schema, chdb_status* st);
+/* compute_value(rec, aliases, expr): a one-column batch named "value"; *is_scalar as ArrayDatum. */
+int32_t chdb_compute_value(chdb_ctx* ctx, const struct ArrowArray* in, const struct ArrowSchema* in_schema,
+                           const char* table_aliases_json, const char* expr_json, struct ArrowArray* out,
+                           struct ArrowSchema* out_schema, int32_t* is_scalar, chdb_status* st);
+
+/* ---- device-resident batches (what the exchanges carry between read_files, filter and
+ *      materialize so only the final result crosses PCIe) ---- */
+typedef struct chdb_device_batch chdb_device_batch;
+int32_t chdb_upload(chdb_ctx* ctx, const struct ArrowArray* in, const struct ArrowSchema* in_schema,
+                    chdb_device_batch** out, chdb_status* st);
+/* Wrap device buffers the caller already owns (no copy; they must outlive the batch).
+ * Per column c: values[c] (Utf8: value bytes), validity[c] or NULL, offsets[c] (Utf8 only, int32[n+1]).
+ * Every buffer must be 16-byte aligned and readable for 32 bytes past its logical end. */
+int32_t chdb_device_batch_wrap(chdb_ctx* ctx, const struct ArrowSchema* schema, int64_t num_rows,
+                               const void* const* values, const void* const* validity,
+                               const void* const* offsets, chdb_device_batch** out, chdb_status* st);
+/* Asynchronous on the ctx stream; the result's row count is known after the stream is
+ * synchronised (chdb_device_batch_num_rows does that). Runs whatever the program holds
+ * (filter, project or fused). */
+int32_t chdb_run_device(chdb_ctx* ctx, const chdb_program* prog, const chdb_device_batch* in,
+                        chdb_device_batch** out, chdb_status* st);
+/* Checks the device error word of a finished run (ArithmeticOverflow / DivideByZero). */
+int32_t chdb_device_batch_status(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
+int64_t chdb_device_batch_num_rows(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
+int32_t chdb_device_batch_num_columns(const chdb_device_batch* b);
+/* Bytes of HBM written for this batch's columns (values + validity + offsets), after sync. */
+int64_t chdb_device_batch_nbytes(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
+int32_t chdb_download(chdb_ctx* ctx, const chdb_device_batch* b, struct ArrowArray* out,
+                      struct ArrowSchema* out_schema, chdb_status* st);
+/* Copy a finished batch's buffers to another ctx's GPU (cudaMemcpyPeerAsync over NVLink):
+ * the materialize-side gather of per-GPU results. */
+int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_batch* src,
+                       chdb_device_batch** out, chdb_status* st);
+void chdb_device_batch_release(chdb_device_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHDB_GPU_H */
