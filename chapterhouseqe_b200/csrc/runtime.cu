@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -39,12 +40,44 @@ struct CtxCore {
   std::mutex mu;
   std::vector<void*> pinned_free;   // small pinned blocks for count read-back
   static constexpr size_t kPinnedBlock = 1024;
+  // size-class cache of pinned host buffers: downloaded batches land in page-locked memory so the
+  // D2H copies run at PCIe speed; ArrowArray.release hands the blocks back here.
+  std::map<size_t, std::vector<void*>> host_free;
 
   ~CtxCore() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     for (void* p : pinned_free) cudaFreeHost(p);
+    for (auto& kv : host_free)
+      for (void* p : kv.second) cudaFreeHost(p);
     if (stream) cudaStreamDestroy(stream);
+  }
+  static size_t host_class(size_t bytes) {
+    size_t c = 4096;
+    while (c < bytes) c <<= 1;
+    return c;
+  }
+  void* host_get(size_t bytes, size_t* cls) {
+    *cls = host_class(bytes + 64);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = host_free.find(*cls);
+      if (it != host_free.end() && !it->second.empty()) {
+        void* p = it->second.back();
+        it->second.pop_back();
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaHostAlloc(&p, *cls, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      throw Error(CHDB_ERR_CUDA, "cudaHostAlloc failed for a " + std::to_string(*cls) + "-byte output buffer");
+    }
+    return p;
+  }
+  void host_put(void* p, size_t cls) {
+    std::lock_guard<std::mutex> g(mu);
+    host_free[cls].push_back(p);
   }
   void* pinned_get() {
     {
@@ -260,7 +293,8 @@ static std::unique_ptr<chdb_device_batch> upload_batch(const Core& core, const :
 // Arrow C Data Interface: export (download)
 // ------------------------------------------------------------------------------------------
 struct ExportedArray {
-  std::vector<void*> owned;                 // aligned_alloc'ed buffers
+  Core core;
+  std::vector<std::pair<void*, size_t>> owned;   // pinned blocks (pointer, size class) from core->host_get
   std::vector<const void*> buffers;
   std::vector<::ArrowArray> child_storage;
   std::vector<::ArrowArray*> children;
@@ -270,7 +304,7 @@ static void release_array(::ArrowArray* a) {
   auto* ex = (ExportedArray*)a->private_data;
   for (auto& c : ex->child_storage)
     if (c.release) c.release(&c);
-  for (void* p : ex->owned) std::free(p);
+  for (auto& p : ex->owned) ex->core->host_put(p.first, p.second);
   delete ex;
   a->release = nullptr;
 }
@@ -302,9 +336,10 @@ static void make_schema(::ArrowSchema* out, const std::string& format, const std
   out->release = release_schema;
   out->private_data = ex;
 }
-static void* host_alloc(size_t bytes) {
-  void* p = std::aligned_alloc(64, round_up(bytes + 64, 64));
-  if (!p) throw std::bad_alloc();
+static void* host_alloc(ExportedArray* ex, size_t bytes) {
+  size_t cls = 0;
+  void* p = ex->core->host_get(bytes, &cls);
+  ex->owned.push_back({p, cls});
   return p;
 }
 
@@ -315,6 +350,7 @@ static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchem
   resolve(b);
   const int64_t n = b->num_rows;
   auto* top = new ExportedArray;
+  top->core = core;
   std::unique_ptr<ExportedArray> top_guard(top);
   top->child_storage.resize(b->cols.size());
   for (auto& c : top->child_storage) std::memset(&c, 0, sizeof(c));
@@ -323,13 +359,13 @@ static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchem
   std::vector<ExportedArray*> exs(b->cols.size(), nullptr);
   for (size_t ci = 0; ci < b->cols.size(); ci++) {
     exs[ci] = new ExportedArray;
+    exs[ci]->core = core;
     ::ArrowArray& a = top->child_storage[ci];
     a.private_data = exs[ci];
     a.release = release_array;
     DeviceColumn& c = b->cols[ci];
     if (c.meta.type == T_UTF8) {
-      int32_t* ho = (int32_t*)host_alloc((size_t)(n + 1) * 4);
-      exs[ci]->owned.push_back(ho);
+      int32_t* ho = (int32_t*)host_alloc(exs[ci], (size_t)(n + 1) * 4);
       ho[0] = 0;
       if (n) CUDA_CHECK(cudaMemcpyAsync(ho, c.offsets, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, core->stream));
       host_offsets[ci] = ho;
@@ -343,29 +379,25 @@ static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchem
     void* hv = nullptr;
     uint8_t* hval = nullptr;
     if (c.validity != nullptr && c.null_count != 0 && n) {
-      hval = (uint8_t*)host_alloc(bitmap_bytes(n));
-      ex->owned.push_back(hval);
+      hval = (uint8_t*)host_alloc(ex, bitmap_bytes(n));
       CUDA_CHECK(cudaMemcpyAsync(hval, c.validity, bitmap_bytes(n), cudaMemcpyDeviceToHost, core->stream));
     }
     if (c.meta.type == T_UTF8) {
       int32_t* ho = host_offsets[ci];
       const int64_t first = n ? ho[0] : 0, last = n ? ho[n] : 0;
-      hv = host_alloc((size_t)(last - first));
-      ex->owned.push_back(hv);
+      hv = host_alloc(ex, (size_t)(last - first));
       if (last > first)
         CUDA_CHECK(cudaMemcpyAsync(hv, (const uint8_t*)c.values + first, (size_t)(last - first), cudaMemcpyDeviceToHost, core->stream));
       if (first != 0)
         for (int64_t i = 0; i <= n; i++) ho[i] -= (int32_t)first;
       ex->buffers = {hval, ho, hv};
     } else if (c.meta.type == T_BOOL) {
-      hv = host_alloc(bitmap_bytes(n));
-      ex->owned.push_back(hv);
+      hv = host_alloc(ex, bitmap_bytes(n));
       if (n) CUDA_CHECK(cudaMemcpyAsync(hv, c.values, bitmap_bytes(n), cudaMemcpyDeviceToHost, core->stream));
       ex->buffers = {hval, hv};
     } else {
       const size_t w = (size_t)c.meta.width;
-      hv = host_alloc((size_t)n * w);
-      ex->owned.push_back(hv);
+      hv = host_alloc(ex, (size_t)n * w);
       if (n) CUDA_CHECK(cudaMemcpyAsync(hv, c.values, (size_t)n * w, cudaMemcpyDeviceToHost, core->stream));
       ex->buffers = {hval, hv};
     }
