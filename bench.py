@@ -341,9 +341,11 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     ev0.record(stream)
     prev = None
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         cur = one_step()
         prev = cur   # the previous step's outputs are released here (cudaFreeAsync on the same stream)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     ev1.record(stream)
     ctx.synchronize()
     torch.cuda.synchronize(device)
@@ -385,7 +387,7 @@ def run_ours(args, rank, world, local_rank):
         "config": workload_config(args),
         "selectivity": selectivity, "rows_out_per_step": all_rows_out,
         "hbm_gbs_per_gpu": per_gpu_gbs, "pct_of_8TBs": per_gpu_gbs / 8000.0 * 100.0,
-        "clocks": clocks, "gpu_launches": int(all_launches),
+        "clocks": clocks, "gpu_launches": int(all_launches), "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
         "roofline": {"bound": "hbm", "kernel": "filter_project_kernel<u64,2>", "achieved": per_gpu_gbs, "peak": peak,
                      "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_bytes_per_launch": algo_bytes_per_launch,

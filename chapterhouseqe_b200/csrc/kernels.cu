@@ -1,6 +1,8 @@
 // Fused WHERE-evaluation -> selection -> decoupled-look-back scan -> compaction kernel (sm_100a).
 //
 // One CTA owns one tile of kTileRows rows.  Per tile:
+//   0. the tile's slice of every input column is prefetched into L2 (one 128-byte line per thread
+//      and iteration), so the dependent loads below find their data on chip
 //   1. every thread runs the predicate bytecode over its rows (128-bit coalesced column loads,
 //      accumulator in registers) and gets a selection mask                     [compute_value.rs]
 //   2. warp shuffles + one shared-memory pass rank the selected rows; for each Utf8 output the
@@ -9,11 +11,15 @@
 //      into exclusive prefixes (rows, and bytes per Utf8 output)               [filter_record.rs:37]
 //   4. every output column is gathered: values are staged in shared memory at the same
 //      16-byte phase as their destination and written with full 16-byte stores; validity and
-//      Boolean bits are packed with REDUX.OR; Utf8 bytes are produced output-chunk-centric so
-//      every global store is an aligned 16-byte store.
+//      Boolean bits are staged one byte per row and packed 32 at a time; short Utf8 values are
+//      staged the same way, long ones are produced output-chunk-centric, so every global store in
+//      the middle of a tile is an aligned 16-byte store.
 // HBM traffic is therefore each referenced input byte once and each output byte once.
 // Projection expressions are evaluated in step 4 under the selection mask, so checked-integer
 // errors are raised for surviving rows only (the reference projects after filtering).
+//
+// Accumulator convention: for 8/16/32-bit integers and Float32 only the low 32 bits of the
+// container are meaningful (integers sign-/zero-extended to 32 bits); 64-bit types use all of it.
 //
 // Build with -fmad=false: float results must be the IEEE single operations arrow-rs performs.
 #include <cuda_runtime.h>
@@ -26,23 +32,40 @@ namespace chdb {
 namespace {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr int kBitStageWords = kTileRows / 32 + 8;
+constexpr int kBitStageBytes = kTileRows + 64;   // one byte per output row + word-alignment slack
 
 template <typename V> struct Cont;
-template <> struct Cont<uint32_t> { using S = int32_t; static constexpr bool k64 = false; };
-template <> struct Cont<uint64_t> { using S = int64_t; static constexpr bool k64 = true; };
+template <> struct Cont<uint32_t> { static constexpr bool k64 = false; };
+template <> struct Cont<uint64_t> { static constexpr bool k64 = true; };
 
 // ------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void report_error(const KernelParams& P, uint32_t order, int64_t row, uint32_t code) {
+__device__ __noinline__ void report_error(const KernelParams& P, uint32_t order, int64_t row, uint32_t code) {
   unsigned long long packed = ((unsigned long long)order << 56) | (((unsigned long long)row & 0xFFFFFFFFFFFFull) << 8) | code;
   atomicMax((unsigned long long*)P.error_word, ~packed);
+}
+
+// bad / divz: per-thread row masks of failing rows (already restricted to evaluated rows)
+template <int QPT>
+__device__ __forceinline__ void report_rows(const KernelParams& P, const Instr& in, uint32_t ovf, uint32_t divz,
+                                            const int64_t (&qbase)[QPT]) {
+  const uint32_t any = ovf | divz;
+  if (any) {
+    const int j = __ffs(any) - 1;   // rows ascend with j inside a thread
+    int64_t row = qbase[0];
+#pragma unroll
+    for (int q = 1; q < QPT; q++)
+      if ((j >> 2) == q) row = qbase[q];   // static indexing keeps qbase in registers
+    report_error(P, in.order, row + (j & 3), ((divz >> j) & 1u) ? CHDB_ERR_DIVIDE_BY_ZERO : CHDB_ERR_ARITHMETIC_OVERFLOW);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // loads
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int QPT>
 __device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ bits, const int64_t (&qbase)[QPT], uint32_t need) {
   if (bits == nullptr) return FULL;
@@ -50,52 +73,67 @@ __device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ bits, 
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
     if ((need >> (4 * q)) & 0xFu) {
-      uint32_t byte = __ldg(bits + (qbase[q] >> 3));
+      const uint32_t byte = __ldg(bits + (qbase[q] >> 3));
       m |= ((byte >> (uint32_t)(qbase[q] & 4)) & 0xFu) << (4 * q);
     }
   }
   return m;
 }
 
-// Raw little-endian values of the thread's rows, zero-extended to 64 bits (width 1/2/4/8).
-template <int QPT>
-__device__ __forceinline__ void fetch_raw(const ColumnDesc& c, const int64_t (&qbase)[QPT], uint32_t need,
-                                          uint64_t (&e)[4 * QPT]) {
+// Column values of the thread's rows in accumulator form (see the convention above).
+template <typename V, int QPT>
+__device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type, const int64_t (&qbase)[QPT], uint32_t need,
+                                          V (&b)[4 * QPT]) {
   const uint8_t* __restrict__ base = (const uint8_t*)c.values;
-  const int width = c.width;
 #pragma unroll
-  for (int j = 0; j < 4 * QPT; j++) e[j] = 0;
+  for (int j = 0; j < 4 * QPT; j++) b[j] = 0;
+  switch (from_type) {
+    case T_I32: case T_U32: case T_F32:
 #pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    if (!((need >> (4 * q)) & 0xFu)) continue;
-    const int64_t r = qbase[q];
-    if (width == 4) {
-      uint4 x = __ldg((const uint4*)(base + r * 4));
-      e[4 * q + 0] = x.x; e[4 * q + 1] = x.y; e[4 * q + 2] = x.z; e[4 * q + 3] = x.w;
-    } else if (width == 8) {
-      uint4 x = __ldg((const uint4*)(base + r * 8));
-      uint4 y = __ldg((const uint4*)(base + r * 8 + 16));
-      e[4 * q + 0] = x.x | ((uint64_t)x.y << 32); e[4 * q + 1] = x.z | ((uint64_t)x.w << 32);
-      e[4 * q + 2] = y.x | ((uint64_t)y.y << 32); e[4 * q + 3] = y.z | ((uint64_t)y.w << 32);
-    } else if (width == 2) {
-      uint2 x = __ldg((const uint2*)(base + r * 2));
-      e[4 * q + 0] = x.x & 0xFFFFu; e[4 * q + 1] = x.x >> 16; e[4 * q + 2] = x.y & 0xFFFFu; e[4 * q + 3] = x.y >> 16;
-    } else {
-      uint32_t x = __ldg((const uint32_t*)(base + r));
-      e[4 * q + 0] = x & 0xFFu; e[4 * q + 1] = (x >> 8) & 0xFFu; e[4 * q + 2] = (x >> 16) & 0xFFu; e[4 * q + 3] = x >> 24;
-    }
-  }
-}
-
-// Canonical accumulator form: integers sign-/zero-extended to the whole container.
-template <typename V>
-__device__ __forceinline__ V extend(uint64_t raw, uint8_t t) {
-  using S = typename Cont<V>::S;
-  switch (t) {
-    case T_I8: return (V)(S)(int8_t)raw;
-    case T_I16: return (V)(S)(int16_t)raw;
-    case T_I32: return (V)(S)(int32_t)raw;
-    default: return (V)raw;
+      for (int q = 0; q < QPT; q++) {
+        if (!((need >> (4 * q)) & 0xFu)) continue;
+        const uint4 x = __ldg((const uint4*)(base + qbase[q] * 4));
+        b[4 * q + 0] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+      }
+      break;
+    case T_I64: case T_U64: case T_F64:
+      if constexpr (Cont<V>::k64) {
+#pragma unroll
+        for (int q = 0; q < QPT; q++) {
+          if (!((need >> (4 * q)) & 0xFu)) continue;
+          const uint4 x = __ldg((const uint4*)(base + qbase[q] * 8));
+          const uint4 y = __ldg((const uint4*)(base + qbase[q] * 8 + 16));
+          b[4 * q + 0] = x.x | ((uint64_t)x.y << 32); b[4 * q + 1] = x.z | ((uint64_t)x.w << 32);
+          b[4 * q + 2] = y.x | ((uint64_t)y.y << 32); b[4 * q + 3] = y.z | ((uint64_t)y.w << 32);
+        }
+      }
+      break;
+    case T_I16: case T_U16:
+#pragma unroll
+      for (int q = 0; q < QPT; q++) {
+        if (!((need >> (4 * q)) & 0xFu)) continue;
+        const uint2 x = __ldg((const uint2*)(base + qbase[q] * 2));
+        if (from_type == T_I16) {
+          b[4 * q + 0] = (uint32_t)(int32_t)(int16_t)(x.x & 0xFFFFu); b[4 * q + 1] = (uint32_t)(int32_t)(int16_t)(x.x >> 16);
+          b[4 * q + 2] = (uint32_t)(int32_t)(int16_t)(x.y & 0xFFFFu); b[4 * q + 3] = (uint32_t)(int32_t)(int16_t)(x.y >> 16);
+        } else {
+          b[4 * q + 0] = x.x & 0xFFFFu; b[4 * q + 1] = x.x >> 16; b[4 * q + 2] = x.y & 0xFFFFu; b[4 * q + 3] = x.y >> 16;
+        }
+      }
+      break;
+    default:  // T_I8 / T_U8
+#pragma unroll
+      for (int q = 0; q < QPT; q++) {
+        if (!((need >> (4 * q)) & 0xFu)) continue;
+        const uint32_t x = __ldg((const uint32_t*)(base + qbase[q]));
+        if (from_type == T_I8) {
+          b[4 * q + 0] = (uint32_t)(int32_t)(int8_t)(x & 0xFFu); b[4 * q + 1] = (uint32_t)(int32_t)(int8_t)((x >> 8) & 0xFFu);
+          b[4 * q + 2] = (uint32_t)(int32_t)(int8_t)((x >> 16) & 0xFFu); b[4 * q + 3] = (uint32_t)(int32_t)(int8_t)(x >> 24);
+        } else {
+          b[4 * q + 0] = x & 0xFFu; b[4 * q + 1] = (x >> 8) & 0xFFu; b[4 * q + 2] = (x >> 16) & 0xFFu; b[4 * q + 3] = x >> 24;
+        }
+      }
+      break;
   }
 }
 
@@ -104,30 +142,43 @@ __device__ __forceinline__ V extend(uint64_t raw, uint8_t t) {
 // ------------------------------------------------------------------------------------------
 template <typename V, int R>
 __device__ __forceinline__ void cast_vals(V (&a)[R], uint8_t from, uint8_t to) {
-  using S = typename Cont<V>::S;
   const TypeClass fc = type_class(from), tc = type_class(to);
   if (fc == tc) return;
   if (tc == C_F32) {
-    if (fc == C_SINT || fc == C_S64) {
+    if (fc == C_SINT) {
 #pragma unroll
-      for (int j = 0; j < R; j++) a[j] = (V)__float_as_uint((float)(S)a[j]);
-    } else if (fc == C_UINT || fc == C_U64) {
+      for (int j = 0; j < R; j++) a[j] = (V)__float_as_uint((float)(int32_t)(uint32_t)a[j]);
+    } else if (fc == C_UINT) {
 #pragma unroll
-      for (int j = 0; j < R; j++) a[j] = (V)__float_as_uint((float)a[j]);
+      for (int j = 0; j < R; j++) a[j] = (V)__float_as_uint((float)(uint32_t)a[j]);
+    } else if (fc == C_S64) {
+#pragma unroll
+      for (int j = 0; j < R; j++) a[j] = (V)__float_as_uint((float)(int64_t)a[j]);
+    } else if (fc == C_U64) {
+#pragma unroll
+      for (int j = 0; j < R; j++) a[j] = (V)__float_as_uint((float)(uint64_t)a[j]);
     }
-  } else if (tc == C_F64) {
-    if constexpr (Cont<V>::k64) {
-      if (fc == C_SINT || fc == C_S64) {
+    return;
+  }
+  if constexpr (Cont<V>::k64) {
+    if (tc == C_F64) {
+      if (fc == C_SINT) {
+#pragma unroll
+        for (int j = 0; j < R; j++) a[j] = (V)__double_as_longlong((double)(int32_t)(uint32_t)a[j]);
+      } else if (fc == C_UINT) {
+#pragma unroll
+        for (int j = 0; j < R; j++) a[j] = (V)__double_as_longlong((double)(uint32_t)a[j]);
+      } else if (fc == C_S64) {
 #pragma unroll
         for (int j = 0; j < R; j++) a[j] = (V)__double_as_longlong((double)(int64_t)a[j]);
-      } else if (fc == C_UINT || fc == C_U64) {
+      } else if (fc == C_U64) {
 #pragma unroll
         for (int j = 0; j < R; j++) a[j] = (V)__double_as_longlong((double)(uint64_t)a[j]);
       } else if (fc == C_F32) {
 #pragma unroll
         for (int j = 0; j < R; j++) {
-          uint32_t u = (uint32_t)a[j];
-          float x = __uint_as_float(u);
+          const uint32_t u = (uint32_t)a[j];
+          const float x = __uint_as_float(u);
           uint64_t r;
           if (x != x)  // keep sign and payload, quiet (x86 cvtss2sd)
             r = ((uint64_t)(u & 0x80000000u) << 32) | 0x7FF8000000000000ull | ((uint64_t)(u & 0x007FFFFFu) << 29);
@@ -136,22 +187,34 @@ __device__ __forceinline__ void cast_vals(V (&a)[R], uint8_t from, uint8_t to) {
           a[j] = (V)r;
         }
       }
+    } else if (tc == C_S64 || tc == C_U64) {   // widening from a 32-bit container
+      if (fc == C_SINT) {
+#pragma unroll
+        for (int j = 0; j < R; j++) a[j] = (V)(int64_t)(int32_t)(uint32_t)a[j];
+      } else if (fc == C_UINT) {
+#pragma unroll
+        for (int j = 0; j < R; j++) a[j] = (V)(uint32_t)a[j];
+      }
     }
   }
-  // integer -> integer widening: the canonical container already holds the value
 }
 
 template <typename V, int R>
 __device__ __forceinline__ uint32_t tobool_vals(const V (&a)[R], uint8_t t) {
   const TypeClass c = type_class(t);
   uint32_t m = 0;
+  if (c == C_F32) {
 #pragma unroll
-  for (int j = 0; j < R; j++) {
-    bool b;
-    if (c == C_F32) b = __uint_as_float((uint32_t)a[j]) != 0.0f;   // NaN -> true, -0.0 -> false
-    else if (c == C_F64) b = __longlong_as_double((long long)(uint64_t)a[j]) != 0.0;
-    else b = a[j] != 0;
-    m |= (b ? 1u : 0u) << j;
+    for (int j = 0; j < R; j++) m |= (__uint_as_float((uint32_t)a[j]) != 0.0f ? 1u : 0u) << j;   // NaN -> true, -0.0 -> false
+  } else if (c == C_F64) {
+#pragma unroll
+    for (int j = 0; j < R; j++) m |= (__longlong_as_double((long long)(uint64_t)a[j]) != 0.0 ? 1u : 0u) << j;
+  } else if (c == C_S64 || c == C_U64) {
+#pragma unroll
+    for (int j = 0; j < R; j++) m |= (a[j] != 0 ? 1u : 0u) << j;
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; j++) m |= ((uint32_t)a[j] != 0 ? 1u : 0u) << j;
   }
   return m;
 }
@@ -180,63 +243,131 @@ __device__ __forceinline__ double nanfix64(double r, double x, double y) {
   return r;
 }
 
-template <typename V>
-__device__ __forceinline__ int64_t narrow_i64(V x, bool is_signed) {
-  if constexpr (Cont<V>::k64) return (int64_t)x;
-  else return is_signed ? (int64_t)(int32_t)x : (int64_t)(uint32_t)x;
+// Rare, slow scalar paths stay out of line so the unrolled row loops around them remain small
+// (and the accumulator arrays are only ever indexed statically, i.e. stay in registers).
+// flags: 1 = overflow, 2 = divide by zero.
+struct Slow64 { uint64_t r; uint32_t flags; };
+struct Slow32 { int32_t r; uint32_t flags; };
+__device__ __noinline__ Slow64 slow_i64(uint32_t op, int64_t x, int64_t y) {
+  uint32_t fl = 0, *flags = &fl;
+  int64_t r = 0;
+  if (op == OP_DIV || op == OP_REM) {
+    if (y == 0) *flags |= 2u;
+    else if (x == INT64_MIN && y == -1) *flags |= 1u;
+    else r = op == OP_DIV ? x / y : x % y;
+  } else if (op == OP_ADD) {
+    r = (int64_t)((uint64_t)x + (uint64_t)y);
+    if (((x ^ r) & (y ^ r)) < 0) *flags |= 1u;
+  } else if (op == OP_MUL) {
+    r = (int64_t)((uint64_t)x * (uint64_t)y);
+    if (__mul64hi(x, y) != (r >> 63)) *flags |= 1u;
+  } else {
+    r = (int64_t)((uint64_t)x - (uint64_t)y);
+    if (((x ^ y) & (x ^ r)) < 0) *flags |= 1u;
+  }
+  return Slow64{(uint64_t)r, fl};
+}
+__device__ __noinline__ Slow64 slow_u64(uint32_t op, uint64_t x, uint64_t y) {
+  uint32_t fl = 0, *flags = &fl;
+  uint64_t r = 0;
+  if (op == OP_DIV || op == OP_REM) {
+    if (y == 0) *flags |= 2u;
+    else r = op == OP_DIV ? x / y : x % y;
+  } else if (op == OP_ADD) {
+    r = x + y;
+    if (r < x) *flags |= 1u;
+  } else if (op == OP_MUL) {
+    r = x * y;
+    if (__umul64hi(x, y) != 0) *flags |= 1u;
+  } else {
+    r = x - y;
+    if (x < y) *flags |= 1u;
+  }
+  return Slow64{r, fl};
+}
+// 8/16-bit integers: exact in 64 bits, then range-checked against [lo, hi]
+__device__ __noinline__ Slow32 slow_narrow(uint32_t op, int32_t x32, int32_t y32, int32_t lo, int32_t hi) {
+  uint32_t fl = 0, *flags = &fl;
+  const int64_t x = x32, y = y32;
+  int64_t r = 0;
+  if (op == OP_DIV || op == OP_REM) {
+    if (y == 0) *flags |= 2u;
+    else if (lo < 0 && x == lo && y == -1) *flags |= 1u;
+    else r = op == OP_DIV ? x / y : x % y;
+  } else {
+    r = op == OP_ADD ? x + y : op == OP_MUL ? x * y : x - y;
+    if (r < lo || r > hi) { *flags |= 1u; r = 0; }
+  }
+  return Slow32{(int32_t)r, fl};
 }
 
-template <typename V, int QPT>
+// IMM: the operand is the instruction's immediate (uniform); SWAP: operand is the LEFT side.
+// Rows that are null or filtered out may hold anything afterwards: arrow leaves them unobservable.
+template <bool IMM, bool SWAP, typename V, int QPT>
 __device__ __forceinline__ void arith(const KernelParams& P, const Instr& in, V (&a)[4 * QPT], uint32_t& av, const V (&b)[4 * QPT],
                                       uint32_t bv, uint32_t active, const int64_t (&qbase)[QPT]) {
   constexpr int R = 4 * QPT;
-  const bool swap = (in.flags & OPF_SWAP) != 0;
-  const uint8_t op = in.op;
-  const TypeClass tc = type_class(in.type);
+  const uint8_t op = in.op, t = in.type;
   const uint32_t valid = av & bv;
   av = valid;
-  const uint32_t m = valid & active;  // fallible ops run on valid, live rows only; other slots hold 0
-#define CHDB_ROW(j) (qbase[(j) >> 2] + ((j) & 3))
-  if (tc == C_SINT || tc == C_UINT) {
-    const bool sgn = tc == C_SINT;
-    int64_t lo, hi;
-    switch (in.type) {
-      case T_I8: lo = -128; hi = 127; break;
-      case T_I16: lo = -32768; hi = 32767; break;
-      case T_I32: lo = -2147483648ll; hi = 2147483647ll; break;
-      case T_U8: lo = 0; hi = 255; break;
-      case T_U16: lo = 0; hi = 65535; break;
-      default: lo = 0; hi = 4294967295ll; break;
-    }
+  const uint32_t m = valid & active;   // fallible ops are only *checked* on valid, live rows
+  const V immv = (V)in.imm;
+#define CHDB_B(j) (IMM ? immv : b[j])
+#define CHDB_X(j) (SWAP ? CHDB_B(j) : a[j])
+#define CHDB_Y(j) (SWAP ? a[j] : CHDB_B(j))
+  uint32_t ovf = 0, divz = 0;
+  if (t == T_I32) {
+    if (op == OP_ADD) {
 #pragma unroll
-    for (int j = 0; j < R; j++) {
-      int64_t r = 0;
-      if ((m >> j) & 1u) {
-        const int64_t x = narrow_i64<V>(swap ? b[j] : a[j], sgn), y = narrow_i64<V>(swap ? a[j] : b[j], sgn);
-        if (op == OP_DIV || op == OP_REM) {
-          if (y == 0) {
-            report_error(P, in.order, CHDB_ROW(j), CHDB_ERR_DIVIDE_BY_ZERO);
-          } else if (sgn && x == lo && y == -1) {
-            report_error(P, in.order, CHDB_ROW(j), CHDB_ERR_ARITHMETIC_OVERFLOW);
-          } else if (sgn) {
-            r = op == OP_DIV ? (int64_t)((int32_t)x / (int32_t)y) : (int64_t)((int32_t)x % (int32_t)y);
-          } else {
-            r = op == OP_DIV ? (int64_t)((uint32_t)x / (uint32_t)y) : (int64_t)((uint32_t)x % (uint32_t)y);
-          }
-        } else {
-          r = op == OP_ADD ? x + y : op == OP_MUL ? x * y : x - y;
-          if (r < lo || r > hi) {
-            report_error(P, in.order, CHDB_ROW(j), CHDB_ERR_ARITHMETIC_OVERFLOW);
-            r = 0;
-          }
+      for (int j = 0; j < R; j++) {
+        const int32_t x = (int32_t)(uint32_t)CHDB_X(j), y = (int32_t)(uint32_t)CHDB_Y(j);
+        const int32_t r = (int32_t)((uint32_t)x + (uint32_t)y);
+        ovf |= ((uint32_t)((x ^ r) & (y ^ r)) >> 31) << j;
+        a[j] = (V)(uint32_t)r;
+      }
+    } else if (op == OP_MUL) {
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        const int32_t x = (int32_t)(uint32_t)CHDB_X(j), y = (int32_t)(uint32_t)CHDB_Y(j);
+        const int64_t p = (int64_t)x * (int64_t)y;
+        const int32_t r = (int32_t)p;
+        ovf |= (p != (int64_t)r ? 1u : 0u) << j;
+        a[j] = (V)(uint32_t)r;
+      }
+    } else if (op == OP_SUB) {
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        const int32_t x = (int32_t)(uint32_t)CHDB_X(j), y = (int32_t)(uint32_t)CHDB_Y(j);
+        const int32_t r = (int32_t)((uint32_t)x - (uint32_t)y);
+        ovf |= ((uint32_t)((x ^ y) & (x ^ r)) >> 31) << j;
+        a[j] = (V)(uint32_t)r;
+      }
+    } else {
+      const int32_t d = (int32_t)(uint32_t)in.imm;
+      if (IMM && !SWAP && d > 0 && (d & (d - 1)) == 0) {   // divisor 2^k: no error is possible
+        const int k = __ffs(d) - 1;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          const int32_t x = (int32_t)(uint32_t)a[j];
+          const int32_t q = (x + ((x >> 31) & (d - 1))) >> k;   // truncating division
+          a[j] = (V)(uint32_t)(op == OP_DIV ? q : x - (q << k));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          const int32_t x = (int32_t)(uint32_t)CHDB_X(j), y = (int32_t)(uint32_t)CHDB_Y(j);
+          const bool z = y == 0, o = x == INT32_MIN && y == -1;
+          divz |= (z ? 1u : 0u) << j;
+          ovf |= (o ? 1u : 0u) << j;
+          const int32_t ys = (z || o) ? 1 : y;
+          a[j] = (V)(uint32_t)(op == OP_DIV ? x / ys : x % ys);
         }
       }
-      a[j] = (V)r;
     }
-  } else if (tc == C_F32) {
+  } else if (t == T_F32) {
 #pragma unroll
     for (int j = 0; j < R; j++) {
-      const float x = __uint_as_float((uint32_t)(swap ? b[j] : a[j])), y = __uint_as_float((uint32_t)(swap ? a[j] : b[j]));
+      const float x = __uint_as_float((uint32_t)CHDB_X(j)), y = __uint_as_float((uint32_t)CHDB_Y(j));
       float r;
       switch (op) {
         case OP_ADD: r = __fadd_rn(x, y); break;
@@ -247,12 +378,43 @@ __device__ __forceinline__ void arith(const KernelParams& P, const Instr& in, V 
       }
       a[j] = (V)__float_as_uint(nanfix32(r, x, y));
     }
+  } else if (t == T_U32) {
+    const uint32_t d = (uint32_t)in.imm;
+    if ((op == OP_DIV || op == OP_REM) && IMM && !SWAP && d != 0 && (d & (d - 1)) == 0) {
+      const int k = __ffs((int)d) - 1;
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        const uint32_t x = (uint32_t)a[j];
+        a[j] = (V)(op == OP_DIV ? x >> k : x & (d - 1));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        const uint32_t x = (uint32_t)CHDB_X(j), y = (uint32_t)CHDB_Y(j);
+        uint32_t r;
+        if (op == OP_ADD) { r = x + y; ovf |= (r < x ? 1u : 0u) << j; }
+        else if (op == OP_MUL) { const uint64_t p = (uint64_t)x * y; r = (uint32_t)p; ovf |= ((p >> 32) != 0 ? 1u : 0u) << j; }
+        else if (op == OP_SUB) { r = x - y; ovf |= (x < y ? 1u : 0u) << j; }
+        else { const bool z = y == 0; divz |= (z ? 1u : 0u) << j; const uint32_t ys = z ? 1u : y; r = op == OP_DIV ? x / ys : x % ys; }
+        a[j] = (V)r;
+      }
+    }
+  } else if (t == T_I8 || t == T_I16 || t == T_U8 || t == T_U16) {
+    const int32_t lo = t == T_I8 ? -128 : t == T_I16 ? -32768 : 0;
+    const int32_t hi = t == T_I8 ? 127 : t == T_I16 ? 32767 : t == T_U8 ? 255 : 65535;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      const Slow32 sr = slow_narrow(op, (int32_t)(uint32_t)CHDB_X(j), (int32_t)(uint32_t)CHDB_Y(j), lo, hi);
+      a[j] = (V)(uint32_t)sr.r;
+      ovf |= (sr.flags & 1u) << j;
+      divz |= (sr.flags >> 1) << j;
+    }
   } else {
     if constexpr (Cont<V>::k64) {
-      if (tc == C_F64) {
+      if (t == T_F64) {
 #pragma unroll
         for (int j = 0; j < R; j++) {
-          const double x = __longlong_as_double((long long)(swap ? b[j] : a[j])), y = __longlong_as_double((long long)(swap ? a[j] : b[j]));
+          const double x = __longlong_as_double((long long)CHDB_X(j)), y = __longlong_as_double((long long)CHDB_Y(j));
           double r;
           switch (op) {
             case OP_ADD: r = __dadd_rn(x, y); break;
@@ -263,126 +425,96 @@ __device__ __forceinline__ void arith(const KernelParams& P, const Instr& in, V 
           }
           a[j] = (V)__double_as_longlong(nanfix64(r, x, y));
         }
-      } else if (tc == C_S64) {
+      } else if (t == T_I64) {
 #pragma unroll
         for (int j = 0; j < R; j++) {
-          int64_t r = 0;
-          if ((m >> j) & 1u) {
-            const int64_t x = (int64_t)(swap ? b[j] : a[j]), y = (int64_t)(swap ? a[j] : b[j]);
-            bool ovf = false;
-            if (op == OP_DIV || op == OP_REM) {
-              if (y == 0) report_error(P, in.order, CHDB_ROW(j), CHDB_ERR_DIVIDE_BY_ZERO);
-              else if (x == INT64_MIN && y == -1) ovf = true;
-              else r = op == OP_DIV ? x / y : x % y;
-            } else if (op == OP_ADD) {
-              r = (int64_t)((uint64_t)x + (uint64_t)y);
-              ovf = ((x ^ r) & (y ^ r)) < 0;
-            } else if (op == OP_MUL) {
-              r = (int64_t)((uint64_t)x * (uint64_t)y);
-              ovf = __mul64hi(x, y) != (r >> 63);
-            } else {
-              r = (int64_t)((uint64_t)x - (uint64_t)y);
-              ovf = ((x ^ y) & (x ^ r)) < 0;
-            }
-            if (ovf) {
-              report_error(P, in.order, CHDB_ROW(j), CHDB_ERR_ARITHMETIC_OVERFLOW);
-              r = 0;
-            }
-          }
-          a[j] = (V)r;
+          const Slow64 sr = slow_i64(op, (int64_t)CHDB_X(j), (int64_t)CHDB_Y(j));
+          a[j] = (V)sr.r;
+          ovf |= (sr.flags & 1u) << j;
+          divz |= (sr.flags >> 1) << j;
         }
-      } else {  // C_U64
+      } else {  // T_U64
 #pragma unroll
         for (int j = 0; j < R; j++) {
-          uint64_t r = 0;
-          if ((m >> j) & 1u) {
-            const uint64_t x = (uint64_t)(swap ? b[j] : a[j]), y = (uint64_t)(swap ? a[j] : b[j]);
-            bool ovf = false;
-            if (op == OP_DIV || op == OP_REM) {
-              if (y == 0) report_error(P, in.order, CHDB_ROW(j), CHDB_ERR_DIVIDE_BY_ZERO);
-              else r = op == OP_DIV ? x / y : x % y;
-            } else if (op == OP_ADD) {
-              r = x + y;
-              ovf = r < x;
-            } else if (op == OP_MUL) {
-              r = x * y;
-              ovf = __umul64hi(x, y) != 0;
-            } else {
-              r = x - y;
-              ovf = x < y;
-            }
-            if (ovf) {
-              report_error(P, in.order, CHDB_ROW(j), CHDB_ERR_ARITHMETIC_OVERFLOW);
-              r = 0;
-            }
-          }
-          a[j] = (V)r;
+          const Slow64 sr = slow_u64(op, (uint64_t)CHDB_X(j), (uint64_t)CHDB_Y(j));
+          a[j] = (V)sr.r;
+          ovf |= (sr.flags & 1u) << j;
+          divz |= (sr.flags >> 1) << j;
         }
       }
     }
   }
-#undef CHDB_ROW
+#undef CHDB_B
+#undef CHDB_X
+#undef CHDB_Y
+  report_rows<QPT>(P, in, ovf & m, divz & m, qbase);
 }
 
 // ------------------------------------------------------------------------------------------
 // comparisons (arrow-ord cmp.rs: natural integer order, IEEE-754 totalOrder for floats)
+//   eq(a,b) | lt(a,b) | gt(a,b) = lt(b,a);  ne / ge / le are their complements
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cmp_select(uint8_t kind, uint32_t lt, uint32_t eq) {
-  switch (kind) {
-    case CMP_EQ: return eq;
-    case CMP_NE: return ~eq;
-    case CMP_LT: return lt;
-    case CMP_LE: return lt | eq;
-    case CMP_GT: return ~(lt | eq);
-    default: return ~lt;
-  }
+__device__ __forceinline__ int32_t total_key32(uint32_t u) {
+  int32_t k = (int32_t)u;
+  return k ^ (int32_t)(((uint32_t)(k >> 31)) >> 1);
+}
+__device__ __forceinline__ int64_t total_key64(uint64_t u) {
+  int64_t k = (int64_t)u;
+  return k ^ (int64_t)(((uint64_t)(k >> 63)) >> 1);
 }
 
-template <typename V, int R>
-__device__ __forceinline__ uint32_t compare(const Instr& in, const V (&a)[R], uint32_t am, const V (&b)[R], uint32_t bm) {
-  using S = typename Cont<V>::S;
-  const TypeClass tc = type_class(in.type);
-  uint32_t lt = 0, eq = 0;
-  if (tc == C_BOOL) {  // false < true
-    lt = ~am & bm;
-    eq = ~(am ^ bm);
-  } else {
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      bool l, e;
-      if (tc == C_SINT) {
-        l = (S)a[j] < (S)b[j];
-        e = a[j] == b[j];
-      } else if (tc == C_F32) {
-        int32_t x = (int32_t)(uint32_t)a[j], y = (int32_t)(uint32_t)b[j];
-        e = x == y;  // bitwise: NaN == NaN with equal payloads, -0.0 != +0.0
-        x ^= (int32_t)(((uint32_t)(x >> 31)) >> 1);
-        y ^= (int32_t)(((uint32_t)(y >> 31)) >> 1);
-        l = x < y;
-      } else if (tc == C_S64) {
-        l = (int64_t)a[j] < (int64_t)b[j];
-        e = a[j] == b[j];
-      } else if (tc == C_F64) {
-        int64_t x = (int64_t)a[j], y = (int64_t)b[j];
-        e = x == y;
-        x ^= (int64_t)(((uint64_t)(x >> 63)) >> 1);
-        y ^= (int64_t)(((uint64_t)(y >> 63)) >> 1);
-        l = x < y;
-      } else {  // C_UINT, C_U64: zero-extended containers compare unsigned
-        l = a[j] < b[j];
-        e = a[j] == b[j];
-      }
-      lt |= (l ? 1u : 0u) << j;
-      eq |= (e ? 1u : 0u) << j;
-    }
+#define CHDB_CMP_LOOP(XT, XEXPR, YEXPR)                                                   \
+  if (mode == 0) {                                                                        \
+    _Pragma("unroll") for (int j = 0; j < R; j++) { const XT x = XEXPR, y = YEXPR; r |= (x == y ? 1u : 0u) << j; } \
+  } else if (mode == 1) {                                                                 \
+    _Pragma("unroll") for (int j = 0; j < R; j++) { const XT x = XEXPR, y = YEXPR; r |= (x < y ? 1u : 0u) << j; }  \
+  } else {                                                                                \
+    _Pragma("unroll") for (int j = 0; j < R; j++) { const XT x = XEXPR, y = YEXPR; r |= (y < x ? 1u : 0u) << j; }  \
   }
-  return cmp_select(in.aux, lt, eq);
+
+template <bool IMM, typename V, int R>
+__device__ __forceinline__ uint32_t compare(const Instr& in, const V (&a)[R], uint32_t am, const V (&b)[R], uint32_t bm) {
+  const uint8_t kind = in.aux;
+  const TypeClass tc = type_class(in.type);
+  const int mode = (kind == CMP_EQ || kind == CMP_NE) ? 0 : (kind == CMP_LT || kind == CMP_GE) ? 1 : 2;
+  const bool negate = kind == CMP_NE || kind == CMP_GE || kind == CMP_LE;
+  const V immv = (V)in.imm;
+#define CHDB_B(j) (IMM ? immv : b[j])
+  uint32_t r = 0;
+  switch (tc) {
+    case C_BOOL:  // false < true
+      r = mode == 0 ? ~(am ^ bm) : mode == 1 ? (~am & bm) : (am & ~bm);
+      break;
+    case C_SINT: CHDB_CMP_LOOP(int32_t, (int32_t)(uint32_t)a[j], (int32_t)(uint32_t)CHDB_B(j)) break;
+    case C_UINT: CHDB_CMP_LOOP(uint32_t, (uint32_t)a[j], (uint32_t)CHDB_B(j)) break;
+    case C_F32:
+      if (mode == 0) {  // bitwise: NaN == NaN with equal payloads, -0.0 != +0.0
+        CHDB_CMP_LOOP(uint32_t, (uint32_t)a[j], (uint32_t)CHDB_B(j))
+      } else {
+        CHDB_CMP_LOOP(int32_t, total_key32((uint32_t)a[j]), total_key32((uint32_t)CHDB_B(j)))
+      }
+      break;
+    default:
+      if constexpr (Cont<V>::k64) {
+        if (tc == C_S64) { CHDB_CMP_LOOP(int64_t, (int64_t)a[j], (int64_t)CHDB_B(j)) }
+        else if (tc == C_U64) { CHDB_CMP_LOOP(uint64_t, (uint64_t)a[j], (uint64_t)CHDB_B(j)) }
+        else if (mode == 0) { CHDB_CMP_LOOP(uint64_t, (uint64_t)a[j], (uint64_t)CHDB_B(j)) }
+        else { CHDB_CMP_LOOP(int64_t, total_key64((uint64_t)a[j]), total_key64((uint64_t)CHDB_B(j))) }
+      }
+      break;
+  }
+#undef CHDB_B
+  return negate ? ~r : r;
 }
 
 // Utf8: bytewise lexicographic; operands are columns or a literal from the string pool.
+template <int QPT> struct QuadBases { int64_t v[QPT]; };
+
 template <int QPT>
-__device__ __forceinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr& in, const int64_t (&qbase)[QPT], uint32_t inrange,
-                                             const uint8_t* s_pool, uint32_t& valid) {
+__device__ __noinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr in, const QuadBases<QPT> qb, uint32_t inrange,
+                                          const uint8_t* s_pool, uint32_t* valid_out) {
+  const int64_t (&qbase)[QPT] = qb.v;
+  uint32_t valid;
   const uint32_t slot_a = in.slot, slot_b = (uint32_t)(in.imm >> 56);
   const uint32_t pool_off = (uint32_t)in.imm, pool_len = (uint32_t)(in.imm >> 32) & 0xFFFFFFu;
   valid = FULL;
@@ -397,7 +529,7 @@ __device__ __forceinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr&
     int la, lb;
     if (slot_a != 0xFFu) {
       const int32_t* off = P.in[slot_a].offsets;
-      int o0 = __ldg(off + row), o1 = __ldg(off + row + 1);
+      const int o0 = __ldg(off + row), o1 = __ldg(off + row + 1);
       pa = (const uint8_t*)P.in[slot_a].values + o0;
       la = o1 - o0;
     } else {
@@ -406,7 +538,7 @@ __device__ __forceinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr&
     }
     if (slot_b != 0xFFu) {
       const int32_t* off = P.in[slot_b].offsets;
-      int o0 = __ldg(off + row), o1 = __ldg(off + row + 1);
+      const int o0 = __ldg(off + row), o1 = __ldg(off + row + 1);
       pb = (const uint8_t*)P.in[slot_b].values + o0;
       lb = o1 - o0;
     } else {
@@ -423,7 +555,15 @@ __device__ __forceinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr&
     lt |= (c < 0 ? 1u : 0u) << j;
     eq |= (c == 0 ? 1u : 0u) << j;
   }
-  return cmp_select(in.aux, lt, eq);
+  *valid_out = valid;
+  switch (in.aux) {
+    case CMP_EQ: return eq;
+    case CMP_NE: return ~eq;
+    case CMP_LT: return lt;
+    case CMP_LE: return lt | eq;
+    case CMP_GT: return ~(lt | eq);
+    default: return ~lt;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -445,11 +585,8 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
     const Instr in = P.instrs[pc];
     V b[R];
     uint32_t bm = 0, bv = FULL;
-#pragma unroll
-    for (int j = 0; j < R; j++) b[j] = 0;
-    if (in.src == SRC_IMM) {
-#pragma unroll
-      for (int j = 0; j < R; j++) b[j] = (V)in.imm;
+    const bool imm = in.src == SRC_IMM;
+    if (imm) {
       bm = in.imm ? FULL : 0u;
     } else if (in.src == SRC_STK) {
       if (in.type != T_BOOL) {   // Boolean spills only carry the two masks
@@ -464,27 +601,35 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
       if (c.type == T_BOOL) {
         bm = load_bits<QPT>((const uint8_t*)c.values, qbase, inrange);
       } else {
-        uint64_t raw[R];
-        fetch_raw<QPT>(c, qbase, inrange, raw);
-#pragma unroll
-        for (int j = 0; j < R; j++) b[j] = extend<V>(raw[j], in.from_type);
+        fetch_col<V, QPT>(c, in.from_type, qbase, inrange, b);
         if (in.type == T_BOOL) bm = tobool_vals<V, R>(b, in.from_type);
         else cast_vals<V, R>(b, in.from_type, in.type);
       }
     }
     switch (in.op) {
       case OP_LOAD:
+        if (imm) {
 #pragma unroll
-        for (int j = 0; j < R; j++) acc[j] = b[j];
+          for (int j = 0; j < R; j++) acc[j] = (V)in.imm;
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; j++) acc[j] = b[j];
+        }
         accm = bm;
         accv = bv;
         break;
       case OP_CAST: cast_vals<V, R>(acc, in.from_type, in.type); break;
       case OP_ADD: case OP_MUL: case OP_DIV: case OP_REM: case OP_SUB:
-        arith<V, QPT>(P, in, acc, accv, b, bv, active, qbase);
+        if (imm) {
+          if (in.flags & OPF_SWAP) arith<true, true, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
+          else arith<true, false, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
+        } else {
+          if (in.flags & OPF_SWAP) arith<false, true, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
+          else arith<false, false, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
+        }
         break;
       case OP_CMP:
-        accm = compare<V, R>(in, acc, accm, b, bm);
+        accm = imm ? compare<true, V, R>(in, acc, accm, b, bm) : compare<false, V, R>(in, acc, accm, b, bm);
         accv &= bv;
         break;
       case OP_TOBOOL: accm = tobool_vals<V, R>(acc, in.type); break;
@@ -498,7 +643,15 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
         stkm[in.slot] = accm;
         stkv[in.slot] = accv;
         break;
-      case OP_CMP_UTF8: accm = cmp_utf8<QPT>(P, in, qbase, inrange, s_pool, accv); break;
+      case OP_CMP_UTF8: {
+        QuadBases<QPT> qb;
+#pragma unroll
+        for (int q = 0; q < QPT; q++) qb.v[q] = qbase[q];
+        uint32_t v = FULL;
+        accm = cmp_utf8<QPT>(P, in, qb, inrange, s_pool, &v);
+        accv = v;
+        break;
+      }
       default: break;
     }
   }
@@ -517,7 +670,7 @@ __device__ __forceinline__ void block_scan(const uint32_t (&val)[QPT], uint32_t 
     uint32_t x = val[q];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t y = __shfl_up_sync(FULL, x, d);
+      const uint32_t y = __shfl_up_sync(FULL, x, d);
       if (lane >= d) x += y;
     }
     incl[q] = x;
@@ -579,31 +732,10 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc, uint32_t tile, uint
 // ------------------------------------------------------------------------------------------
 // output staging
 // ------------------------------------------------------------------------------------------
-template <int QPT>
-__device__ __forceinline__ void stage_scatter(uint8_t* stage, uint32_t mis, int W, const uint64_t (&e)[4 * QPT], uint32_t sel,
-                                              const uint32_t (&rank0)[QPT]) {
-#pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    uint32_t r = rank0[q];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int j = 4 * q + i;
-      if ((sel >> j) & 1u) {
-        uint8_t* p = stage + mis + (size_t)r * W;
-        if (W == 4) *(uint32_t*)p = (uint32_t)e[j];
-        else if (W == 8) *(uint64_t*)p = e[j];
-        else if (W == 2) *(uint16_t*)p = (uint16_t)e[j];
-        else *p = (uint8_t)e[j];
-        r++;
-      }
-    }
-  }
-}
-
 // stage[mis, mis + nbytes) -> gdst_aligned[mis, ...): aligned 16-byte stores in the middle,
-// element stores in the (at most two) chunks shared with neighbouring tiles.
-__device__ __forceinline__ void stage_writeout(const uint8_t* stage, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int W,
-                                               int tid) {
+// W-byte element stores in the (at most two) chunks shared with neighbouring tiles.
+template <int W>
+__device__ __forceinline__ void stage_writeout(const uint8_t* stage, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int tid) {
   const uint32_t end = mis + nbytes;
   const uint32_t nchunks = (end + 15u) >> 4;
   for (uint32_t c = tid; c < nchunks; c += kThreads) {
@@ -622,46 +754,115 @@ __device__ __forceinline__ void stage_writeout(const uint8_t* stage, uint8_t* gd
   }
 }
 
-// Compacts one bit per row (validity or Boolean values) into gbits at bit offset tile_prefix.
-// gbits is zero-initialised; words shared with neighbouring tiles are merged with atomicOr.
-template <int QPT>
-__device__ __forceinline__ void compact_bits(uint32_t bits, uint32_t sel, const uint32_t (&rank0)[QPT], uint64_t tile_prefix,
-                                             uint32_t tile_count, uint32_t* bitstage, uint32_t* gbits, int tid, int lane) {
-  const uint32_t o = (uint32_t)(tile_prefix & 31);
-  const uint32_t nwords = (o + tile_count + 31u) >> 5;
-  for (uint32_t k = tid; k < nwords; k += kThreads) bitstage[k] = 0;
-  __syncthreads();
+// Gathers the selected rows of a W-byte pass-through column: 128-bit loads, shared-memory staging
+// at the destination's 16-byte phase, aligned 128-bit stores.  Ends with the stage free again.
+template <int W, int QPT>
+__device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, uint8_t* dst, const int64_t (&qbase)[QPT], uint32_t sel,
+                                             const uint32_t (&rank0)[QPT], uint64_t tile_prefix, uint32_t tile_count, uint8_t* stage,
+                                             int tid) {
+  const uint32_t mis = (uint32_t)((tile_prefix * W) & 15u);
+  uint8_t* base = stage + mis;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    const uint32_t s4 = (sel >> (4 * q)) & 0xFu, b4 = (bits >> (4 * q)) & 0xFu;
-    uint32_t cb = 0, n = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if ((s4 >> i) & 1u) {
-        cb |= ((b4 >> i) & 1u) << n;
-        n++;
-      }
-    }
-    const uint32_t pos = o + rank0[q];
-    const uint32_t w0 = __shfl_sync(FULL, pos, 0) >> 5;   // first staging word this warp touches
-    const uint32_t rel = pos - (w0 << 5);                  // < 32 + 128
-    const uint64_t v = (uint64_t)cb << (rel & 31u);
-    const uint32_t wi = rel >> 5;
-#pragma unroll
-    for (uint32_t k = 0; k < 6; k++) {
-      const uint32_t contrib = (wi == k) ? (uint32_t)v : ((wi + 1 == k) ? (uint32_t)(v >> 32) : 0u);
-      const uint32_t word = __reduce_or_sync(FULL, contrib);
-      if (lane == (int)k && word) atomicOr(&bitstage[w0 + k], word);
+    const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
+    if (!s4) continue;
+    uint32_t r = rank0[q];
+    if (W == 4) {
+      const uint4 x = __ldg((const uint4*)(src + qbase[q] * 4));
+      uint32_t* p = (uint32_t*)base;
+      if (s4 & 1u) p[r++] = x.x;
+      if (s4 & 2u) p[r++] = x.y;
+      if (s4 & 4u) p[r++] = x.z;
+      if (s4 & 8u) p[r++] = x.w;
+    } else if (W == 8) {
+      const uint4 x = __ldg((const uint4*)(src + qbase[q] * 8));
+      const uint4 y = __ldg((const uint4*)(src + qbase[q] * 8 + 16));
+      uint2* p = (uint2*)base;
+      if (s4 & 1u) p[r++] = make_uint2(x.x, x.y);
+      if (s4 & 2u) p[r++] = make_uint2(x.z, x.w);
+      if (s4 & 4u) p[r++] = make_uint2(y.x, y.y);
+      if (s4 & 8u) p[r++] = make_uint2(y.z, y.w);
+    } else if (W == 2) {
+      const uint2 x = __ldg((const uint2*)(src + qbase[q] * 2));
+      uint16_t* p = (uint16_t*)base;
+      if (s4 & 1u) p[r++] = (uint16_t)(x.x & 0xFFFFu);
+      if (s4 & 2u) p[r++] = (uint16_t)(x.x >> 16);
+      if (s4 & 4u) p[r++] = (uint16_t)(x.y & 0xFFFFu);
+      if (s4 & 8u) p[r++] = (uint16_t)(x.y >> 16);
+    } else {
+      const uint32_t x = __ldg((const uint32_t*)(src + qbase[q]));
+      uint8_t* p = base;
+      if (s4 & 1u) p[r++] = (uint8_t)x;
+      if (s4 & 2u) p[r++] = (uint8_t)(x >> 8);
+      if (s4 & 4u) p[r++] = (uint8_t)(x >> 16);
+      if (s4 & 8u) p[r++] = (uint8_t)(x >> 24);
     }
   }
   __syncthreads();
+  stage_writeout<W>(stage, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
+  __syncthreads();
+}
+
+// Same, for values that already sit in registers (projection expressions, rebuilt Utf8 offsets).
+template <int W, typename E, int QPT>
+__device__ __forceinline__ void scatter_regs(const E (&e)[4 * QPT], uint8_t* dst, uint32_t sel, const uint32_t (&rank0)[QPT],
+                                             uint64_t tile_prefix, uint32_t tile_count, uint8_t* stage, int tid) {
+  const uint32_t mis = (uint32_t)((tile_prefix * W) & 15u);
+  uint8_t* base = stage + mis;
+#pragma unroll
+  for (int q = 0; q < QPT; q++) {
+    uint32_t r = rank0[q];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int j = 4 * q + i;
+      if ((sel >> j) & 1u) {
+        if (W == 4) ((uint32_t*)base)[r] = (uint32_t)e[j];
+        else if (W == 8) ((uint64_t*)base)[r] = (uint64_t)e[j];
+        else if (W == 2) ((uint16_t*)base)[r] = (uint16_t)e[j];
+        else base[r] = (uint8_t)e[j];
+        r++;
+      }
+    }
+  }
+  __syncthreads();
+  stage_writeout<W>(stage, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
+  __syncthreads();
+}
+
+// Compacts one bit per row (validity or Boolean values) into gbits at bit offset tile_prefix:
+// every selected row drops its bit as one byte at its rank, then one thread per output word packs
+// 32 bytes with four multiplies.  gbits is zero-initialised; the (at most two) words shared with
+// neighbouring tiles are merged with atomicOr.
+template <int QPT>
+__device__ __forceinline__ void compact_bits(uint32_t bits, uint32_t sel, const uint32_t (&rank0)[QPT], uint64_t tile_prefix,
+                                             uint32_t tile_count, uint8_t* bstage, uint32_t* gbits, int tid) {
+  const uint32_t o = (uint32_t)(tile_prefix & 31);
+  uint8_t* base = bstage + o;
+#pragma unroll
+  for (int q = 0; q < QPT; q++) {
+    uint32_t r = rank0[q];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int j = 4 * q + i;
+      if ((sel >> j) & 1u) base[r++] = (uint8_t)((bits >> j) & 1u);
+    }
+  }
+  __syncthreads();
+  const uint32_t end = o + tile_count;
+  const uint32_t nwords = (end + 31u) >> 5;
   const uint64_t g0 = tile_prefix >> 5;
   for (uint32_t k = tid; k < nwords; k += kThreads) {
-    const uint32_t w = bitstage[k];
-    const uint64_t bit_lo = (g0 + k) << 5;
-    const bool full = bit_lo >= tile_prefix && bit_lo + 32 <= tile_prefix + tile_count;
-    if (full) gbits[g0 + k] = w;
-    else if (w) atomicOr(&gbits[g0 + k], w);
+    const uint4 lo4 = *(const uint4*)(bstage + 32 * k), hi4 = *(const uint4*)(bstage + 32 * k + 16);
+    const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) word |= (((w[i] & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << (4 * i);
+    // bytes outside [o, end) of the first / last word are stale: mask them off
+    const uint32_t lo = 32 * k < o ? o - 32 * k : 0, hi = 32 * k + 32 > end ? end - 32 * k : 32;
+    const uint32_t mask = (hi >= 32 ? FULL : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+    word &= mask;
+    if (mask == FULL) gbits[g0 + k] = word;
+    else if (word) atomicOr(&gbits[g0 + k], word);
   }
   __syncthreads();
 }
@@ -671,8 +872,8 @@ __device__ __forceinline__ void add_count(uint64_t* slot, uint32_t mine, int lan
   if (lane == 0 && s) atomicAdd((unsigned long long*)slot, (unsigned long long)s);
 }
 
-// 16 bytes from an arbitrarily aligned global address (buffers are padded, so the aligned words
-// around it are always readable).
+// 16 / 4 bytes from an arbitrarily aligned global address (buffers are padded, so the aligned
+// words around it are always readable).
 __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* p) {
   const uintptr_t a = (uintptr_t)p;
   if ((a & 15u) == 0) return __ldg((const uint4*)p);
@@ -697,7 +898,7 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* p) {
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <typename V, int QPT>
-__global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __grid_constant__ KernelParams P) {
   constexpr int R = 4 * QPT;
   constexpr int T = kThreads * R;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -711,15 +912,32 @@ __global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_c
   const bool has_pred = P.pred_end > P.pred_begin;
 
   uint8_t* stage = smem;
-  uint32_t* bitstage = (uint32_t*)(smem + P.stage_bytes);
-  uint32_t* s_oo = bitstage + kBitStageWords;   // [T + 1] tile-local output byte offsets (Utf8)
-  int32_t* s_src = (int32_t*)(s_oo + T + 4);    // [T] source byte offsets (Utf8)
+  uint8_t* bstage = smem + P.stage_bytes;                          // [T + 64] one byte per output row
+  uint32_t* s_oo = (uint32_t*)(bstage + kBitStageBytes);           // [T + 4] tile-local output byte offsets (long Utf8)
+  int32_t* s_src = (int32_t*)(s_oo + T + 4);                       // [T] source byte offsets (long Utf8)
 
   if (tid == 0) s_tile = has_pred ? atomicAdd(P.ticket, 1u) : blockIdx.x;
   if (tid < kStrPoolBytes) s_pool[tid] = (uint8_t)P.strpool[tid];
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t row0 = (int64_t)tile * T;
+  const int64_t row_end = row0 + T < P.num_rows ? row0 + T : P.num_rows;
+
+  // ---- 0. pull this tile's slice of every input buffer towards L2 --------------------------
+  for (int s = 0; s < P.n_in; s++) {
+    const ColumnDesc& c = P.in[s];
+    const uint8_t* v = (const uint8_t*)(c.type == T_UTF8 ? (const void*)c.offsets : c.values);
+    const int w = c.type == T_UTF8 ? 4 : c.width;
+    if (w > 0) {
+      const uint8_t* p0 = v + row0 * w;
+      const int64_t nbytes = (row_end - row0) * w;
+      for (int64_t b = (int64_t)tid * 128; b < nbytes; b += (int64_t)kThreads * 128) prefetch_l2(p0 + b);
+    } else if (tid < 2 && (int64_t)tid * 1024 < row_end - row0) {
+      prefetch_l2(v + (row0 >> 3) + tid * 128);   // Boolean values: T / 8 bytes
+    }
+    if (c.validity != nullptr && tid >= 32 && tid < 34 && (int64_t)(tid - 32) * 1024 < row_end - row0)
+      prefetch_l2(c.validity + (row0 >> 3) + (tid - 32) * 128);
+  }
 
   int64_t qbase[QPT];
   uint32_t inrange = 0;
@@ -747,11 +965,12 @@ __global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_c
   block_scan<QPT>(cnt, rank0, tile_count, s_w, lane, warp);
   if (tid == 0) s_agg[0] = tile_count;
 
-  // selected value bytes per Utf8 output
+  // selected value bytes per Utf8 output (and a prefetch of exactly those bytes)
   for (int k = 0; k < P.n_out; k++) {
     const OutDesc& o = P.out[k];
     if (o.utf8_index == 0xFFu) continue;   // uniform branch
     const int32_t* __restrict__ off = P.in[o.slot].offsets;
+    const uint8_t* __restrict__ sv = (const uint8_t*)P.in[o.slot].values;
     uint32_t bytes[QPT], bexcl[QPT], btotal;
 #pragma unroll
     for (int q = 0; q < QPT; q++) {
@@ -764,6 +983,10 @@ __global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_c
         if (s4 & 2u) bytes[q] += (uint32_t)(a.z - a.y);
         if (s4 & 4u) bytes[q] += (uint32_t)(a.w - a.z);
         if (s4 & 8u) bytes[q] += (uint32_t)(a4 - a.w);
+        // lines that START inside this quad's byte range (the quad before covers the shared one)
+        const uintptr_t pa = (uintptr_t)(sv + a.x), pe = (uintptr_t)(sv + a4);
+        prefetch_l2((const void*)pa);
+        for (uintptr_t line = (pa + 128) & ~(uintptr_t)127; line < pe; line += 128) prefetch_l2((const void*)line);
       }
     }
     block_scan<QPT>(bytes, bexcl, btotal, s_w, lane, warp);
@@ -806,27 +1029,21 @@ __global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_c
       // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
       run_program<V, QPT>(P, o.begin, o.end, qbase, inrange, sel, s_pool, acc, accm, accv);
       vbits = accv;
-      if (o.type == T_BOOL) {
-        compact_bits<QPT>(accm, sel, rank0, tile_prefix, tile_count, bitstage, (uint32_t*)o.values, tid, lane);
-      } else {
-        uint64_t e[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) e[j] = (uint64_t)acc[j];
-        const uint32_t mis = (uint32_t)((tile_prefix * o.width) & 15u);
-        stage_scatter<QPT>(stage, mis, o.width, e, sel, rank0);
-        __syncthreads();
-        stage_writeout(stage, (uint8_t*)o.values + ((tile_prefix * o.width) & ~15ull), mis, tile_count * o.width, o.width, tid);
-        __syncthreads();
-      }
+      if (o.type == T_BOOL) compact_bits<QPT>(accm, sel, rank0, tile_prefix, tile_count, bstage, (uint32_t*)o.values, tid);
+      else if (o.width == 4) scatter_regs<4, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
+      else if (o.width == 8) scatter_regs<8, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
+      else if (o.width == 2) scatter_regs<2, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
+      else scatter_regs<1, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
     } else {
       const ColumnDesc& c = P.in[o.slot];
       vbits = load_bits<QPT>(c.validity, qbase, sel);
       if (o.type == T_BOOL) {
         const uint32_t vals = load_bits<QPT>((const uint8_t*)c.values, qbase, sel);
-        compact_bits<QPT>(vals, sel, rank0, tile_prefix, tile_count, bitstage, (uint32_t*)o.values, tid, lane);
+        compact_bits<QPT>(vals, sel, rank0, tile_prefix, tile_count, bstage, (uint32_t*)o.values, tid);
       } else if (o.type == T_UTF8) {
         // -- offsets: running sum of the selected lengths, restarted at 0 for the output --
         const int32_t* __restrict__ off = c.offsets;
+        const uint8_t* __restrict__ sv = (const uint8_t*)c.values;
         const uint64_t byte_prefix = s_excl[1 + o.utf8_index];
         const uint32_t tile_bytes = (uint32_t)s_agg[1 + o.utf8_index];
         uint32_t len[R], bytes[QPT], bexcl[QPT], btotal;
@@ -849,65 +1066,96 @@ __global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_c
           }
         }
         block_scan<QPT>(bytes, bexcl, btotal, s_w, lane, warp);
+        uint32_t boff[R];   // tile-local output byte offset of each selected row
 #pragma unroll
         for (int q = 0; q < QPT; q++) {
-          uint32_t r = rank0[q], bo = bexcl[q];
+          uint32_t bo = bexcl[q];
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const int j = 4 * q + i;
-            if ((sel >> j) & 1u) {
-              s_oo[r] = bo;
-              s_src[r] = src[j];
-              bo += len[j];
-              r++;
-            }
+            boff[4 * q + i] = bo;
+            bo += len[4 * q + i];
           }
         }
-        if (tid == 0) s_oo[tile_count] = tile_bytes;
-        __syncthreads();
-        for (uint32_t r = tid; r < tile_count; r += kThreads) o.offsets[tile_prefix + r] = (int32_t)(byte_prefix + s_oo[r]);
-        // -- value bytes: each thread produces aligned 16-byte output chunks --
-        const uint8_t* __restrict__ sv = (const uint8_t*)c.values;
+        {
+          uint32_t newoff[R];
+#pragma unroll
+          for (int j = 0; j < R; j++) newoff[j] = (uint32_t)(byte_prefix + boff[j]);
+          scatter_regs<4, uint32_t, QPT>(newoff, (uint8_t*)o.offsets, sel, rank0, tile_prefix, tile_count, stage, tid);
+        }
         const uint32_t mis = (uint32_t)(byte_prefix & 15u);
         uint8_t* gal = (uint8_t*)o.values + (byte_prefix - mis);
-        const uint32_t end = mis + tile_bytes;
-        const uint32_t nchunks = (end + 15u) >> 4;
-        for (uint32_t ch = tid; ch < nchunks; ch += kThreads) {
-          const uint32_t lo = ch << 4, hi = lo + 16;
-          const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
-          if (s >= t) continue;
-          const uint32_t x = s - mis;  // tile-local output byte index of the first byte produced
-          uint32_t lo_r = 0, hi_r = tile_count;  // first r in (0, count] with s_oo[r] > x
-          while (lo_r < hi_r) {
-            const uint32_t mid = (lo_r + hi_r) >> 1;
-            if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
+        if (mis + tile_bytes <= (uint32_t)P.stage_bytes - 16u) {
+          // -- short strings: every selected row copies its bytes into the stage, then aligned write-out --
+#pragma unroll
+          for (int j = 0; j < R; j++) {
+            if (!((sel >> j) & 1u) || len[j] == 0) continue;
+            const uint8_t* sp = sv + src[j];
+            uint8_t* dp = stage + mis + boff[j];
+            uint32_t n = len[j];
+            if ((((uintptr_t)sp | (uintptr_t)dp) & 3u) == 0) {
+              for (; n >= 4; n -= 4, sp += 4, dp += 4) *(uint32_t*)dp = __ldg((const uint32_t*)sp);
+            }
+            for (; n > 0; n--, sp++, dp++) *dp = __ldg(sp);
           }
-          uint32_t r = lo_r - 1;  // row holding byte x (never an empty string)
-          const bool full = (t - s) == 16u;
-          if (full && x + 16u <= s_oo[r + 1]) {
-            *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
-            continue;
-          }
-          uint32_t words[4] = {0u, 0u, 0u, 0u};
-          for (uint32_t b = s; b < t;) {
-            const uint32_t xb = b - mis;
-            while (xb >= s_oo[r + 1]) r++;
-            const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
-            if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) {
-              words[(b - lo) >> 2] = load4_unaligned(sp);
-              b += 4;
-            } else {
-              words[(b - lo) >> 2] |= (uint32_t)__ldg(sp) << (8u * (b & 3u));
-              b += 1;
+          __syncthreads();
+          stage_writeout<1>(stage, gal, mis, tile_bytes, tid);
+          __syncthreads();
+        } else {
+          // -- long strings: each thread produces aligned 16-byte output chunks --
+#pragma unroll
+          for (int q = 0; q < QPT; q++) {
+            uint32_t r = rank0[q];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int j = 4 * q + i;
+              if ((sel >> j) & 1u) {
+                s_oo[r] = boff[j];
+                s_src[r] = src[j];
+                r++;
+              }
             }
           }
-          if (full) {
-            *(uint4*)(gal + lo) = make_uint4(words[0], words[1], words[2], words[3]);
-          } else {
-            for (uint32_t b = s; b < t; b++) gal[b] = (uint8_t)(words[(b - lo) >> 2] >> (8u * (b & 3u)));
+          if (tid == 0) s_oo[tile_count] = tile_bytes;
+          __syncthreads();
+          const uint32_t end = mis + tile_bytes;
+          const uint32_t nchunks = (end + 15u) >> 4;
+          for (uint32_t ch = tid; ch < nchunks; ch += kThreads) {
+            const uint32_t lo = ch << 4, hi = lo + 16;
+            const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
+            if (s >= t) continue;
+            const uint32_t x = s - mis;  // tile-local output byte index of the first byte produced
+            uint32_t lo_r = 0, hi_r = tile_count;  // first r in (0, count] with s_oo[r] > x
+            while (lo_r < hi_r) {
+              const uint32_t mid = (lo_r + hi_r) >> 1;
+              if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
+            }
+            uint32_t r = lo_r - 1;  // row holding byte x (never an empty string)
+            const bool full = (t - s) == 16u;
+            if (full && x + 16u <= s_oo[r + 1]) {
+              *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
+              continue;
+            }
+            uint32_t words[4] = {0u, 0u, 0u, 0u};
+            for (uint32_t b = s; b < t;) {
+              const uint32_t xb = b - mis;
+              while (xb >= s_oo[r + 1]) r++;
+              const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
+              if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) {
+                words[(b - lo) >> 2] = load4_unaligned(sp);
+                b += 4;
+              } else {
+                words[(b - lo) >> 2] |= (uint32_t)__ldg(sp) << (8u * (b & 3u));
+                b += 1;
+              }
+            }
+            if (full) {
+              *(uint4*)(gal + lo) = make_uint4(words[0], words[1], words[2], words[3]);
+            } else {
+              for (uint32_t b = s; b < t; b++) gal[b] = (uint8_t)(words[(b - lo) >> 2] >> (8u * (b & 3u)));
+            }
           }
+          __syncthreads();
         }
-        __syncthreads();
       } else if (o.width == 16) {
         const uint4* __restrict__ src = (const uint4*)c.values;
         uint4* st = (uint4*)stage;
@@ -922,18 +1170,18 @@ __global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_c
         uint4* dst = (uint4*)o.values + tile_prefix;
         for (uint32_t r = tid; r < tile_count; r += kThreads) dst[r] = st[r];
         __syncthreads();
+      } else if (o.width == 4) {
+        gather_fixed<4, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
+      } else if (o.width == 8) {
+        gather_fixed<8, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
+      } else if (o.width == 2) {
+        gather_fixed<2, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
       } else {
-        uint64_t e[R];
-        fetch_raw<QPT>(c, qbase, sel, e);
-        const uint32_t mis = (uint32_t)((tile_prefix * o.width) & 15u);
-        stage_scatter<QPT>(stage, mis, o.width, e, sel, rank0);
-        __syncthreads();
-        stage_writeout(stage, (uint8_t*)o.values + ((tile_prefix * o.width) & ~15ull), mis, tile_count * o.width, o.width, tid);
-        __syncthreads();
+        gather_fixed<1, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
       }
     }
     if (o.validity != nullptr) {
-      compact_bits<QPT>(vbits, sel, rank0, tile_prefix, tile_count, bitstage, (uint32_t*)o.validity, tid, lane);
+      compact_bits<QPT>(vbits, sel, rank0, tile_prefix, tile_count, bstage, (uint32_t*)o.validity, tid);
       add_count(P.counts + o.count_index, (uint32_t)__popc(sel & ~vbits), lane);
     }
   }
@@ -941,10 +1189,18 @@ __global__ void __launch_bounds__(kThreads) filter_project_kernel(const __grid_c
 
 }  // namespace
 
-size_t filter_project_smem_bytes(int max_out_width, bool has_utf8_out) {
+size_t filter_project_stage_bytes(int max_out_width, int64_t avg_utf8_len) {
   size_t stage = (size_t)kTileRows * (size_t)(max_out_width < 4 ? 4 : max_out_width) + 32;
-  stage = (stage + 15) & ~(size_t)15;
-  size_t total = stage + (size_t)kBitStageWords * 4;
+  if (avg_utf8_len > 0) {   // room for a whole tile of short strings (the staged Utf8 path)
+    size_t want = (size_t)kTileRows * (size_t)avg_utf8_len + 64;
+    if (want > 40 * 1024) want = 40 * 1024;
+    if (want > stage) stage = want;
+  }
+  return (stage + 15) & ~(size_t)15;
+}
+
+size_t filter_project_smem_bytes(size_t stage_bytes, bool has_utf8_out) {
+  size_t total = stage_bytes + (size_t)kBitStageBytes;
   if (has_utf8_out) total += (size_t)(kTileRows + 4) * 4 + (size_t)kTileRows * 4 + 16;
   return total;
 }

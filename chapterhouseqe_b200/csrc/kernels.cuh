@@ -58,6 +58,8 @@ static_assert(sizeof(KernelParams) <= 4096, "KernelParams must fit the 4 KB kern
 
 // has64: the program touches 64-bit types (selects the 64-bit accumulator container).
 cudaError_t launch_filter_project(const KernelParams& p, bool has64, size_t dyn_smem, cudaStream_t stream);
-size_t filter_project_smem_bytes(int max_out_width, bool has_utf8_out);
+// Output staging area: a tile of the widest fixed-width output, or of short Utf8 values.
+size_t filter_project_stage_bytes(int max_out_width, int64_t avg_utf8_len);
+size_t filter_project_smem_bytes(size_t stage_bytes, bool has_utf8_out);
 
 }  // namespace chdb

@@ -631,7 +631,8 @@ struct Lowering {
       case TNode::CAST: {
         emit(n->l.get(), spill);
         uint8_t from = n->l->type, to = n->type;
-        if (is_int(from) && is_int(to)) return;  // canonical container: widening is a no-op
+        // 8/16/32-bit integers share one 32-bit accumulator form: widening among them is a no-op
+        if (is_int(from) && is_int(to) && type_is_64(from) == type_is_64(to)) return;
         Instr in = mk(OP_CAST, to);
         in.from_type = from;
         push(in);
@@ -667,7 +668,11 @@ struct Lowering {
     bool lo = as_operand(l, ol), ro = as_operand(r, orr);
     auto swapped = [&]() {  // acc holds the RIGHT child, operand is the LEFT one
       if (n->k == TNode::CMP) in.aux = mirror(in.aux);
-      else if (n->k == TNode::ARITH) in.flags |= OPF_SWAP;
+      else if (n->k == TNode::ARITH) {
+        // integer + and * commute exactly; floats keep source order (which NaN operand propagates)
+        const bool commutes = (n->op == OP_ADD || n->op == OP_MUL) && is_int(n->type);
+        if (!commutes) in.flags |= OPF_SWAP;
+      }
     };
     if (ro && !(lo && ol.src == SRC_IMM && orr.src != SRC_IMM)) {
       emit(l, spill);

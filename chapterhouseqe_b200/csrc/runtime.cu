@@ -568,6 +568,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   };
 
   int utf8_seen = 0, ko = 0;
+  int64_t avg_utf8 = 0;   // mean value length of the longest Utf8 output (sizes the staging area)
   std::vector<std::pair<void*, size_t>> to_zero;
   for (size_t k = 0; k < p.outputs.size(); k++) {
     const OutputColumn& o = p.outputs[k];
@@ -615,6 +616,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
           const DeviceColumn& src = in->cols[o.in_col];
           int64_t vb = src.value_bytes;
           if (vb < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "filtering a sliced Utf8 view");
+          avg_utf8 = std::max<int64_t>(avg_utf8, (vb + n - 1) / n);
           dc.values_buf = dev_alloc(core, (size_t)vb);
           dc.offsets_buf = dev_alloc(core, (size_t)(n + 1) * 4);
           dc.offsets = (const int32_t*)dc.offsets_buf->ptr;
@@ -683,8 +685,9 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   kp.pred_end = compact ? p.pred_end : 0;
   std::memcpy(kp.instrs, p.instrs.data(), p.instrs.size() * sizeof(Instr));
   std::memcpy(kp.strpool, p.strpool.data(), p.strpool.size());
-  const size_t smem = filter_project_smem_bytes(max_w, n_utf8 > 0);
-  kp.stage_bytes = (int32_t)(((size_t)kTileRows * (size_t)max_w + 32 + 15) & ~(size_t)15);
+  const size_t stage_bytes = filter_project_stage_bytes(max_w, avg_utf8);
+  const size_t smem = filter_project_smem_bytes(stage_bytes, n_utf8 > 0);
+  kp.stage_bytes = (int32_t)stage_bytes;
 
   cudaError_t le = launch_filter_project(kp, p.has64, smem, core->stream);
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
