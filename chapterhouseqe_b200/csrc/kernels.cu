@@ -85,13 +85,12 @@ template <typename V, int QPT>
 __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type, const int64_t (&qbase)[QPT], uint32_t need,
                                           V (&b)[4 * QPT]) {
   const uint8_t* __restrict__ base = (const uint8_t*)c.values;
-#pragma unroll
-  for (int j = 0; j < 4 * QPT; j++) b[j] = 0;
+#define CHDB_SKIP_QUAD(q) if (!((need >> (4 * (q))) & 0xFu)) { b[4 * (q)] = 0; b[4 * (q) + 1] = 0; b[4 * (q) + 2] = 0; b[4 * (q) + 3] = 0; continue; }
   switch (from_type) {
     case T_I32: case T_U32: case T_F32:
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
-        if (!((need >> (4 * q)) & 0xFu)) continue;
+        CHDB_SKIP_QUAD(q)
         const uint4 x = __ldg((const uint4*)(base + qbase[q] * 4));
         b[4 * q + 0] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
       }
@@ -100,7 +99,7 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
       if constexpr (Cont<V>::k64) {
 #pragma unroll
         for (int q = 0; q < QPT; q++) {
-          if (!((need >> (4 * q)) & 0xFu)) continue;
+          CHDB_SKIP_QUAD(q)
           const uint4 x = __ldg((const uint4*)(base + qbase[q] * 8));
           const uint4 y = __ldg((const uint4*)(base + qbase[q] * 8 + 16));
           b[4 * q + 0] = x.x | ((uint64_t)x.y << 32); b[4 * q + 1] = x.z | ((uint64_t)x.w << 32);
@@ -111,7 +110,7 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
     case T_I16: case T_U16:
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
-        if (!((need >> (4 * q)) & 0xFu)) continue;
+        CHDB_SKIP_QUAD(q)
         const uint2 x = __ldg((const uint2*)(base + qbase[q] * 2));
         if (from_type == T_I16) {
           b[4 * q + 0] = (uint32_t)(int32_t)(int16_t)(x.x & 0xFFFFu); b[4 * q + 1] = (uint32_t)(int32_t)(int16_t)(x.x >> 16);
@@ -124,7 +123,7 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
     default:  // T_I8 / T_U8
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
-        if (!((need >> (4 * q)) & 0xFu)) continue;
+        CHDB_SKIP_QUAD(q)
         const uint32_t x = __ldg((const uint32_t*)(base + qbase[q]));
         if (from_type == T_I8) {
           b[4 * q + 0] = (uint32_t)(int32_t)(int8_t)(x & 0xFFu); b[4 * q + 1] = (uint32_t)(int32_t)(int8_t)((x >> 8) & 0xFFu);
@@ -136,6 +135,8 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
       break;
   }
 }
+
+#undef CHDB_SKIP_QUAD
 
 // ------------------------------------------------------------------------------------------
 // casts (arrow-cast on the coercion lattice; int -> float is round-to-nearest-even)
@@ -566,82 +567,123 @@ __device__ __noinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr in,
   }
 }
 
+
 // ------------------------------------------------------------------------------------------
-// the interpreter: accumulator in registers, one operand per instruction
+// the interpreter: accumulator in registers, one operand per instruction.
+// Every handler updates the accumulator in place and keeps its operand array local to its own
+// scope, so nothing but (acc, accm, accv) is carried around the dispatch loop.
 // ------------------------------------------------------------------------------------------
+template <typename V, int QPT>
+struct Spill {
+  V v[kMaxSpill][4 * QPT];
+  uint32_t m[kMaxSpill], valid[kMaxSpill];
+};
+
+// Fetches the operand of `in` (column or spill slot; immediates are handled by the IMM templates).
+template <typename V, int QPT>
+__device__ __forceinline__ void fetch_operand(const KernelParams& P, const Instr& in, const int64_t (&qbase)[QPT], uint32_t inrange,
+                                              const Spill<V, QPT>& stk, V (&b)[4 * QPT], uint32_t& bm, uint32_t& bv) {
+  constexpr int R = 4 * QPT;
+  if (in.src == SRC_COL) {
+    const ColumnDesc& c = P.in[in.slot];
+    bv = load_bits<QPT>(c.validity, qbase, inrange);
+    if (c.type == T_BOOL) {
+      bm = load_bits<QPT>((const uint8_t*)c.values, qbase, inrange);
+#pragma unroll
+      for (int j = 0; j < R; j++) b[j] = 0;
+    } else {
+      fetch_col<V, QPT>(c, in.from_type, qbase, inrange, b);
+      if (in.type == T_BOOL) bm = tobool_vals<V, R>(b, in.from_type);
+      else { bm = 0; cast_vals<V, R>(b, in.from_type, in.type); }
+    }
+  } else {  // SRC_STK
+    if (in.type != T_BOOL) {   // Boolean spills only carry the two masks
+#pragma unroll
+      for (int j = 0; j < R; j++) b[j] = stk.v[in.slot][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; j++) b[j] = 0;
+    }
+    bm = stk.m[in.slot];
+    bv = stk.valid[in.slot];
+  }
+}
+
 template <typename V, int QPT>
 __device__ __forceinline__ void run_program(const KernelParams& P, int begin, int end, const int64_t (&qbase)[QPT], uint32_t inrange,
                                             uint32_t active, const uint8_t* s_pool, V (&acc)[4 * QPT], uint32_t& accm,
                                             uint32_t& accv) {
   constexpr int R = 4 * QPT;
-  V stk[kMaxSpill][R];
-  uint32_t stkm[kMaxSpill], stkv[kMaxSpill];
+  Spill<V, QPT> stk;
 #pragma unroll
   for (int j = 0; j < R; j++) acc[j] = 0;
   accm = 0;
   accv = FULL;
 #pragma unroll 1
   for (int pc = begin; pc < end; pc++) {
-    const Instr in = P.instrs[pc];
-    V b[R];
-    uint32_t bm = 0, bv = FULL;
+    // one 16-byte instruction = two 64-bit constant-bank loads, fields peeled off with shifts
+    const uint2 w = *reinterpret_cast<const uint2*>(&P.instrs[pc]);
+    Instr in;
+    in.op = (uint8_t)w.x; in.type = (uint8_t)(w.x >> 8); in.src = (uint8_t)(w.x >> 16); in.flags = (uint8_t)(w.x >> 24);
+    in.slot = (uint8_t)w.y; in.from_type = (uint8_t)(w.y >> 8); in.aux = (uint8_t)(w.y >> 16); in.order = (uint8_t)(w.y >> 24);
+    in.imm = P.instrs[pc].imm;
     const bool imm = in.src == SRC_IMM;
-    if (imm) {
-      bm = in.imm ? FULL : 0u;
-    } else if (in.src == SRC_STK) {
-      if (in.type != T_BOOL) {   // Boolean spills only carry the two masks
-#pragma unroll
-        for (int j = 0; j < R; j++) b[j] = stk[in.slot][j];
-      }
-      bm = stkm[in.slot];
-      bv = stkv[in.slot];
-    } else if (in.src == SRC_COL) {
-      const ColumnDesc& c = P.in[in.slot];
-      bv = load_bits<QPT>(c.validity, qbase, inrange);
-      if (c.type == T_BOOL) {
-        bm = load_bits<QPT>((const uint8_t*)c.values, qbase, inrange);
-      } else {
-        fetch_col<V, QPT>(c, in.from_type, qbase, inrange, b);
-        if (in.type == T_BOOL) bm = tobool_vals<V, R>(b, in.from_type);
-        else cast_vals<V, R>(b, in.from_type, in.type);
-      }
-    }
     switch (in.op) {
       case OP_LOAD:
         if (imm) {
 #pragma unroll
           for (int j = 0; j < R; j++) acc[j] = (V)in.imm;
+          accm = in.imm ? FULL : 0u;
+          accv = FULL;
         } else {
-#pragma unroll
-          for (int j = 0; j < R; j++) acc[j] = b[j];
+          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, acc, accm, accv);   // straight into the accumulator
         }
-        accm = bm;
-        accv = bv;
         break;
       case OP_CAST: cast_vals<V, R>(acc, in.from_type, in.type); break;
       case OP_ADD: case OP_MUL: case OP_DIV: case OP_REM: case OP_SUB:
         if (imm) {
-          if (in.flags & OPF_SWAP) arith<true, true, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
-          else arith<true, false, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
+          if (in.flags & OPF_SWAP) arith<true, true, V, QPT>(P, in, acc, accv, acc, FULL, active, qbase);
+          else arith<true, false, V, QPT>(P, in, acc, accv, acc, FULL, active, qbase);
         } else {
+          V b[R];
+          uint32_t bm, bv;
+          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, b, bm, bv);
           if (in.flags & OPF_SWAP) arith<false, true, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
           else arith<false, false, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
         }
         break;
       case OP_CMP:
-        accm = imm ? compare<true, V, R>(in, acc, accm, b, bm) : compare<false, V, R>(in, acc, accm, b, bm);
-        accv &= bv;
+        if (imm) {
+          accm = compare<true, V, R>(in, acc, accm, acc, in.imm ? FULL : 0u);
+        } else {
+          V b[R];
+          uint32_t bm, bv;
+          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, b, bm, bv);
+          accm = compare<false, V, R>(in, acc, accm, b, bm);
+          accv &= bv;
+        }
         break;
       case OP_TOBOOL: accm = tobool_vals<V, R>(acc, in.type); break;
-      case OP_AND: accm &= bm; accv &= bv; break;   // non-Kleene: null if either side is null
-      case OP_OR: accm |= bm; accv &= bv; break;
+      case OP_AND: case OP_OR: {   // non-Kleene: null if either side is null
+        uint32_t bm = in.imm ? FULL : 0u, bv = FULL;
+        if (in.src == SRC_STK) {
+          bm = stk.m[in.slot];
+          bv = stk.valid[in.slot];
+        } else if (in.src == SRC_COL) {
+          V b[R];
+          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, b, bm, bv);
+        }
+        accm = in.op == OP_AND ? (accm & bm) : (accm | bm);
+        accv &= bv;
+        break;
+      }
       case OP_PUSH:
         if (in.type != T_BOOL) {
 #pragma unroll
-          for (int j = 0; j < R; j++) stk[in.slot][j] = acc[j];
+          for (int j = 0; j < R; j++) stk.v[in.slot][j] = acc[j];
         }
-        stkm[in.slot] = accm;
-        stkv[in.slot] = accv;
+        stk.m[in.slot] = accm;
+        stk.valid[in.slot] = accv;
         break;
       case OP_CMP_UTF8: {
         QuadBases<QPT> qb;
@@ -661,9 +703,12 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
 // scans
 // ------------------------------------------------------------------------------------------
 // Exclusive scan of per-(thread, quad) values in output order (quad group, warp, lane).
+// s_w: kWarps * QPT words, used by one scan at a time (callers alternate two buffers so that one
+// barrier per scan is enough).
 template <int QPT>
-__device__ __forceinline__ void block_scan(const uint32_t (&val)[QPT], uint32_t (&excl)[QPT], uint32_t& total,
-                                           uint32_t (*s_w)[kWarps], int lane, int warp) {
+__device__ __forceinline__ void block_scan(const uint32_t (&val)[QPT], uint32_t (&excl)[QPT], uint32_t& total, uint32_t* s_w, int lane,
+                                           int warp) {
+  static_assert(QPT * kWarps <= 32, "warp totals must fit one warp");
   uint32_t incl[QPT];
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
@@ -674,20 +719,19 @@ __device__ __forceinline__ void block_scan(const uint32_t (&val)[QPT], uint32_t 
       if (lane >= d) x += y;
     }
     incl[q] = x;
-    if (lane == 31) s_w[q][warp] = x;
+    if (lane == 31) s_w[q * kWarps + warp] = x;
   }
   __syncthreads();
-  uint32_t run = 0;
+  const uint32_t t = lane < QPT * kWarps ? s_w[lane] : 0u;
+  uint32_t x = t;
 #pragma unroll
-  for (int q = 0; q < QPT; q++) {
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) {
-      if (w == warp) excl[q] = run + incl[q] - val[q];
-      run += s_w[q][w];
-    }
+  for (int d = 1; d < QPT * kWarps; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, x, d);
+    if (lane >= d) x += y;
   }
-  total = run;
-  __syncthreads();
+  total = __shfl_sync(FULL, x, QPT * kWarps - 1);
+#pragma unroll
+  for (int q = 0; q < QPT; q++) excl[q] = __shfl_sync(FULL, x - t, q * kWarps + warp) + incl[q] - val[q];
 }
 
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
@@ -730,27 +774,50 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc, uint32_t tile, uint
 }
 
 // ------------------------------------------------------------------------------------------
-// output staging
+// output staging.  Shared memory is addressed with explicit 32-bit shared-window addresses
+// (computed once per kernel) so the hot loops are plain LDS / STS with register bases.
 // ------------------------------------------------------------------------------------------
-// stage[mis, mis + nbytes) -> gdst_aligned[mis, ...): aligned 16-byte stores in the middle,
-// W-byte element stores in the (at most two) chunks shared with neighbouring tiles.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t lo, uint32_t hi) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 template <int W>
-__device__ __forceinline__ void stage_writeout(const uint8_t* stage, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int tid) {
+__device__ __forceinline__ void copy_elem_s2g(uint8_t* g, uint32_t s) {   // one W-byte element, shared -> global
+  if (W == 4) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(s) : "memory"); *(uint32_t*)g = v; }
+  else if (W == 8) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s) : "memory"); *(uint2*)g = v; }
+  else if (W == 2) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(s) : "memory"); *(uint16_t*)g = v; }
+  else { *g = (uint8_t)lds8(s); }
+}
+
+// stage[mis, mis + nbytes) -> gdst_aligned[mis, ...): aligned 16-byte stores in the middle,
+// W-byte element stores in the (at most two) 16-byte chunks shared with neighbouring tiles.
+template <int W>
+__device__ __forceinline__ void stage_writeout(uint32_t stage_s, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int tid) {
   const uint32_t end = mis + nbytes;
-  const uint32_t nchunks = (end + 15u) >> 4;
-  for (uint32_t c = tid; c < nchunks; c += kThreads) {
-    const uint32_t lo = c << 4, hi = lo + 16;
-    if (lo >= mis && hi <= end) {
-      *(uint4*)(gdst_aligned + lo) = *(const uint4*)(stage + lo);
-    } else {
-      const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
-      for (uint32_t b = s; b < t; b += W) {
-        if (W == 4) *(uint32_t*)(gdst_aligned + b) = *(const uint32_t*)(stage + b);
-        else if (W == 8) *(uint64_t*)(gdst_aligned + b) = *(const uint64_t*)(stage + b);
-        else if (W == 2) *(uint16_t*)(gdst_aligned + b) = *(const uint16_t*)(stage + b);
-        else gdst_aligned[b] = stage[b];
-      }
-    }
+  const uint32_t first_full = (mis + 15u) >> 4, end_full = end >> 4;   // full chunks: [first_full, end_full)
+  for (uint32_t c = first_full + tid; c < end_full; c += kThreads) *(uint4*)(gdst_aligned + (c << 4)) = lds128(stage_s + (c << 4));
+  if (tid == 0 && mis != 0) {                 // head chunk (chunk 0 is partial)
+    const uint32_t t = end < 16u ? end : 16u;
+    for (uint32_t b = mis; b < t; b += W) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
+  }
+  if (tid == 32 && (end & 15u) != 0 && (end_full > 0 || mis == 0)) {   // tail chunk, unless it is also the head chunk
+    for (uint32_t b = end_full << 4; b < end; b += W) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
   }
 }
 
@@ -758,93 +825,100 @@ __device__ __forceinline__ void stage_writeout(const uint8_t* stage, uint8_t* gd
 // at the destination's 16-byte phase, aligned 128-bit stores.  Ends with the stage free again.
 template <int W, int QPT>
 __device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, uint8_t* dst, const int64_t (&qbase)[QPT], uint32_t sel,
-                                             const uint32_t (&rank0)[QPT], uint64_t tile_prefix, uint32_t tile_count, uint8_t* stage,
+                                             const uint32_t (&rank0)[QPT], uint64_t tile_prefix, uint32_t tile_count, uint32_t stage_s,
                                              int tid) {
   const uint32_t mis = (uint32_t)((tile_prefix * W) & 15u);
-  uint8_t* base = stage + mis;
+  // all loads first (independent, in flight together), then the shared-memory stores
+  uint4 x[QPT], y[QPT];
+#pragma unroll
+  for (int q = 0; q < QPT; q++) {
+    x[q] = make_uint4(0, 0, 0, 0);
+    y[q] = make_uint4(0, 0, 0, 0);
+    if (!((sel >> (4 * q)) & 0xFu)) continue;
+    if (W == 4) {
+      x[q] = __ldg((const uint4*)(src + qbase[q] * 4));
+    } else if (W == 8) {
+      x[q] = __ldg((const uint4*)(src + qbase[q] * 8));
+      y[q] = __ldg((const uint4*)(src + qbase[q] * 8 + 16));
+    } else if (W == 2) {
+      const uint2 t = __ldg((const uint2*)(src + qbase[q] * 2));
+      x[q].x = t.x; x[q].y = t.y;
+    } else {
+      x[q].x = __ldg((const uint32_t*)(src + qbase[q]));
+    }
+  }
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
     const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
     if (!s4) continue;
-    uint32_t r = rank0[q];
+    uint32_t a = stage_s + mis + rank0[q] * W;
     if (W == 4) {
-      const uint4 x = __ldg((const uint4*)(src + qbase[q] * 4));
-      uint32_t* p = (uint32_t*)base;
-      if (s4 & 1u) p[r++] = x.x;
-      if (s4 & 2u) p[r++] = x.y;
-      if (s4 & 4u) p[r++] = x.z;
-      if (s4 & 8u) p[r++] = x.w;
+      if (s4 & 1u) { sts32(a, x[q].x); a += 4; }
+      if (s4 & 2u) { sts32(a, x[q].y); a += 4; }
+      if (s4 & 4u) { sts32(a, x[q].z); a += 4; }
+      if (s4 & 8u) { sts32(a, x[q].w); }
     } else if (W == 8) {
-      const uint4 x = __ldg((const uint4*)(src + qbase[q] * 8));
-      const uint4 y = __ldg((const uint4*)(src + qbase[q] * 8 + 16));
-      uint2* p = (uint2*)base;
-      if (s4 & 1u) p[r++] = make_uint2(x.x, x.y);
-      if (s4 & 2u) p[r++] = make_uint2(x.z, x.w);
-      if (s4 & 4u) p[r++] = make_uint2(y.x, y.y);
-      if (s4 & 8u) p[r++] = make_uint2(y.z, y.w);
+      if (s4 & 1u) { sts64(a, x[q].x, x[q].y); a += 8; }
+      if (s4 & 2u) { sts64(a, x[q].z, x[q].w); a += 8; }
+      if (s4 & 4u) { sts64(a, y[q].x, y[q].y); a += 8; }
+      if (s4 & 8u) { sts64(a, y[q].z, y[q].w); }
     } else if (W == 2) {
-      const uint2 x = __ldg((const uint2*)(src + qbase[q] * 2));
-      uint16_t* p = (uint16_t*)base;
-      if (s4 & 1u) p[r++] = (uint16_t)(x.x & 0xFFFFu);
-      if (s4 & 2u) p[r++] = (uint16_t)(x.x >> 16);
-      if (s4 & 4u) p[r++] = (uint16_t)(x.y & 0xFFFFu);
-      if (s4 & 8u) p[r++] = (uint16_t)(x.y >> 16);
+      if (s4 & 1u) { sts16(a, x[q].x & 0xFFFFu); a += 2; }
+      if (s4 & 2u) { sts16(a, x[q].x >> 16); a += 2; }
+      if (s4 & 4u) { sts16(a, x[q].y & 0xFFFFu); a += 2; }
+      if (s4 & 8u) { sts16(a, x[q].y >> 16); }
     } else {
-      const uint32_t x = __ldg((const uint32_t*)(src + qbase[q]));
-      uint8_t* p = base;
-      if (s4 & 1u) p[r++] = (uint8_t)x;
-      if (s4 & 2u) p[r++] = (uint8_t)(x >> 8);
-      if (s4 & 4u) p[r++] = (uint8_t)(x >> 16);
-      if (s4 & 8u) p[r++] = (uint8_t)(x >> 24);
+      if (s4 & 1u) { sts8(a, x[q].x & 0xFFu); a += 1; }
+      if (s4 & 2u) { sts8(a, (x[q].x >> 8) & 0xFFu); a += 1; }
+      if (s4 & 4u) { sts8(a, (x[q].x >> 16) & 0xFFu); a += 1; }
+      if (s4 & 8u) { sts8(a, x[q].x >> 24); }
     }
   }
   __syncthreads();
-  stage_writeout<W>(stage, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
+  stage_writeout<W>(stage_s, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
   __syncthreads();
 }
 
 // Same, for values that already sit in registers (projection expressions, rebuilt Utf8 offsets).
 template <int W, typename E, int QPT>
 __device__ __forceinline__ void scatter_regs(const E (&e)[4 * QPT], uint8_t* dst, uint32_t sel, const uint32_t (&rank0)[QPT],
-                                             uint64_t tile_prefix, uint32_t tile_count, uint8_t* stage, int tid) {
+                                             uint64_t tile_prefix, uint32_t tile_count, uint32_t stage_s, int tid) {
   const uint32_t mis = (uint32_t)((tile_prefix * W) & 15u);
-  uint8_t* base = stage + mis;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    uint32_t r = rank0[q];
+    uint32_t a = stage_s + mis + rank0[q] * W;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int j = 4 * q + i;
       if ((sel >> j) & 1u) {
-        if (W == 4) ((uint32_t*)base)[r] = (uint32_t)e[j];
-        else if (W == 8) ((uint64_t*)base)[r] = (uint64_t)e[j];
-        else if (W == 2) ((uint16_t*)base)[r] = (uint16_t)e[j];
-        else base[r] = (uint8_t)e[j];
-        r++;
+        if (W == 4) sts32(a, (uint32_t)e[j]);
+        else if (W == 8) sts64(a, (uint32_t)e[j], (uint32_t)((uint64_t)e[j] >> 32));
+        else if (W == 2) sts16(a, (uint32_t)e[j] & 0xFFFFu);
+        else sts8(a, (uint32_t)e[j] & 0xFFu);
+        a += W;
       }
     }
   }
   __syncthreads();
-  stage_writeout<W>(stage, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
+  stage_writeout<W>(stage_s, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
   __syncthreads();
 }
 
 // Compacts one bit per row (validity or Boolean values) into gbits at bit offset tile_prefix:
 // every selected row drops its bit as one byte at its rank, then one thread per output word packs
-// 32 bytes with four multiplies.  gbits is zero-initialised; the (at most two) words shared with
+// 32 bytes with eight multiplies.  gbits is zero-initialised; the (at most two) words shared with
 // neighbouring tiles are merged with atomicOr.
 template <int QPT>
 __device__ __forceinline__ void compact_bits(uint32_t bits, uint32_t sel, const uint32_t (&rank0)[QPT], uint64_t tile_prefix,
-                                             uint32_t tile_count, uint8_t* bstage, uint32_t* gbits, int tid) {
+                                             uint32_t tile_count, uint32_t bstage_s, uint32_t* gbits, int tid) {
   const uint32_t o = (uint32_t)(tile_prefix & 31);
-  uint8_t* base = bstage + o;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    uint32_t r = rank0[q];
+    uint32_t a = bstage_s + o + rank0[q];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int j = 4 * q + i;
-      if ((sel >> j) & 1u) base[r++] = (uint8_t)((bits >> j) & 1u);
+      if ((sel >> j) & 1u) { sts8(a, (bits >> j) & 1u); a++; }
     }
   }
   __syncthreads();
@@ -852,7 +926,7 @@ __device__ __forceinline__ void compact_bits(uint32_t bits, uint32_t sel, const 
   const uint32_t nwords = (end + 31u) >> 5;
   const uint64_t g0 = tile_prefix >> 5;
   for (uint32_t k = tid; k < nwords; k += kThreads) {
-    const uint4 lo4 = *(const uint4*)(bstage + 32 * k), hi4 = *(const uint4*)(bstage + 32 * k + 16);
+    const uint4 lo4 = lds128(bstage_s + 32 * k), hi4 = lds128(bstage_s + 32 * k + 16);
     const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
     uint32_t word = 0;
 #pragma unroll
@@ -894,6 +968,33 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* p) {
   return __funnelshift_r(w0, __ldg(w + 1), sh);
 }
 
+// One selected row's value bytes -> the shared-memory stage (the short-string path).
+__device__ __forceinline__ void copy_row_g2s(const uint8_t* sp, uint32_t da, uint32_t n) {
+  if ((((uint32_t)(uintptr_t)sp | da) & 3u) == 0) {
+    const uint32_t nw = n >> 2;
+    if (nw <= 4) {   // up to 16 bytes: straight-line
+      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      if (nw > 0) w0 = __ldg((const uint32_t*)sp);
+      if (nw > 1) w1 = __ldg((const uint32_t*)sp + 1);
+      if (nw > 2) w2 = __ldg((const uint32_t*)sp + 2);
+      if (nw > 3) w3 = __ldg((const uint32_t*)sp + 3);
+      if (nw > 0) sts32(da, w0);
+      if (nw > 1) sts32(da + 4, w1);
+      if (nw > 2) sts32(da + 8, w2);
+      if (nw > 3) sts32(da + 12, w3);
+    } else {
+#pragma unroll 1
+      for (uint32_t i = 0; i < nw; i++) sts32(da + 4 * i, __ldg((const uint32_t*)sp + i));
+    }
+    const uint32_t done = nw << 2;
+#pragma unroll 1
+    for (uint32_t i = done; i < n; i++) sts8(da + i, __ldg(sp + i));
+  } else {
+#pragma unroll 1
+    for (uint32_t i = 0; i < n; i++) sts8(da + i, __ldg(sp + i));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -903,7 +1004,7 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
   constexpr int T = kThreads * R;
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_w[QPT][kWarps];
+  __shared__ uint32_t s_w[2][QPT * kWarps];
   __shared__ uint64_t s_agg[1 + kMaxOutCols];
   __shared__ uint64_t s_excl[1 + kMaxOutCols];
   __shared__ uint8_t s_pool[kStrPoolBytes];
@@ -911,31 +1012,29 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_pred = P.pred_end > P.pred_begin;
 
-  uint8_t* stage = smem;
-  uint8_t* bstage = smem + P.stage_bytes;                          // [T + 64] one byte per output row
-  uint32_t* s_oo = (uint32_t*)(bstage + kBitStageBytes);           // [T + 4] tile-local output byte offsets (long Utf8)
-  int32_t* s_src = (int32_t*)(s_oo + T + 4);                       // [T] source byte offsets (long Utf8)
+  const uint32_t stage_s = smem_u32(smem);                           // output staging area
+  const uint32_t bstage_s = stage_s + (uint32_t)P.stage_bytes;       // [T + 64] one byte per output row
+  uint32_t* s_oo = (uint32_t*)(smem + P.stage_bytes + kBitStageBytes);   // [T + 4] output byte offsets (long Utf8)
+  int32_t* s_src = (int32_t*)(s_oo + T + 4);                         // [T] source byte offsets (long Utf8)
 
   if (tid == 0) s_tile = has_pred ? atomicAdd(P.ticket, 1u) : blockIdx.x;
   if (tid < kStrPoolBytes) s_pool[tid] = (uint8_t)P.strpool[tid];
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t row0 = (int64_t)tile * T;
-  const int64_t row_end = row0 + T < P.num_rows ? row0 + T : P.num_rows;
+  const int32_t tile_rows = (int32_t)(row0 + T < P.num_rows ? T : P.num_rows - row0);
 
-  // ---- 0. pull this tile's slice of every input buffer towards L2 --------------------------
+  // ---- 0. pull this tile's slice of every input buffer towards L2 (one 128-byte line per thread) ----
   for (int s = 0; s < P.n_in; s++) {
     const ColumnDesc& c = P.in[s];
-    const uint8_t* v = (const uint8_t*)(c.type == T_UTF8 ? (const void*)c.offsets : c.values);
     const int w = c.type == T_UTF8 ? 4 : c.width;
+    const uint8_t* v = (const uint8_t*)(c.type == T_UTF8 ? (const void*)c.offsets : c.values);
     if (w > 0) {
-      const uint8_t* p0 = v + row0 * w;
-      const int64_t nbytes = (row_end - row0) * w;
-      for (int64_t b = (int64_t)tid * 128; b < nbytes; b += (int64_t)kThreads * 128) prefetch_l2(p0 + b);
-    } else if (tid < 2 && (int64_t)tid * 1024 < row_end - row0) {
+      if (tid * 128 < tile_rows * w) prefetch_l2(v + row0 * w + tid * 128);
+    } else if (tid < 2 && tid * 1024 < tile_rows) {
       prefetch_l2(v + (row0 >> 3) + tid * 128);   // Boolean values: T / 8 bytes
     }
-    if (c.validity != nullptr && tid >= 32 && tid < 34 && (int64_t)(tid - 32) * 1024 < row_end - row0)
+    if (c.validity != nullptr && tid >= 32 && tid < 34 && (tid - 32) * 1024 < tile_rows)
       prefetch_l2(c.validity + (row0 >> 3) + (tid - 32) * 128);
   }
 
@@ -943,10 +1042,10 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
   uint32_t inrange = 0;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    qbase[q] = row0 + (int64_t)q * (kThreads * 4) + warp * 128 + lane * 4;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (qbase[q] + i < P.num_rows) inrange |= 1u << (4 * q + i);
+    const int local = q * (kThreads * 4) + warp * 128 + lane * 4;
+    qbase[q] = row0 + local;
+    const int left = tile_rows - local;
+    inrange |= (left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u)) << (4 * q);
   }
 
   // ---- 1. predicate -> selection mask -----------------------------------------------------
@@ -962,7 +1061,9 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
   uint32_t cnt[QPT], rank0[QPT], tile_count;
 #pragma unroll
   for (int q = 0; q < QPT; q++) cnt[q] = __popc((sel >> (4 * q)) & 0xFu);
-  block_scan<QPT>(cnt, rank0, tile_count, s_w, lane, warp);
+  int scan_buf = 0;
+  block_scan<QPT>(cnt, rank0, tile_count, s_w[scan_buf], lane, warp);
+  scan_buf ^= 1;
   if (tid == 0) s_agg[0] = tile_count;
 
   // selected value bytes per Utf8 output (and a prefetch of exactly those bytes)
@@ -983,13 +1084,13 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
         if (s4 & 2u) bytes[q] += (uint32_t)(a.z - a.y);
         if (s4 & 4u) bytes[q] += (uint32_t)(a.w - a.z);
         if (s4 & 8u) bytes[q] += (uint32_t)(a4 - a.w);
-        // lines that START inside this quad's byte range (the quad before covers the shared one)
         const uintptr_t pa = (uintptr_t)(sv + a.x), pe = (uintptr_t)(sv + a4);
         prefetch_l2((const void*)pa);
         for (uintptr_t line = (pa + 128) & ~(uintptr_t)127; line < pe; line += 128) prefetch_l2((const void*)line);
       }
     }
-    block_scan<QPT>(bytes, bexcl, btotal, s_w, lane, warp);
+    block_scan<QPT>(bytes, bexcl, btotal, s_w[scan_buf], lane, warp);
+    scan_buf ^= 1;
     if (tid == 0) s_agg[1 + o.utf8_index] = btotal;
   }
   __syncthreads();
@@ -1020,32 +1121,39 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
   if (tile_count == 0) return;  // block-uniform
 
   // ---- 4. gather every output column --------------------------------------------------------
+#pragma unroll 1
   for (int k = 0; k < P.n_out; k++) {
-    const OutDesc o = P.out[k];
+    // the eight small fields of OutDesc arrive as one 64-bit constant load
+    const uint64_t meta = reinterpret_cast<const uint64_t*>(&P.out[k])[3];
+    const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
+    const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
+    const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_count = (uint32_t)(meta >> 56);
+    uint8_t* const o_values = (uint8_t*)P.out[k].values;
+    uint8_t* const o_validity = P.out[k].validity;
     uint32_t vbits = FULL;  // validity of this output for the thread's rows
-    if (o.kind == OUT_EXPR) {
+    if (o_kind == OUT_EXPR) {
       V acc[R];
       uint32_t accm, accv;
       // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
-      run_program<V, QPT>(P, o.begin, o.end, qbase, inrange, sel, s_pool, acc, accm, accv);
+      run_program<V, QPT>(P, (int)o_begin, (int)o_end, qbase, inrange, sel, s_pool, acc, accm, accv);
       vbits = accv;
-      if (o.type == T_BOOL) compact_bits<QPT>(accm, sel, rank0, tile_prefix, tile_count, bstage, (uint32_t*)o.values, tid);
-      else if (o.width == 4) scatter_regs<4, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
-      else if (o.width == 8) scatter_regs<8, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
-      else if (o.width == 2) scatter_regs<2, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
-      else scatter_regs<1, V, QPT>(acc, (uint8_t*)o.values, sel, rank0, tile_prefix, tile_count, stage, tid);
+      if (o_type == T_BOOL) compact_bits<QPT>(accm, sel, rank0, tile_prefix, tile_count, bstage_s, (uint32_t*)o_values, tid);
+      else if (o_width == 4) scatter_regs<4, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+      else if (o_width == 8) scatter_regs<8, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+      else if (o_width == 2) scatter_regs<2, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+      else scatter_regs<1, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
     } else {
-      const ColumnDesc& c = P.in[o.slot];
+      const ColumnDesc& c = P.in[o_slot];
       vbits = load_bits<QPT>(c.validity, qbase, sel);
-      if (o.type == T_BOOL) {
+      if (o_type == T_BOOL) {
         const uint32_t vals = load_bits<QPT>((const uint8_t*)c.values, qbase, sel);
-        compact_bits<QPT>(vals, sel, rank0, tile_prefix, tile_count, bstage, (uint32_t*)o.values, tid);
-      } else if (o.type == T_UTF8) {
+        compact_bits<QPT>(vals, sel, rank0, tile_prefix, tile_count, bstage_s, (uint32_t*)o_values, tid);
+      } else if (o_type == T_UTF8) {
         // -- offsets: running sum of the selected lengths, restarted at 0 for the output --
         const int32_t* __restrict__ off = c.offsets;
         const uint8_t* __restrict__ sv = (const uint8_t*)c.values;
-        const uint64_t byte_prefix = s_excl[1 + o.utf8_index];
-        const uint32_t tile_bytes = (uint32_t)s_agg[1 + o.utf8_index];
+        const uint64_t byte_prefix = s_excl[1 + o_utf8];
+        const uint32_t tile_bytes = (uint32_t)s_agg[1 + o_utf8];
         uint32_t len[R], bytes[QPT], bexcl[QPT], btotal;
         int32_t src[R];
 #pragma unroll
@@ -1065,7 +1173,8 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
             bytes[q] = len[4 * q] + len[4 * q + 1] + len[4 * q + 2] + len[4 * q + 3];
           }
         }
-        block_scan<QPT>(bytes, bexcl, btotal, s_w, lane, warp);
+        block_scan<QPT>(bytes, bexcl, btotal, s_w[scan_buf], lane, warp);
+        scan_buf ^= 1;
         uint32_t boff[R];   // tile-local output byte offset of each selected row
 #pragma unroll
         for (int q = 0; q < QPT; q++) {
@@ -1079,26 +1188,18 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
         {
           uint32_t newoff[R];
 #pragma unroll
-          for (int j = 0; j < R; j++) newoff[j] = (uint32_t)(byte_prefix + boff[j]);
-          scatter_regs<4, uint32_t, QPT>(newoff, (uint8_t*)o.offsets, sel, rank0, tile_prefix, tile_count, stage, tid);
+          for (int j = 0; j < R; j++) newoff[j] = (uint32_t)byte_prefix + boff[j];
+          scatter_regs<4, uint32_t, QPT>(newoff, (uint8_t*)P.out[k].offsets, sel, rank0, tile_prefix, tile_count, stage_s, tid);
         }
         const uint32_t mis = (uint32_t)(byte_prefix & 15u);
-        uint8_t* gal = (uint8_t*)o.values + (byte_prefix - mis);
+        uint8_t* gal = o_values + (byte_prefix - mis);
         if (mis + tile_bytes <= (uint32_t)P.stage_bytes - 16u) {
           // -- short strings: every selected row copies its bytes into the stage, then aligned write-out --
 #pragma unroll
-          for (int j = 0; j < R; j++) {
-            if (!((sel >> j) & 1u) || len[j] == 0) continue;
-            const uint8_t* sp = sv + src[j];
-            uint8_t* dp = stage + mis + boff[j];
-            uint32_t n = len[j];
-            if ((((uintptr_t)sp | (uintptr_t)dp) & 3u) == 0) {
-              for (; n >= 4; n -= 4, sp += 4, dp += 4) *(uint32_t*)dp = __ldg((const uint32_t*)sp);
-            }
-            for (; n > 0; n--, sp++, dp++) *dp = __ldg(sp);
-          }
+          for (int j = 0; j < R; j++)
+            if (((sel >> j) & 1u) && len[j] != 0) copy_row_g2s(sv + src[j], stage_s + mis + boff[j], len[j]);
           __syncthreads();
-          stage_writeout<1>(stage, gal, mis, tile_bytes, tid);
+          stage_writeout<1>(stage_s, gal, mis, tile_bytes, tid);
           __syncthreads();
         } else {
           // -- long strings: each thread produces aligned 16-byte output chunks --
@@ -1119,6 +1220,7 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
           __syncthreads();
           const uint32_t end = mis + tile_bytes;
           const uint32_t nchunks = (end + 15u) >> 4;
+#pragma unroll 1
           for (uint32_t ch = tid; ch < nchunks; ch += kThreads) {
             const uint32_t lo = ch << 4, hi = lo + 16;
             const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
@@ -1135,54 +1237,57 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
               *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
               continue;
             }
-            uint32_t words[4] = {0u, 0u, 0u, 0u};
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll 1
             for (uint32_t b = s; b < t;) {
               const uint32_t xb = b - mis;
               while (xb >= s_oo[r + 1]) r++;
               const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
-              if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) {
-                words[(b - lo) >> 2] = load4_unaligned(sp);
-                b += 4;
-              } else {
-                words[(b - lo) >> 2] |= (uint32_t)__ldg(sp) << (8u * (b & 3u));
-                b += 1;
-              }
+              uint32_t piece, step;
+              if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) { piece = load4_unaligned(sp); step = 4; }
+              else { piece = (uint32_t)__ldg(sp) << (8u * (b & 3u)); step = 1; }
+              const uint32_t wi = (b - lo) >> 2;
+              if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
+              b += step;
             }
             if (full) {
-              *(uint4*)(gal + lo) = make_uint4(words[0], words[1], words[2], words[3]);
+              *(uint4*)(gal + lo) = make_uint4(w0, w1, w2, w3);
             } else {
-              for (uint32_t b = s; b < t; b++) gal[b] = (uint8_t)(words[(b - lo) >> 2] >> (8u * (b & 3u)));
+              for (uint32_t b = s; b < t; b++) {
+                const uint32_t wi = (b - lo) >> 2;
+                const uint32_t word = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
+                gal[b] = (uint8_t)(word >> (8u * (b & 3u)));
+              }
             }
           }
           __syncthreads();
         }
-      } else if (o.width == 16) {
+      } else if (o_width == 16) {
         const uint4* __restrict__ src = (const uint4*)c.values;
-        uint4* st = (uint4*)stage;
 #pragma unroll
         for (int q = 0; q < QPT; q++) {
-          uint32_t r = rank0[q];
+          uint32_t a = stage_s + rank0[q] * 16;
 #pragma unroll
           for (int i = 0; i < 4; i++)
-            if ((sel >> (4 * q + i)) & 1u) st[r++] = __ldg(src + qbase[q] + i);
+            if ((sel >> (4 * q + i)) & 1u) { sts128(a, __ldg(src + qbase[q] + i)); a += 16; }
         }
         __syncthreads();
-        uint4* dst = (uint4*)o.values + tile_prefix;
-        for (uint32_t r = tid; r < tile_count; r += kThreads) dst[r] = st[r];
+        uint4* dst = (uint4*)o_values + tile_prefix;
+        for (uint32_t r = tid; r < tile_count; r += kThreads) dst[r] = lds128(stage_s + r * 16);
         __syncthreads();
-      } else if (o.width == 4) {
-        gather_fixed<4, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
-      } else if (o.width == 8) {
-        gather_fixed<8, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
-      } else if (o.width == 2) {
-        gather_fixed<2, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
+      } else if (o_width == 4) {
+        gather_fixed<4, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+      } else if (o_width == 8) {
+        gather_fixed<8, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+      } else if (o_width == 2) {
+        gather_fixed<2, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
       } else {
-        gather_fixed<1, QPT>((const uint8_t*)c.values, (uint8_t*)o.values, qbase, sel, rank0, tile_prefix, tile_count, stage, tid);
+        gather_fixed<1, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
       }
     }
-    if (o.validity != nullptr) {
-      compact_bits<QPT>(vbits, sel, rank0, tile_prefix, tile_count, bstage, (uint32_t*)o.validity, tid);
-      add_count(P.counts + o.count_index, (uint32_t)__popc(sel & ~vbits), lane);
+    if (o_validity != nullptr) {
+      compact_bits<QPT>(vbits, sel, rank0, tile_prefix, tile_count, bstage_s, (uint32_t*)o_validity, tid);
+      add_count(P.counts + o_count, (uint32_t)__popc(sel & ~vbits), lane);
     }
   }
 }
@@ -1209,7 +1314,7 @@ cudaError_t launch_filter_project(const KernelParams& p, bool has64, size_t dyn_
   auto k32 = filter_project_kernel<uint32_t, kQuadsPerThread>;
   auto k64 = filter_project_kernel<uint64_t, kQuadsPerThread>;
   auto kern = has64 ? k64 : k32;
-  if (dyn_smem > 48 * 1024) {  // only 16-byte (decimal128) columns need more than the default window
+  if (dyn_smem > 48 * 1024) {  // only 16-byte (decimal128) columns or long-ish strings need more than the default window
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     if (e != cudaSuccess) return e;
   }
