@@ -5,15 +5,15 @@
 //      and iteration), so the dependent loads below find their data on chip
 //   1. every thread runs the predicate bytecode over its rows (128-bit coalesced column loads,
 //      accumulator in registers) and gets a selection mask                     [compute_value.rs]
-//   2. warp shuffles + one shared-memory pass rank the selected rows; for each Utf8 output the
-//      selected value bytes are summed the same way
+//   2. warp shuffles rank the selected rows inside each warp's 256-row slice; for each Utf8 output
+//      the selected value bytes are summed the same way; warp totals meet in shared memory
 //   3. a decoupled look-back over 64-bit {flag | value} tile descriptors turns the tile totals
 //      into exclusive prefixes (rows, and bytes per Utf8 output)               [filter_record.rs:37]
-//   4. every output column is gathered: values are staged in shared memory at the same
-//      16-byte phase as their destination and written with full 16-byte stores; validity and
-//      Boolean bits are staged one byte per row and packed 32 at a time; short Utf8 values are
-//      staged the same way, long ones are produced output-chunk-centric, so every global store in
-//      the middle of a tile is an aligned 16-byte store.
+//   4. from here on every WARP works alone (no block barriers): per output column it stages its
+//      selected values in its private slice of shared memory at the destination's 16-byte phase
+//      and writes them with aligned 16-byte stores; validity and Boolean bits are staged one byte
+//      per row and packed 32 at a time; short Utf8 values are staged the same way, long ones are
+//      produced output-chunk-centric.
 // HBM traffic is therefore each referenced input byte once and each output byte once.
 // Projection expressions are evaluated in step 4 under the selection mask, so checked-integer
 // errors are raised for surviving rows only (the reference projects after filtering).
@@ -32,7 +32,7 @@ namespace chdb {
 namespace {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr int kBitStageBytes = kTileRows + 64;   // one byte per output row + word-alignment slack
+constexpr int kWarpBitStage = kTileRows / kWarps + 64;   // per warp: one byte per output row + word-alignment slack
 
 template <typename V> struct Cont;
 template <> struct Cont<uint32_t> { static constexpr bool k64 = false; };
@@ -571,28 +571,29 @@ __device__ __noinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr in,
 // ------------------------------------------------------------------------------------------
 // the interpreter: accumulator in registers, one operand per instruction.
 // Every handler updates the accumulator in place and keeps its operand array local to its own
-// scope, so nothing but (acc, accm, accv) is carried around the dispatch loop.
+// scope, so nothing but (acc, accm, accv) is carried around the dispatch loop.  It runs on QI
+// quads (4 * QI rows per thread) at a time.
 // ------------------------------------------------------------------------------------------
-template <typename V, int QPT>
+template <typename V, int QI>
 struct Spill {
-  V v[kMaxSpill][4 * QPT];
+  V v[kMaxSpill][4 * QI];
   uint32_t m[kMaxSpill], valid[kMaxSpill];
 };
 
 // Fetches the operand of `in` (column or spill slot; immediates are handled by the IMM templates).
-template <typename V, int QPT>
-__device__ __forceinline__ void fetch_operand(const KernelParams& P, const Instr& in, const int64_t (&qbase)[QPT], uint32_t inrange,
-                                              const Spill<V, QPT>& stk, V (&b)[4 * QPT], uint32_t& bm, uint32_t& bv) {
-  constexpr int R = 4 * QPT;
+template <typename V, int QI>
+__device__ __forceinline__ void fetch_operand(const KernelParams& P, const Instr& in, const int64_t (&qbase)[QI], uint32_t inrange,
+                                              const Spill<V, QI>& stk, V (&b)[4 * QI], uint32_t& bm, uint32_t& bv) {
+  constexpr int R = 4 * QI;
   if (in.src == SRC_COL) {
     const ColumnDesc& c = P.in[in.slot];
-    bv = load_bits<QPT>(c.validity, qbase, inrange);
+    bv = load_bits<QI>(c.validity, qbase, inrange);
     if (c.type == T_BOOL) {
-      bm = load_bits<QPT>((const uint8_t*)c.values, qbase, inrange);
+      bm = load_bits<QI>((const uint8_t*)c.values, qbase, inrange);
 #pragma unroll
       for (int j = 0; j < R; j++) b[j] = 0;
     } else {
-      fetch_col<V, QPT>(c, in.from_type, qbase, inrange, b);
+      fetch_col<V, QI>(c, in.from_type, qbase, inrange, b);
       if (in.type == T_BOOL) bm = tobool_vals<V, R>(b, in.from_type);
       else { bm = 0; cast_vals<V, R>(b, in.from_type, in.type); }
     }
@@ -609,12 +610,12 @@ __device__ __forceinline__ void fetch_operand(const KernelParams& P, const Instr
   }
 }
 
-template <typename V, int QPT>
-__device__ __forceinline__ void run_program(const KernelParams& P, int begin, int end, const int64_t (&qbase)[QPT], uint32_t inrange,
-                                            uint32_t active, const uint8_t* s_pool, V (&acc)[4 * QPT], uint32_t& accm,
+template <typename V, int QI>
+__device__ __forceinline__ void run_program(const KernelParams& P, int begin, int end, const int64_t (&qbase)[QI], uint32_t inrange,
+                                            uint32_t active, const uint8_t* s_pool, V (&acc)[4 * QI], uint32_t& accm,
                                             uint32_t& accv) {
-  constexpr int R = 4 * QPT;
-  Spill<V, QPT> stk;
+  constexpr int R = 4 * QI;
+  Spill<V, QI> stk;
 #pragma unroll
   for (int j = 0; j < R; j++) acc[j] = 0;
   accm = 0;
@@ -636,20 +637,20 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
           accm = in.imm ? FULL : 0u;
           accv = FULL;
         } else {
-          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, acc, accm, accv);   // straight into the accumulator
+          fetch_operand<V, QI>(P, in, qbase, inrange, stk, acc, accm, accv);   // straight into the accumulator
         }
         break;
       case OP_CAST: cast_vals<V, R>(acc, in.from_type, in.type); break;
       case OP_ADD: case OP_MUL: case OP_DIV: case OP_REM: case OP_SUB:
         if (imm) {
-          if (in.flags & OPF_SWAP) arith<true, true, V, QPT>(P, in, acc, accv, acc, FULL, active, qbase);
-          else arith<true, false, V, QPT>(P, in, acc, accv, acc, FULL, active, qbase);
+          if (in.flags & OPF_SWAP) arith<true, true, V, QI>(P, in, acc, accv, acc, FULL, active, qbase);
+          else arith<true, false, V, QI>(P, in, acc, accv, acc, FULL, active, qbase);
         } else {
           V b[R];
           uint32_t bm, bv;
-          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, b, bm, bv);
-          if (in.flags & OPF_SWAP) arith<false, true, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
-          else arith<false, false, V, QPT>(P, in, acc, accv, b, bv, active, qbase);
+          fetch_operand<V, QI>(P, in, qbase, inrange, stk, b, bm, bv);
+          if (in.flags & OPF_SWAP) arith<false, true, V, QI>(P, in, acc, accv, b, bv, active, qbase);
+          else arith<false, false, V, QI>(P, in, acc, accv, b, bv, active, qbase);
         }
         break;
       case OP_CMP:
@@ -658,7 +659,7 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
         } else {
           V b[R];
           uint32_t bm, bv;
-          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, b, bm, bv);
+          fetch_operand<V, QI>(P, in, qbase, inrange, stk, b, bm, bv);
           accm = compare<false, V, R>(in, acc, accm, b, bm);
           accv &= bv;
         }
@@ -671,7 +672,7 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
           bv = stk.valid[in.slot];
         } else if (in.src == SRC_COL) {
           V b[R];
-          fetch_operand<V, QPT>(P, in, qbase, inrange, stk, b, bm, bv);
+          fetch_operand<V, QI>(P, in, qbase, inrange, stk, b, bm, bv);
         }
         accm = in.op == OP_AND ? (accm & bm) : (accm | bm);
         accv &= bv;
@@ -686,11 +687,11 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
         stk.valid[in.slot] = accv;
         break;
       case OP_CMP_UTF8: {
-        QuadBases<QPT> qb;
+        QuadBases<QI> qb;
 #pragma unroll
-        for (int q = 0; q < QPT; q++) qb.v[q] = qbase[q];
+        for (int q = 0; q < QI; q++) qb.v[q] = qbase[q];
         uint32_t v = FULL;
-        accm = cmp_utf8<QPT>(P, in, qb, inrange, s_pool, &v);
+        accm = cmp_utf8<QI>(P, in, qb, inrange, s_pool, &v);
         accv = v;
         break;
       }
@@ -702,36 +703,15 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
 // ------------------------------------------------------------------------------------------
 // scans
 // ------------------------------------------------------------------------------------------
-// Exclusive scan of per-(thread, quad) values in output order (quad group, warp, lane).
-// s_w: kWarps * QPT words, used by one scan at a time (callers alternate two buffers so that one
-// barrier per scan is enough).
-template <int QPT>
-__device__ __forceinline__ void block_scan(const uint32_t (&val)[QPT], uint32_t (&excl)[QPT], uint32_t& total, uint32_t* s_w, int lane,
-                                           int warp) {
-  static_assert(QPT * kWarps <= 32, "warp totals must fit one warp");
-  uint32_t incl[QPT];
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+  uint32_t x = v;
 #pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    uint32_t x = val[q];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(FULL, x, d);
-      if (lane >= d) x += y;
-    }
-    incl[q] = x;
-    if (lane == 31) s_w[q * kWarps + warp] = x;
-  }
-  __syncthreads();
-  const uint32_t t = lane < QPT * kWarps ? s_w[lane] : 0u;
-  uint32_t x = t;
-#pragma unroll
-  for (int d = 1; d < QPT * kWarps; d <<= 1) {
+  for (int d = 1; d < 32; d <<= 1) {
     const uint32_t y = __shfl_up_sync(FULL, x, d);
     if (lane >= d) x += y;
   }
-  total = __shfl_sync(FULL, x, QPT * kWarps - 1);
-#pragma unroll
-  for (int q = 0; q < QPT; q++) excl[q] = __shfl_sync(FULL, x - t, q * kWarps + warp) + incl[q] - val[q];
+  total = __shfl_sync(FULL, x, 31);
+  return x - v;
 }
 
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
@@ -774,8 +754,12 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc, uint32_t tile, uint
 }
 
 // ------------------------------------------------------------------------------------------
-// output staging.  Shared memory is addressed with explicit 32-bit shared-window addresses
-// (computed once per kernel) so the hot loops are plain LDS / STS with register bases.
+// output staging -- per WARP.  After the tile prefixes are known every warp gathers its own 256
+// rows on its own: it stages the selected values of one column in its private slice of shared
+// memory at the destination's 16-byte phase and writes them with aligned 16-byte stores, with
+// only __syncwarp() in between, so no warp ever waits for another one in this phase.
+// Shared memory is addressed with explicit 32-bit shared-window addresses (computed once per
+// kernel) so the hot loops are plain LDS / STS with register bases.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -792,6 +776,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t lds8(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -799,42 +788,49 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a) {
 }
 template <int W>
 __device__ __forceinline__ void copy_elem_s2g(uint8_t* g, uint32_t s) {   // one W-byte element, shared -> global
-  if (W == 4) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(s) : "memory"); *(uint32_t*)g = v; }
+  if (W == 4) { *(uint32_t*)g = lds32(s); }
   else if (W == 8) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s) : "memory"); *(uint2*)g = v; }
   else if (W == 2) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(s) : "memory"); *(uint16_t*)g = v; }
   else { *g = (uint8_t)lds8(s); }
 }
 
-// stage[mis, mis + nbytes) -> gdst_aligned[mis, ...): aligned 16-byte stores in the middle,
-// W-byte element stores in the (at most two) 16-byte chunks shared with neighbouring tiles.
+// stage[mis, mis + nbytes) -> gdst_aligned[mis, ...), by one warp: aligned 16-byte stores in the
+// middle, W-byte element stores in the (at most two) 16-byte chunks shared with the neighbours.
 template <int W>
-__device__ __forceinline__ void stage_writeout(uint32_t stage_s, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int tid) {
+__device__ __forceinline__ void warp_writeout(uint32_t stage_s, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int lane) {
   const uint32_t end = mis + nbytes;
   const uint32_t first_full = (mis + 15u) >> 4, end_full = end >> 4;   // full chunks: [first_full, end_full)
-  for (uint32_t c = first_full + tid; c < end_full; c += kThreads) *(uint4*)(gdst_aligned + (c << 4)) = lds128(stage_s + (c << 4));
-  if (tid == 0 && mis != 0) {                 // head chunk (chunk 0 is partial)
+  for (uint32_t c = first_full + lane; c < end_full; c += 32) *(uint4*)(gdst_aligned + (c << 4)) = lds128(stage_s + (c << 4));
+  if (lane == 0 && mis != 0) {                 // head chunk (chunk 0 is partial)
     const uint32_t t = end < 16u ? end : 16u;
     for (uint32_t b = mis; b < t; b += W) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
   }
-  if (tid == 32 && (end & 15u) != 0 && (end_full > 0 || mis == 0)) {   // tail chunk, unless it is also the head chunk
+  if (lane == 1 && (end & 15u) != 0 && (end_full > 0 || mis == 0)) {   // tail chunk, unless it is also the head chunk
     for (uint32_t b = end_full << 4; b < end; b += W) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
   }
 }
 
-// Gathers the selected rows of a W-byte pass-through column: 128-bit loads, shared-memory staging
-// at the destination's 16-byte phase, aligned 128-bit stores.  Ends with the stage free again.
+// What a warp knows about its slice of the output once the prefixes are in.
+template <int QPT>
+struct WarpOut {
+  uint64_t base;          // global output row index of the warp's first selected row
+  uint32_t count;         // selected rows of this warp
+  uint32_t rank[QPT];     // warp-local rank of the first selected row of each of this lane's quads
+  uint32_t sel;           // selection bits of this lane's rows
+};
+
+// Gathers the selected rows of a W-byte pass-through column.
 template <int W, int QPT>
-__device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, uint8_t* dst, const int64_t (&qbase)[QPT], uint32_t sel,
-                                             const uint32_t (&rank0)[QPT], uint64_t tile_prefix, uint32_t tile_count, uint32_t stage_s,
-                                             int tid) {
-  const uint32_t mis = (uint32_t)((tile_prefix * W) & 15u);
+__device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, uint8_t* dst, const int64_t (&qbase)[QPT],
+                                             const WarpOut<QPT>& wo, uint32_t stage_s, int lane) {
+  const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
   // all loads first (independent, in flight together), then the shared-memory stores
   uint4 x[QPT], y[QPT];
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
     x[q] = make_uint4(0, 0, 0, 0);
     y[q] = make_uint4(0, 0, 0, 0);
-    if (!((sel >> (4 * q)) & 0xFu)) continue;
+    if (!((wo.sel >> (4 * q)) & 0xFu)) continue;
     if (W == 4) {
       x[q] = __ldg((const uint4*)(src + qbase[q] * 4));
     } else if (W == 8) {
@@ -849,9 +845,9 @@ __device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, ui
   }
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
+    const uint32_t s4 = (wo.sel >> (4 * q)) & 0xFu;
     if (!s4) continue;
-    uint32_t a = stage_s + mis + rank0[q] * W;
+    uint32_t a = stage_s + mis + wo.rank[q] * W;
     if (W == 4) {
       if (s4 & 1u) { sts32(a, x[q].x); a += 4; }
       if (s4 & 2u) { sts32(a, x[q].y); a += 4; }
@@ -874,23 +870,22 @@ __device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, ui
       if (s4 & 8u) { sts8(a, x[q].x >> 24); }
     }
   }
-  __syncthreads();
-  stage_writeout<W>(stage_s, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
-  __syncthreads();
+  __syncwarp();
+  warp_writeout<W>(stage_s, dst + ((wo.base * W) & ~15ull), mis, wo.count * W, lane);
+  __syncwarp();
 }
 
 // Same, for values that already sit in registers (projection expressions, rebuilt Utf8 offsets).
 template <int W, typename E, int QPT>
-__device__ __forceinline__ void scatter_regs(const E (&e)[4 * QPT], uint8_t* dst, uint32_t sel, const uint32_t (&rank0)[QPT],
-                                             uint64_t tile_prefix, uint32_t tile_count, uint32_t stage_s, int tid) {
-  const uint32_t mis = (uint32_t)((tile_prefix * W) & 15u);
+__device__ __forceinline__ void scatter_regs(const E (&e)[4 * QPT], uint8_t* dst, const WarpOut<QPT>& wo, uint32_t stage_s, int lane) {
+  const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    uint32_t a = stage_s + mis + rank0[q] * W;
+    uint32_t a = stage_s + mis + wo.rank[q] * W;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int j = 4 * q + i;
-      if ((sel >> j) & 1u) {
+      if ((wo.sel >> j) & 1u) {
         if (W == 4) sts32(a, (uint32_t)e[j]);
         else if (W == 8) sts64(a, (uint32_t)e[j], (uint32_t)((uint64_t)e[j] >> 32));
         else if (W == 2) sts16(a, (uint32_t)e[j] & 0xFFFFu);
@@ -899,33 +894,32 @@ __device__ __forceinline__ void scatter_regs(const E (&e)[4 * QPT], uint8_t* dst
       }
     }
   }
-  __syncthreads();
-  stage_writeout<W>(stage_s, dst + (((uint64_t)tile_prefix * W) & ~15ull), mis, tile_count * W, tid);
-  __syncthreads();
+  __syncwarp();
+  warp_writeout<W>(stage_s, dst + ((wo.base * W) & ~15ull), mis, wo.count * W, lane);
+  __syncwarp();
 }
 
-// Compacts one bit per row (validity or Boolean values) into gbits at bit offset tile_prefix:
-// every selected row drops its bit as one byte at its rank, then one thread per output word packs
+// Compacts one bit per row (validity or Boolean values) into gbits at bit offset wo.base:
+// every selected row drops its bit as one byte at its rank, then one lane per output word packs
 // 32 bytes with eight multiplies.  gbits is zero-initialised; the (at most two) words shared with
-// neighbouring tiles are merged with atomicOr.
+// neighbouring warps are merged with atomicOr.
 template <int QPT>
-__device__ __forceinline__ void compact_bits(uint32_t bits, uint32_t sel, const uint32_t (&rank0)[QPT], uint64_t tile_prefix,
-                                             uint32_t tile_count, uint32_t bstage_s, uint32_t* gbits, int tid) {
-  const uint32_t o = (uint32_t)(tile_prefix & 31);
+__device__ __forceinline__ void compact_bits(uint32_t bits, const WarpOut<QPT>& wo, uint32_t bstage_s, uint32_t* gbits, int lane) {
+  const uint32_t o = (uint32_t)(wo.base & 31);
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    uint32_t a = bstage_s + o + rank0[q];
+    uint32_t a = bstage_s + o + wo.rank[q];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int j = 4 * q + i;
-      if ((sel >> j) & 1u) { sts8(a, (bits >> j) & 1u); a++; }
+      if ((wo.sel >> j) & 1u) { sts8(a, (bits >> j) & 1u); a++; }
     }
   }
-  __syncthreads();
-  const uint32_t end = o + tile_count;
-  const uint32_t nwords = (end + 31u) >> 5;
-  const uint64_t g0 = tile_prefix >> 5;
-  for (uint32_t k = tid; k < nwords; k += kThreads) {
+  __syncwarp();
+  const uint32_t end = o + wo.count;
+  const uint32_t nwords = (end + 31u) >> 5;     // <= 9 for a 256-row warp slice
+  const uint64_t g0 = wo.base >> 5;
+  for (uint32_t k = lane; k < nwords; k += 32) {
     const uint4 lo4 = lds128(bstage_s + 32 * k), hi4 = lds128(bstage_s + 32 * k + 16);
     const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
     uint32_t word = 0;
@@ -938,7 +932,7 @@ __device__ __forceinline__ void compact_bits(uint32_t bits, uint32_t sel, const 
     if (mask == FULL) gbits[g0 + k] = word;
     else if (word) atomicOr(&gbits[g0 + k], word);
   }
-  __syncthreads();
+  __syncwarp();
 }
 
 __device__ __forceinline__ void add_count(uint64_t* slot, uint32_t mine, int lane) {
@@ -995,27 +989,77 @@ __device__ __forceinline__ void copy_row_g2s(const uint8_t* sp, uint32_t da, uin
   }
 }
 
+// Long strings: the warp's output byte range is produced chunk-centric -- each lane builds aligned
+// 16-byte output chunks, finding the source row of a byte by binary search over the warp's
+// selected rows (s_oo: warp-local output byte offsets, s_src: source byte offsets).
+__device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, uint8_t* gal, uint32_t mis, uint32_t nbytes, uint32_t nrows,
+                                               const uint32_t* s_oo, const int32_t* s_src, int lane) {
+  const uint32_t end = mis + nbytes;
+  const uint32_t nchunks = (end + 15u) >> 4;
+#pragma unroll 1
+  for (uint32_t ch = lane; ch < nchunks; ch += 32) {
+    const uint32_t lo = ch << 4, hi = lo + 16;
+    const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
+    if (s >= t) continue;
+    const uint32_t x = s - mis;  // warp-local output byte index of the first byte produced
+    uint32_t lo_r = 0, hi_r = nrows;  // first r in (0, nrows] with s_oo[r] > x
+    while (lo_r < hi_r) {
+      const uint32_t mid = (lo_r + hi_r) >> 1;
+      if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
+    }
+    uint32_t r = lo_r - 1;  // row holding byte x (never an empty string)
+    const bool full = (t - s) == 16u;
+    if (full && x + 16u <= s_oo[r + 1]) {
+      *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
+      continue;
+    }
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll 1
+    for (uint32_t b = s; b < t;) {
+      const uint32_t xb = b - mis;
+      while (xb >= s_oo[r + 1]) r++;
+      const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
+      uint32_t piece, step;
+      if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) { piece = load4_unaligned(sp); step = 4; }
+      else { piece = (uint32_t)__ldg(sp) << (8u * (b & 3u)); step = 1; }
+      const uint32_t wi = (b - lo) >> 2;
+      if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
+      b += step;
+    }
+    if (full) {
+      *(uint4*)(gal + lo) = make_uint4(w0, w1, w2, w3);
+    } else {
+      for (uint32_t b = s; b < t; b++) {
+        const uint32_t wi = (b - lo) >> 2;
+        const uint32_t word = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
+        gal[b] = (uint8_t)(word >> (8u * (b & 3u)));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <typename V, int QPT>
-__global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(kThreads, 3) filter_project_kernel(const __grid_constant__ KernelParams P) {
   constexpr int R = 4 * QPT;
   constexpr int T = kThreads * R;
+  constexpr int WR = 32 * R;                    // rows per warp slice
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_w[2][QPT * kWarps];
-  __shared__ uint64_t s_agg[1 + kMaxOutCols];
-  __shared__ uint64_t s_excl[1 + kMaxOutCols];
+  __shared__ uint32_t s_wtot[1 + kMaxOutCols][kWarps];   // per-warp totals: [0] rows, [1 + u] bytes of Utf8 output u
+  __shared__ uint64_t s_excl[1 + kMaxOutCols];           // tile prefixes from the look-back
   __shared__ uint8_t s_pool[kStrPoolBytes];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_pred = P.pred_end > P.pred_begin;
 
-  const uint32_t stage_s = smem_u32(smem);                           // output staging area
-  const uint32_t bstage_s = stage_s + (uint32_t)P.stage_bytes;       // [T + 64] one byte per output row
-  uint32_t* s_oo = (uint32_t*)(smem + P.stage_bytes + kBitStageBytes);   // [T + 4] output byte offsets (long Utf8)
-  int32_t* s_src = (int32_t*)(s_oo + T + 4);                         // [T] source byte offsets (long Utf8)
+  const uint32_t wstage_bytes = (uint32_t)P.stage_bytes;                            // per warp
+  const uint32_t stage_s = smem_u32(smem) + warp * wstage_bytes;                    // this warp's staging slice
+  const uint32_t bstage_s = smem_u32(smem) + kWarps * wstage_bytes + warp * kWarpBitStage;   // one byte per output row
+  uint32_t* s_oo = (uint32_t*)(smem + kWarps * (wstage_bytes + kWarpBitStage)) + warp * (WR + 4);   // long Utf8 only
+  int32_t* s_src = (int32_t*)((uint32_t*)(smem + kWarps * (wstage_bytes + kWarpBitStage)) + kWarps * (WR + 4)) + warp * WR;
 
   if (tid == 0) s_tile = has_pred ? atomicAdd(P.ticket, 1u) : blockIdx.x;
   if (tid < kStrPoolBytes) s_pool[tid] = (uint8_t)P.strpool[tid];
@@ -1038,33 +1082,45 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
       prefetch_l2(c.validity + (row0 >> 3) + (tid - 32) * 128);
   }
 
+  // rows of this lane: quad q covers rows  row0 + warp * WR + q * 128 + lane * 4 .. + 3
   int64_t qbase[QPT];
   uint32_t inrange = 0;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    const int local = q * (kThreads * 4) + warp * 128 + lane * 4;
+    const int local = warp * WR + q * 128 + lane * 4;
     qbase[q] = row0 + local;
     const int left = tile_rows - local;
     inrange |= (left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u)) << (4 * q);
   }
 
-  // ---- 1. predicate -> selection mask -----------------------------------------------------
+  // ---- 1. predicate -> selection mask (one quad at a time: small register footprint) ---------
   uint32_t sel = inrange;
   if (has_pred) {
-    V acc[R];
-    uint32_t accm, accv;
-    run_program<V, QPT>(P, P.pred_begin, P.pred_end, qbase, inrange, inrange, s_pool, acc, accm, accv);
-    sel = accm & accv & inrange;  // NULL predicate rows are dropped (arrow-select filter)
+    sel = 0;
+#pragma unroll 1
+    for (int q = 0; q < QPT; q++) {
+      const int64_t qb[1] = {q == 0 ? qbase[0] : qbase[QPT - 1]};
+      static_assert(QPT <= 2, "quad selection below assumes QPT <= 2");
+      const uint32_t in4 = (inrange >> (4 * q)) & 0xFu;
+      V acc[4];
+      uint32_t accm, accv;
+      run_program<V, 1>(P, P.pred_begin, P.pred_end, qb, in4, in4, s_pool, acc, accm, accv);
+      sel |= (accm & accv & in4) << (4 * q);  // NULL predicate rows are dropped (arrow-select filter)
+    }
   }
 
-  // ---- 2. rank the selected rows ------------------------------------------------------------
-  uint32_t cnt[QPT], rank0[QPT], tile_count;
+  // ---- 2. rank the selected rows inside the warp; publish the warp totals --------------------
+  WarpOut<QPT> wo;
+  wo.sel = sel;
+  uint32_t warp_rows = 0;
 #pragma unroll
-  for (int q = 0; q < QPT; q++) cnt[q] = __popc((sel >> (4 * q)) & 0xFu);
-  int scan_buf = 0;
-  block_scan<QPT>(cnt, rank0, tile_count, s_w[scan_buf], lane, warp);
-  scan_buf ^= 1;
-  if (tid == 0) s_agg[0] = tile_count;
+  for (int q = 0; q < QPT; q++) {
+    uint32_t tot;
+    wo.rank[q] = warp_rows + warp_excl_scan((uint32_t)__popc((sel >> (4 * q)) & 0xFu), lane, tot);
+    warp_rows += tot;
+  }
+  wo.count = warp_rows;
+  if (lane == 0) s_wtot[0][warp] = warp_rows;
 
   // selected value bytes per Utf8 output (and a prefetch of exactly those bytes)
   for (int k = 0; k < P.n_out; k++) {
@@ -1072,34 +1128,34 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
     if (o.utf8_index == 0xFFu) continue;   // uniform branch
     const int32_t* __restrict__ off = P.in[o.slot].offsets;
     const uint8_t* __restrict__ sv = (const uint8_t*)P.in[o.slot].values;
-    uint32_t bytes[QPT], bexcl[QPT], btotal;
+    uint32_t bytes = 0;
 #pragma unroll
     for (int q = 0; q < QPT; q++) {
-      bytes[q] = 0;
       const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
       if (s4) {
         const int4 a = __ldg((const int4*)(off + qbase[q]));
         const int a4 = __ldg(off + qbase[q] + 4);
-        if (s4 & 1u) bytes[q] += (uint32_t)(a.y - a.x);
-        if (s4 & 2u) bytes[q] += (uint32_t)(a.z - a.y);
-        if (s4 & 4u) bytes[q] += (uint32_t)(a.w - a.z);
-        if (s4 & 8u) bytes[q] += (uint32_t)(a4 - a.w);
+        if (s4 & 1u) bytes += (uint32_t)(a.y - a.x);
+        if (s4 & 2u) bytes += (uint32_t)(a.z - a.y);
+        if (s4 & 4u) bytes += (uint32_t)(a.w - a.z);
+        if (s4 & 8u) bytes += (uint32_t)(a4 - a.w);
         const uintptr_t pa = (uintptr_t)(sv + a.x), pe = (uintptr_t)(sv + a4);
         prefetch_l2((const void*)pa);
         for (uintptr_t line = (pa + 128) & ~(uintptr_t)127; line < pe; line += 128) prefetch_l2((const void*)line);
       }
     }
-    block_scan<QPT>(bytes, bexcl, btotal, s_w[scan_buf], lane, warp);
-    scan_buf ^= 1;
-    if (tid == 0) s_agg[1 + o.utf8_index] = btotal;
+    const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+    if (lane == 0) s_wtot[1 + o.utf8_index][warp] = wbytes;
   }
   __syncthreads();
 
-  // ---- 3. tile prefixes ---------------------------------------------------------------------
+  // ---- 3. tile prefixes: warp qi runs the look-back for quantity qi ---------------------------
   const int nq = 1 + P.n_utf8;
   if (has_pred) {
     for (int qi = warp; qi < nq; qi += kWarps) {
-      const uint64_t agg = s_agg[qi];
+      uint64_t agg = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) agg += s_wtot[qi][w];
       const uint64_t excl = lookback(P.tile_desc + (size_t)qi * P.num_tiles, tile, agg, lane);
       if (lane == 0) {
         s_excl[qi] = excl;
@@ -1111,16 +1167,27 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
     if (tile == (uint32_t)P.num_tiles - 1) P.counts[0] = (uint64_t)P.num_rows;
   }
   __syncthreads();
-  const uint64_t tile_prefix = s_excl[0];
+  // from here on every warp works alone
+  uint32_t rows_before = 0, tile_count = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) {
+    const uint32_t t = s_wtot[0][w];
+    if (w < warp) rows_before += t;
+    tile_count += t;
+  }
+  wo.base = s_excl[0] + rows_before;
   if (tile == (uint32_t)P.num_tiles - 1 && tid < P.n_out) {
     // closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
     const OutDesc& o = P.out[tid];
-    if (o.utf8_index != 0xFFu)
-      o.offsets[tile_prefix + tile_count] = (int32_t)(s_excl[1 + o.utf8_index] + s_agg[1 + o.utf8_index]);
+    if (o.utf8_index != 0xFFu) {
+      uint64_t tb = s_excl[1 + o.utf8_index];
+      for (int w = 0; w < kWarps; w++) tb += s_wtot[1 + o.utf8_index][w];
+      o.offsets[s_excl[0] + tile_count] = (int32_t)tb;
+    }
   }
-  if (tile_count == 0) return;  // block-uniform
+  if (wo.count == 0) return;  // warp-uniform; no block-wide barrier follows
 
-  // ---- 4. gather every output column --------------------------------------------------------
+  // ---- 4. gather every output column (per warp) ------------------------------------------------
 #pragma unroll 1
   for (int k = 0; k < P.n_out; k++) {
     // the eight small fields of OutDesc arrive as one 64-bit constant load
@@ -1130,35 +1197,49 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
     const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_count = (uint32_t)(meta >> 56);
     uint8_t* const o_values = (uint8_t*)P.out[k].values;
     uint8_t* const o_validity = P.out[k].validity;
-    uint32_t vbits = FULL;  // validity of this output for the thread's rows
+    uint32_t vbits = FULL;  // validity of this output for the lane's rows
     if (o_kind == OUT_EXPR) {
       V acc[R];
-      uint32_t accm, accv;
-      // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
-      run_program<V, QPT>(P, (int)o_begin, (int)o_end, qbase, inrange, sel, s_pool, acc, accm, accv);
-      vbits = accv;
-      if (o_type == T_BOOL) compact_bits<QPT>(accm, sel, rank0, tile_prefix, tile_count, bstage_s, (uint32_t*)o_values, tid);
-      else if (o_width == 4) scatter_regs<4, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
-      else if (o_width == 8) scatter_regs<8, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
-      else if (o_width == 2) scatter_regs<2, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
-      else scatter_regs<1, V, QPT>(acc, o_values, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+      uint32_t accm = 0;
+      vbits = 0;
+#pragma unroll 1
+      for (int q = 0; q < QPT; q++) {
+        const int64_t qb[1] = {q == 0 ? qbase[0] : qbase[QPT - 1]};
+        const uint32_t in4 = (inrange >> (4 * q)) & 0xFu, sel4 = (sel >> (4 * q)) & 0xFu;
+        V a4[4];
+        uint32_t m4, v4;
+        // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
+        run_program<V, 1>(P, (int)o_begin, (int)o_end, qb, in4, sel4, s_pool, a4, m4, v4);
+        if (q == 0) { acc[0] = a4[0]; acc[1] = a4[1]; acc[2] = a4[2]; acc[3] = a4[3]; }
+        else { acc[R - 4] = a4[0]; acc[R - 3] = a4[1]; acc[R - 2] = a4[2]; acc[R - 1] = a4[3]; }
+        accm |= (m4 & 0xFu) << (4 * q);
+        vbits |= (v4 & 0xFu) << (4 * q);
+      }
+      if (o_type == T_BOOL) compact_bits<QPT>(accm, wo, bstage_s, (uint32_t*)o_values, lane);
+      else if (o_width == 4) scatter_regs<4, V, QPT>(acc, o_values, wo, stage_s, lane);
+      else if (o_width == 8) scatter_regs<8, V, QPT>(acc, o_values, wo, stage_s, lane);
+      else if (o_width == 2) scatter_regs<2, V, QPT>(acc, o_values, wo, stage_s, lane);
+      else scatter_regs<1, V, QPT>(acc, o_values, wo, stage_s, lane);
     } else {
       const ColumnDesc& c = P.in[o_slot];
       vbits = load_bits<QPT>(c.validity, qbase, sel);
       if (o_type == T_BOOL) {
         const uint32_t vals = load_bits<QPT>((const uint8_t*)c.values, qbase, sel);
-        compact_bits<QPT>(vals, sel, rank0, tile_prefix, tile_count, bstage_s, (uint32_t*)o_values, tid);
+        compact_bits<QPT>(vals, wo, bstage_s, (uint32_t*)o_values, lane);
       } else if (o_type == T_UTF8) {
         // -- offsets: running sum of the selected lengths, restarted at 0 for the output --
         const int32_t* __restrict__ off = c.offsets;
         const uint8_t* __restrict__ sv = (const uint8_t*)c.values;
-        const uint64_t byte_prefix = s_excl[1 + o_utf8];
-        const uint32_t tile_bytes = (uint32_t)s_agg[1 + o_utf8];
-        uint32_t len[R], bytes[QPT], bexcl[QPT], btotal;
+        uint32_t bytes_before = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++)
+          if (w < warp) bytes_before += s_wtot[1 + o_utf8][w];
+        const uint64_t byte_base = s_excl[1 + o_utf8] + bytes_before;   // output byte offset of this warp's first value
+        uint32_t len[R], boff[R];
         int32_t src[R];
+        uint32_t warp_bytes = 0;
 #pragma unroll
         for (int q = 0; q < QPT; q++) {
-          bytes[q] = 0;
 #pragma unroll
           for (int i = 0; i < 4; i++) { len[4 * q + i] = 0; src[4 * q + i] = 0; }
           const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
@@ -1170,42 +1251,36 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
             if (s4 & 2u) len[4 * q + 1] = (uint32_t)(a.z - a.y);
             if (s4 & 4u) len[4 * q + 2] = (uint32_t)(a.w - a.z);
             if (s4 & 8u) len[4 * q + 3] = (uint32_t)(a4 - a.w);
-            bytes[q] = len[4 * q] + len[4 * q + 1] + len[4 * q + 2] + len[4 * q + 3];
           }
-        }
-        block_scan<QPT>(bytes, bexcl, btotal, s_w[scan_buf], lane, warp);
-        scan_buf ^= 1;
-        uint32_t boff[R];   // tile-local output byte offset of each selected row
-#pragma unroll
-        for (int q = 0; q < QPT; q++) {
-          uint32_t bo = bexcl[q];
+          uint32_t tot;
+          uint32_t bo = warp_bytes + warp_excl_scan(len[4 * q] + len[4 * q + 1] + len[4 * q + 2] + len[4 * q + 3], lane, tot);
+          warp_bytes += tot;
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            boff[4 * q + i] = bo;
+            boff[4 * q + i] = bo;   // warp-local output byte offset of each selected row
             bo += len[4 * q + i];
           }
         }
         {
           uint32_t newoff[R];
 #pragma unroll
-          for (int j = 0; j < R; j++) newoff[j] = (uint32_t)byte_prefix + boff[j];
-          scatter_regs<4, uint32_t, QPT>(newoff, (uint8_t*)P.out[k].offsets, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+          for (int j = 0; j < R; j++) newoff[j] = (uint32_t)byte_base + boff[j];
+          scatter_regs<4, uint32_t, QPT>(newoff, (uint8_t*)P.out[k].offsets, wo, stage_s, lane);
         }
-        const uint32_t mis = (uint32_t)(byte_prefix & 15u);
-        uint8_t* gal = o_values + (byte_prefix - mis);
-        if (mis + tile_bytes <= (uint32_t)P.stage_bytes - 16u) {
+        const uint32_t mis = (uint32_t)(byte_base & 15u);
+        uint8_t* gal = o_values + (byte_base - mis);
+        if (mis + warp_bytes <= wstage_bytes - 16u) {
           // -- short strings: every selected row copies its bytes into the stage, then aligned write-out --
 #pragma unroll
           for (int j = 0; j < R; j++)
             if (((sel >> j) & 1u) && len[j] != 0) copy_row_g2s(sv + src[j], stage_s + mis + boff[j], len[j]);
-          __syncthreads();
-          stage_writeout<1>(stage_s, gal, mis, tile_bytes, tid);
-          __syncthreads();
+          __syncwarp();
+          warp_writeout<1>(stage_s, gal, mis, warp_bytes, lane);
+          __syncwarp();
         } else {
-          // -- long strings: each thread produces aligned 16-byte output chunks --
 #pragma unroll
           for (int q = 0; q < QPT; q++) {
-            uint32_t r = rank0[q];
+            uint32_t r = wo.rank[q];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
               const int j = 4 * q + i;
@@ -1216,77 +1291,36 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
               }
             }
           }
-          if (tid == 0) s_oo[tile_count] = tile_bytes;
-          __syncthreads();
-          const uint32_t end = mis + tile_bytes;
-          const uint32_t nchunks = (end + 15u) >> 4;
-#pragma unroll 1
-          for (uint32_t ch = tid; ch < nchunks; ch += kThreads) {
-            const uint32_t lo = ch << 4, hi = lo + 16;
-            const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
-            if (s >= t) continue;
-            const uint32_t x = s - mis;  // tile-local output byte index of the first byte produced
-            uint32_t lo_r = 0, hi_r = tile_count;  // first r in (0, count] with s_oo[r] > x
-            while (lo_r < hi_r) {
-              const uint32_t mid = (lo_r + hi_r) >> 1;
-              if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
-            }
-            uint32_t r = lo_r - 1;  // row holding byte x (never an empty string)
-            const bool full = (t - s) == 16u;
-            if (full && x + 16u <= s_oo[r + 1]) {
-              *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
-              continue;
-            }
-            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-#pragma unroll 1
-            for (uint32_t b = s; b < t;) {
-              const uint32_t xb = b - mis;
-              while (xb >= s_oo[r + 1]) r++;
-              const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
-              uint32_t piece, step;
-              if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) { piece = load4_unaligned(sp); step = 4; }
-              else { piece = (uint32_t)__ldg(sp) << (8u * (b & 3u)); step = 1; }
-              const uint32_t wi = (b - lo) >> 2;
-              if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
-              b += step;
-            }
-            if (full) {
-              *(uint4*)(gal + lo) = make_uint4(w0, w1, w2, w3);
-            } else {
-              for (uint32_t b = s; b < t; b++) {
-                const uint32_t wi = (b - lo) >> 2;
-                const uint32_t word = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
-                gal[b] = (uint8_t)(word >> (8u * (b & 3u)));
-              }
-            }
-          }
-          __syncthreads();
+          if (lane == 0) s_oo[wo.count] = warp_bytes;
+          __syncwarp();
+          copy_long_strings(sv, gal, mis, warp_bytes, wo.count, s_oo, s_src, lane);
+          __syncwarp();
         }
       } else if (o_width == 16) {
         const uint4* __restrict__ src = (const uint4*)c.values;
 #pragma unroll
         for (int q = 0; q < QPT; q++) {
-          uint32_t a = stage_s + rank0[q] * 16;
+          uint32_t a = stage_s + wo.rank[q] * 16;
 #pragma unroll
           for (int i = 0; i < 4; i++)
             if ((sel >> (4 * q + i)) & 1u) { sts128(a, __ldg(src + qbase[q] + i)); a += 16; }
         }
-        __syncthreads();
-        uint4* dst = (uint4*)o_values + tile_prefix;
-        for (uint32_t r = tid; r < tile_count; r += kThreads) dst[r] = lds128(stage_s + r * 16);
-        __syncthreads();
+        __syncwarp();
+        uint4* dst = (uint4*)o_values + wo.base;
+        for (uint32_t r = lane; r < wo.count; r += 32) dst[r] = lds128(stage_s + r * 16);
+        __syncwarp();
       } else if (o_width == 4) {
-        gather_fixed<4, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+        gather_fixed<4, QPT>((const uint8_t*)c.values, o_values, qbase, wo, stage_s, lane);
       } else if (o_width == 8) {
-        gather_fixed<8, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+        gather_fixed<8, QPT>((const uint8_t*)c.values, o_values, qbase, wo, stage_s, lane);
       } else if (o_width == 2) {
-        gather_fixed<2, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+        gather_fixed<2, QPT>((const uint8_t*)c.values, o_values, qbase, wo, stage_s, lane);
       } else {
-        gather_fixed<1, QPT>((const uint8_t*)c.values, o_values, qbase, sel, rank0, tile_prefix, tile_count, stage_s, tid);
+        gather_fixed<1, QPT>((const uint8_t*)c.values, o_values, qbase, wo, stage_s, lane);
       }
     }
     if (o_validity != nullptr) {
-      compact_bits<QPT>(vbits, sel, rank0, tile_prefix, tile_count, bstage_s, (uint32_t*)o_validity, tid);
+      compact_bits<QPT>(vbits, wo, bstage_s, (uint32_t*)o_validity, lane);
       add_count(P.counts + o_count, (uint32_t)__popc(sel & ~vbits), lane);
     }
   }
@@ -1294,19 +1328,22 @@ __global__ void __launch_bounds__(kThreads, 2) filter_project_kernel(const __gri
 
 }  // namespace
 
+// Per-warp staging slice: 256 rows of the widest fixed-width output, or of short Utf8 values.
 size_t filter_project_stage_bytes(int max_out_width, int64_t avg_utf8_len) {
-  size_t stage = (size_t)kTileRows * (size_t)(max_out_width < 4 ? 4 : max_out_width) + 32;
-  if (avg_utf8_len > 0) {   // room for a whole tile of short strings (the staged Utf8 path)
-    size_t want = (size_t)kTileRows * (size_t)avg_utf8_len + 64;
-    if (want > 40 * 1024) want = 40 * 1024;
+  const size_t rows = kTileRows / kWarps;
+  size_t stage = rows * (size_t)(max_out_width < 4 ? 4 : max_out_width) + 32;
+  if (avg_utf8_len > 0) {   // room for a warp slice of short strings (the staged Utf8 path)
+    size_t want = rows * (size_t)avg_utf8_len + 64;
+    if (want > 6 * 1024) want = 6 * 1024;
     if (want > stage) stage = want;
   }
   return (stage + 15) & ~(size_t)15;
 }
 
 size_t filter_project_smem_bytes(size_t stage_bytes, bool has_utf8_out) {
-  size_t total = stage_bytes + (size_t)kBitStageBytes;
-  if (has_utf8_out) total += (size_t)(kTileRows + 4) * 4 + (size_t)kTileRows * 4 + 16;
+  const size_t rows = kTileRows / kWarps;
+  size_t total = (size_t)kWarps * (stage_bytes + (size_t)kWarpBitStage);
+  if (has_utf8_out) total += (size_t)kWarps * ((rows + 4) * 4 + rows * 4) + 16;
   return total;
 }
 
@@ -1314,7 +1351,7 @@ cudaError_t launch_filter_project(const KernelParams& p, bool has64, size_t dyn_
   auto k32 = filter_project_kernel<uint32_t, kQuadsPerThread>;
   auto k64 = filter_project_kernel<uint64_t, kQuadsPerThread>;
   auto kern = has64 ? k64 : k32;
-  if (dyn_smem > 48 * 1024) {  // only 16-byte (decimal128) columns or long-ish strings need more than the default window
+  if (dyn_smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     if (e != cudaSuccess) return e;
   }
