@@ -80,6 +80,10 @@ def load_library():
     sig("chdb_ctx_device", i32, vp)
     sig("chdb_ctx_synchronize", i32, vp, stp)
     sig("chdb_ctx_launch_count", i64, vp)
+    sig("chdb_ctx_jit_launch_count", i64, vp)
+    sig("chdb_jit_available", i32, ctypes.c_char_p, ctypes.c_size_t)
+    sig("chdb_program_jit_source", ctypes.c_size_t, vp, ctypes.c_char_p, ctypes.c_size_t)
+    sig("chdb_program_jit_check", i32, vp, ctypes.POINTER(i64), ctypes.c_char_p, ctypes.c_size_t, stp)
     sig("chdb_program_compile_filter", i32, cp, vp, cp, pvp, stp)
     sig("chdb_program_compile_project", i32, cp, vp, cp, pvp, stp)
     sig("chdb_program_compile_filter_project", i32, cp, cp, vp, cp, pvp, stp)
@@ -107,7 +111,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "chdb_code_name", "chdb_version", "chdb_compiled_arch", "chdb_ctx_create", "chdb_ctx_destroy", "chdb_ctx_stream",
-    "chdb_ctx_device", "chdb_ctx_synchronize", "chdb_ctx_launch_count", "chdb_program_compile_filter",
+    "chdb_ctx_device", "chdb_ctx_synchronize", "chdb_ctx_launch_count", "chdb_ctx_jit_launch_count",
+    "chdb_jit_available", "chdb_program_jit_source", "chdb_program_jit_check", "chdb_program_compile_filter",
     "chdb_program_compile_project", "chdb_program_compile_filter_project", "chdb_program_release",
     "chdb_program_disassemble", "chdb_program_num_instructions", "chdb_filter_record", "chdb_project_record",
     "chdb_filter_record_expr", "chdb_project_record_items", "chdb_compute_value", "chdb_upload",
@@ -115,6 +120,12 @@ EXPORTED_SYMBOLS = [
     "chdb_device_batch_num_columns", "chdb_device_batch_nbytes", "chdb_download", "chdb_peer_copy",
     "chdb_device_batch_release",
 ]
+
+
+def jit_available() -> tuple[bool, str]:
+    buf = ctypes.create_string_buffer(512)
+    ok = load_library().chdb_jit_available(buf, len(buf))
+    return bool(ok), buf.value.decode()
 
 
 def _check(rc: int, st: _Status):
@@ -185,6 +196,11 @@ class Context:
     def launch_count(self) -> int:
         return int(load_library().chdb_ctx_launch_count(self._h))
 
+    @property
+    def jit_launch_count(self) -> int:
+        """Launches that ran an NVRTC-specialised kernel (subset of launch_count)."""
+        return int(load_library().chdb_ctx_jit_launch_count(self._h))
+
     def synchronize(self):
         st = _Status()
         _check(load_library().chdb_ctx_synchronize(self._h, ctypes.byref(st)), st)
@@ -247,6 +263,22 @@ class Program:
     @property
     def num_instructions(self) -> int:
         return int(load_library().chdb_program_num_instructions(self._h))
+
+    def jit_source(self) -> str:
+        """The constants NVRTC sees in front of device_code.cuh when this program is specialised."""
+        L = load_library()
+        n = L.chdb_program_jit_source(self._h, None, 0)
+        buf = ctypes.create_string_buffer(n + 1)
+        L.chdb_program_jit_source(self._h, buf, n + 1)
+        return buf.value.decode()
+
+    def jit_check(self) -> tuple[int, str]:
+        """Compile the specialised kernel for sm_100a (no GPU needed). Returns (cubin bytes, log)."""
+        L = load_library()
+        n, st = ctypes.c_int64(0), _Status()
+        log = ctypes.create_string_buffer(1 << 16)
+        _check(L.chdb_program_jit_check(self._h, ctypes.byref(n), log, len(log), ctypes.byref(st)), st)
+        return int(n.value), log.value.decode(errors="replace")
 
     def run(self, rb: pa.RecordBatch, ctx: Context | None = None) -> pa.RecordBatch:
         """Host batch in, host batch out (upload -> fused kernel -> download)."""

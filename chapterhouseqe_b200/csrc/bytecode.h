@@ -4,7 +4,23 @@
 // or spill slot), and a small spill stack used only when both children of a node are
 // non-leaf expressions.
 #pragma once
+#ifdef __CUDACC_RTC__
+// NVRTC (run-time specialisation, see jit.cpp) has no system headers: spell the basics out.
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+typedef unsigned long size_t;
+#define INT32_MIN (-2147483647 - 1)
+#define INT64_MIN (-9223372036854775807ll - 1)
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __CUDACC__
 #define CHDB_HD __host__ __device__
@@ -93,6 +109,10 @@ constexpr int kMaxOutCols = 24;
 constexpr int kMaxSpill = 6;
 constexpr int kStrPoolBytes = 256;
 // (sized so that the whole KernelParams block stays under the classic 4 KB parameter limit)
+
+// chdb_code values the kernels can raise (static_assert'ed against include/chdb_gpu.h in runtime.cu)
+constexpr uint32_t kErrArithmeticOverflow = 12;
+constexpr uint32_t kErrDivideByZero = 13;
 
 // Device error word: atomicMax of ~packed, packed = [63:56] order, [55:8] row, [7:0] chdb_code;
 // 0 = no error, larger = earlier in the reference's evaluation order.

@@ -1,7 +1,9 @@
 // Kernel parameter block of the fused evaluate -> scan -> compact kernel.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "bytecode.h"
 
@@ -56,10 +58,12 @@ struct KernelParams {
 };
 static_assert(sizeof(KernelParams) <= 4096, "KernelParams must fit the 4 KB kernel parameter space");
 
+#ifndef __CUDACC_RTC__
 // has64: the program touches 64-bit types (selects the 64-bit accumulator container).
 cudaError_t launch_filter_project(const KernelParams& p, bool has64, size_t dyn_smem, cudaStream_t stream);
-// Output staging area: a tile of the widest fixed-width output, or of short Utf8 values.
+// Per-warp output staging slice: 256 rows of the widest fixed-width output, or of short Utf8 values.
 size_t filter_project_stage_bytes(int max_out_width, int64_t avg_utf8_len);
 size_t filter_project_smem_bytes(size_t stage_bytes, bool has_utf8_out);
+#endif
 
 }  // namespace chdb

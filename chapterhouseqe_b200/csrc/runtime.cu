@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "jit.hpp"
 #include "kernels.cuh"
 #include "program.hpp"
 
@@ -37,6 +38,7 @@ struct CtxCore {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::atomic<int64_t> launches{0};
+  std::atomic<int64_t> jit_launches{0};   // launches that ran an NVRTC-specialised kernel
   std::mutex mu;
   std::vector<void*> pinned_free;   // small pinned blocks for count read-back
   static constexpr size_t kPinnedBlock = 1024;
@@ -689,7 +691,21 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   const size_t smem = filter_project_smem_bytes(stage_bytes, n_utf8 > 0);
   kp.stage_bytes = (int32_t)stage_bytes;
 
-  cudaError_t le = launch_filter_project(kp, p.has64, smem, core->stream);
+  // Long scans run the same device code specialised for this program by NVRTC (jit.cpp); short
+  // batches, or boxes without NVRTC, run the bytecode interpreter kernel.
+  cudaError_t le = cudaSuccess;
+  const JitKernel* jk = nullptr;
+  const JitMode jm = jit_mode();
+  if (jm == JitMode::Always || (jm == JitMode::Auto && n >= kJitAutoRows)) {
+    std::string why;
+    jk = jit_get(kp, p.has64, &why);
+  }
+  if (jk) {
+    le = jit_launch(jk, kp, smem, core->stream);
+    core->jit_launches++;
+  } else {
+    le = launch_filter_project(kp, p.has64, smem, core->stream);
+  }
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
   core->launches++;
   CUDA_CHECK(cudaMemcpyAsync(res->host, ws, (size_t)(n_counts + 1) * 8, cudaMemcpyDeviceToHost, core->stream));
@@ -698,6 +714,50 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   out->num_rows = compact ? -1 : n;
   return out;
 }
+
+// Kernel parameter block with the *shape* execute() would produce for a batch whose nullable
+// columns all carry validity bitmaps (pointers stay null): enough to build the specialised source.
+static void shape_params(const Program& p, KernelParams& kp) {
+  std::memset(&kp, 0, sizeof(kp));
+  const bool compact = p.has_pred && !p.pred_const;
+  kp.n_in = (int)p.slot_to_col.size();
+  for (size_t s = 0; s < p.slot_to_col.size(); s++) {
+    kp.in[s].type = p.schema[p.slot_to_col[s]].type;
+    kp.in[s].width = (uint8_t)p.schema[p.slot_to_col[s]].width;
+  }
+  auto slot_nullable = [&](int slot) { return (p.schema[p.slot_to_col[slot]].flags & ARROW_FLAG_NULLABLE) != 0; };
+  int ko = 0, n_utf8 = 0, n_counts = 1;
+  for (auto& o : p.outputs)
+    if ((o.kind == OutputColumn::EXPR || (o.kind == OutputColumn::PASS && compact)) && o.type == T_UTF8) n_utf8++;
+  n_counts = 1 + n_utf8;
+  int utf8_seen = 0;
+  for (auto& o : p.outputs) {
+    if (!(o.kind == OutputColumn::EXPR || (o.kind == OutputColumn::PASS && compact))) continue;
+    OutDesc& od = kp.out[ko++];
+    od.kind = o.kind == OutputColumn::EXPR ? OUT_EXPR : OUT_PASS;
+    od.type = o.type;
+    od.width = (uint8_t)o.width;
+    od.slot = (uint8_t)(o.slot >= 0 ? o.slot : 0);
+    od.begin = (uint8_t)o.begin;
+    od.end = (uint8_t)o.end;
+    od.utf8_index = o.type == T_UTF8 ? (uint8_t)utf8_seen++ : 0xFF;
+    bool nullable = false;
+    if (o.kind == OutputColumn::PASS) nullable = (p.schema[o.in_col].flags & ARROW_FLAG_NULLABLE) != 0;
+    else
+      for (int i = o.begin; i < o.end; i++)
+        if (p.instrs[i].src == SRC_COL && slot_nullable(p.instrs[i].slot)) nullable = true;
+    if (nullable) od.count_index = (uint8_t)n_counts++;
+  }
+  kp.n_out = ko;
+  kp.n_utf8 = n_utf8;
+  kp.pred_begin = compact ? p.pred_begin : 0;
+  kp.pred_end = compact ? p.pred_end : 0;
+  std::memcpy(kp.instrs, p.instrs.data(), p.instrs.size() * sizeof(Instr));
+  std::memcpy(kp.strpool, p.strpool.data(), p.strpool.size());
+}
+
+static_assert(kErrArithmeticOverflow == CHDB_ERR_ARITHMETIC_OVERFLOW && kErrDivideByZero == CHDB_ERR_DIVIDE_BY_ZERO,
+              "device error codes must match include/chdb_gpu.h");
 
 }  // namespace chdb
 
@@ -753,6 +813,37 @@ int32_t chdb_ctx_synchronize(chdb_ctx* ctx, chdb_status* st) {
   });
 }
 int64_t chdb_ctx_launch_count(chdb_ctx* ctx) { return ctx ? ctx->core->launches.load() : 0; }
+int64_t chdb_ctx_jit_launch_count(chdb_ctx* ctx) { return ctx ? ctx->core->jit_launches.load() : 0; }
+
+int32_t chdb_jit_available(char* why, size_t cap) {
+  std::string reason;
+  const bool ok = jit_available(&reason) && jit_mode() != JitMode::Never;
+  if (why && cap) std::snprintf(why, cap, "%s", ok ? "" : (reason.empty() ? "disabled by CHDB_JIT" : reason.c_str()));
+  return ok ? 1 : 0;
+}
+size_t chdb_program_jit_source(const chdb_program* prog, char* buf, size_t cap) {
+  if (!prog) return 0;
+  KernelParams kp;
+  shape_params(*prog->p, kp);
+  std::string s = jit_prologue(kp, prog->p->has64, prog->p->has64 ? 3 : 4);
+  if (buf && cap) {
+    size_t n = std::min(cap - 1, s.size());
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return s.size();
+}
+int32_t chdb_program_jit_check(const chdb_program* prog, int64_t* cubin_bytes, char* log, size_t cap, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!prog) throw Error(CHDB_ERR_INVALID_ARGUMENT, "program is null");
+    KernelParams kp;
+    shape_params(*prog->p, kp);
+    std::string l;
+    std::vector<char> cubin = jit_compile_offline(kp, prog->p->has64, &l);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    if (log && cap) std::snprintf(log, cap, "%s", l.c_str());
+  });
+}
 
 static int32_t compile_into(chdb_program** out, chdb_status* st, Program::Mode mode, const char* expr, const char* items,
                             const struct ArrowSchema* schema, const char* aliases) {

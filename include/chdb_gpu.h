@@ -124,6 +124,15 @@ int32_t chdb_ctx_device(chdb_ctx* ctx);
 int32_t chdb_ctx_synchronize(chdb_ctx* ctx, chdb_status* st);
 /* Number of kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 int64_t chdb_ctx_launch_count(chdb_ctx* ctx);
+/* ...and how many of them ran a kernel specialised for the program at run time (see below). */
+int64_t chdb_ctx_jit_launch_count(chdb_ctx* ctx);
+
+/* ---- run-time specialisation ----
+ * Long scans run the fused kernel's own source compiled by NVRTC with the program's bytecode baked
+ * in as constants (same code, dispatch folded away).  Controlled by the CHDB_JIT environment
+ * variable: "0" interpreter kernel only, unset / "1" batches of >= 2^18 rows, "always" every launch.
+ * Without libnvrtc the interpreter kernel is used; results are identical either way. */
+int32_t chdb_jit_available(char* why, size_t cap);
 
 /* ---- programs: an expression tree lowered to register bytecode for one input schema ----
  * compile_filter  : predicate = `expr`,  outputs = every input column       (filter_record)
@@ -143,9 +152,11 @@ int32_t chdb_program_compile_filter_project(const char* expr_json, const char* s
 void chdb_program_release(chdb_program* prog);
 /* Human-readable bytecode listing; returns the number of bytes needed (excluding NUL). */
 size_t chdb_program_disassemble(const chdb_program* prog, char* buf, size_t cap);
-/* Algorithmic bytes per input row read by the program (sum over referenced columns of value
- * width + validity/8; Utf8 counts its 4-byte offset only) -- used for roofline accounting. */
 int32_t chdb_program_num_instructions(const chdb_program* prog);
+/* The generated specialisation prologue (constants only; device_code.cuh follows it). */
+size_t chdb_program_jit_source(const chdb_program* prog, char* buf, size_t cap);
+/* Compiles the specialised kernel for sm_100a without a GPU (build / test check). */
+int32_t chdb_program_jit_check(const chdb_program* prog, int64_t* cubin_bytes, char* log, size_t cap, chdb_status* st);
 
 /* ---- host batches: same contract as the reference's functions ----
  * `in` / `in_schema`: a struct array whose children are the batch columns.
