@@ -187,6 +187,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def measured_traffic(batch_rows: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same workload (profiles/traffic.json); None if never captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if int(t.get("batch_rows", -1)) == int(batch_rows):
+            return t["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -335,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = ctx.launch_count
+    launches0, jit0 = ctx.launch_count, ctx.jit_launch_count
     barrier()
     torch.cuda.synchronize(device)
     sampler.start()
@@ -353,6 +366,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
+    jit_launches = ctx.jit_launch_count - jit0
     if rows_out == 0 and prev:
         rows_out = sum(o.num_rows for o in prev)
         bytes_out = sum(o.nbytes for o in prev)
@@ -388,8 +402,13 @@ def run_ours(args, rank, world, local_rank):
         "selectivity": selectivity, "rows_out_per_step": all_rows_out,
         "hbm_gbs_per_gpu": per_gpu_gbs, "pct_of_8TBs": per_gpu_gbs / 8000.0 * 100.0,
         "clocks": clocks, "gpu_launches": int(all_launches), "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "filter_project_kernel<u64,2>", "achieved": per_gpu_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None, "peak_source": peak_src,
+        "specialised_launches": int(jit_launches),
+        "roofline": {"bound": "hbm",
+                     "kernel": ("chdb_jit_kernel (device_code.cuh specialised for the program by NVRTC)" if jit_launches
+                                else "filter_project_kernel<uint64_t,4> (bytecode interpreter)"),
+                     "achieved": per_gpu_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": measured_traffic(args.batch_rows),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                      "avg_launch_us": avg_launch_us, "launches_per_step": launches_per_step},
     }

@@ -93,6 +93,14 @@ __device__ __forceinline__ void report_rows(const KernelParams& P, const Instr& 
 // ------------------------------------------------------------------------------------------
 // loads
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// phase stamps of one tile (debugging aid, enabled by CHDB_PHASE_TIMING=1 in the environment)
+#define CHDB_STAMP(i) do { if (P.timing != nullptr && (threadIdx.x & 31) == 0) { if ((i) < 4) { if (threadIdx.x == 0) P.timing[(size_t)tile * 8 + (i)] = global_ns(); } else atomicMax((unsigned long long*)&P.timing[(size_t)tile * 8 + (i)], (unsigned long long)global_ns()); } } while (0)
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int QPT>
@@ -793,20 +801,29 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc, uint32_t tile, uint
   uint64_t excl = 0;
   int64_t base = (int64_t)tile - 1;
   while (true) {
-    const int64_t idx = base - lane;
-    uint64_t v = kFlagPrefix;  // tiles "before 0" contribute an inclusive prefix of 0
-    if (idx >= 0) {
-      do { v = d[idx]; } while ((v >> 62) == 0);
+    // each lane inspects 4 consecutive predecessors (nearest first): 128 tiles per hop
+    uint64_t part = 0;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int64_t idx = base - (lane * 4 + j);
+      uint64_t v = kFlagPrefix;  // tiles "before 0" contribute an inclusive prefix of 0
+      if (idx >= 0 && !found) {
+        do { v = d[idx]; } while ((v >> 62) == 0);
+      }
+      if (!found) {
+        part += v & kValueMask;
+        found = (v >> 62) == 2;
+      }
     }
-    const uint32_t pm = __ballot_sync(FULL, (v >> 62) == 2);
-    const uint64_t val = v & kValueMask;
+    const uint32_t pm = __ballot_sync(FULL, found);
     if (pm) {
-      const int first = __ffs(pm) - 1;  // nearest predecessor that already knows its prefix
-      excl += warp_sum64(lane <= first ? val : 0);
+      const int first = __ffs(pm) - 1;  // lane holding the nearest predecessor that already knows its prefix
+      excl += warp_sum64(lane <= first ? part : 0);
       break;
     }
-    excl += warp_sum64(val);
-    base -= 32;
+    excl += warp_sum64(part);
+    base -= 128;
   }
   if (lane == 0) d[tile] = kFlagPrefix | (excl + agg);
   return excl;
@@ -847,6 +864,29 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a) {
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+// Asynchronous global -> shared copies (LDGSTS): the data of the next output column streams into the
+// warp's second buffer while the current column is being compacted.
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// nbytes is rounded up to 16 (buffers are padded); src and dst_s must be 16-byte aligned
+__device__ __forceinline__ void async_copy_slice(uint32_t dst_s, const uint8_t* src, uint32_t nbytes, int lane) {
+  for (uint32_t b = (uint32_t)lane * 16u; b < nbytes; b += 512u) cp_async16(dst_s + b, src + b);
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+
 template <int W>
 __device__ __forceinline__ void copy_elem_s2g(uint8_t* g, uint32_t s) {   // one W-byte element, shared -> global
   if (W == 4) { *(uint32_t*)g = lds32(s); }
@@ -856,18 +896,27 @@ __device__ __forceinline__ void copy_elem_s2g(uint8_t* g, uint32_t s) {   // one
 }
 
 // stage[mis, mis + nbytes) -> gdst_aligned[mis, ...), by one warp: aligned 16-byte stores in the
-// middle, W-byte element stores in the (at most two) 16-byte chunks shared with the neighbours.
+// middle; the (at most two) 16-byte chunks shared with the neighbours are written element-wise,
+// one element per lane.
 template <int W>
 __device__ __forceinline__ void warp_writeout(uint32_t stage_s, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int lane) {
   const uint32_t end = mis + nbytes;
   const uint32_t first_full = (mis + 15u) >> 4, end_full = end >> 4;   // full chunks: [first_full, end_full)
-  for (uint32_t c = first_full + lane; c < end_full; c += 32) *(uint4*)(gdst_aligned + (c << 4)) = lds128(stage_s + (c << 4));
-  if (lane == 0 && mis != 0) {                 // head chunk (chunk 0 is partial)
-    const uint32_t t = end < 16u ? end : 16u;
-    for (uint32_t b = mis; b < t; b += W) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
+  uint32_t c = first_full + lane;
+  for (; c + 32 < end_full; c += 64) {   // two independent 16-byte copies per trip
+    const uint4 a = lds128(stage_s + (c << 4)), b = lds128(stage_s + ((c + 32) << 4));
+    *(uint4*)(gdst_aligned + (c << 4)) = a;
+    *(uint4*)(gdst_aligned + ((c + 32) << 4)) = b;
   }
-  if (lane == 1 && (end & 15u) != 0 && (end_full > 0 || mis == 0)) {   // tail chunk, unless it is also the head chunk
-    for (uint32_t b = end_full << 4; b < end; b += W) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
+  if (c < end_full) *(uint4*)(gdst_aligned + (c << 4)) = lds128(stage_s + (c << 4));
+  constexpr uint32_t EPC = 16 / W;   // elements per chunk
+  if (mis != 0) {                    // head chunk 0: lanes 0 .. EPC-1 take one element each
+    const uint32_t b = (uint32_t)lane * W;
+    if ((uint32_t)lane < EPC && b >= mis && b < end) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
+  }
+  if ((end & 15u) != 0 && (end_full > 0 || mis == 0)) {   // tail chunk (unless it is also the head): lanes 16 .. 16+EPC-1
+    const uint32_t b = (end_full << 4) + ((uint32_t)lane - 16u) * W;
+    if ((uint32_t)lane >= 16u && (uint32_t)lane < 16u + EPC && b < end) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
   }
 }
 
@@ -877,58 +926,69 @@ struct WarpOut {
   uint64_t base;          // global output row index of the warp's first selected row
   uint32_t count;         // selected rows of this warp
   uint32_t rank[QPT];     // warp-local rank of the first selected row of each of this lane's quads
-  uint32_t sel;           // selection bits of this lane's rows
+  uint32_t sel;           // selection bits of this lane's rows (4 per quad)
 };
 
-// Gathers the selected rows of a W-byte pass-through column.
-template <int W, int QPT>
-__device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, uint8_t* dst, const int64_t (&qbase)[QPT],
-                                             const WarpOut<QPT>& wo, uint32_t stage_s, int lane) {
-  const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
-  // all loads first (independent, in flight together), then the shared-memory stores
-  uint4 x[QPT], y[QPT];
-#pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    x[q] = make_uint4(0, 0, 0, 0);
-    y[q] = make_uint4(0, 0, 0, 0);
-    if (!((wo.sel >> (4 * q)) & 0xFu)) continue;
-    if (W == 4) {
-      x[q] = __ldg((const uint4*)(src + qbase[q] * 4));
-    } else if (W == 8) {
-      x[q] = __ldg((const uint4*)(src + qbase[q] * 8));
-      y[q] = __ldg((const uint4*)(src + qbase[q] * 8 + 16));
-    } else if (W == 2) {
-      const uint2 t = __ldg((const uint2*)(src + qbase[q] * 2));
-      x[q].x = t.x; x[q].y = t.y;
-    } else {
-      x[q].x = __ldg((const uint32_t*)(src + qbase[q]));
-    }
+// Stages the selected rows of quad q of a W-byte pass-through column (the load was issued by the caller).
+template <int W>
+__device__ __forceinline__ void stage_quad(uint32_t a, uint32_t s4, const uint4& x, const uint4& y) {
+  if (W == 4) {
+    if (s4 & 1u) { sts32(a, x.x); a += 4; }
+    if (s4 & 2u) { sts32(a, x.y); a += 4; }
+    if (s4 & 4u) { sts32(a, x.z); a += 4; }
+    if (s4 & 8u) { sts32(a, x.w); }
+  } else if (W == 8) {
+    if (s4 & 1u) { sts64(a, x.x, x.y); a += 8; }
+    if (s4 & 2u) { sts64(a, x.z, x.w); a += 8; }
+    if (s4 & 4u) { sts64(a, y.x, y.y); a += 8; }
+    if (s4 & 8u) { sts64(a, y.z, y.w); }
+  } else if (W == 2) {
+    if (s4 & 1u) { sts16(a, x.x & 0xFFFFu); a += 2; }
+    if (s4 & 2u) { sts16(a, x.x >> 16); a += 2; }
+    if (s4 & 4u) { sts16(a, x.y & 0xFFFFu); a += 2; }
+    if (s4 & 8u) { sts16(a, x.y >> 16); }
+  } else {
+    if (s4 & 1u) { sts8(a, x.x & 0xFFu); a += 1; }
+    if (s4 & 2u) { sts8(a, (x.x >> 8) & 0xFFu); a += 1; }
+    if (s4 & 4u) { sts8(a, (x.x >> 16) & 0xFFu); a += 1; }
+    if (s4 & 8u) { sts8(a, x.x >> 24); }
   }
+}
+
+// Gathers the selected rows of a W-byte pass-through column: loads two quads at a time (in flight
+// together), stages them, one write-out for the whole warp slice.
+template <int W, int QPT>
+__device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, uint8_t* dst, int64_t row_base, const WarpOut<QPT>& wo,
+                                             uint32_t stage_s, int lane) {
+  const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
 #pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    const uint32_t s4 = (wo.sel >> (4 * q)) & 0xFu;
-    if (!s4) continue;
-    uint32_t a = stage_s + mis + wo.rank[q] * W;
-    if (W == 4) {
-      if (s4 & 1u) { sts32(a, x[q].x); a += 4; }
-      if (s4 & 2u) { sts32(a, x[q].y); a += 4; }
-      if (s4 & 4u) { sts32(a, x[q].z); a += 4; }
-      if (s4 & 8u) { sts32(a, x[q].w); }
-    } else if (W == 8) {
-      if (s4 & 1u) { sts64(a, x[q].x, x[q].y); a += 8; }
-      if (s4 & 2u) { sts64(a, x[q].z, x[q].w); a += 8; }
-      if (s4 & 4u) { sts64(a, y[q].x, y[q].y); a += 8; }
-      if (s4 & 8u) { sts64(a, y[q].z, y[q].w); }
-    } else if (W == 2) {
-      if (s4 & 1u) { sts16(a, x[q].x & 0xFFFFu); a += 2; }
-      if (s4 & 2u) { sts16(a, x[q].x >> 16); a += 2; }
-      if (s4 & 4u) { sts16(a, x[q].y & 0xFFFFu); a += 2; }
-      if (s4 & 8u) { sts16(a, x[q].y >> 16); }
-    } else {
-      if (s4 & 1u) { sts8(a, x[q].x & 0xFFu); a += 1; }
-      if (s4 & 2u) { sts8(a, (x[q].x >> 8) & 0xFFu); a += 1; }
-      if (s4 & 4u) { sts8(a, (x[q].x >> 16) & 0xFFu); a += 1; }
-      if (s4 & 8u) { sts8(a, x[q].x >> 24); }
+  for (int g = 0; g < QPT; g += 2) {
+    uint4 x[2], y[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int q = g + h;
+      x[h] = make_uint4(0, 0, 0, 0);
+      y[h] = make_uint4(0, 0, 0, 0);
+      if (q >= QPT || !((wo.sel >> (4 * q)) & 0xFu)) continue;
+      const int64_t r = row_base + q * 128;
+      if (W == 4) {
+        x[h] = __ldg((const uint4*)(src + r * 4));
+      } else if (W == 8) {
+        x[h] = __ldg((const uint4*)(src + r * 8));
+        y[h] = __ldg((const uint4*)(src + r * 8 + 16));
+      } else if (W == 2) {
+        const uint2 t = __ldg((const uint2*)(src + r * 2));
+        x[h].x = t.x; x[h].y = t.y;
+      } else {
+        x[h].x = __ldg((const uint32_t*)(src + r));
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int q = g + h;
+      if (q >= QPT) continue;
+      const uint32_t s4 = (wo.sel >> (4 * q)) & 0xFu;
+      if (s4) stage_quad<W>(stage_s + mis + wo.rank[q] * W, s4, x[h], y[h]);
     }
   }
   __syncwarp();
@@ -936,28 +996,20 @@ __device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, ui
   __syncwarp();
 }
 
-// Same, for values that already sit in registers (projection expressions, rebuilt Utf8 offsets).
-template <int W, typename E, int QPT>
-__device__ __forceinline__ void scatter_regs(const E (&e)[4 * QPT], uint8_t* dst, const WarpOut<QPT>& wo, uint32_t stage_s, int lane) {
-  const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
+// Stages four values that already sit in registers (one quad of a projection expression / of the
+// rebuilt Utf8 offsets); the caller writes the slice out once all quads are staged.
+template <int W, typename E>
+__device__ __forceinline__ void stage_regs(uint32_t a, uint32_t s4, const E (&e)[4]) {
 #pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    uint32_t a = stage_s + mis + wo.rank[q] * W;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int j = 4 * q + i;
-      if ((wo.sel >> j) & 1u) {
-        if (W == 4) sts32(a, (uint32_t)e[j]);
-        else if (W == 8) sts64(a, (uint32_t)e[j], (uint32_t)((uint64_t)e[j] >> 32));
-        else if (W == 2) sts16(a, (uint32_t)e[j] & 0xFFFFu);
-        else sts8(a, (uint32_t)e[j] & 0xFFu);
-        a += W;
-      }
+  for (int i = 0; i < 4; i++) {
+    if ((s4 >> i) & 1u) {
+      if (W == 4) sts32(a, (uint32_t)e[i]);
+      else if (W == 8) sts64(a, (uint32_t)e[i], (uint32_t)((uint64_t)e[i] >> 32));
+      else if (W == 2) sts16(a, (uint32_t)e[i] & 0xFFFFu);
+      else sts8(a, (uint32_t)e[i] & 0xFFu);
+      a += W;
     }
   }
-  __syncwarp();
-  warp_writeout<W>(stage_s, dst + ((wo.base * W) & ~15ull), mis, wo.count * W, lane);
-  __syncwarp();
 }
 
 // Compacts one bit per row (validity or Boolean values) into gbits at bit offset wo.base:
@@ -1105,21 +1157,35 @@ __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, u
 // What every lane carries through the per-warp gather phase.
 template <int QPT>
 struct LaneCtx {
-  int64_t qbase[QPT];     // first row of each of the lane's quads
-  uint32_t inrange;       // rows that exist (tail tile)
+  int64_t row_base;       // first row of the lane's quad 0; quad q starts at row_base + q * 128
+  uint32_t inrange;       // rows that exist (tail tile), 4 bits per quad
   uint32_t stage_s, bstage_s, wstage_bytes;
-  uint32_t* s_oo;
-  int32_t* s_src;
   int lane, warp;
 };
 
+template <int QPT>
+__device__ __forceinline__ uint32_t load_bits_all(const uint8_t* __restrict__ bits, int64_t row_base, uint32_t need) {
+  if (bits == nullptr) return FULL;
+  uint32_t m = 0;
+#pragma unroll
+  for (int q = 0; q < QPT; q++) {
+    if ((need >> (4 * q)) & 0xFu) {
+      const int64_t r = row_base + q * 128;
+      const uint32_t byte = __ldg(bits + (r >> 3));
+      m |= ((byte >> (uint32_t)(r & 4)) & 0xFu) << (4 * q);
+    }
+  }
+  return m;
+}
+
 // Gathers output column k for this warp.  `meta` packs the eight small OutDesc fields; under
 // CHDB_JIT it is a compile-time constant and BEGIN/END carry the expression's instruction range.
+// `vpre`: validity bits of a pass-through column, loaded before the look-back so that their latency
+// hides behind it.
 template <typename V, int QPT, int BEGIN = -1, int END = -1>
-__device__ __forceinline__ void exec_output(const KernelParams& P, const int k, const uint64_t meta, const LaneCtx<QPT>& L,
-                                            const WarpOut<QPT>& wo, const uint32_t (*s_wtot)[kWarps], const uint64_t* s_excl,
-                                            const uint8_t* s_pool) {
-  constexpr int R = 4 * QPT;
+__device__ __forceinline__ void exec_output(const KernelParams& P, const int k, const uint64_t meta, const uint32_t vpre,
+                                            const LaneCtx<QPT>& L, const WarpOut<QPT>& wo, const uint32_t (*s_wtot)[kWarps],
+                                            const uint64_t* s_excl, const uint8_t* s_pool) {
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
   const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_count = (uint32_t)(meta >> 56);
@@ -1129,107 +1195,114 @@ __device__ __forceinline__ void exec_output(const KernelParams& P, const int k, 
   const int lane = L.lane;
   uint32_t vbits = FULL;  // validity of this output for the lane's rows
   if (o_kind == OUT_EXPR) {
-    V acc[R];
     uint32_t accm = 0;
     vbits = 0;
+    const uint32_t W = o_type == T_BOOL ? 0u : o_width;
+    const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
 #ifdef CHDB_JIT
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
     for (int q = 0; q < QPT; q++) {
-      const int64_t qb[1] = {q == 0 ? L.qbase[0] : L.qbase[QPT - 1]};
+      const int64_t qb[1] = {L.row_base + q * 128};
       const uint32_t in4 = (L.inrange >> (4 * q)) & 0xFu, sel4 = (sel >> (4 * q)) & 0xFu;
       V a4[4];
       uint32_t m4, v4;
       // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
       run_program<V, 1, BEGIN, END>(P, (int)o_begin, (int)o_end, qb, in4, sel4, s_pool, a4, m4, v4);
-      if (q == 0) { acc[0] = a4[0]; acc[1] = a4[1]; acc[2] = a4[2]; acc[3] = a4[3]; }
-      else { acc[R - 4] = a4[0]; acc[R - 3] = a4[1]; acc[R - 2] = a4[2]; acc[R - 1] = a4[3]; }
       accm |= (m4 & 0xFu) << (4 * q);
       vbits |= (v4 & 0xFu) << (4 * q);
+      uint32_t rk = wo.rank[0];
+#pragma unroll
+      for (int t = 1; t < QPT; t++)
+        if (t == q) rk = wo.rank[t];     // static indexing keeps the ranks in registers
+      const uint32_t a = stage_s + mis + rk * W;
+      if (W == 4) stage_regs<4, V>(a, sel4, a4);
+      else if (W == 8) stage_regs<8, V>(a, sel4, a4);
+      else if (W == 2) stage_regs<2, V>(a, sel4, a4);
+      else if (W == 1) stage_regs<1, V>(a, sel4, a4);
     }
-    if (o_type == T_BOOL) compact_bits<QPT>(accm, wo, bstage_s, (uint32_t*)o_values, lane);
-    else if (o_width == 4) scatter_regs<4, V, QPT>(acc, o_values, wo, stage_s, lane);
-    else if (o_width == 8) scatter_regs<8, V, QPT>(acc, o_values, wo, stage_s, lane);
-    else if (o_width == 2) scatter_regs<2, V, QPT>(acc, o_values, wo, stage_s, lane);
-    else scatter_regs<1, V, QPT>(acc, o_values, wo, stage_s, lane);
+    if (o_type == T_BOOL) {
+      compact_bits<QPT>(accm, wo, bstage_s, (uint32_t*)o_values, lane);
+    } else {
+      __syncwarp();
+      uint8_t* gd = o_values + ((wo.base * W) & ~15ull);
+      if (W == 4) warp_writeout<4>(stage_s, gd, mis, wo.count * 4, lane);
+      else if (W == 8) warp_writeout<8>(stage_s, gd, mis, wo.count * 8, lane);
+      else if (W == 2) warp_writeout<2>(stage_s, gd, mis, wo.count * 2, lane);
+      else warp_writeout<1>(stage_s, gd, mis, wo.count, lane);
+      __syncwarp();
+    }
   } else {
     const ColumnDesc& c = P.in[o_slot];
-    vbits = load_bits<QPT>(c.validity, L.qbase, sel);
+    vbits = vpre;
     if (o_type == T_BOOL) {
-      const uint32_t vals = load_bits<QPT>((const uint8_t*)c.values, L.qbase, sel);
+      const uint32_t vals = load_bits_all<QPT>((const uint8_t*)c.values, L.row_base, sel);
       compact_bits<QPT>(vals, wo, bstage_s, (uint32_t*)o_values, lane);
     } else if (o_type == T_UTF8) {
-      // -- offsets: running sum of the selected lengths, restarted at 0 for the output --
+      // -- offsets: running sum of the selected lengths, restarted at 0 for the output.
+      //    The warp's stage holds the rebuilt offsets in its first kWarpRows * 4 + 16 bytes and the
+      //    value bytes (short strings) behind them, so both are written out once per warp slice.
+      constexpr uint32_t kOffStage = (uint32_t)(32 * 4 * QPT) * 4u + 16u;
       const int32_t* __restrict__ off = c.offsets;
       const uint8_t* __restrict__ sv = (const uint8_t*)c.values;
       uint32_t bytes_before = 0;
 #pragma unroll
       for (int w = 0; w < kWarps; w++)
         if (w < L.warp) bytes_before += s_wtot[1 + o_utf8][w];
+      const uint32_t warp_bytes = s_wtot[1 + o_utf8][L.warp];
       const uint64_t byte_base = s_excl[1 + o_utf8] + bytes_before;   // output byte offset of this warp's first value
-      uint32_t len[R], boff[R];
-      int32_t src[R];
-      uint32_t warp_bytes = 0;
+      const uint32_t omis = (uint32_t)((wo.base * 4) & 15u);
+      const uint32_t mis = (uint32_t)(byte_base & 15u);
+      const uint32_t str_s = stage_s + kOffStage;
+      const bool staged = mis + warp_bytes + 16u <= L.wstage_bytes - kOffStage;   // short strings fit the stage
+      uint32_t* s_oo = (uint32_t*)__cvta_shared_to_generic(str_s);                // long strings: per-row tables instead
+      int32_t* s_src = (int32_t*)(s_oo + 32 * 4 * QPT + 4);
+      uint32_t run = 0;   // bytes of the quads handled so far
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) { len[4 * q + i] = 0; src[4 * q + i] = 0; }
         const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
+        uint32_t len[4] = {0u, 0u, 0u, 0u}, boff[4];
+        int32_t src[4] = {0, 0, 0, 0};
         if (s4) {
-          const int4 a = __ldg((const int4*)(off + L.qbase[q]));
-          const int a4 = __ldg(off + L.qbase[q] + 4);
-          src[4 * q + 0] = a.x; src[4 * q + 1] = a.y; src[4 * q + 2] = a.z; src[4 * q + 3] = a.w;
-          if (s4 & 1u) len[4 * q + 0] = (uint32_t)(a.y - a.x);
-          if (s4 & 2u) len[4 * q + 1] = (uint32_t)(a.z - a.y);
-          if (s4 & 4u) len[4 * q + 2] = (uint32_t)(a.w - a.z);
-          if (s4 & 8u) len[4 * q + 3] = (uint32_t)(a4 - a.w);
+          const int4 a = __ldg((const int4*)(off + L.row_base + q * 128));
+          const int a4 = __ldg(off + L.row_base + q * 128 + 4);
+          src[0] = a.x; src[1] = a.y; src[2] = a.z; src[3] = a.w;
+          if (s4 & 1u) len[0] = (uint32_t)(a.y - a.x);
+          if (s4 & 2u) len[1] = (uint32_t)(a.z - a.y);
+          if (s4 & 4u) len[2] = (uint32_t)(a.w - a.z);
+          if (s4 & 8u) len[3] = (uint32_t)(a4 - a.w);
         }
         uint32_t tot;
-        uint32_t bo = warp_bytes + warp_excl_scan(len[4 * q] + len[4 * q + 1] + len[4 * q + 2] + len[4 * q + 3], lane, tot);
-        warp_bytes += tot;
+        uint32_t bo = run + warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, tot);
+        run += tot;
+        uint32_t newoff[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          boff[4 * q + i] = bo;   // warp-local output byte offset of each selected row
-          bo += len[4 * q + i];
+          boff[i] = bo;                                   // warp-local output byte offset of the row
+          newoff[i] = (uint32_t)byte_base + bo;
+          bo += len[i];
         }
-      }
-      {
-        uint32_t newoff[R];
+        stage_regs<4, uint32_t>(stage_s + omis + wo.rank[q] * 4, s4, newoff);
+        if (staged) {
 #pragma unroll
-        for (int j = 0; j < R; j++) newoff[j] = (uint32_t)byte_base + boff[j];
-        scatter_regs<4, uint32_t, QPT>(newoff, (uint8_t*)P.out[k].offsets, wo, stage_s, lane);
-      }
-      const uint32_t mis = (uint32_t)(byte_base & 15u);
-      uint8_t* gal = o_values + (byte_base - mis);
-      if (mis + warp_bytes <= L.wstage_bytes - 16u) {
-        // -- short strings: every selected row copies its bytes into the stage, then aligned write-out --
-#pragma unroll
-        for (int j = 0; j < R; j++)
-          if (((sel >> j) & 1u) && len[j] != 0) copy_row_g2s(sv + src[j], stage_s + mis + boff[j], len[j]);
-        __syncwarp();
-        warp_writeout<1>(stage_s, gal, mis, warp_bytes, lane);
-        __syncwarp();
-      } else {
-#pragma unroll
-        for (int q = 0; q < QPT; q++) {
+          for (int i = 0; i < 4; i++)
+            if (((s4 >> i) & 1u) && len[i] != 0) copy_row_g2s(sv + src[i], str_s + mis + boff[i], len[i]);
+        } else {
           uint32_t r = wo.rank[q];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int j = 4 * q + i;
-            if ((sel >> j) & 1u) {
-              L.s_oo[r] = boff[j];
-              L.s_src[r] = src[j];
-              r++;
-            }
-          }
+          for (int i = 0; i < 4; i++)
+            if ((s4 >> i) & 1u) { s_oo[r] = boff[i]; s_src[r] = src[i]; r++; }
         }
-        if (lane == 0) L.s_oo[wo.count] = warp_bytes;
-        __syncwarp();
-        copy_long_strings(sv, gal, mis, warp_bytes, wo.count, L.s_oo, L.s_src, lane);
-        __syncwarp();
       }
+      if (!staged && lane == 0) s_oo[wo.count] = warp_bytes;
+      __syncwarp();
+      warp_writeout<4>(stage_s, (uint8_t*)P.out[k].offsets + ((wo.base * 4) & ~15ull), omis, wo.count * 4, lane);
+      uint8_t* gal = o_values + (byte_base - mis);
+      if (staged) warp_writeout<1>(str_s, gal, mis, warp_bytes, lane);
+      else copy_long_strings(sv, gal, mis, warp_bytes, wo.count, s_oo, s_src, lane);
+      __syncwarp();
     } else if (o_width == 16) {
       const uint4* __restrict__ src = (const uint4*)c.values;
 #pragma unroll
@@ -1237,20 +1310,20 @@ __device__ __forceinline__ void exec_output(const KernelParams& P, const int k, 
         uint32_t a = stage_s + wo.rank[q] * 16;
 #pragma unroll
         for (int i = 0; i < 4; i++)
-          if ((sel >> (4 * q + i)) & 1u) { sts128(a, __ldg(src + L.qbase[q] + i)); a += 16; }
+          if ((sel >> (4 * q + i)) & 1u) { sts128(a, __ldg(src + L.row_base + q * 128 + i)); a += 16; }
       }
       __syncwarp();
       uint4* dst = (uint4*)o_values + wo.base;
       for (uint32_t r = lane; r < wo.count; r += 32) dst[r] = lds128(stage_s + r * 16);
       __syncwarp();
     } else if (o_width == 4) {
-      gather_fixed<4, QPT>((const uint8_t*)c.values, o_values, L.qbase, wo, stage_s, lane);
+      gather_fixed<4, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
     } else if (o_width == 8) {
-      gather_fixed<8, QPT>((const uint8_t*)c.values, o_values, L.qbase, wo, stage_s, lane);
+      gather_fixed<8, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
     } else if (o_width == 2) {
-      gather_fixed<2, QPT>((const uint8_t*)c.values, o_values, L.qbase, wo, stage_s, lane);
+      gather_fixed<2, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
     } else {
-      gather_fixed<1, QPT>((const uint8_t*)c.values, o_values, L.qbase, wo, stage_s, lane);
+      gather_fixed<1, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
     }
   }
   if (o_validity != nullptr) {
@@ -1261,21 +1334,41 @@ __device__ __forceinline__ void exec_output(const KernelParams& P, const int k, 
 
 #ifdef CHDB_JIT
 template <typename V, int QPT, int K, int N>
-__device__ __forceinline__ void outputs_range(const KernelParams& P, const LaneCtx<QPT>& L, const WarpOut<QPT>& wo,
-                                              const uint32_t (*s_wtot)[kWarps], const uint64_t* s_excl, const uint8_t* s_pool) {
+__device__ __forceinline__ void outputs_range(const KernelParams& P, const uint32_t (&vpre)[kMaxOutCols], const LaneCtx<QPT>& L,
+                                              const WarpOut<QPT>& wo, const uint32_t (*s_wtot)[kWarps], const uint64_t* s_excl,
+                                              const uint8_t* s_pool) {
   if constexpr (K < N) {
     constexpr uint64_t meta = chdb_jit::kOutMeta[K];
-    exec_output<V, QPT, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, K, meta, L, wo, s_wtot, s_excl, s_pool);
-    outputs_range<V, QPT, K + 1, N>(P, L, wo, s_wtot, s_excl, s_pool);
+    exec_output<V, QPT, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, K, meta, vpre[K], L, wo, s_wtot, s_excl, s_pool);
+    outputs_range<V, QPT, K + 1, N>(P, vpre, L, wo, s_wtot, s_excl, s_pool);
   }
 }
 #endif
+
+// Pulls one tile's slice of every input buffer towards L2 (one 128-byte line per thread).
+__device__ __forceinline__ void prefetch_tile(const KernelParams& P, int64_t row0, int32_t tile_rows, int tid) {
+  CHDB_STATIC_UNROLL
+  for (int s = 0; s < CHDB_N_IN; s++) {
+    const ColumnDesc& c = P.in[s];
+    const uint32_t ctype = CHDB_COL_TYPE(P, s);
+    const int w = ctype == T_UTF8 ? 4 : (int)CHDB_COL_WIDTH(P, s);
+    const uint8_t* v = (const uint8_t*)(ctype == T_UTF8 ? (const void*)c.offsets : c.values);
+    if (w > 0) {
+      for (int b = tid * 128; b < tile_rows * w; b += kThreads * 128) prefetch_l2(v + row0 * w + b);
+    } else if (tid < 4 && tid * 1024 < tile_rows) {
+      prefetch_l2(v + (row0 >> 3) + tid * 128);   // Boolean values: rows / 8 bytes
+    }
+    if (c.validity != nullptr && tid >= 32 && tid < 36 && (tid - 32) * 1024 < tile_rows)
+      prefetch_l2(c.validity + (row0 >> 3) + (tid - 32) * 128);
+  }
+}
 
 template <typename V, int QPT>
 __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
   constexpr int R = 4 * QPT;
   constexpr int T = kThreads * R;
   constexpr int WR = 32 * R;                    // rows per warp slice
+  static_assert(R <= 32, "selection masks are 32-bit");
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_wtot[1 + kMaxOutCols][kWarps];   // per-warp totals: [0] rows, [1 + u] bytes of Utf8 output u
@@ -1291,8 +1384,6 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
   L.wstage_bytes = (uint32_t)P.stage_bytes;                                           // per warp
   L.stage_s = smem_u32(smem) + warp * L.wstage_bytes;                                 // this warp's staging slice
   L.bstage_s = smem_u32(smem) + kWarps * L.wstage_bytes + warp * kWarpBitStage;       // one byte per output row
-  L.s_oo = (uint32_t*)(smem + kWarps * (L.wstage_bytes + kWarpBitStage)) + warp * (WR + 4);   // long Utf8 only
-  L.s_src = (int32_t*)((uint32_t*)(smem + kWarps * (L.wstage_bytes + kWarpBitStage)) + kWarps * (WR + 4)) + warp * WR;
 
   if (tid == 0) s_tile = has_pred ? atomicAdd(P.ticket, 1u) : blockIdx.x;
   if (tid < kStrPoolBytes) s_pool[tid] = (uint8_t)P.strpool[tid];
@@ -1300,30 +1391,25 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
   const uint32_t tile = s_tile;
   const int64_t row0 = (int64_t)tile * T;
   const int32_t tile_rows = (int32_t)(row0 + T < P.num_rows ? T : P.num_rows - row0);
+  CHDB_STAMP(0);
 
-  // ---- 0. pull this tile's slice of every input buffer towards L2 (one 128-byte line per thread) ----
-  CHDB_STATIC_UNROLL
-  for (int s = 0; s < CHDB_N_IN; s++) {
-    const ColumnDesc& c = P.in[s];
-    const uint32_t ctype = CHDB_COL_TYPE(P, s);
-    const int w = ctype == T_UTF8 ? 4 : (int)CHDB_COL_WIDTH(P, s);
-    const uint8_t* v = (const uint8_t*)(ctype == T_UTF8 ? (const void*)c.offsets : c.values);
-    if (w > 0) {
-      if (tid * 128 < tile_rows * w) prefetch_l2(v + row0 * w + tid * 128);
-    } else if (tid < 2 && tid * 1024 < tile_rows) {
-      prefetch_l2(v + (row0 >> 3) + tid * 128);   // Boolean values: T / 8 bytes
+  // ---- 0. prefetch: the tile that will start about one wave from now, so that by then its
+  //         columns wait in L2; the first wave has nobody to do that for it and fetches its own ----
+  {
+    const int64_t ahead = (int64_t)tile + P.prefetch_tiles;
+    if (P.prefetch_tiles > 0 && ahead < P.num_tiles) {
+      const int64_t r0 = ahead * T;
+      prefetch_tile(P, r0, (int32_t)(r0 + T < P.num_rows ? T : P.num_rows - r0), tid);
     }
-    if (c.validity != nullptr && tid >= 32 && tid < 34 && (tid - 32) * 1024 < tile_rows)
-      prefetch_l2(c.validity + (row0 >> 3) + (tid - 32) * 128);
+    if ((int64_t)tile < P.prefetch_tiles || P.prefetch_tiles <= 0) prefetch_tile(P, row0, tile_rows, tid);
   }
 
   // rows of this lane: quad q covers rows  row0 + warp * WR + q * 128 + lane * 4 .. + 3
+  L.row_base = row0 + warp * WR + lane * 4;
   L.inrange = 0;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    const int local = warp * WR + q * 128 + lane * 4;
-    L.qbase[q] = row0 + local;
-    const int left = tile_rows - local;
+    const int left = tile_rows - (warp * WR + q * 128 + lane * 4);
     L.inrange |= (left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u)) << (4 * q);
   }
   const uint32_t inrange = L.inrange;
@@ -1332,14 +1418,13 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
   uint32_t sel = inrange;
   if (has_pred) {
     sel = 0;
-    static_assert(QPT <= 2, "quad selection below assumes QPT <= 2");
 #ifdef CHDB_JIT
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
     for (int q = 0; q < QPT; q++) {
-      const int64_t qb[1] = {q == 0 ? L.qbase[0] : L.qbase[QPT - 1]};
+      const int64_t qb[1] = {L.row_base + q * 128};
       const uint32_t in4 = (inrange >> (4 * q)) & 0xFu;
       V acc[4];
       uint32_t accm, accv;
@@ -1352,6 +1437,7 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
     }
   }
 
+  CHDB_STAMP(1);
   // ---- 2. rank the selected rows inside the warp; publish the warp totals --------------------
   WarpOut<QPT> wo;
   wo.sel = sel;
@@ -1378,8 +1464,8 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
     for (int q = 0; q < QPT; q++) {
       const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
       if (s4) {
-        const int4 a = __ldg((const int4*)(off + L.qbase[q]));
-        const int a4 = __ldg(off + L.qbase[q] + 4);
+        const int4 a = __ldg((const int4*)(off + L.row_base + q * 128));
+        const int a4 = __ldg(off + L.row_base + q * 128 + 4);
         if (s4 & 1u) bytes += (uint32_t)(a.y - a.x);
         if (s4 & 2u) bytes += (uint32_t)(a.z - a.y);
         if (s4 & 4u) bytes += (uint32_t)(a.w - a.z);
@@ -1392,7 +1478,16 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
     const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
     if (lane == 0) s_wtot[1 + o_utf8][warp] = wbytes;
   }
+  // validity bits of the pass-through outputs: requested now, consumed after the look-back
+  uint32_t vpre[kMaxOutCols];
+  CHDB_STATIC_UNROLL
+  for (int k = 0; k < CHDB_N_OUT; k++) {
+    const uint64_t meta = CHDB_OUT_META(P, k);
+    vpre[k] = FULL;
+    if (((uint32_t)meta & 0xFFu) == OUT_PASS) vpre[k] = load_bits_all<QPT>(P.in[(uint32_t)(meta >> 24) & 0xFFu].validity, L.row_base, sel);
+  }
   __syncthreads();
+  CHDB_STAMP(2);
 
   // ---- 3. tile prefixes: warp qi runs the look-back for quantity qi ---------------------------
   const int nq = 1 + CHDB_N_UTF8;
@@ -1412,6 +1507,7 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
     if (tile == (uint32_t)P.num_tiles - 1) P.counts[0] = (uint64_t)P.num_rows;
   }
   __syncthreads();
+  CHDB_STAMP(3);
   // from here on every warp works alone
   uint32_t rows_before = 0, tile_count = 0;
 #pragma unroll
@@ -1434,11 +1530,12 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
 
   // ---- 4. gather every output column (per warp) ------------------------------------------------
 #ifdef CHDB_JIT
-  outputs_range<V, QPT, 0, chdb_jit::kNumOut>(P, L, wo, s_wtot, s_excl, s_pool);
+  outputs_range<V, QPT, 0, chdb_jit::kNumOut>(P, vpre, L, wo, s_wtot, s_excl, s_pool);
 #else
 #pragma unroll 1
-  for (int k = 0; k < P.n_out; k++) exec_output<V, QPT>(P, k, CHDB_OUT_META(P, k), L, wo, s_wtot, s_excl, s_pool);
+  for (int k = 0; k < P.n_out; k++) exec_output<V, QPT>(P, k, CHDB_OUT_META(P, k), vpre[k], L, wo, s_wtot, s_excl, s_pool);
 #endif
+  CHDB_STAMP(4);
 }
 
 }  // namespace

@@ -20,6 +20,7 @@ struct JitKernel {
   std::vector<char> cubin;
   cudaLibrary_t library = nullptr;
   cudaKernel_t kernel = nullptr;
+  size_t smem_granted = 0;   // dynamic shared memory opted in to so far (single device per process rank)
 };
 
 bool jit_available(std::string* why);

@@ -11,8 +11,8 @@ namespace chdb {
 
 constexpr int kThreads = 256;               // 8 warps per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kQuadsPerThread = 2;          // each thread owns QPT groups of 4 consecutive rows
-constexpr int kTileRows = kThreads * 4 * kQuadsPerThread;   // 2048 rows per tile
+constexpr int kQuadsPerThread = 4;          // each thread owns QPT groups of 4 consecutive rows
+constexpr int kTileRows = kThreads * 4 * kQuadsPerThread;   // 4096 rows per tile, 512 per warp
 
 struct ColumnDesc {          // one input column slot (32 bytes)
   const void* values;        // fixed width: values; Boolean: bit-packed values; Utf8: value bytes
@@ -46,11 +46,12 @@ struct KernelParams {
   uint32_t* ticket;          // dynamic tile id counter (zeroed)
   uint64_t* counts;          // see above (zeroed)
   uint64_t* error_word;      // zeroed; atomicMax(~packed)
+  uint64_t* timing;          // debug (CHDB_PHASE_TIMING): 8 globaltimer stamps per tile, or nullptr
   int32_t num_tiles;
   int32_t n_in, n_out, n_utf8;
   int32_t pred_begin, pred_end;  // pred_begin == pred_end: no predicate (every row is kept)
-  int32_t stage_bytes;           // bytes of the output staging area in dynamic shared memory
-  int32_t pad;
+  int32_t stage_bytes;           // bytes of ONE warp's output staging slice in dynamic shared memory
+  int32_t prefetch_tiles;        // L2 prefetch distance in tiles (about one wave of resident CTAs)
   ColumnDesc in[kMaxInCols];
   OutDesc out[kMaxOutCols];
   Instr instrs[kMaxInstr];

@@ -1,7 +1,7 @@
 """Summarise an ncu report: key raw metrics + instructions / stall samples per function and line."""
 import collections, csv, re, subprocess, sys
 rep = sys.argv[1]
-src_path = sys.argv[2] if len(sys.argv) > 2 else '/root/repo/chapterhouseqe_b200/csrc/kernels.cu'
+src_path = sys.argv[2] if len(sys.argv) > 2 else '/root/repo/chapterhouseqe_b200/csrc/device_code.cuh'
 rows_per_launch = float(sys.argv[3]) if len(sys.argv) > 3 else 4194304.0
 raw = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -43,10 +43,10 @@ for r in rows:
         try: ln = int(r[0])
         except: continue
         lines.append((cur_file, ln, r[1].strip()[:100], toi(r[ie]), toi(r[ss])))
-nl = max(1, len([1 for r in rows if r and r[0]=='File Path' and r[1].endswith('kernels.cu')]))
+nl = max(1, len([1 for r in rows if r and r[0]=='File Path' and (r[1].endswith('kernels.cu') or r[1].endswith('device_code.cuh'))]))
 agg = collections.Counter(); sm = collections.Counter()
 for f, ln, _, ins, s in lines:
-    key = fn_at.get(ln, '?') if f == 'kernels.cu' else f
+    key = fn_at.get(ln, '?') if f in ('kernels.cu', 'device_code.cuh') else f
     agg[key] += ins; sm[key] += s
 tot = sum(agg.values()); tots = sum(sm.values())
 print(f"total warp-instr (all captured launches) {tot}, launches~{nl}; instr/row = {tot/nl/rows_per_launch*32:.1f}")
