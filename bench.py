@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--e2e-instances", type=int, default=3, help="filter operator instances (ctx + stream each) for e2e")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the single-thread cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip the N>1 materialize-gather measurement")
+    ap.add_argument("--gather-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -178,7 +180,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.004)
 
     def stop(self):
         self._stop_evt.set()
@@ -302,6 +304,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import chapterhouseqe_b200 as C
+    from chapterhouseqe_b200 import multigpu
     from chapterhouseqe_b200 import sqlparser_lite as sp
 
     if not torch.cuda.is_available():
@@ -372,15 +375,9 @@ def run_ours(args, rank, world, local_rank):
         bytes_out = sum(o.nbytes for o in prev)
     prev = None
 
-    if world > 1:
-        tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tmax.item())
-        tot = torch.tensor([float(total_rows), float(rows_out), float(launches)], dtype=torch.float64, device=device)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        all_rows, all_rows_out, all_launches = (float(x) for x in tot.tolist())
-    else:
-        all_rows, all_rows_out, all_launches = float(total_rows), float(rows_out), float(launches)
+    # whole-job numbers: MAX over ranks of the device time, SUM of rows / launches (no data-path collective)
+    elapsed_ms, (all_rows, all_rows_out, all_launches, jit_launches) = multigpu.reduce_step(
+        elapsed_ms, [total_rows, rows_out, launches, jit_launches], device)
 
     selectivity = rows_out / total_rows
     # algorithmic bytes: every referenced input byte once + every output byte once
@@ -413,6 +410,30 @@ def run_ours(args, rank, world, local_rank):
                      "avg_launch_us": avg_launch_us, "launches_per_step": launches_per_step},
     }
 
+    # ---- materialize-side gather (N > 1): every rank's compacted batches travel to rank 0 over NVLink ----
+    if world > 1 and not args.no_gather:
+        def gather_step():
+            outs_ = one_step()
+            bufs = [t_ for o in outs_ for t_ in multigpu.device_batch_buffers(o)]
+            torch.cuda.current_stream(device).wait_stream(stream)
+            got = multigpu.gather_buffers(bufs, dst=0)
+            return outs_, got
+        gather_step()
+        barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(args.gather_steps):
+            keep = gather_step()
+        torch.cuda.synchronize(device)
+        barrier()
+        dtg = time.perf_counter() - t0
+        del keep
+        dtg_ms, _ = multigpu.reduce_step(dtg * 1e3, [0.0], device)
+        line["gather"] = {"value": all_rows * args.gather_steps / (dtg_ms / 1e3), "unit": UNIT, "steps": args.gather_steps,
+                          "to_rank": 0, "transport": "torch.distributed isend/irecv (NCCL p2p over NVLink)",
+                          "note": "filter + variable-size gather of every output buffer to rank 0; the reference's per-record "
+                                  "result files allow per-GPU materialize instead, which is what `value` measures"}
+
     # ---- e2e: host batches (pinned) -> chdb_filter_record -> host batches, copies inside the timed region ----
     if not args.no_e2e:
         import concurrent.futures as cf
@@ -443,10 +464,7 @@ def run_ours(args, rank, world, local_rank):
             _, d2h = e2e_step()
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device=device)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
+        dt = multigpu.reduce_step(dt * 1e3, [0.0], device)[0] / 1e3
         h2d = sum(batch_nbytes(rb) for rb, _ in host)
         line["e2e"] = {"value": all_rows * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "instances": n_inst,

@@ -102,6 +102,8 @@ def load_library():
     sig("chdb_device_batch_num_rows", i64, vp, vp, stp)
     sig("chdb_device_batch_num_columns", i32, vp)
     sig("chdb_device_batch_nbytes", i64, vp, vp, stp)
+    sig("chdb_device_batch_column", i32, vp, vp, i32, pvp, ctypes.POINTER(i64), pvp, ctypes.POINTER(i64), pvp,
+        ctypes.POINTER(i64), stp)
     sig("chdb_download", i32, vp, vp, vp, vp, stp)
     sig("chdb_peer_copy", i32, vp, vp, vp, pvp, stp)
     sig("chdb_device_batch_release", None, vp)
@@ -117,7 +119,8 @@ EXPORTED_SYMBOLS = [
     "chdb_program_disassemble", "chdb_program_num_instructions", "chdb_filter_record", "chdb_project_record",
     "chdb_filter_record_expr", "chdb_project_record_items", "chdb_compute_value", "chdb_upload",
     "chdb_device_batch_wrap", "chdb_run_device", "chdb_device_batch_status", "chdb_device_batch_num_rows",
-    "chdb_device_batch_num_columns", "chdb_device_batch_nbytes", "chdb_download", "chdb_peer_copy",
+    "chdb_device_batch_num_columns", "chdb_device_batch_column", "chdb_device_batch_nbytes", "chdb_download",
+    "chdb_peer_copy",
     "chdb_device_batch_release",
 ]
 
@@ -379,6 +382,16 @@ class DeviceBatch:
         n = load_library().chdb_device_batch_nbytes(self.ctx._h, self._h, ctypes.byref(st))
         _check(st.code, st)
         return int(n)
+
+    def column_buffers(self, col: int) -> dict:
+        """Device pointers / sizes of one column: {"values": (ptr, nbytes), "validity": .., "offsets": ..}."""
+        L = load_library()
+        v, va, o = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        nv, nva, no = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        st = _Status()
+        _check(L.chdb_device_batch_column(self.ctx._h, self._h, col, ctypes.byref(v), ctypes.byref(nv), ctypes.byref(va),
+                                          ctypes.byref(nva), ctypes.byref(o), ctypes.byref(no), ctypes.byref(st)), st)
+        return {"values": (v.value or 0, nv.value), "validity": (va.value or 0, nva.value), "offsets": (o.value or 0, no.value)}
 
     def download(self) -> pa.RecordBatch:
         L = load_library()

@@ -990,6 +990,31 @@ int64_t chdb_device_batch_num_rows(chdb_ctx* ctx, const chdb_device_batch* b, ch
   return n;
 }
 int32_t chdb_device_batch_num_columns(const chdb_device_batch* b) { return b ? (int32_t)b->cols.size() : 0; }
+int32_t chdb_device_batch_column(chdb_ctx* ctx, const chdb_device_batch* b, int32_t col, const void** values, int64_t* values_bytes,
+                                 const void** validity, int64_t* validity_bytes, const void** offsets, int64_t* offsets_bytes,
+                                 chdb_status* st) {
+  (void)ctx;
+  return guarded(st, [&] {
+    if (!b || col < 0 || col >= (int32_t)b->cols.size()) throw Error(CHDB_ERR_INVALID_ARGUMENT, "bad batch / column index");
+    check_run_error(b);
+    resolve(const_cast<chdb_device_batch*>(b));
+    const DeviceColumn& c = b->cols[col];
+    const int64_t n = b->num_rows;
+    const bool has_validity = c.validity != nullptr && c.null_count != 0;
+    if (validity) *validity = has_validity ? c.validity : nullptr;
+    if (validity_bytes) *validity_bytes = has_validity ? (int64_t)bitmap_bytes(n) : 0;
+    if (offsets) *offsets = c.meta.type == T_UTF8 ? c.offsets : nullptr;
+    if (offsets_bytes) *offsets_bytes = c.meta.type == T_UTF8 ? (n + 1) * 4 : 0;
+    if (c.meta.type == T_UTF8) {
+      if (c.value_bytes < 0 || c.first_offset < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "column buffers of a sliced Utf8 view");
+      if (values) *values = (const uint8_t*)c.values + c.first_offset;
+      if (values_bytes) *values_bytes = c.value_bytes;
+    } else {
+      if (values) *values = c.values;
+      if (values_bytes) *values_bytes = c.meta.type == T_BOOL ? (int64_t)bitmap_bytes(n) : n * c.meta.width;
+    }
+  });
+}
 int64_t chdb_device_batch_nbytes(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st) {
   (void)ctx;
   int64_t total = -1;

@@ -199,6 +199,12 @@ int32_t chdb_run_device(chdb_ctx* ctx, const chdb_program* prog, const chdb_devi
 int32_t chdb_device_batch_status(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
 int64_t chdb_device_batch_num_rows(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
 int32_t chdb_device_batch_num_columns(const chdb_device_batch* b);
+/* Device pointers and byte sizes of column `col` (after sync): values (Utf8: the value bytes the
+ * offsets index, i.e. buffer start + offsets[0]), validity bitmap or NULL, Utf8 offsets or NULL.
+ * For zero-copy hand-off to other device code (peer gather at materialize, a GPU Parquet encoder). */
+int32_t chdb_device_batch_column(chdb_ctx* ctx, const chdb_device_batch* b, int32_t col, const void** values,
+                                 int64_t* values_bytes, const void** validity, int64_t* validity_bytes,
+                                 const void** offsets, int64_t* offsets_bytes, chdb_status* st);
 /* Bytes of HBM written for this batch's columns (values + validity + offsets), after sync. */
 int64_t chdb_device_batch_nbytes(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
 int32_t chdb_download(chdb_ctx* ctx, const chdb_device_batch* b, struct ArrowArray* out,
