@@ -163,3 +163,16 @@ def test_sqlparser_lite_precedence_matches_sqlparser():
     s = sp.parse_select("select *, t.*, x as y, z w from read_files('a/*.parquet') t where id < 25;")
     assert [next(iter(i)) for i in s["projection"]] == ["Wildcard", "QualifiedWildcard", "ExprWithAlias", "ExprWithAlias"]
     assert s["alias"] == "t" and s["from"] == "read_files('a/*.parquet')"
+
+
+def test_specialised_kernel_builds_offline():
+    """The NVRTC specialisation of a program compiles to an sm_100a cubin without a GPU
+    (same device source as the interpreter kernel, bytecode baked in as constants)."""
+    ok, why = api.jit_available()
+    if not ok:
+        pytest.skip(f"NVRTC unavailable: {why}")
+    p = C.Program.compile_filter(sp.parse_expr("id % 2 = 0"), _schema())
+    src = p.jit_source()
+    assert "#define CHDB_JIT 1" in src and "kInstrs[]" in src and "kOutMeta[]" in src
+    nbytes, log = p.jit_check()
+    assert nbytes > 10_000, log
