@@ -1,21 +1,31 @@
 // Fused WHERE-evaluation -> selection -> decoupled-look-back scan -> compaction kernel (sm_100a).
 //
-// One CTA owns one tile of kTileRows rows.  Per tile:
-//   0. the tile's slice of every input column is prefetched into L2 (one 128-byte line per thread
-//      and iteration), so the dependent loads below find their data on chip
-//   1. every thread runs the predicate bytecode over its rows (128-bit coalesced column loads,
-//      accumulator in registers) and gets a selection mask                     [compute_value.rs]
-//   2. warp shuffles rank the selected rows inside each warp's 256-row slice; for each Utf8 output
-//      the selected value bytes are summed the same way; warp totals meet in shared memory
-//   3. a decoupled look-back over 64-bit {flag | value} tile descriptors turns the tile totals
-//      into exclusive prefixes (rows, and bytes per Utf8 output)               [filter_record.rs:37]
-//   4. from here on every WARP works alone (no block barriers): per output column it stages its
-//      selected values in its private slice of shared memory at the destination's 16-byte phase
-//      and writes them with aligned 16-byte stores; validity and Boolean bits are staged one byte
-//      per row and packed 32 at a time; short Utf8 values are staged the same way, long ones are
-//      produced output-chunk-centric.
-// HBM traffic is therefore each referenced input byte once and each output byte once.
-// Projection expressions are evaluated in step 4 under the selection mask, so checked-integer
+// Persistent, warp-specialised CTAs.  A tile is kTileRows consecutive rows; tiles are handed out by
+// an atomic ticket, so a tile's predecessors are always resident or finished.
+//
+//   producer warp (one lane)   takes tickets and streams each tile's slice of every staged input
+//                              buffer (values, validity bitmaps, Utf8 offsets and short-string
+//                              bytes) into a ring of shared-memory stages with TMA bulk copies
+//                              (cp.async.bulk + mbarrier complete_tx); buffers that are not staged
+//                              get a bulk L2 prefetch instead.  HBM requests for the next tiles are
+//                              therefore in flight while the current ones are being processed.
+//   consumer warps             phase A(t): run the predicate bytecode over the staged tile (128-bit
+//                              shared-memory loads, accumulator in registers) -> selection mask;
+//                              per-warp totals (rows, value bytes per Utf8 output); the last warp
+//                              to arrive publishes the tile aggregate.     [compute_value.rs]
+//                              phase B(t): rank the selected rows, then for every output column write
+//                              the selected values straight to their final position (neighbouring
+//                              lanes hit neighbouring addresses); bit-packed outputs (validity,
+//                              Boolean) are assembled in shared memory and written as whole words;
+//                              Utf8 offsets restart at 0.                  [filter_record.rs:37]
+//                              Software-pipelined: A(t+1) runs before B(t), so a tile's aggregate is
+//                              public one phase before anybody needs its prefix.
+//   look-back warp             turns tile aggregates into exclusive prefixes with a decoupled
+//                              look-back over 64-bit {flag | value} descriptors while the consumers
+//                              are busy with A(t+1).
+//
+// HBM traffic is each referenced input byte once and each output byte once.
+// Projection expressions are evaluated in phase B under the selection mask, so checked-integer
 // errors are raised for surviving rows only (the reference projects after filtering).
 //
 // Accumulator convention: for 8/16/32-bit integers and Float32 only the low 32 bits of the
@@ -30,7 +40,6 @@ namespace {
 
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr int kWarpBitStage = kTileRows / kWarps + 64;   // per warp: one byte per output row + word-alignment slack
 
 // ------------------------------------------------------------------------------------------
 // program access: at run time from the kernel parameters (generic interpreter), or at compile
@@ -93,14 +102,6 @@ __device__ __forceinline__ void report_rows(const KernelParams& P, const Instr& 
 // ------------------------------------------------------------------------------------------
 // loads
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t global_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// phase stamps of one tile (debugging aid, enabled by CHDB_PHASE_TIMING=1 in the environment)
-#define CHDB_STAMP(i) do { if (P.timing != nullptr && (threadIdx.x & 31) == 0) { if ((i) < 4) { if (threadIdx.x == 0) P.timing[(size_t)tile * 8 + (i)] = global_ns(); } else atomicMax((unsigned long long*)&P.timing[(size_t)tile * 8 + (i)], (unsigned long long)global_ns()); } } while (0)
-
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int QPT>
@@ -110,7 +111,7 @@ __device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ bits, 
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
     if ((need >> (4 * q)) & 0xFu) {
-      const uint32_t byte = __ldg(bits + (qbase[q] >> 3));
+      const uint32_t byte = bits[qbase[q] >> 3];
       m |= ((byte >> (uint32_t)(qbase[q] & 4)) & 0xFu) << (4 * q);
     }
   }
@@ -128,7 +129,7 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
         CHDB_SKIP_QUAD(q)
-        const uint4 x = __ldg((const uint4*)(base + qbase[q] * 4));
+        const uint4 x = *(const uint4*)(base + qbase[q] * 4);
         b[4 * q + 0] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
       }
       break;
@@ -137,8 +138,8 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
 #pragma unroll
         for (int q = 0; q < QPT; q++) {
           CHDB_SKIP_QUAD(q)
-          const uint4 x = __ldg((const uint4*)(base + qbase[q] * 8));
-          const uint4 y = __ldg((const uint4*)(base + qbase[q] * 8 + 16));
+          const uint4 x = *(const uint4*)(base + qbase[q] * 8);
+          const uint4 y = *(const uint4*)(base + qbase[q] * 8 + 16);
           b[4 * q + 0] = x.x | ((uint64_t)x.y << 32); b[4 * q + 1] = x.z | ((uint64_t)x.w << 32);
           b[4 * q + 2] = y.x | ((uint64_t)y.y << 32); b[4 * q + 3] = y.z | ((uint64_t)y.w << 32);
         }
@@ -148,7 +149,7 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
         CHDB_SKIP_QUAD(q)
-        const uint2 x = __ldg((const uint2*)(base + qbase[q] * 2));
+        const uint2 x = *(const uint2*)(base + qbase[q] * 2);
         if (from_type == T_I16) {
           b[4 * q + 0] = (uint32_t)(int32_t)(int16_t)(x.x & 0xFFFFu); b[4 * q + 1] = (uint32_t)(int32_t)(int16_t)(x.x >> 16);
           b[4 * q + 2] = (uint32_t)(int32_t)(int16_t)(x.y & 0xFFFFu); b[4 * q + 3] = (uint32_t)(int32_t)(int16_t)(x.y >> 16);
@@ -161,7 +162,7 @@ __device__ __forceinline__ void fetch_col(const ColumnDesc& c, uint8_t from_type
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
         CHDB_SKIP_QUAD(q)
-        const uint32_t x = __ldg((const uint32_t*)(base + qbase[q]));
+        const uint32_t x = *(const uint32_t*)(base + qbase[q]);
         if (from_type == T_I8) {
           b[4 * q + 0] = (uint32_t)(int32_t)(int8_t)(x & 0xFFu); b[4 * q + 1] = (uint32_t)(int32_t)(int8_t)((x >> 8) & 0xFFu);
           b[4 * q + 2] = (uint32_t)(int32_t)(int8_t)((x >> 16) & 0xFFu); b[4 * q + 3] = (uint32_t)(int32_t)(int8_t)(x >> 24);
@@ -549,15 +550,15 @@ __device__ __forceinline__ uint32_t compare(const Instr& in, const V (&a)[R], ui
 template <int QPT> struct QuadBases { int64_t v[QPT]; };
 
 template <int QPT>
-__device__ __noinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr in, const QuadBases<QPT> qb, uint32_t inrange,
+__device__ __noinline__ uint32_t cmp_utf8(const ColumnDesc* cols, const Instr in, const QuadBases<QPT> qb, uint32_t inrange,
                                           const uint8_t* s_pool, uint32_t* valid_out) {
   const int64_t (&qbase)[QPT] = qb.v;
   uint32_t valid;
   const uint32_t slot_a = in.slot, slot_b = (uint32_t)(in.imm >> 56);
   const uint32_t pool_off = (uint32_t)in.imm, pool_len = (uint32_t)(in.imm >> 32) & 0xFFFFFFu;
   valid = FULL;
-  if (slot_a != 0xFFu) valid &= load_bits<QPT>(P.in[slot_a].validity, qbase, inrange);
-  if (slot_b != 0xFFu) valid &= load_bits<QPT>(P.in[slot_b].validity, qbase, inrange);
+  if (slot_a != 0xFFu) valid &= load_bits<QPT>(cols[slot_a].validity, qbase, inrange);
+  if (slot_b != 0xFFu) valid &= load_bits<QPT>(cols[slot_b].validity, qbase, inrange);
   uint32_t lt = 0, eq = 0;
 #pragma unroll 1
   for (int j = 0; j < 4 * QPT; j++) {
@@ -566,18 +567,18 @@ __device__ __noinline__ uint32_t cmp_utf8(const KernelParams& P, const Instr in,
     const uint8_t *pa, *pb;
     int la, lb;
     if (slot_a != 0xFFu) {
-      const int32_t* off = P.in[slot_a].offsets;
-      const int o0 = __ldg(off + row), o1 = __ldg(off + row + 1);
-      pa = (const uint8_t*)P.in[slot_a].values + o0;
+      const int32_t* off = cols[slot_a].offsets;
+      const int o0 = off[row], o1 = off[row + 1];
+      pa = (const uint8_t*)cols[slot_a].values + o0;
       la = o1 - o0;
     } else {
       pa = s_pool + pool_off;
       la = (int)pool_len;
     }
     if (slot_b != 0xFFu) {
-      const int32_t* off = P.in[slot_b].offsets;
-      const int o0 = __ldg(off + row), o1 = __ldg(off + row + 1);
-      pb = (const uint8_t*)P.in[slot_b].values + o0;
+      const int32_t* off = cols[slot_b].offsets;
+      const int o0 = off[row], o1 = off[row + 1];
+      pb = (const uint8_t*)cols[slot_b].values + o0;
       lb = o1 - o0;
     } else {
       pb = s_pool + pool_off;
@@ -619,11 +620,11 @@ struct Spill {
 
 // Fetches the operand of `in` (column or spill slot; immediates are handled by the IMM templates).
 template <typename V, int QI>
-__device__ __forceinline__ void fetch_operand(const KernelParams& P, const Instr& in, const int64_t (&qbase)[QI], uint32_t inrange,
+__device__ __forceinline__ void fetch_operand(const KernelParams& P, const ColumnDesc* cols, const Instr& in, const int64_t (&qbase)[QI], uint32_t inrange,
                                               const Spill<V, QI>& stk, V (&b)[4 * QI], uint32_t& bm, uint32_t& bv) {
   constexpr int R = 4 * QI;
   if (in.src == SRC_COL) {
-    const ColumnDesc& c = P.in[in.slot];
+    const ColumnDesc& c = cols[in.slot];
     bv = load_bits<QI>(c.validity, qbase, inrange);
     if (CHDB_COL_TYPE(P, in.slot) == T_BOOL) {
       bm = load_bits<QI>((const uint8_t*)c.values, qbase, inrange);
@@ -650,7 +651,7 @@ __device__ __forceinline__ void fetch_operand(const KernelParams& P, const Instr
 // Executes one instruction on the accumulator.  `in` is a run-time value in the generic kernel and
 // a compile-time constant under CHDB_JIT (everything below then folds to the one handler).
 template <typename V, int QI>
-__device__ __forceinline__ void exec_instr(const KernelParams& P, const Instr in, const int64_t (&qbase)[QI], uint32_t inrange,
+__device__ __forceinline__ void exec_instr(const KernelParams& P, const ColumnDesc* cols, const Instr in, const int64_t (&qbase)[QI], uint32_t inrange,
                                            uint32_t active, const uint8_t* s_pool, Spill<V, QI>& stk, V (&acc)[4 * QI],
                                            uint32_t& accm, uint32_t& accv) {
   constexpr int R = 4 * QI;
@@ -663,7 +664,7 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, const Instr in
         accm = in.imm ? FULL : 0u;
         accv = FULL;
       } else {
-        fetch_operand<V, QI>(P, in, qbase, inrange, stk, acc, accm, accv);   // straight into the accumulator
+        fetch_operand<V, QI>(P, cols, in, qbase, inrange, stk, acc, accm, accv);   // straight into the accumulator
       }
       break;
     case OP_CAST: cast_vals<V, R>(acc, in.from_type, in.type); break;
@@ -674,7 +675,7 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, const Instr in
       } else {
         V b[R];
         uint32_t bm, bv;
-        fetch_operand<V, QI>(P, in, qbase, inrange, stk, b, bm, bv);
+        fetch_operand<V, QI>(P, cols, in, qbase, inrange, stk, b, bm, bv);
         if (in.flags & OPF_SWAP) arith<false, true, V, QI>(P, in, acc, accv, b, bv, active, qbase);
         else arith<false, false, V, QI>(P, in, acc, accv, b, bv, active, qbase);
       }
@@ -685,7 +686,7 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, const Instr in
       } else {
         V b[R];
         uint32_t bm, bv;
-        fetch_operand<V, QI>(P, in, qbase, inrange, stk, b, bm, bv);
+        fetch_operand<V, QI>(P, cols, in, qbase, inrange, stk, b, bm, bv);
         accm = compare<false, V, R>(in, acc, accm, b, bm);
         accv &= bv;
       }
@@ -698,7 +699,7 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, const Instr in
         bv = stk.valid[in.slot];
       } else if (in.src == SRC_COL) {
         V b[R];
-        fetch_operand<V, QI>(P, in, qbase, inrange, stk, b, bm, bv);
+        fetch_operand<V, QI>(P, cols, in, qbase, inrange, stk, b, bm, bv);
       }
       accm = in.op == OP_AND ? (accm & bm) : (accm | bm);
       accv &= bv;
@@ -717,7 +718,7 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, const Instr in
 #pragma unroll
       for (int q = 0; q < QI; q++) qb.v[q] = qbase[q];
       uint32_t v = FULL;
-      accm = cmp_utf8<QI>(P, in, qb, inrange, s_pool, &v);
+      accm = cmp_utf8<QI>(cols, in, qb, inrange, s_pool, &v);
       accv = v;
       break;
     }
@@ -727,20 +728,20 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, const Instr in
 
 #ifdef CHDB_JIT
 template <typename V, int QI, int PC, int END>
-__device__ __forceinline__ void run_range(const KernelParams& P, const int64_t (&qbase)[QI], uint32_t inrange, uint32_t active,
+__device__ __forceinline__ void run_range(const KernelParams& P, const ColumnDesc* cols, const int64_t (&qbase)[QI], uint32_t inrange, uint32_t active,
                                           const uint8_t* s_pool, Spill<V, QI>& stk, V (&acc)[4 * QI], uint32_t& accm,
                                           uint32_t& accv) {
   if constexpr (PC < END) {
     constexpr Instr in = chdb_jit::kInstrs[PC];
-    exec_instr<V, QI>(P, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
-    run_range<V, QI, PC + 1, END>(P, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    exec_instr<V, QI>(P, cols, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    run_range<V, QI, PC + 1, END>(P, cols, qbase, inrange, active, s_pool, stk, acc, accm, accv);
   }
 }
 #endif
 
 // BEGIN/END >= 0: instruction range known at compile time (CHDB_JIT); otherwise [begin, end).
 template <typename V, int QI, int BEGIN = -1, int END = -1>
-__device__ __forceinline__ void run_program(const KernelParams& P, int begin, int end, const int64_t (&qbase)[QI], uint32_t inrange,
+__device__ __forceinline__ void run_program(const KernelParams& P, const ColumnDesc* cols, int begin, int end, const int64_t (&qbase)[QI], uint32_t inrange,
                                             uint32_t active, const uint8_t* s_pool, V (&acc)[4 * QI], uint32_t& accm,
                                             uint32_t& accv) {
   constexpr int R = 4 * QI;
@@ -751,7 +752,7 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
   accv = FULL;
 #ifdef CHDB_JIT
   if constexpr (BEGIN >= 0) {
-    run_range<V, QI, BEGIN, END>(P, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    run_range<V, QI, BEGIN, END>(P, cols, qbase, inrange, active, s_pool, stk, acc, accm, accv);
     return;
   }
 #endif
@@ -763,7 +764,7 @@ __device__ __forceinline__ void run_program(const KernelParams& P, int begin, in
     in.op = (uint8_t)w.x; in.type = (uint8_t)(w.x >> 8); in.src = (uint8_t)(w.x >> 16); in.flags = (uint8_t)(w.x >> 24);
     in.slot = (uint8_t)w.y; in.from_type = (uint8_t)(w.y >> 8); in.aux = (uint8_t)(w.y >> 16); in.order = (uint8_t)(w.y >> 24);
     in.imm = P.instrs[pc].imm;
-    exec_instr<V, QI>(P, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    exec_instr<V, QI>(P, cols, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
   }
 }
 
@@ -788,32 +789,34 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 }
 
 // Decoupled look-back (Merrill & Garland) on packed {flag:2 | value:62} descriptors; executed by
-// one full warp.  Tiles are numbered by an atomic ticket, so every predecessor is already
-// resident or finished and the spin always terminates.
+// one full warp.  The tile's own descriptor already holds its aggregate (published by the consumer
+// warps).  Tiles are numbered by an atomic ticket, so every predecessor is resident or finished and
+// publishes its aggregate without waiting for anybody: the spin always terminates.
 constexpr uint64_t kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
+constexpr int kLookBackPerLane = 8;   // 256 predecessors per hop, all loads of a hop in flight together
 __device__ __forceinline__ uint64_t lookback(uint64_t* desc, uint32_t tile, uint64_t agg, int lane) {
   volatile uint64_t* d = desc;
-  if (tile == 0) {
-    if (lane == 0) d[0] = kFlagPrefix | agg;
-    return 0;
-  }
-  if (lane == 0) d[tile] = kFlagAgg | agg;
+  if (tile == 0) return 0;
   uint64_t excl = 0;
   int64_t base = (int64_t)tile - 1;
   while (true) {
-    // each lane inspects 4 consecutive predecessors (nearest first): 128 tiles per hop
+    // each lane inspects kLookBackPerLane consecutive predecessors (nearest first)
+    uint64_t v[kLookBackPerLane];
+#pragma unroll
+    for (int j = 0; j < kLookBackPerLane; j++) {
+      const int64_t idx = base - (lane * kLookBackPerLane + j);
+      v[j] = 2ull << 62;   // tiles "before 0" contribute an inclusive prefix of 0
+      if (idx >= 0) v[j] = d[idx];
+    }
     uint64_t part = 0;
     bool found = false;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int64_t idx = base - (lane * 4 + j);
-      uint64_t v = kFlagPrefix;  // tiles "before 0" contribute an inclusive prefix of 0
-      if (idx >= 0 && !found) {
-        do { v = d[idx]; } while ((v >> 62) == 0);
-      }
+    for (int j = 0; j < kLookBackPerLane; j++) {
       if (!found) {
-        part += v & kValueMask;
-        found = (v >> 62) == 2;
+        const int64_t idx = base - (lane * kLookBackPerLane + j);
+        while ((v[j] >> 62) == 0) v[j] = d[idx];
+        part += v[j] & kValueMask;
+        found = (v[j] >> 62) == 2;
       }
     }
     const uint32_t pm = __ballot_sync(FULL, found);
@@ -823,246 +826,135 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc, uint32_t tile, uint
       break;
     }
     excl += warp_sum64(part);
-    base -= 128;
+    base -= 32 * kLookBackPerLane;
   }
   if (lane == 0) d[tile] = kFlagPrefix | (excl + agg);
   return excl;
 }
 
 // ------------------------------------------------------------------------------------------
-// output staging -- per WARP.  After the tile prefixes are known every warp gathers its own 256
-// rows on its own: it stages the selected values of one column in its private slice of shared
-// memory at the destination's 16-byte phase and writes them with aligned 16-byte stores, with
-// only __syncwarp() in between, so no warp ever waits for another one in this phase.
-// Shared memory is addressed with explicit 32-bit shared-window addresses (computed once per
-// kernel) so the hot loops are plain LDS / STS with register bases.
+// shared-memory plumbing: mbarriers, TMA bulk copies, named barriers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { uint64_t a;
   asm("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
   return (uint32_t)a; }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts64(uint32_t a, uint32_t lo, uint32_t hi) {
-  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(lo), "r"(hi) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-  return v;
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
+// global -> shared bulk copy (TMA, 1-D); dst, src and bytes are multiples of 16
+__device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// Asynchronous global -> shared copies (LDGSTS): the data of the next output column streams into the
-// warp's second buffer while the current column is being compacted.
-__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// nbytes is rounded up to 16 (buffers are padded); src and dst_s must be 16-byte aligned
-__device__ __forceinline__ void async_copy_slice(uint32_t dst_s, const uint8_t* src, uint32_t nbytes, int lane) {
-  for (uint32_t b = (uint32_t)lane * 16u; b < nbytes; b += 512u) cp_async16(dst_s + b, src + b);
-}
-__device__ __forceinline__ uint2 lds64(uint32_t a) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
-  return v;
+__device__ __forceinline__ void consumer_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
 }
 
-template <int W>
-__device__ __forceinline__ void copy_elem_s2g(uint8_t* g, uint32_t s) {   // one W-byte element, shared -> global
-  if (W == 4) { *(uint32_t*)g = lds32(s); }
-  else if (W == 8) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s) : "memory"); *(uint2*)g = v; }
-  else if (W == 2) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(s) : "memory"); *(uint16_t*)g = v; }
-  else { *g = (uint8_t)lds8(s); }
-}
-
-// stage[mis, mis + nbytes) -> gdst_aligned[mis, ...), by one warp: aligned 16-byte stores in the
-// middle; the (at most two) 16-byte chunks shared with the neighbours are written element-wise,
-// one element per lane.
-template <int W>
-__device__ __forceinline__ void warp_writeout(uint32_t stage_s, uint8_t* gdst_aligned, uint32_t mis, uint32_t nbytes, int lane) {
-  const uint32_t end = mis + nbytes;
-  const uint32_t first_full = (mis + 15u) >> 4, end_full = end >> 4;   // full chunks: [first_full, end_full)
-  uint32_t c = first_full + lane;
-  for (; c + 32 < end_full; c += 64) {   // two independent 16-byte copies per trip
-    const uint4 a = lds128(stage_s + (c << 4)), b = lds128(stage_s + ((c + 32) << 4));
-    *(uint4*)(gdst_aligned + (c << 4)) = a;
-    *(uint4*)(gdst_aligned + ((c + 32) << 4)) = b;
-  }
-  if (c < end_full) *(uint4*)(gdst_aligned + (c << 4)) = lds128(stage_s + (c << 4));
-  constexpr uint32_t EPC = 16 / W;   // elements per chunk
-  if (mis != 0) {                    // head chunk 0: lanes 0 .. EPC-1 take one element each
-    const uint32_t b = (uint32_t)lane * W;
-    if ((uint32_t)lane < EPC && b >= mis && b < end) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
-  }
-  if ((end & 15u) != 0 && (end_full > 0 || mis == 0)) {   // tail chunk (unless it is also the head): lanes 16 .. 16+EPC-1
-    const uint32_t b = (end_full << 4) + ((uint32_t)lane - 16u) * W;
-    if ((uint32_t)lane >= 16u && (uint32_t)lane < 16u + EPC && b < end) copy_elem_s2g<W>(gdst_aligned + b, stage_s + b);
-  }
-}
-
-// What a warp knows about its slice of the output once the prefixes are in.
-template <int QPT>
-struct WarpOut {
-  uint64_t base;          // global output row index of the warp's first selected row
-  uint32_t count;         // selected rows of this warp
-  uint32_t rank[QPT];     // warp-local rank of the first selected row of each of this lane's quads
-  uint32_t sel;           // selection bits of this lane's rows (4 per quad)
+// Everything one tile needs besides its staged bytes; one per stage of the ring.
+struct TileCtl {
+  int32_t tile;                                   // ticket, or -1: no more tiles
+  uint32_t arrive;                                // consumer warps that finished phase A
+  uint32_t wtot[kMaxQuantities][kConsumerWarps];  // per-warp totals: [0] rows, [1 + u] bytes of Utf8 output u
+  uint64_t agg[kMaxQuantities];                   // tile totals
+  uint64_t excl[kMaxQuantities];                  // exclusive prefixes from the look-back
+  ColumnDesc cols[kMaxInCols];                    // the input columns as seen by this tile: pointers are biased so that
+                                                  // indexing with the ABSOLUTE row lands in the stage (or in global memory)
+};
+struct SharedState {
+  uint64_t full[kMaxStages], empty[kMaxStages], aggbar[kMaxStages], prebar[kMaxStages];
+  TileCtl ctl[kMaxStages];
+  uint32_t nulls[kMaxOutCols];
+  uint8_t pext4[256];                             // [sel4 << 4 | bits4] -> the selected bits, packed
+  uint8_t pool[kStrPoolBytes];
 };
 
-// Stages the selected rows of quad q of a W-byte pass-through column (the load was issued by the caller).
-template <int W>
-__device__ __forceinline__ void stage_quad(uint32_t a, uint32_t s4, const uint4& x, const uint4& y) {
-  if (W == 4) {
-    if (s4 & 1u) { sts32(a, x.x); a += 4; }
-    if (s4 & 2u) { sts32(a, x.y); a += 4; }
-    if (s4 & 4u) { sts32(a, x.z); a += 4; }
-    if (s4 & 8u) { sts32(a, x.w); }
-  } else if (W == 8) {
-    if (s4 & 1u) { sts64(a, x.x, x.y); a += 8; }
-    if (s4 & 2u) { sts64(a, x.z, x.w); a += 8; }
-    if (s4 & 4u) { sts64(a, y.x, y.y); a += 8; }
-    if (s4 & 8u) { sts64(a, y.z, y.w); }
-  } else if (W == 2) {
-    if (s4 & 1u) { sts16(a, x.x & 0xFFFFu); a += 2; }
-    if (s4 & 2u) { sts16(a, x.x >> 16); a += 2; }
-    if (s4 & 4u) { sts16(a, x.y & 0xFFFFu); a += 2; }
-    if (s4 & 8u) { sts16(a, x.y >> 16); }
-  } else {
-    if (s4 & 1u) { sts8(a, x.x & 0xFFu); a += 1; }
-    if (s4 & 2u) { sts8(a, (x.x >> 8) & 0xFFu); a += 1; }
-    if (s4 & 4u) { sts8(a, (x.x >> 16) & 0xFFu); a += 1; }
-    if (s4 & 8u) { sts8(a, x.x >> 24); }
-  }
-}
-
-// Gathers the selected rows of a W-byte pass-through column: loads two quads at a time (in flight
-// together), stages them, one write-out for the whole warp slice.
-template <int W, int QPT>
-__device__ __forceinline__ void gather_fixed(const uint8_t* __restrict__ src, uint8_t* dst, int64_t row_base, const WarpOut<QPT>& wo,
-                                             uint32_t stage_s, int lane) {
-  const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
-#pragma unroll
-  for (int g = 0; g < QPT; g += 2) {
-    uint4 x[2], y[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int q = g + h;
-      x[h] = make_uint4(0, 0, 0, 0);
-      y[h] = make_uint4(0, 0, 0, 0);
-      if (q >= QPT || !((wo.sel >> (4 * q)) & 0xFu)) continue;
-      const int64_t r = row_base + q * 128;
-      if (W == 4) {
-        x[h] = __ldg((const uint4*)(src + r * 4));
-      } else if (W == 8) {
-        x[h] = __ldg((const uint4*)(src + r * 8));
-        y[h] = __ldg((const uint4*)(src + r * 8 + 16));
-      } else if (W == 2) {
-        const uint2 t = __ldg((const uint2*)(src + r * 2));
-        x[h].x = t.x; x[h].y = t.y;
-      } else {
-        x[h].x = __ldg((const uint32_t*)(src + r));
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int q = g + h;
-      if (q >= QPT) continue;
-      const uint32_t s4 = (wo.sel >> (4 * q)) & 0xFu;
-      if (s4) stage_quad<W>(stage_s + mis + wo.rank[q] * W, s4, x[h], y[h]);
-    }
-  }
-  __syncwarp();
-  warp_writeout<W>(stage_s, dst + ((wo.base * W) & ~15ull), mis, wo.count * W, lane);
-  __syncwarp();
-}
-
-// Stages four values that already sit in registers (one quad of a projection expression / of the
-// rebuilt Utf8 offsets); the caller writes the slice out once all quads are staged.
-template <int W, typename E>
-__device__ __forceinline__ void stage_regs(uint32_t a, uint32_t s4, const E (&e)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    if ((s4 >> i) & 1u) {
-      if (W == 4) sts32(a, (uint32_t)e[i]);
-      else if (W == 8) sts64(a, (uint32_t)e[i], (uint32_t)((uint64_t)e[i] >> 32));
-      else if (W == 2) sts16(a, (uint32_t)e[i] & 0xFFFFu);
-      else sts8(a, (uint32_t)e[i] & 0xFFu);
-      a += W;
-    }
-  }
-}
-
-// Compacts one bit per row (validity or Boolean values) into gbits at bit offset wo.base:
-// every selected row drops its bit as one byte at its rank, then one lane per output word packs
-// 32 bytes with eight multiplies.  gbits is zero-initialised; the (at most two) words shared with
-// neighbouring warps are merged with atomicOr.
+// ------------------------------------------------------------------------------------------
+// phase B: writing the selected rows
+// ------------------------------------------------------------------------------------------
+// What a lane knows about its rows of the current tile once the prefixes are in.
 template <int QPT>
-__device__ __forceinline__ void compact_bits(uint32_t bits, const WarpOut<QPT>& wo, uint32_t bstage_s, uint32_t* gbits, int lane) {
-  const uint32_t o = (uint32_t)(wo.base & 31);
+struct LaneCtx {
+  int64_t row_base;       // absolute row of the lane's quad 0; quad q starts at row_base + q * 128
+  uint32_t inrange;       // rows that exist (tail tile), 4 bits per quad
+  uint32_t sel;           // selected rows, 4 bits per quad
+  uint32_t rank[QPT];     // tile-local rank of the first selected row of each quad
+  uint64_t obase;         // output row of the tile's first selected row
+  uint32_t warp_first;    // tile-local rank of the warp's first selected row
+  uint32_t warp_count;    // selected rows of this warp
+  int lane, warp;
+};
+
+// Drops the selected bits of the lane's rows into the tile's bit stage (zero-initialised): bit for
+// output row obase + r sits at stage bit (obase & 31) + r.
+template <int QPT>
+__device__ __forceinline__ void put_bits(uint32_t bits, const LaneCtx<QPT>& L, uint32_t* sb, const uint8_t* pext4) {
+  const uint32_t o = (uint32_t)L.obase & 31u;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
-    uint32_t a = bstage_s + o + wo.rank[q];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int j = 4 * q + i;
-      if ((wo.sel >> j) & 1u) { sts8(a, (bits >> j) & 1u); a++; }
+    const uint32_t s4 = (L.sel >> (4 * q)) & 0xFu, b4 = (bits >> (4 * q)) & 0xFu & s4;
+    if (b4) {
+      const uint32_t c = pext4[(s4 << 4) | b4];
+      const uint32_t p = o + L.rank[q], sh = p & 31u;
+      atomicOr(&sb[p >> 5], c << sh);
+      if (sh > 28u && (c >> (32u - sh))) atomicOr(&sb[(p >> 5) + 1], c >> (32u - sh));
     }
   }
-  __syncwarp();
-  const uint32_t end = o + wo.count;
-  const uint32_t nwords = (end + 31u) >> 5;     // <= 9 for a 256-row warp slice
-  const uint64_t g0 = wo.base >> 5;
-  for (uint32_t k = lane; k < nwords; k += 32) {
-    const uint4 lo4 = lds128(bstage_s + 32 * k), hi4 = lds128(bstage_s + 32 * k + 16);
-    const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-    uint32_t word = 0;
+}
+
+template <int QPT>
+__device__ __forceinline__ uint32_t load_bits_all(const uint8_t* __restrict__ bits, int64_t row_base, uint32_t need) {
+  if (bits == nullptr) return FULL;
+  uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) word |= (((w[i] & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << (4 * i);
-    // bytes outside [o, end) of the first / last word are stale: mask them off
-    const uint32_t lo = 32 * k < o ? o - 32 * k : 0, hi = 32 * k + 32 > end ? end - 32 * k : 32;
-    const uint32_t mask = (hi >= 32 ? FULL : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-    word &= mask;
-    if (mask == FULL) gbits[g0 + k] = word;
-    else if (word) atomicOr(&gbits[g0 + k], word);
+  for (int q = 0; q < QPT; q++) {
+    if ((need >> (4 * q)) & 0xFu) {
+      const int64_t r = row_base + q * 128;
+      const uint32_t byte = bits[r >> 3];
+      m |= ((byte >> (uint32_t)(r & 4)) & 0xFu) << (4 * q);
+    }
   }
-  __syncwarp();
+  return m;
 }
 
-__device__ __forceinline__ void add_count(uint64_t* slot, uint32_t mine, int lane) {
-  const uint32_t s = __reduce_add_sync(FULL, mine);
-  if (lane == 0 && s) atomicAdd((unsigned long long*)slot, (unsigned long long)s);
+// Stores the selected elements of one quad at consecutive output positions.
+template <typename E>
+__device__ __forceinline__ void store_sel(E* d, uint32_t s4, const E& e0, const E& e1, const E& e2, const E& e3) {
+  if (s4 & 1u) { *d = e0; d++; }
+  if (s4 & 2u) { *d = e1; d++; }
+  if (s4 & 4u) { *d = e2; d++; }
+  if (s4 & 8u) { *d = e3; }
 }
 
-// 16 / 4 bytes from an arbitrarily aligned global address (buffers are padded, so the aligned
-// words around it are always readable).
+// 16 / 4 bytes from an arbitrarily aligned address (buffers are padded, so the aligned words around
+// it are always readable).
 __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* p) {
   const uintptr_t a = (uintptr_t)p;
-  if ((a & 15u) == 0) return __ldg((const uint4*)p);
+  if ((a & 15u) == 0) return *(const uint4*)p;
   const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
   const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
   if (sh == 0) return make_uint4(w0, w1, w2, w3);
-  const uint32_t w4 = __ldg(w + 4);
+  const uint32_t w4 = w[4];
   return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
                     __funnelshift_r(w3, w4, sh));
 }
@@ -1070,35 +962,24 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* p) {
   const uintptr_t a = (uintptr_t)p;
   const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
   const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  const uint32_t w0 = __ldg(w);
+  const uint32_t w0 = w[0];
   if (sh == 0) return w0;
-  return __funnelshift_r(w0, __ldg(w + 1), sh);
+  return __funnelshift_r(w0, w[1], sh);
 }
 
-// One selected row's value bytes -> the shared-memory stage (the short-string path).
-__device__ __forceinline__ void copy_row_g2s(const uint8_t* sp, uint32_t da, uint32_t n) {
-  if ((((uint32_t)(uintptr_t)sp | da) & 3u) == 0) {
-    const uint32_t nw = n >> 2;
-    if (nw <= 4) {   // up to 16 bytes: straight-line
-      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-      if (nw > 0) w0 = __ldg((const uint32_t*)sp);
-      if (nw > 1) w1 = __ldg((const uint32_t*)sp + 1);
-      if (nw > 2) w2 = __ldg((const uint32_t*)sp + 2);
-      if (nw > 3) w3 = __ldg((const uint32_t*)sp + 3);
-      if (nw > 0) sts32(da, w0);
-      if (nw > 1) sts32(da + 4, w1);
-      if (nw > 2) sts32(da + 8, w2);
-      if (nw > 3) sts32(da + 12, w3);
-    } else {
+// One short value: by one thread, in the widest unit source, destination and length allow.
+__device__ __forceinline__ void copy_value(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  const uint32_t a = (uint32_t)(uintptr_t)dst | (uint32_t)(uintptr_t)src | n;
+  if ((a & 7u) == 0) {
+    if (n == 8) { *(uint2*)dst = *(const uint2*)src; return; }
 #pragma unroll 1
-      for (uint32_t i = 0; i < nw; i++) sts32(da + 4 * i, __ldg((const uint32_t*)sp + i));
-    }
-    const uint32_t done = nw << 2;
+    for (uint32_t i = 0; i < n; i += 8) *(uint2*)(dst + i) = *(const uint2*)(src + i);
+  } else if ((a & 3u) == 0) {
 #pragma unroll 1
-    for (uint32_t i = done; i < n; i++) sts8(da + i, __ldg(sp + i));
+    for (uint32_t i = 0; i < n; i += 4) *(uint32_t*)(dst + i) = *(const uint32_t*)(src + i);
   } else {
 #pragma unroll 1
-    for (uint32_t i = 0; i < n; i++) sts8(da + i, __ldg(sp + i));
+    for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
   }
 }
 
@@ -1134,7 +1015,7 @@ __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, u
       const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
       uint32_t piece, step;
       if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) { piece = load4_unaligned(sp); step = 4; }
-      else { piece = (uint32_t)__ldg(sp) << (8u * (b & 3u)); step = 1; }
+      else { piece = (uint32_t)*sp << (8u * (b & 3u)); step = 1; }
       const uint32_t wi = (b - lo) >> 2;
       if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
       b += step;
@@ -1151,391 +1032,499 @@ __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, u
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// the kernel
-// ------------------------------------------------------------------------------------------
-// What every lane carries through the per-warp gather phase.
-template <int QPT>
-struct LaneCtx {
-  int64_t row_base;       // first row of the lane's quad 0; quad q starts at row_base + q * 128
-  uint32_t inrange;       // rows that exist (tail tile), 4 bits per quad
-  uint32_t stage_s, bstage_s, wstage_bytes;
-  int lane, warp;
-};
-
-template <int QPT>
-__device__ __forceinline__ uint32_t load_bits_all(const uint8_t* __restrict__ bits, int64_t row_base, uint32_t need) {
-  if (bits == nullptr) return FULL;
-  uint32_t m = 0;
-#pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    if ((need >> (4 * q)) & 0xFu) {
-      const int64_t r = row_base + q * 128;
-      const uint32_t byte = __ldg(bits + (r >> 3));
-      m |= ((byte >> (uint32_t)(r & 4)) & 0xFu) << (4 * q);
-    }
-  }
-  return m;
-}
-
-// Gathers output column k for this warp.  `meta` packs the eight small OutDesc fields; under
+// Writes output column k for this lane's rows.  `meta` packs the eight small OutDesc fields; under
 // CHDB_JIT it is a compile-time constant and BEGIN/END carry the expression's instruction range.
-// `vpre`: validity bits of a pass-through column, loaded before the look-back so that their latency
-// hides behind it.
+// kb: running index of the bit-packed outputs (Boolean values, validity bitmaps) in the bit stage.
 template <typename V, int QPT, int BEGIN = -1, int END = -1>
-__device__ __forceinline__ void exec_output(const KernelParams& P, const int k, const uint64_t meta, const uint32_t vpre,
-                                            const LaneCtx<QPT>& L, const WarpOut<QPT>& wo, const uint32_t (*s_wtot)[kWarps],
-                                            const uint64_t* s_excl, const uint8_t* s_pool) {
+__device__ __forceinline__ void emit_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
+                                            const LaneCtx<QPT>& L, const SharedState& sh, uint32_t* bitstage, uint32_t* ltab, int& kb) {
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
-  const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_count = (uint32_t)(meta >> 56);
+  const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu;
   uint8_t* const o_values = (uint8_t*)P.out[k].values;
-  uint8_t* const o_validity = P.out[k].validity;
-  const uint32_t sel = wo.sel, stage_s = L.stage_s, bstage_s = L.bstage_s;
+  const bool o_has_validity = P.out[k].validity != nullptr;
+  const uint32_t sel = L.sel;
   const int lane = L.lane;
+  const ColumnDesc* cols = C.cols;
   uint32_t vbits = FULL;  // validity of this output for the lane's rows
   if (o_kind == OUT_EXPR) {
     uint32_t accm = 0;
     vbits = 0;
-    const uint32_t W = o_type == T_BOOL ? 0u : o_width;
-    const uint32_t mis = (uint32_t)((wo.base * W) & 15u);
-#ifdef CHDB_JIT
 #pragma unroll
-#else
-#pragma unroll 1
-#endif
     for (int q = 0; q < QPT; q++) {
-      const int64_t qb[1] = {L.row_base + q * 128};
       const uint32_t in4 = (L.inrange >> (4 * q)) & 0xFu, sel4 = (sel >> (4 * q)) & 0xFu;
+      if (!sel4) continue;
+      const int64_t qb[1] = {L.row_base + q * 128};
       V a4[4];
       uint32_t m4, v4;
       // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
-      run_program<V, 1, BEGIN, END>(P, (int)o_begin, (int)o_end, qb, in4, sel4, s_pool, a4, m4, v4);
+      run_program<V, 1, BEGIN, END>(P, cols, (int)o_begin, (int)o_end, qb, in4, sel4, sh.pool, a4, m4, v4);
       accm |= (m4 & 0xFu) << (4 * q);
       vbits |= (v4 & 0xFu) << (4 * q);
-      uint32_t rk = wo.rank[0];
-#pragma unroll
-      for (int t = 1; t < QPT; t++)
-        if (t == q) rk = wo.rank[t];     // static indexing keeps the ranks in registers
-      const uint32_t a = stage_s + mis + rk * W;
-      if (W == 4) stage_regs<4, V>(a, sel4, a4);
-      else if (W == 8) stage_regs<8, V>(a, sel4, a4);
-      else if (W == 2) stage_regs<2, V>(a, sel4, a4);
-      else if (W == 1) stage_regs<1, V>(a, sel4, a4);
+      const uint64_t o = L.obase + L.rank[q];
+      if (o_type == T_BOOL) continue;
+      if (o_width == 4) store_sel<uint32_t>((uint32_t*)o_values + o, sel4, (uint32_t)a4[0], (uint32_t)a4[1], (uint32_t)a4[2], (uint32_t)a4[3]);
+      else if (o_width == 8) store_sel<uint64_t>((uint64_t*)o_values + o, sel4, (uint64_t)a4[0], (uint64_t)a4[1], (uint64_t)a4[2], (uint64_t)a4[3]);
+      else if (o_width == 2) store_sel<uint16_t>((uint16_t*)o_values + o, sel4, (uint16_t)a4[0], (uint16_t)a4[1], (uint16_t)a4[2], (uint16_t)a4[3]);
+      else store_sel<uint8_t>((uint8_t*)o_values + o, sel4, (uint8_t)a4[0], (uint8_t)a4[1], (uint8_t)a4[2], (uint8_t)a4[3]);
     }
-    if (o_type == T_BOOL) {
-      compact_bits<QPT>(accm, wo, bstage_s, (uint32_t*)o_values, lane);
-    } else {
-      __syncwarp();
-      uint8_t* gd = o_values + ((wo.base * W) & ~15ull);
-      if (W == 4) warp_writeout<4>(stage_s, gd, mis, wo.count * 4, lane);
-      else if (W == 8) warp_writeout<8>(stage_s, gd, mis, wo.count * 8, lane);
-      else if (W == 2) warp_writeout<2>(stage_s, gd, mis, wo.count * 2, lane);
-      else warp_writeout<1>(stage_s, gd, mis, wo.count, lane);
-      __syncwarp();
-    }
+    if (o_type == T_BOOL) { put_bits<QPT>(accm, L, bitstage + kb * kBitWords, sh.pext4); kb++; }
   } else {
-    const ColumnDesc& c = P.in[o_slot];
-    vbits = vpre;
+    const ColumnDesc& c = cols[o_slot];
+    if (o_has_validity) vbits = load_bits_all<QPT>(c.validity, L.row_base, sel);
     if (o_type == T_BOOL) {
       const uint32_t vals = load_bits_all<QPT>((const uint8_t*)c.values, L.row_base, sel);
-      compact_bits<QPT>(vals, wo, bstage_s, (uint32_t*)o_values, lane);
+      put_bits<QPT>(vals, L, bitstage + kb * kBitWords, sh.pext4);
+      kb++;
     } else if (o_type == T_UTF8) {
-      // -- offsets: running sum of the selected lengths, restarted at 0 for the output.
-      //    The warp's stage holds the rebuilt offsets in its first kWarpRows * 4 + 16 bytes and the
-      //    value bytes (short strings) behind them, so both are written out once per warp slice.
-      constexpr uint32_t kOffStage = (uint32_t)(32 * 4 * QPT) * 4u + 16u;
-      const int32_t* __restrict__ off = c.offsets;
-      const uint8_t* __restrict__ sv = (const uint8_t*)c.values;
+      // offsets: running sum of the selected lengths, restarted at 0 for the output
+      const int32_t* off = c.offsets;
+      const uint8_t* sv = (const uint8_t*)c.values;
       uint32_t bytes_before = 0;
 #pragma unroll
-      for (int w = 0; w < kWarps; w++)
-        if (w < L.warp) bytes_before += s_wtot[1 + o_utf8][w];
-      const uint32_t warp_bytes = s_wtot[1 + o_utf8][L.warp];
-      const uint64_t byte_base = s_excl[1 + o_utf8] + bytes_before;   // output byte offset of this warp's first value
-      const uint32_t omis = (uint32_t)((wo.base * 4) & 15u);
-      const uint32_t mis = (uint32_t)(byte_base & 15u);
-      const uint32_t str_s = stage_s + kOffStage;
-      const bool staged = mis + warp_bytes + 16u <= L.wstage_bytes - kOffStage;   // short strings fit the stage
-      uint32_t* s_oo = (uint32_t*)__cvta_shared_to_generic(str_s);                // long strings: per-row tables instead
-      int32_t* s_src = (int32_t*)(s_oo + 32 * 4 * QPT + 4);
+      for (int w = 0; w < kConsumerWarps; w++)
+        if (w < L.warp) bytes_before += C.wtot[1 + o_utf8][w];
+      const uint32_t warp_bytes = C.wtot[1 + o_utf8][L.warp];
+      const uint64_t warp_byte_base = C.excl[1 + o_utf8] + bytes_before;   // output byte offset of this warp's first value
+      int32_t* const o_off = P.out[k].offsets;
+      // long values are copied by the whole warp, chunk-centric; short ones by the lane that owns the row
+      const bool chunked = P.long_strings != 0 && warp_bytes > 24u * L.warp_count;
+      uint32_t* s_oo = ltab + L.warp * (2 * (kWarpRows + 4));
+      int32_t* s_src = (int32_t*)(s_oo + kWarpRows + 4);
       uint32_t run = 0;   // bytes of the quads handled so far
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
         const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
-        uint32_t len[4] = {0u, 0u, 0u, 0u}, boff[4];
-        int32_t src[4] = {0, 0, 0, 0};
+        int32_t o5[5] = {0, 0, 0, 0, 0};
         if (s4) {
-          const int4 a = __ldg((const int4*)(off + L.row_base + q * 128));
-          const int a4 = __ldg(off + L.row_base + q * 128 + 4);
-          src[0] = a.x; src[1] = a.y; src[2] = a.z; src[3] = a.w;
-          if (s4 & 1u) len[0] = (uint32_t)(a.y - a.x);
-          if (s4 & 2u) len[1] = (uint32_t)(a.z - a.y);
-          if (s4 & 4u) len[2] = (uint32_t)(a.w - a.z);
-          if (s4 & 8u) len[3] = (uint32_t)(a4 - a.w);
+          const int4 a = *(const int4*)(off + L.row_base + q * 128);
+          o5[0] = a.x; o5[1] = a.y; o5[2] = a.z; o5[3] = a.w;
+          o5[4] = off[L.row_base + q * 128 + 4];
         }
+        uint32_t len[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) len[i] = ((s4 >> i) & 1u) ? (uint32_t)(o5[i + 1] - o5[i]) : 0u;
         uint32_t tot;
-        uint32_t bo = run + warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, tot);
+        uint32_t bo = run + warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, tot);   // warp-local output byte offset
         run += tot;
-        uint32_t newoff[4];
+        int32_t* d = o_off + (L.obase + L.rank[q]);
+        uint32_t wr = L.rank[q] - L.warp_first;   // warp-local rank
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          boff[i] = bo;                                   // warp-local output byte offset of the row
-          newoff[i] = (uint32_t)byte_base + bo;
-          bo += len[i];
-        }
-        stage_regs<4, uint32_t>(stage_s + omis + wo.rank[q] * 4, s4, newoff);
-        if (staged) {
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            if (((s4 >> i) & 1u) && len[i] != 0) copy_row_g2s(sv + src[i], str_s + mis + boff[i], len[i]);
-        } else {
-          uint32_t r = wo.rank[q];
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            if ((s4 >> i) & 1u) { s_oo[r] = boff[i]; s_src[r] = src[i]; r++; }
+          if ((s4 >> i) & 1u) {
+            *d = (int32_t)(uint32_t)(warp_byte_base + bo);
+            d++;
+            if (chunked) { s_oo[wr] = bo; s_src[wr] = o5[i]; wr++; }
+            else if (len[i]) copy_value(o_values + warp_byte_base + bo, sv + o5[i], len[i]);
+            bo += len[i];
+          }
         }
       }
-      if (!staged && lane == 0) s_oo[wo.count] = warp_bytes;
-      __syncwarp();
-      warp_writeout<4>(stage_s, (uint8_t*)P.out[k].offsets + ((wo.base * 4) & ~15ull), omis, wo.count * 4, lane);
-      uint8_t* gal = o_values + (byte_base - mis);
-      if (staged) warp_writeout<1>(str_s, gal, mis, warp_bytes, lane);
-      else copy_long_strings(sv, gal, mis, warp_bytes, wo.count, s_oo, s_src, lane);
-      __syncwarp();
-    } else if (o_width == 16) {
-      const uint4* __restrict__ src = (const uint4*)c.values;
+      if (chunked) {
+        if (lane == 0) s_oo[L.warp_count] = warp_bytes;
+        __syncwarp();
+        const uint32_t mis = (uint32_t)(warp_byte_base & 15u);
+        copy_long_strings(sv, o_values + (warp_byte_base - mis), mis, warp_bytes, L.warp_count, s_oo, s_src, lane);
+        __syncwarp();
+      }
+    } else {
 #pragma unroll
       for (int q = 0; q < QPT; q++) {
-        uint32_t a = stage_s + wo.rank[q] * 16;
+        const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
+        if (!s4) continue;
+        const int64_t r = L.row_base + q * 128;
+        const uint64_t o = L.obase + L.rank[q];
+        const uint8_t* src = (const uint8_t*)c.values;
+        if (o_width == 4) {
+          const uint4 x = *(const uint4*)(src + r * 4);
+          store_sel<uint32_t>((uint32_t*)o_values + o, s4, x.x, x.y, x.z, x.w);
+        } else if (o_width == 8) {
+          const uint4 x = *(const uint4*)(src + r * 8), y = *(const uint4*)(src + r * 8 + 16);
+          store_sel<uint2>((uint2*)o_values + o, s4, make_uint2(x.x, x.y), make_uint2(x.z, x.w), make_uint2(y.x, y.y), make_uint2(y.z, y.w));
+        } else if (o_width == 16) {
+          const uint4* s16 = (const uint4*)src + r;
+          uint4* d = (uint4*)o_values + o;
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-          if ((sel >> (4 * q + i)) & 1u) { sts128(a, __ldg(src + L.row_base + q * 128 + i)); a += 16; }
+          for (int i = 0; i < 4; i++)
+            if ((s4 >> i) & 1u) { *d = s16[i]; d++; }
+        } else if (o_width == 2) {
+          const uint2 x = *(const uint2*)(src + r * 2);
+          store_sel<uint16_t>((uint16_t*)o_values + o, s4, (uint16_t)x.x, (uint16_t)(x.x >> 16), (uint16_t)x.y, (uint16_t)(x.y >> 16));
+        } else {
+          const uint32_t x = *(const uint32_t*)(src + r);
+          store_sel<uint8_t>(o_values + o, s4, (uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24));
+        }
       }
-      __syncwarp();
-      uint4* dst = (uint4*)o_values + wo.base;
-      for (uint32_t r = lane; r < wo.count; r += 32) dst[r] = lds128(stage_s + r * 16);
-      __syncwarp();
-    } else if (o_width == 4) {
-      gather_fixed<4, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
-    } else if (o_width == 8) {
-      gather_fixed<8, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
-    } else if (o_width == 2) {
-      gather_fixed<2, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
-    } else {
-      gather_fixed<1, QPT>((const uint8_t*)c.values, o_values, L.row_base, wo, stage_s, lane);
     }
   }
-  if (o_validity != nullptr) {
-    compact_bits<QPT>(vbits, wo, bstage_s, (uint32_t*)o_validity, lane);
-    add_count(P.counts + o_count, (uint32_t)__popc(sel & ~vbits), lane);
+  if (o_has_validity) {
+    // nulls are the rare case: the stage collects the NULL bits (most lanes have nothing to add)
+    put_bits<QPT>(~vbits, L, bitstage + kb * kBitWords, sh.pext4);
+    kb++;
   }
 }
 
 #ifdef CHDB_JIT
 template <typename V, int QPT, int K, int N>
-__device__ __forceinline__ void outputs_range(const KernelParams& P, const uint32_t (&vpre)[kMaxOutCols], const LaneCtx<QPT>& L,
-                                              const WarpOut<QPT>& wo, const uint32_t (*s_wtot)[kWarps], const uint64_t* s_excl,
-                                              const uint8_t* s_pool) {
+__device__ __forceinline__ void outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx<QPT>& L, const SharedState& sh,
+                                              uint32_t* bitstage, uint32_t* ltab, int& kb) {
   if constexpr (K < N) {
     constexpr uint64_t meta = chdb_jit::kOutMeta[K];
-    exec_output<V, QPT, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, K, meta, vpre[K], L, wo, s_wtot, s_excl, s_pool);
-    outputs_range<V, QPT, K + 1, N>(P, vpre, L, wo, s_wtot, s_excl, s_pool);
+    emit_output<V, QPT, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, C, K, meta, L, sh, bitstage, ltab, kb);
+    outputs_range<V, QPT, K + 1, N>(P, C, L, sh, bitstage, ltab, kb);
   }
 }
 #endif
 
-// Pulls one tile's slice of every input buffer towards L2 (one 128-byte line per thread).
-__device__ __forceinline__ void prefetch_tile(const KernelParams& P, int64_t row0, int32_t tile_rows, int tid) {
+// The bit stage of one tile -> global bitmaps.  Stage bit (obase & 31) + r belongs to output row
+// obase + r; whole words are stored, the (at most two) words shared with neighbouring tiles are
+// merged with atomicOr (the bitmaps are zero-initialised).  Bit array kb is written by consumer
+// warp kb % kConsumerWarps, which also zeroes it for the tile after next.
+__device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& sh, uint32_t* bitstage, uint64_t obase, uint32_t count,
+                                           int warp, int lane) {
+  const uint32_t o = (uint32_t)obase & 31u, end = o + count;
+  const uint32_t nwords = (end + 31u) >> 5;
+  const uint64_t g0 = obase >> 5;
+  int kb = 0;
   CHDB_STATIC_UNROLL
-  for (int s = 0; s < CHDB_N_IN; s++) {
-    const ColumnDesc& c = P.in[s];
-    const uint32_t ctype = CHDB_COL_TYPE(P, s);
-    const int w = ctype == T_UTF8 ? 4 : (int)CHDB_COL_WIDTH(P, s);
-    const uint8_t* v = (const uint8_t*)(ctype == T_UTF8 ? (const void*)c.offsets : c.values);
-    if (w > 0) {
-      for (int b = tid * 128; b < tile_rows * w; b += kThreads * 128) prefetch_l2(v + row0 * w + b);
-    } else if (tid < 4 && tid * 1024 < tile_rows) {
-      prefetch_l2(v + (row0 >> 3) + tid * 128);   // Boolean values: rows / 8 bytes
+  for (int k = 0; k < CHDB_N_OUT; k++) {
+    const uint64_t meta = CHDB_OUT_META(P, k);
+    const bool is_bool = ((uint32_t)(meta >> 8) & 0xFFu) == T_BOOL;
+    uint8_t* const validity = P.out[k].validity;
+#pragma unroll
+    for (int which = 0; which < 2; which++) {   // 0: Boolean values, 1: validity
+      if (which == 0 ? !is_bool : validity == nullptr) continue;
+      if (kb % kConsumerWarps == warp) {
+        uint32_t* sb = bitstage + kb * kBitWords;
+        uint32_t* g = (uint32_t*)(which == 0 ? (uint8_t*)P.out[k].values : validity);
+        uint32_t nulls = 0;
+        for (uint32_t w = lane; w < (uint32_t)kBitWords; w += 32) {
+          uint32_t word = sb[w];
+          sb[w] = 0;
+          if (w < nwords) {
+            const uint32_t lo = w == 0 ? o : 0u, hi = 32 * w + 32 > end ? end - 32 * w : 32u;
+            const uint32_t mask = (hi >= 32 ? FULL : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+            if (which == 1) { nulls += (uint32_t)__popc(word & mask); word = ~word; }
+            word &= mask;
+            if (mask == FULL) g[g0 + w] = word;
+            else if (word) atomicOr(&g[g0 + w], word);
+          }
+        }
+        if (which == 1) {
+          nulls = __reduce_add_sync(FULL, nulls);
+          if (lane == 0 && nulls) sh.nulls[k] += nulls;   // array kb is always this warp's: no race
+        }
+      }
+      kb++;
     }
-    if (c.validity != nullptr && tid >= 32 && tid < 36 && (tid - 32) * 1024 < tile_rows)
-      prefetch_l2(c.validity + (row0 >> 3) + (tid - 32) * 128);
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
 template <typename V, int QPT>
 __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
-  constexpr int R = 4 * QPT;
-  constexpr int T = kThreads * R;
-  constexpr int WR = 32 * R;                    // rows per warp slice
-  static_assert(R <= 32, "selection masks are 32-bit");
-  extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_wtot[1 + kMaxOutCols][kWarps];   // per-warp totals: [0] rows, [1 + u] bytes of Utf8 output u
-  __shared__ uint64_t s_excl[1 + kMaxOutCols];           // tile prefixes from the look-back
-  __shared__ uint8_t s_pool[kStrPoolBytes];
+  static_assert(4 * QPT <= 32, "selection masks are 32-bit");
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) SharedState sh;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
-
-  LaneCtx<QPT> L;
-  L.lane = lane;
-  L.warp = warp;
-  L.wstage_bytes = (uint32_t)P.stage_bytes;                                           // per warp
-  L.stage_s = smem_u32(smem) + warp * L.wstage_bytes;                                 // this warp's staging slice
-  L.bstage_s = smem_u32(smem) + kWarps * L.wstage_bytes + warp * kWarpBitStage;       // one byte per output row
-
-  if (tid == 0) s_tile = has_pred ? atomicAdd(P.ticket, 1u) : blockIdx.x;
-  if (tid < kStrPoolBytes) s_pool[tid] = (uint8_t)P.strpool[tid];
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const int64_t row0 = (int64_t)tile * T;
-  const int32_t tile_rows = (int32_t)(row0 + T < P.num_rows ? T : P.num_rows - row0);
-  CHDB_STAMP(0);
-
-  // ---- 0. prefetch: the tile that will start about one wave from now, so that by then its
-  //         columns wait in L2; the first wave has nobody to do that for it and fetches its own ----
-  {
-    const int64_t ahead = (int64_t)tile + P.prefetch_tiles;
-    if (P.prefetch_tiles > 0 && ahead < P.num_tiles) {
-      const int64_t r0 = ahead * T;
-      prefetch_tile(P, r0, (int32_t)(r0 + T < P.num_rows ? T : P.num_rows - r0), tid);
-    }
-    if ((int64_t)tile < P.prefetch_tiles || P.prefetch_tiles <= 0) prefetch_tile(P, row0, tile_rows, tid);
-  }
-
-  // rows of this lane: quad q covers rows  row0 + warp * WR + q * 128 + lane * 4 .. + 3
-  L.row_base = row0 + warp * WR + lane * 4;
-  L.inrange = 0;
-#pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    const int left = tile_rows - (warp * WR + q * 128 + lane * 4);
-    L.inrange |= (left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u)) << (4 * q);
-  }
-  const uint32_t inrange = L.inrange;
-
-  // ---- 1. predicate -> selection mask (one quad at a time: small register footprint) ---------
-  uint32_t sel = inrange;
-  if (has_pred) {
-    sel = 0;
-#ifdef CHDB_JIT
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-    for (int q = 0; q < QPT; q++) {
-      const int64_t qb[1] = {L.row_base + q * 128};
-      const uint32_t in4 = (inrange >> (4 * q)) & 0xFu;
-      V acc[4];
-      uint32_t accm, accv;
-#ifdef CHDB_JIT
-      run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, 0, 0, qb, in4, in4, s_pool, acc, accm, accv);
-#else
-      run_program<V, 1>(P, P.pred_begin, P.pred_end, qb, in4, in4, s_pool, acc, accm, accv);
-#endif
-      sel |= (accm & accv & in4) << (4 * q);  // NULL predicate rows are dropped (arrow-select filter)
-    }
-  }
-
-  CHDB_STAMP(1);
-  // ---- 2. rank the selected rows inside the warp; publish the warp totals --------------------
-  WarpOut<QPT> wo;
-  wo.sel = sel;
-  uint32_t warp_rows = 0;
-#pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    uint32_t tot;
-    wo.rank[q] = warp_rows + warp_excl_scan((uint32_t)__popc((sel >> (4 * q)) & 0xFu), lane, tot);
-    warp_rows += tot;
-  }
-  wo.count = warp_rows;
-  if (lane == 0) s_wtot[0][warp] = warp_rows;
-
-  // selected value bytes per Utf8 output (and a prefetch of exactly those bytes)
-  CHDB_STATIC_UNROLL
-  for (int k = 0; k < CHDB_N_OUT; k++) {
-    const uint64_t meta = CHDB_OUT_META(P, k);
-    const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
-    if (o_utf8 == 0xFFu) continue;   // uniform branch
-    const int32_t* __restrict__ off = P.in[o_slot].offsets;
-    const uint8_t* __restrict__ sv = (const uint8_t*)P.in[o_slot].values;
-    uint32_t bytes = 0;
-#pragma unroll
-    for (int q = 0; q < QPT; q++) {
-      const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
-      if (s4) {
-        const int4 a = __ldg((const int4*)(off + L.row_base + q * 128));
-        const int a4 = __ldg(off + L.row_base + q * 128 + 4);
-        if (s4 & 1u) bytes += (uint32_t)(a.y - a.x);
-        if (s4 & 2u) bytes += (uint32_t)(a.z - a.y);
-        if (s4 & 4u) bytes += (uint32_t)(a.w - a.z);
-        if (s4 & 8u) bytes += (uint32_t)(a4 - a.w);
-        const uintptr_t pa = (uintptr_t)(sv + a.x), pe = (uintptr_t)(sv + a4);
-        prefetch_l2((const void*)pa);
-        for (uintptr_t line = (pa + 128) & ~(uintptr_t)127; line < pe; line += 128) prefetch_l2((const void*)line);
-      }
-    }
-    const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
-    if (lane == 0) s_wtot[1 + o_utf8][warp] = wbytes;
-  }
-  // validity bits of the pass-through outputs: requested now, consumed after the look-back
-  uint32_t vpre[kMaxOutCols];
-  CHDB_STATIC_UNROLL
-  for (int k = 0; k < CHDB_N_OUT; k++) {
-    const uint64_t meta = CHDB_OUT_META(P, k);
-    vpre[k] = FULL;
-    if (((uint32_t)meta & 0xFFu) == OUT_PASS) vpre[k] = load_bits_all<QPT>(P.in[(uint32_t)(meta >> 24) & 0xFFu].validity, L.row_base, sel);
-  }
-  __syncthreads();
-  CHDB_STAMP(2);
-
-  // ---- 3. tile prefixes: warp qi runs the look-back for quantity qi ---------------------------
+  const uint32_t S = (uint32_t)P.n_stages;
   const int nq = 1 + CHDB_N_UTF8;
-  if (has_pred) {
-    for (int qi = warp; qi < nq; qi += kWarps) {
-      uint64_t agg = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; w++) agg += s_wtot[qi][w];
-      const uint64_t excl = lookback(P.tile_desc + (size_t)qi * P.num_tiles, tile, agg, lane);
+  uint32_t* const bitstages = (uint32_t*)(smem + (size_t)S * P.stage_bytes);          // [2][n_bits][kBitWords]
+  uint32_t* const ltab = bitstages + 2 * P.n_bits * kBitWords;                        // long-string row tables
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < S; s++) {
+      mbar_init(smem_u32(&sh.full[s]), 1);
+      mbar_init(smem_u32(&sh.empty[s]), kConsumerWarps + 1);
+      mbar_init(smem_u32(&sh.aggbar[s]), 1);
+      mbar_init(smem_u32(&sh.prebar[s]), 1);
+      sh.ctl[s].arrive = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < 256; i += kThreads) {
+    const uint32_t s = (uint32_t)i >> 4, v = (uint32_t)i & 15u;
+    uint32_t out = 0, n = 0;
+    for (int j = 0; j < 4; j++)
+      if ((s >> j) & 1u) { out |= ((v >> j) & 1u) << n; n++; }
+    sh.pext4[i] = (uint8_t)out;
+  }
+  for (int i = tid; i < kStrPoolBytes; i += kThreads) sh.pool[i] = (uint8_t)P.strpool[i];
+  for (int i = tid; i < kMaxOutCols; i += kThreads) sh.nulls[i] = 0;
+  for (int i = tid; i < 2 * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
+  __syncthreads();
+  // from here on the three roles only meet through mbarriers (and the consumers' named barrier)
+
+  if (warp == kConsumerWarps) {
+    // =============================== producer: lane s owns input slot s ===============================
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(P.ticket, 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    for (uint32_t n = 0;; n++) {
+      const uint32_t stage = n % S, ph = (n / S) & 1u;
+      mbar_wait(smem_u32(&sh.empty[stage]), ph ^ 1u);
+      TileCtl& C = sh.ctl[stage];
+      const uint32_t full = smem_u32(&sh.full[stage]);
+      if (tile >= (uint32_t)P.num_tiles) {
+        if (lane == 0) { C.tile = -1; mbar_arrive(full); }
+        break;
+      }
+      uint32_t next = 0;
+      if (lane == 0) next = atomicAdd(P.ticket, 1u);
+      const int64_t row0 = (int64_t)tile * kTileRows;
+      const uint32_t rows = (uint32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
+      uint8_t* const sg = smem + (size_t)stage * P.stage_bytes;   // generic address of the stage
+      const uint32_t ss = smem_u32(sg);
+      // what this lane copies: up to three buffers of its slot
+      const void* src[3] = {nullptr, nullptr, nullptr};
+      uint32_t dst[3] = {0, 0, 0}, nbytes[3] = {0, 0, 0};
+      const void* pf_src = nullptr;   // not staged: bulk L2 prefetch instead
+      uint32_t pf_bytes = 0;
+      if (lane < CHDB_N_IN) {
+        const ColumnDesc g = P.in[lane];
+        const StageSlot sl = P.stage[lane];
+        ColumnDesc v = g;
+        const uint32_t bit_bytes = (((rows + 7u) >> 3) + 15u) & ~15u;
+        if (g.validity != nullptr && sl.validity != kNotStaged) {
+          src[0] = g.validity + (row0 >> 3); dst[0] = ss + sl.validity; nbytes[0] = bit_bytes;
+          v.validity = sg + sl.validity - (row0 >> 3);
+        }
+        if (g.type == T_UTF8) {
+          if (sl.offsets != kNotStaged) {
+            src[1] = g.offsets + row0; dst[1] = ss + sl.offsets; nbytes[1] = ((rows + 1u) * 4u + 15u) & ~15u;
+            v.offsets = (const int32_t*)(sg + sl.offsets) - row0;
+          }
+          const uint32_t o0 = (uint32_t)g.offsets[row0], o1 = (uint32_t)g.offsets[row0 + rows];
+          const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
+          if (sl.values != kNotStaged && len <= sl.values_cap) {
+            src[2] = (const uint8_t*)g.values + lo; dst[2] = ss + sl.values; nbytes[2] = len;
+            v.values = sg + sl.values - lo;
+          } else {
+            pf_src = (const uint8_t*)g.values + lo; pf_bytes = len;
+          }
+        } else {
+          const uint32_t w = g.width;
+          const uint32_t vb = w ? (rows * w + 15u) & ~15u : bit_bytes;
+          const int64_t first = w ? row0 * (int64_t)w : (row0 >> 3);
+          if (sl.values != kNotStaged) {
+            src[2] = (const uint8_t*)g.values + first; dst[2] = ss + sl.values; nbytes[2] = vb;
+            v.values = sg + sl.values - first;
+          } else {
+            pf_src = (const uint8_t*)g.values + first; pf_bytes = vb;
+          }
+        }
+        C.cols[lane] = v;
+      }
+      const uint32_t tx = __reduce_add_sync(FULL, nbytes[0] + nbytes[1] + nbytes[2]);
       if (lane == 0) {
-        s_excl[qi] = excl;
-        if (tile == (uint32_t)P.num_tiles - 1) P.counts[qi] = excl + agg;  // totals
+        C.tile = (int32_t)tile;
+        mbar_arrive_expect_tx(full, tx);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        if (nbytes[i]) tma_load(dst[i], src[i], nbytes[i], full);
+      if (pf_bytes) tma_prefetch_l2(pf_src, pf_bytes);
+      tile = __shfl_sync(FULL, next, 0);
+    }
+    return;
+  }
+
+  if (warp == kConsumerWarps + 1) {
+    // =============================== look-back warp ===============================
+    for (uint32_t n = 0;; n++) {
+      const uint32_t stage = n % S, ph = (n / S) & 1u;
+      TileCtl& C = sh.ctl[stage];
+      mbar_wait(smem_u32(&sh.full[stage]), ph);
+      const int32_t tile = *(volatile int32_t*)&C.tile;
+      if (tile < 0) break;
+      mbar_wait(smem_u32(&sh.aggbar[stage]), ph);
+      const bool last = tile == P.num_tiles - 1;
+      if (has_pred) {
+        for (int qi = 0; qi < nq; qi++) {
+          const uint64_t agg = *(volatile uint64_t*)&C.agg[qi];
+          const uint64_t excl = lookback(P.tile_desc + (size_t)qi * P.num_tiles, (uint32_t)tile, agg, lane);
+          if (lane == 0) {
+            C.excl[qi] = excl;
+            if (last) P.counts[qi] = excl + agg;  // totals
+          }
+        }
+      } else if (lane == 0) {
+        C.excl[0] = (uint64_t)tile * kTileRows;
+        if (last) P.counts[0] = (uint64_t)P.num_rows;
+      }
+      __syncwarp();
+      if (last && has_pred) {
+        // closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
+        const uint64_t total_rows = C.excl[0] + C.agg[0];
+        for (int k = lane; k < CHDB_N_OUT; k += 32) {
+          const OutDesc& o = P.out[k];
+          if (o.utf8_index != 0xFFu) o.offsets[total_rows] = (int32_t)(C.excl[1 + o.utf8_index] + C.agg[1 + o.utf8_index]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&sh.prebar[stage]));
+        mbar_arrive(smem_u32(&sh.empty[stage]));
       }
     }
-  } else if (tid == 0) {
-    s_excl[0] = (uint64_t)row0;
-    if (tile == (uint32_t)P.num_tiles - 1) P.counts[0] = (uint64_t)P.num_rows;
+    return;
   }
-  __syncthreads();
-  CHDB_STAMP(3);
-  // from here on every warp works alone
-  uint32_t rows_before = 0, tile_count = 0;
-#pragma unroll
-  for (int w = 0; w < kWarps; w++) {
-    const uint32_t t = s_wtot[0][w];
-    if (w < warp) rows_before += t;
-    tile_count += t;
-  }
-  wo.base = s_excl[0] + rows_before;
-  if (tile == (uint32_t)P.num_tiles - 1 && tid < CHDB_N_OUT) {
-    // closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
-    const OutDesc& o = P.out[tid];
-    if (o.utf8_index != 0xFFu) {
-      uint64_t tb = s_excl[1 + o.utf8_index];
-      for (int w = 0; w < kWarps; w++) tb += s_wtot[1 + o.utf8_index][w];
-      o.offsets[s_excl[0] + tile_count] = (int32_t)tb;
-    }
-  }
-  if (wo.count == 0) return;  // warp-uniform; no block-wide barrier follows
 
-  // ---- 4. gather every output column (per warp) ------------------------------------------------
+  // =============================== consumer warps ===============================
+  // phase A of tile n: selection mask of the lane's rows; returns false when the ring has run dry
+  struct TileRegs { int32_t tile; uint32_t sel, inrange; };
+  auto phase_a = [&](uint32_t n, TileRegs& t) -> bool {
+    const uint32_t stage = n % S, ph = (n / S) & 1u;
+    TileCtl& C = sh.ctl[stage];
+    mbar_wait(smem_u32(&sh.full[stage]), ph);
+    t.tile = *(volatile int32_t*)&C.tile;
+    if (t.tile < 0) return false;
+    const int64_t row0 = (int64_t)t.tile * kTileRows;
+    const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
+    const int64_t row_base = row0 + warp * kWarpRows + lane * 4;   // quad q covers rows row_base + q * 128 .. + 3
+    uint32_t inrange = 0;
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+      const int left = tile_rows - (warp * kWarpRows + q * 128 + lane * 4);
+      inrange |= (left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u)) << (4 * q);
+    }
+    t.inrange = inrange;
+    const ColumnDesc* cols = C.cols;
+    uint32_t sel = inrange;
+    if (has_pred) {
+      sel = 0;
+#pragma unroll
+      for (int q = 0; q < QPT; q++) {
+        const int64_t qb[1] = {row_base + q * 128};
+        const uint32_t in4 = (inrange >> (4 * q)) & 0xFu;
+        V acc[4];
+        uint32_t accm, accv;
 #ifdef CHDB_JIT
-  outputs_range<V, QPT, 0, chdb_jit::kNumOut>(P, vpre, L, wo, s_wtot, s_excl, s_pool);
+        run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
+#else
+        run_program<V, 1>(P, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
+#endif
+        sel |= (accm & accv & in4) << (4 * q);  // NULL predicate rows are dropped (arrow-select filter)
+      }
+    }
+    t.sel = sel;
+    // per-warp totals: selected rows, selected value bytes per Utf8 output
+    const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel));
+    if (lane == 0) C.wtot[0][warp] = wrows;
+    CHDB_STATIC_UNROLL
+    for (int k = 0; k < CHDB_N_OUT; k++) {
+      const uint64_t meta = CHDB_OUT_META(P, k);
+      const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+      if (o_utf8 == 0xFFu) continue;   // uniform branch
+      const int32_t* off = cols[o_slot].offsets;
+      uint32_t bytes = 0;
+#pragma unroll
+      for (int q = 0; q < QPT; q++) {
+        const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
+        if (s4) {
+          const int4 a = *(const int4*)(off + row_base + q * 128);
+          const int a4 = off[row_base + q * 128 + 4];
+          if (s4 & 1u) bytes += (uint32_t)(a.y - a.x);
+          if (s4 & 2u) bytes += (uint32_t)(a.z - a.y);
+          if (s4 & 4u) bytes += (uint32_t)(a.w - a.z);
+          if (s4 & 8u) bytes += (uint32_t)(a4 - a.w);
+        }
+      }
+      const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+      if (lane == 0) C.wtot[1 + o_utf8][warp] = wbytes;
+    }
+    // the last warp to get here publishes the tile aggregate and wakes the look-back warp
+    uint32_t is_last = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      is_last = atomicAdd(&C.arrive, 1u) == (uint32_t)(kConsumerWarps - 1) ? 1u : 0u;
+      __threadfence_block();
+    }
+    is_last = __shfl_sync(FULL, is_last, 0);
+    if (is_last) {
+      if (lane < nq) {
+        uint64_t agg = 0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; w++) agg += *(volatile uint32_t*)&C.wtot[lane][w];
+        C.agg[lane] = agg;
+        if (has_pred) {
+          volatile uint64_t* d = P.tile_desc + (size_t)lane * P.num_tiles;
+          d[t.tile] = (t.tile == 0 ? kFlagPrefix : kFlagAgg) | agg;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        C.arrive = 0;
+        __threadfence();
+        mbar_arrive(smem_u32(&sh.aggbar[stage]));
+      }
+    }
+    return true;
+  };
+
+  // phase B of tile n: write every output column
+  auto phase_b = [&](uint32_t n, const TileRegs& t) {
+    const uint32_t stage = n % S, ph = (n / S) & 1u;
+    TileCtl& C = sh.ctl[stage];
+    mbar_wait(smem_u32(&sh.prebar[stage]), ph);
+    LaneCtx<QPT> L;
+    L.lane = lane;
+    L.warp = warp;
+    L.row_base = (int64_t)t.tile * kTileRows + warp * kWarpRows + lane * 4;
+    L.inrange = t.inrange;
+    L.sel = t.sel;
+    uint32_t rows_before = 0, tile_count = 0;
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; w++) {
+      const uint32_t c = C.wtot[0][w];
+      if (w < warp) rows_before += c;
+      tile_count += c;
+    }
+    L.warp_first = rows_before;
+    L.warp_count = C.wtot[0][warp];
+    L.obase = C.excl[0];
+    uint32_t run = rows_before;
+#pragma unroll
+    for (int q = 0; q < QPT; q++) {
+      uint32_t tot;
+      L.rank[q] = run + warp_excl_scan((uint32_t)__popc((t.sel >> (4 * q)) & 0xFu), lane, tot);
+      run += tot;
+    }
+    uint32_t* const bitstage = bitstages + (n & 1u) * P.n_bits * kBitWords;
+    int kb = 0;
+#ifdef CHDB_JIT
+    outputs_range<V, QPT, 0, chdb_jit::kNumOut>(P, C, L, sh, bitstage, ltab, kb);
 #else
 #pragma unroll 1
-  for (int k = 0; k < P.n_out; k++) exec_output<V, QPT>(P, k, CHDB_OUT_META(P, k), vpre[k], L, wo, s_wtot, s_excl, s_pool);
+    for (int k = 0; k < P.n_out; k++) emit_output<V, QPT>(P, C, k, CHDB_OUT_META(P, k), L, sh, bitstage, ltab, kb);
 #endif
-  CHDB_STAMP(4);
+    if (P.n_bits > 0) {
+      consumer_barrier();
+      flush_bits(P, sh, bitstage, L.obase, tile_count, warp, lane);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&sh.empty[stage]));   // this warp is done with the stage
+  };
+
+  TileRegs cur, nxt;
+  if (phase_a(0, cur)) {
+    for (uint32_t n = 0;; n++) {
+      const bool more = phase_a(n + 1, nxt);
+      phase_b(n, cur);
+      if (!more) break;
+      cur = nxt;
+    }
+  }
+  // null counts of this CTA
+  consumer_barrier();
+  if (tid < CHDB_N_OUT && P.out[tid].validity != nullptr && sh.nulls[tid] != 0)
+    atomicAdd((unsigned long long*)(P.counts + P.out[tid].count_index), (unsigned long long)sh.nulls[tid]);
 }
 
 }  // namespace

@@ -4,53 +4,102 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 #include "device_code.cuh"
 
 namespace chdb {
 
-// Per-warp staging slice: a warp's rows of the widest fixed-width output; with Utf8 outputs the rebuilt
-// offsets sit in front and the value bytes of short strings (or the long-string row tables) behind them.
-size_t filter_project_stage_bytes(int max_out_width, int64_t avg_utf8_len) {
-  const size_t rows = kTileRows / kWarps;
-  size_t stage = rows * (size_t)(max_out_width < 4 ? 4 : max_out_width) + 32;
-  if (avg_utf8_len >= 0) {
-    const size_t off_stage = rows * 4 + 16;
-    size_t strs = rows * (size_t)avg_utf8_len + 64;           // a warp slice of short strings, staged
-    if (strs > 8 * 1024) strs = 0;                            // long strings go global -> global
-    const size_t tables = (rows + 4) * 4 + rows * 4 + 16;     // ...and need the per-row tables instead
-    const size_t want = off_stage + (strs > tables ? strs : tables);
-    if (want > stage) stage = want;
+namespace {
+constexpr size_t kSmemPerSm = 228 * 1024;        // B200: 228 KB per SM, 1 KB of it reserved per resident CTA
+constexpr size_t kSmemPerCtaMax = 227 * 1024;
+inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+}  // namespace
+
+size_t filter_project_static_smem() { return sizeof(SharedState); }
+
+// Decides what is staged.  Every buffer of every slot is a candidate; when one stage of everything
+// does not leave room for a ring of at least two stages, the largest buffers are read from global
+// memory instead (the producer then prefetches their slices into L2).  Utf8 value bytes are staged
+// only when the values are short (long values are copied global -> global by whole warps).
+StagePlan plan_stages(KernelParams& kp, const int64_t* avg_utf8) {
+  struct Buf { int slot; int kind; size_t bytes; };   // kind 0: validity, 1: offsets, 2: values
+  std::vector<Buf> bufs;
+  for (int s = 0; s < kp.n_in; s++) {
+    kp.stage[s] = StageSlot{kNotStaged, kNotStaged, kNotStaged, 0};
+    const ColumnDesc& c = kp.in[s];
+    if (c.validity != nullptr) bufs.push_back({s, 0, (size_t)kTileRows / 8});
+    if (c.type == T_UTF8) {
+      bufs.push_back({s, 1, (size_t)(kTileRows + 4) * 4});
+      const int64_t avg = avg_utf8 ? avg_utf8[s] : -1;
+      if (avg >= 0 && avg <= 32) bufs.push_back({s, 2, up16((size_t)kTileRows * (size_t)avg * 5 / 4 + 64)});
+    } else {
+      bufs.push_back({s, 2, c.width ? (size_t)kTileRows * c.width : (size_t)kTileRows / 8});
+    }
   }
-  return (stage + 15) & ~(size_t)15;
+  const size_t fixed_dyn = (size_t)2 * kp.n_bits * kBitWords * 4 +
+                           (kp.long_strings ? (size_t)kConsumerWarps * 2 * (kWarpRows + 4) * 4 : 0);
+  const size_t fixed = fixed_dyn + sizeof(SharedState) + 1024;
+  auto stage_bytes = [&]() {
+    size_t t = 0;
+    for (auto& b : bufs) t += up16(b.bytes);
+    return (t + 127) & ~(size_t)127;
+  };
+  struct Shape { int ctas, stages; };
+  const Shape shapes[] = {{3, 3}, {2, 3}, {2, 2}, {1, 3}, {1, 2}};
+  Shape pick{0, 0};
+  while (true) {
+    const size_t sb = stage_bytes();
+    for (const Shape& sh : shapes) {
+      const size_t per_cta = fixed + (size_t)sh.stages * sb;
+      if (per_cta * sh.ctas <= kSmemPerSm && per_cta - 1024 <= kSmemPerCtaMax) { pick = sh; break; }
+    }
+    if (pick.ctas || bufs.empty()) break;
+    auto big = std::max_element(bufs.begin(), bufs.end(), [](const Buf& a, const Buf& b) { return a.bytes < b.bytes; });
+    bufs.erase(big);
+  }
+  if (!pick.ctas) pick = Shape{1, 2};
+  size_t off = 0;
+  for (auto& b : bufs) {
+    StageSlot& sl = kp.stage[b.slot];
+    if (b.kind == 0) sl.validity = (uint32_t)off;
+    else if (b.kind == 1) sl.offsets = (uint32_t)off;
+    else { sl.values = (uint32_t)off; sl.values_cap = (uint32_t)b.bytes; }
+    off += up16(b.bytes);
+  }
+  kp.stage_bytes = (int32_t)stage_bytes();
+  kp.n_stages = pick.stages;
+  StagePlan plan;
+  plan.dyn_smem = (size_t)pick.stages * (size_t)kp.stage_bytes + fixed_dyn;
+  plan.ctas_per_sm = pick.ctas;
+  return plan;
 }
 
-size_t filter_project_smem_bytes(size_t stage_bytes, bool has_utf8_out) {
-  (void)has_utf8_out;
-  return (size_t)kWarps * (stage_bytes + (size_t)(kTileRows / kWarps + 64));
-}
-
-cudaError_t launch_filter_project(const KernelParams& p, bool has64, size_t dyn_smem, cudaStream_t stream) {
+cudaError_t launch_filter_project(const KernelParams& p, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream) {
   auto k32 = filter_project_kernel<uint32_t, kQuadsPerThread>;
   auto k64 = filter_project_kernel<uint64_t, kQuadsPerThread>;
   auto kern = has64 ? k64 : k32;
-  if (dyn_smem > 48 * 1024) {   // opt in to the large window once per (kernel, device)
+  if (plan.dyn_smem > 40 * 1024) {   // opt in to the large window once per (kernel, device)
     static std::mutex mu;
     static std::map<std::pair<const void*, int>, size_t> granted;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> g(mu);
     size_t& have = granted[{(const void*)kern, dev}];
-    if (have < dyn_smem) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (have < plan.dyn_smem) {
+      const size_t want = kSmemPerCtaMax - sizeof(SharedState);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
       if (e != cudaSuccess) return e;
-      have = 200 * 1024;
+      have = want;
     }
   }
-  kern<<<dim3((unsigned)p.num_tiles), dim3(kThreads), dyn_smem, stream>>>(p);
+  const int64_t resident = (int64_t)plan.ctas_per_sm * sm_count;
+  const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, resident);
+  kern<<<dim3(grid), dim3(kThreads), plan.dyn_smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -9,10 +9,16 @@
 
 namespace chdb {
 
-constexpr int kThreads = 256;               // 8 warps per CTA
-constexpr int kWarps = kThreads / 32;
-constexpr int kQuadsPerThread = 4;          // each thread owns QPT groups of 4 consecutive rows
-constexpr int kTileRows = kThreads * 4 * kQuadsPerThread;   // 4096 rows per tile, 512 per warp
+// CTA = kConsumerWarps consumer warps + one TMA producer warp + one look-back warp.
+constexpr int kConsumerWarps = 4;
+constexpr int kQuadsPerThread = 1;          // each consumer thread owns QPT groups of 4 consecutive rows per tile
+constexpr int kWarpRows = 32 * 4 * kQuadsPerThread;          // rows of one warp slice
+constexpr int kTileRows = kConsumerWarps * kWarpRows;        // 512 rows per tile
+constexpr int kThreads = (kConsumerWarps + 2) * 32;
+constexpr int kMaxStages = 4;               // depth of the shared-memory input ring
+constexpr int kMaxQuantities = 1 + kMaxOutCols;              // scanned quantities: rows + bytes per Utf8 output
+constexpr int kBitWords = kTileRows / 32 + 2;                // words of one bit-packed output stage
+constexpr uint32_t kNotStaged = 0xFFFFFFFFu;
 
 struct ColumnDesc {          // one input column slot (32 bytes)
   const void* values;        // fixed width: values; Boolean: bit-packed values; Utf8: value bytes
@@ -21,6 +27,15 @@ struct ColumnDesc {          // one input column slot (32 bytes)
   uint8_t type;              // TypeId
   uint8_t width;             // bytes per value (0 for Boolean / Utf8)
   uint8_t pad[6];
+};
+
+// Where a column's slice of one tile sits inside a shared-memory stage (byte offsets from the stage
+// base, 16-byte aligned), or kNotStaged when the kernel reads that buffer from global memory.
+struct StageSlot {
+  uint32_t values;           // fixed width: kTileRows * width bytes; Boolean: kTileRows / 8; Utf8: values_cap bytes
+  uint32_t validity;         // kTileRows / 8 bytes
+  uint32_t offsets;          // Utf8: (kTileRows + 4) * 4 bytes
+  uint32_t values_cap;       // Utf8: capacity for the tile's value bytes (a tile that needs more reads them from global)
 };
 
 enum OutKind : uint8_t { OUT_PASS = 0, OUT_EXPR = 1 };
@@ -46,13 +61,15 @@ struct KernelParams {
   uint32_t* ticket;          // dynamic tile id counter (zeroed)
   uint64_t* counts;          // see above (zeroed)
   uint64_t* error_word;      // zeroed; atomicMax(~packed)
-  uint64_t* timing;          // debug (CHDB_PHASE_TIMING): 8 globaltimer stamps per tile, or nullptr
   int32_t num_tiles;
   int32_t n_in, n_out, n_utf8;
   int32_t pred_begin, pred_end;  // pred_begin == pred_end: no predicate (every row is kept)
-  int32_t stage_bytes;           // bytes of ONE warp's output staging slice in dynamic shared memory
-  int32_t prefetch_tiles;        // L2 prefetch distance in tiles (about one wave of resident CTAs)
+  int32_t n_stages;              // depth of the input ring (2 .. kMaxStages)
+  int32_t stage_bytes;           // bytes of one stage (multiple of 128)
+  int32_t n_bits;                // bit-packed outputs (Boolean values + validity bitmaps)
+  int32_t long_strings;          // 1: per-warp row tables for the chunk-centric long-string copy are allocated
   ColumnDesc in[kMaxInCols];
+  StageSlot stage[kMaxInCols];
   OutDesc out[kMaxOutCols];
   Instr instrs[kMaxInstr];
   char strpool[kStrPoolBytes];
@@ -60,11 +77,14 @@ struct KernelParams {
 static_assert(sizeof(KernelParams) <= 4096, "KernelParams must fit the 4 KB kernel parameter space");
 
 #ifndef __CUDACC_RTC__
+// Fills kp.stage[], kp.n_stages, kp.stage_bytes (needs kp.in[], kp.out[], kp.n_*): decides which
+// buffers are staged in shared memory.  avg_utf8[s]: mean value length of Utf8 slot s (or < 0).
+// Returns the dynamic shared memory the launch needs and the CTAs per SM it was sized for.
+struct StagePlan { size_t dyn_smem; int ctas_per_sm; };
+StagePlan plan_stages(KernelParams& kp, const int64_t* avg_utf8);
+size_t filter_project_static_smem();   // the kernel's static shared memory (barriers, per-stage tile control blocks)
 // has64: the program touches 64-bit types (selects the 64-bit accumulator container).
-cudaError_t launch_filter_project(const KernelParams& p, bool has64, size_t dyn_smem, cudaStream_t stream);
-// Per-warp output staging slice: 256 rows of the widest fixed-width output, or of short Utf8 values.
-size_t filter_project_stage_bytes(int max_out_width, int64_t avg_utf8_len);
-size_t filter_project_smem_bytes(size_t stage_bytes, bool has_utf8_out);
+cudaError_t launch_filter_project(const KernelParams& p, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream);
 #endif
 
 }  // namespace chdb

@@ -39,7 +39,7 @@ struct CtxCore {
   cudaStream_t stream = nullptr;
   std::atomic<int64_t> launches{0};
   std::atomic<int64_t> jit_launches{0};   // launches that ran an NVRTC-specialised kernel
-  int resident_ctas = 444;                // ~ CTAs resident at once (SMs x 3): the L2 prefetch distance
+  int sm_count = 148;                     // persistent grid = CTAs per SM x SMs
   std::mutex mu;
   std::vector<void*> pinned_free;   // small pinned blocks for count read-back
   static constexpr size_t kPinnedBlock = 1024;
@@ -688,21 +688,23 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   kp.pred_end = compact ? p.pred_end : 0;
   std::memcpy(kp.instrs, p.instrs.data(), p.instrs.size() * sizeof(Instr));
   std::memcpy(kp.strpool, p.strpool.data(), p.strpool.size());
-  const size_t stage_bytes = filter_project_stage_bytes(max_w, avg_utf8);
-  const size_t smem = filter_project_smem_bytes(stage_bytes, n_utf8 > 0);
-  kp.stage_bytes = (int32_t)stage_bytes;
-  kp.prefetch_tiles = core->resident_ctas;
+  // bit-packed outputs assembled in shared memory: Boolean values and validity bitmaps
+  kp.n_bits = 0;
+  for (int k = 0; k < ko; k++) kp.n_bits += (kp.out[k].type == T_BOOL ? 1 : 0) + (kp.out[k].validity != nullptr ? 1 : 0);
+  kp.long_strings = avg_utf8 > 16 ? 1 : 0;
+  // what is staged in shared memory: every buffer the kernel reads, budget permitting
+  int64_t slot_avg[kMaxInCols];
+  for (size_t s = 0; s < p.slot_to_col.size(); s++) {
+    const DeviceColumn& c = in->cols[p.slot_to_col[s]];
+    slot_avg[s] = c.meta.type == T_UTF8 && c.value_bytes >= 0 ? (c.value_bytes + n - 1) / n : -1;
+    // TMA bulk copies move 16-byte units
+    if ((((uintptr_t)c.values | (uintptr_t)c.validity | (uintptr_t)c.offsets) & 15u) != 0)
+      throw Error(CHDB_ERR_INVALID_ARGUMENT, "device buffers must be 16-byte aligned");
+  }
+  const StagePlan plan = plan_stages(kp, slot_avg);
 
   // Long scans run the same device code specialised for this program by NVRTC (jit.cpp); short
   // batches, or boxes without NVRTC, run the bytecode interpreter kernel.
-  // CHDB_PHASE_TIMING=1: per-tile phase stamps, summarised on stderr (debugging aid; synchronises)
-  Buf timing_buf;
-  const char* pt = std::getenv("CHDB_PHASE_TIMING");
-  if (pt && *pt == '1') {
-    timing_buf = dev_alloc(core, (size_t)num_tiles * 64);
-    CUDA_CHECK(cudaMemsetAsync(timing_buf->ptr, 0, (size_t)num_tiles * 64, core->stream));
-    kp.timing = (uint64_t*)timing_buf->ptr;
-  }
   cudaError_t le = cudaSuccess;
   const JitKernel* jk = nullptr;
   const JitMode jm = jit_mode();
@@ -711,37 +713,13 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     jk = jit_get(kp, p.has64, &why);
   }
   if (jk) {
-    le = jit_launch(jk, kp, smem, core->stream);
+    le = jit_launch(jk, kp, plan, core->sm_count, core->stream);
     core->jit_launches++;
   } else {
-    le = launch_filter_project(kp, p.has64, smem, core->stream);
+    le = launch_filter_project(kp, p.has64, plan, core->sm_count, core->stream);
   }
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
   core->launches++;
-  if (timing_buf) {
-    std::vector<uint64_t> t((size_t)num_tiles * 8);
-    CUDA_CHECK(cudaMemcpyAsync(t.data(), timing_buf->ptr, t.size() * 8, cudaMemcpyDeviceToHost, core->stream));
-    CUDA_CHECK(cudaStreamSynchronize(core->stream));
-    uint64_t t0 = ~0ull, t1 = 0;
-    double ph[4] = {0, 0, 0, 0};
-    for (int64_t i = 0; i < num_tiles; i++) {
-      const uint64_t* s = &t[(size_t)i * 8];
-      if (!s[0] || !s[4]) continue;
-      t0 = std::min(t0, s[0]);
-      t1 = std::max(t1, s[4]);
-      for (int k = 0; k < 4; k++) ph[k] += (double)(s[k + 1] - s[k]);
-    }
-    std::fprintf(stderr, "[chdb timing] %lld tiles, kernel span %.1f us; mean per tile: predicate %.2f us, rank+barrier %.2f us, "
-                 "look-back+barrier %.2f us, gather %.2f us\n", (long long)num_tiles, (t1 - t0) / 1e3, ph[0] / num_tiles / 1e3,
-                 ph[1] / num_tiles / 1e3, ph[2] / num_tiles / 1e3, ph[3] / num_tiles / 1e3);
-    // start-time profile of the first tiles and of one wave later
-    for (int64_t i : {(int64_t)0, (int64_t)1, (int64_t)100, (int64_t)443, (int64_t)444, (int64_t)600, num_tiles - 1})
-      if (i >= 0 && i < num_tiles) {
-        const uint64_t* s = &t[(size_t)i * 8];
-        std::fprintf(stderr, "[chdb timing]   tile %lld: start +%.1f us, pred %.1f, rank %.1f, lookback %.1f, gather %.1f\n", (long long)i,
-                     (s[0] - t0) / 1e3, (s[1] - s[0]) / 1e3, (s[2] - s[1]) / 1e3, (s[3] - s[2]) / 1e3, (s[4] - s[3]) / 1e3);
-      }
-  }
   CUDA_CHECK(cudaMemcpyAsync(res->host, ws, (size_t)(n_counts + 1) * 8, cudaMemcpyDeviceToHost, core->stream));
   CUDA_CHECK(cudaEventRecord(res->done, core->stream));
   out->result = res;
@@ -828,7 +806,7 @@ int32_t chdb_ctx_create(int32_t device, chdb_ctx** out, chdb_status* st) {
     core->device = device;
     CUDA_CHECK(cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking));
     int sms = 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) core->resident_ctas = 3 * sms;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) core->sm_count = sms;
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;   // keep freed blocks cached: steady-state batches never hit cudaMalloc
