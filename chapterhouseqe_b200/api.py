@@ -49,7 +49,8 @@ _ArrowArray._fields_ = [("length", ctypes.c_int64), ("null_count", ctypes.c_int6
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libchdb_gpu.so")
+    # CHDB_LIB: an alternative build of the same library (kernel-shape experiments)
+    return os.environ.get("CHDB_LIB") or os.path.join(_HERE, "libchdb_gpu.so")
 
 
 def load_library():

@@ -793,43 +793,93 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 // warps).  Tiles are numbered by an atomic ticket, so every predecessor is resident or finished and
 // publishes its aggregate without waiting for anybody: the spin always terminates.
 constexpr uint64_t kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
+// Aggregates are published with a fire-and-forget red.max: {PREFIX | v} > {AGG | v} > 0 as unsigned
+// numbers, so a descriptor can only move forward whatever order the updates reach L2 in, and the
+// publisher needs no fence (the word carries its own flag; nothing else is read through it).
+__device__ __forceinline__ void publish_aggregate(uint64_t* d, bool first_tile, uint64_t agg) {
+  const uint64_t v = (first_tile ? kFlagPrefix : kFlagAgg) | agg;
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(d), "l"(v) : "memory");
+}
+// Descriptor loads are relaxed, gpu-scope loads served by L2.  (Not `volatile`: strong system-scope loads
+// complete one at a time, which turned a 16-load hop into sixteen L2 round trips.)
+__device__ __forceinline__ uint64_t load_descriptor(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 constexpr int kLookBackPerLane = 8;   // 256 predecessors per hop, all loads of a hop in flight together
-__device__ __forceinline__ uint64_t lookback(uint64_t* desc, uint32_t tile, uint64_t agg, int lane) {
-  volatile uint64_t* d = desc;
-  if (tile == 0) return 0;
-  uint64_t excl = 0;
+// NQ quantities (separate descriptor arrays, num_tiles apart) are walked together, so the L2 round
+// trips of a hop are paid once.
+template <int NQ>
+__device__ __forceinline__ void lookback(uint64_t* desc, size_t num_tiles, uint32_t tile, const uint64_t (&agg)[NQ], int lane,
+                                         uint64_t (&excl)[NQ], uint64_t* timing) {
+#pragma unroll
+  for (int qi = 0; qi < NQ; qi++) excl[qi] = 0;
+  if (tile == 0) return;
+  uint64_t* d = desc;
+  bool done[NQ];
+#pragma unroll
+  for (int qi = 0; qi < NQ; qi++) done[qi] = false;
   int64_t base = (int64_t)tile - 1;
+  uint32_t dbg_hops = 0, dbg_spins = 0;
+  long long dbg_t0 = clock64(), dbg_load = 0;
   while (true) {
+    dbg_hops++;
+    const long long dbg_h0 = clock64();
     // each lane inspects kLookBackPerLane consecutive predecessors (nearest first)
-    uint64_t v[kLookBackPerLane];
+    uint64_t v[NQ][kLookBackPerLane];
 #pragma unroll
-    for (int j = 0; j < kLookBackPerLane; j++) {
-      const int64_t idx = base - (lane * kLookBackPerLane + j);
-      v[j] = 2ull << 62;   // tiles "before 0" contribute an inclusive prefix of 0
-      if (idx >= 0) v[j] = d[idx];
-    }
-    uint64_t part = 0;
-    bool found = false;
+    for (int qi = 0; qi < NQ; qi++) {
 #pragma unroll
-    for (int j = 0; j < kLookBackPerLane; j++) {
-      if (!found) {
+      for (int j = 0; j < kLookBackPerLane; j++) {
         const int64_t idx = base - (lane * kLookBackPerLane + j);
-        while ((v[j] >> 62) == 0) v[j] = d[idx];
-        part += v[j] & kValueMask;
-        found = (v[j] >> 62) == 2;
+        v[qi][j] = 2ull << 62;   // tiles "before 0" contribute an inclusive prefix of 0
+        if (idx >= 0 && !done[qi]) v[qi][j] = load_descriptor(d + (size_t)qi * num_tiles + idx);
       }
     }
-    const uint32_t pm = __ballot_sync(FULL, found);
-    if (pm) {
-      const int first = __ffs(pm) - 1;  // lane holding the nearest predecessor that already knows its prefix
-      excl += warp_sum64(lane <= first ? part : 0);
-      break;
+    if (timing != nullptr) { dbg_load += (long long)(v[0][0] & 1) + (long long)(v[NQ - 1][kLookBackPerLane - 1] & 1) + clock64() - dbg_h0; }
+    bool all_done = true;
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) {
+      if (done[qi]) continue;   // warp-uniform
+      uint64_t part = 0;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < kLookBackPerLane; j++) {
+        if (!found) {
+          const int64_t idx = base - (lane * kLookBackPerLane + j);
+          while ((v[qi][j] >> 62) == 0) { dbg_spins++; __nanosleep(40); v[qi][j] = load_descriptor(d + (size_t)qi * num_tiles + idx); }
+          part += v[qi][j] & kValueMask;
+          found = (v[qi][j] >> 62) == 2;
+        }
+      }
+      const uint32_t pm = __ballot_sync(FULL, found);
+      if (pm) {
+        const int first = __ffs(pm) - 1;  // lane holding the nearest predecessor that already knows its prefix
+        excl[qi] += warp_sum64(lane <= first ? part : 0);
+        done[qi] = true;
+      } else {
+        excl[qi] += warp_sum64(part);
+        all_done = false;
+      }
     }
-    excl += warp_sum64(part);
+    if (all_done) break;
     base -= 32 * kLookBackPerLane;
   }
-  if (lane == 0) d[tile] = kFlagPrefix | (excl + agg);
-  return excl;
+  if (lane == 0) {
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++)
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(d + (size_t)qi * num_tiles + tile), "l"(kFlagPrefix | (excl[qi] + agg[qi])) : "memory");
+  }
+  if (timing != nullptr) {   // debugging aid: hops and spin iterations (max over lanes) per walk
+    const uint32_t ms = __reduce_max_sync(FULL, dbg_spins);
+    if (lane == 0) {
+      atomicAdd((unsigned long long*)&timing[6], (unsigned long long)dbg_hops);
+      atomicAdd((unsigned long long*)&timing[7], (unsigned long long)ms);
+      atomicAdd((unsigned long long*)&timing[14], (unsigned long long)dbg_load);
+      atomicAdd((unsigned long long*)&timing[15], (unsigned long long)(clock64() - dbg_t0));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -847,16 +897,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the waiting warp until the phase completes (or ~10 ms
+// pass) instead of returning after the short default limit: waiting warps then cost no issue slots
+// and no shared-memory pipeline traffic.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
+      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 // global -> shared bulk copy (TMA, 1-D); dst, src and bytes are multiples of 16
 __device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar) {
@@ -866,14 +919,32 @@ __device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32
 __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void consumer_barrier() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+// named barriers: 1 + g for writer group g, 15 for all writer warps
+__device__ __forceinline__ void group_barrier(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kConsumerWarps * 32) : "memory");
 }
+__device__ __forceinline__ void writers_barrier() {
+  asm volatile("bar.sync 15, %0;" ::"n"(kWriterWarps * 32) : "memory");
+}
+
+// Role profile (debugging aid, CHDB_PHASE_TIMING=1): lane 0 of every warp accumulates the cycles it
+// spends in each phase and adds them to P.timing[] when it leaves.
+struct PhaseClock {
+  long long t, acc[4];
+  bool on;
+  __device__ __forceinline__ void start(bool enabled) { on = enabled; acc[0] = acc[1] = acc[2] = acc[3] = 0; if (on) t = clock64(); }
+  __device__ __forceinline__ void lap(int i) { if (on) { const long long now = clock64(); acc[i] += now - t; t = now; } }
+  __device__ __forceinline__ void flush(uint64_t* timing, int base, int lane) {
+    if (on && lane == 0)
+      for (int i = 0; i < 4; i++) atomicAdd((unsigned long long*)&timing[base + i], (unsigned long long)acc[i]);
+  }
+};
 
 // Everything one tile needs besides its staged bytes; one per stage of the ring.
 struct TileCtl {
   int32_t tile;                                   // ticket, or -1: no more tiles
-  uint32_t arrive;                                // consumer warps that finished phase A
+  uint32_t arrive;                                // selector warps that finished their slice
+  uint8_t sel[kConsumerWarps][32];                // selection nibble of (slice, lane): its 4 rows
   uint32_t wtot[kMaxQuantities][kConsumerWarps];  // per-warp totals: [0] rows, [1 + u] bytes of Utf8 output u
   uint64_t agg[kMaxQuantities];                   // tile totals
   uint64_t excl[kMaxQuantities];                  // exclusive prefixes from the look-back
@@ -901,7 +972,8 @@ struct LaneCtx {
   uint64_t obase;         // output row of the tile's first selected row
   uint32_t warp_first;    // tile-local rank of the warp's first selected row
   uint32_t warp_count;    // selected rows of this warp
-  int lane, warp;
+  int lane, warp;         // warp: slice of the tile this warp owns
+  int wid;                // writer warp index in the CTA (its private long-string tables)
 };
 
 // Drops the selected bits of the lane's rows into the tile's bit stage (zero-initialised): bit for
@@ -1032,12 +1104,58 @@ __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, u
   }
 }
 
-// Writes output column k for this lane's rows.  `meta` packs the eight small OutDesc fields; under
-// CHDB_JIT it is a compile-time constant and BEGIN/END carry the expression's instruction range.
-// kb: running index of the bit-packed outputs (Boolean values, validity bitmaps) in the bit stage.
+// Phase B handles an output column in two steps so that, with the program known at compile time
+// (CHDB_JIT), the loads of ALL pass-through columns are issued before the first store: the
+// shared-memory latencies overlap instead of adding up column by column.
+struct OutRegs {
+  uint4 x, y;        // the lane's 4 values (widths 1..8), or x = 4 Utf8 offsets
+  uint32_t z;        // 5th Utf8 offset, or Boolean value bits
+  uint32_t vbits;    // validity bits of the lane's rows
+};
+
+// `meta` packs the eight small OutDesc fields; under CHDB_JIT it is a compile-time constant.
+template <int QPT>
+__device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
+                                            const LaneCtx<QPT>& L, OutRegs& R) {
+  const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
+  const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+  R.x = make_uint4(0, 0, 0, 0);
+  R.y = make_uint4(0, 0, 0, 0);
+  R.z = 0;
+  R.vbits = FULL;
+  if (o_kind != OUT_PASS) return;
+  const ColumnDesc& c = C.cols[o_slot];
+  const uint32_t sel = L.sel;
+  const int64_t r = L.row_base;
+  if (P.out[k].validity != nullptr) R.vbits = load_bits_all<QPT>(c.validity, r, sel);
+  if (!sel) return;
+  const uint8_t* src = (const uint8_t*)c.values;
+  if (o_type == T_BOOL) {
+    R.z = load_bits_all<QPT>(src, r, sel);
+  } else if (o_type == T_UTF8) {
+    const int4 a = *(const int4*)(c.offsets + r);
+    R.x = make_uint4((uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w);
+    R.z = (uint32_t)c.offsets[r + 4];
+  } else if (o_width == 4) {
+    R.x = *(const uint4*)(src + r * 4);
+  } else if (o_width == 8) {
+    R.x = *(const uint4*)(src + r * 8);
+    R.y = *(const uint4*)(src + r * 8 + 16);
+  } else if (o_width == 2) {
+    const uint2 t = *(const uint2*)(src + r * 2);
+    R.x.x = t.x; R.x.y = t.y;
+  } else if (o_width == 1) {
+    R.x.x = *(const uint32_t*)(src + r);
+  }
+}
+
+// Writes output column k for this lane's rows.  BEGIN/END: the expression's instruction range when known at
+// compile time.  kb: running index of the bit-packed outputs (Boolean values, validity bitmaps) in the bit stage.
 template <typename V, int QPT, int BEGIN = -1, int END = -1>
-__device__ __forceinline__ void emit_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
-                                            const LaneCtx<QPT>& L, const SharedState& sh, uint32_t* bitstage, uint32_t* ltab, int& kb) {
+__device__ __forceinline__ void store_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
+                                             const LaneCtx<QPT>& L, const OutRegs& R, const SharedState& sh, uint32_t* bitstage,
+                                             uint32_t* ltab, int& kb) {
+  static_assert(QPT == 1, "one quad per writer thread");
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
   const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu;
@@ -1046,39 +1164,30 @@ __device__ __forceinline__ void emit_output(const KernelParams& P, const TileCtl
   const uint32_t sel = L.sel;
   const int lane = L.lane;
   const ColumnDesc* cols = C.cols;
-  uint32_t vbits = FULL;  // validity of this output for the lane's rows
+  const uint64_t o = L.obase + L.rank[0];   // output row of the lane's first selected row
+  uint32_t vbits = R.vbits;  // validity of this output for the lane's rows
   if (o_kind == OUT_EXPR) {
     uint32_t accm = 0;
     vbits = 0;
-#pragma unroll
-    for (int q = 0; q < QPT; q++) {
-      const uint32_t in4 = (L.inrange >> (4 * q)) & 0xFu, sel4 = (sel >> (4 * q)) & 0xFu;
-      if (!sel4) continue;
-      const int64_t qb[1] = {L.row_base + q * 128};
+    if (sel) {
+      const int64_t qb[1] = {L.row_base};
       V a4[4];
-      uint32_t m4, v4;
       // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
-      run_program<V, 1, BEGIN, END>(P, cols, (int)o_begin, (int)o_end, qb, in4, sel4, sh.pool, a4, m4, v4);
-      accm |= (m4 & 0xFu) << (4 * q);
-      vbits |= (v4 & 0xFu) << (4 * q);
-      const uint64_t o = L.obase + L.rank[q];
-      if (o_type == T_BOOL) continue;
-      if (o_width == 4) store_sel<uint32_t>((uint32_t*)o_values + o, sel4, (uint32_t)a4[0], (uint32_t)a4[1], (uint32_t)a4[2], (uint32_t)a4[3]);
-      else if (o_width == 8) store_sel<uint64_t>((uint64_t*)o_values + o, sel4, (uint64_t)a4[0], (uint64_t)a4[1], (uint64_t)a4[2], (uint64_t)a4[3]);
-      else if (o_width == 2) store_sel<uint16_t>((uint16_t*)o_values + o, sel4, (uint16_t)a4[0], (uint16_t)a4[1], (uint16_t)a4[2], (uint16_t)a4[3]);
-      else store_sel<uint8_t>((uint8_t*)o_values + o, sel4, (uint8_t)a4[0], (uint8_t)a4[1], (uint8_t)a4[2], (uint8_t)a4[3]);
+      run_program<V, 1, BEGIN, END>(P, cols, (int)o_begin, (int)o_end, qb, L.inrange, sel, sh.pool, a4, accm, vbits);
+      if (o_type == T_BOOL) {}
+      else if (o_width == 4) store_sel<uint32_t>((uint32_t*)o_values + o, sel, (uint32_t)a4[0], (uint32_t)a4[1], (uint32_t)a4[2], (uint32_t)a4[3]);
+      else if (o_width == 8) store_sel<uint64_t>((uint64_t*)o_values + o, sel, (uint64_t)a4[0], (uint64_t)a4[1], (uint64_t)a4[2], (uint64_t)a4[3]);
+      else if (o_width == 2) store_sel<uint16_t>((uint16_t*)o_values + o, sel, (uint16_t)a4[0], (uint16_t)a4[1], (uint16_t)a4[2], (uint16_t)a4[3]);
+      else store_sel<uint8_t>((uint8_t*)o_values + o, sel, (uint8_t)a4[0], (uint8_t)a4[1], (uint8_t)a4[2], (uint8_t)a4[3]);
     }
     if (o_type == T_BOOL) { put_bits<QPT>(accm, L, bitstage + kb * kBitWords, sh.pext4); kb++; }
   } else {
     const ColumnDesc& c = cols[o_slot];
-    if (o_has_validity) vbits = load_bits_all<QPT>(c.validity, L.row_base, sel);
     if (o_type == T_BOOL) {
-      const uint32_t vals = load_bits_all<QPT>((const uint8_t*)c.values, L.row_base, sel);
-      put_bits<QPT>(vals, L, bitstage + kb * kBitWords, sh.pext4);
+      put_bits<QPT>(R.z, L, bitstage + kb * kBitWords, sh.pext4);
       kb++;
     } else if (o_type == T_UTF8) {
       // offsets: running sum of the selected lengths, restarted at 0 for the output
-      const int32_t* off = c.offsets;
       const uint8_t* sv = (const uint8_t*)c.values;
       uint32_t bytes_before = 0;
 #pragma unroll
@@ -1089,35 +1198,24 @@ __device__ __forceinline__ void emit_output(const KernelParams& P, const TileCtl
       int32_t* const o_off = P.out[k].offsets;
       // long values are copied by the whole warp, chunk-centric; short ones by the lane that owns the row
       const bool chunked = P.long_strings != 0 && warp_bytes > 24u * L.warp_count;
-      uint32_t* s_oo = ltab + L.warp * (2 * (kWarpRows + 4));
+      uint32_t* s_oo = ltab + L.wid * (2 * (kWarpRows + 4));
       int32_t* s_src = (int32_t*)(s_oo + kWarpRows + 4);
-      uint32_t run = 0;   // bytes of the quads handled so far
+      const int32_t o5[5] = {(int32_t)R.x.x, (int32_t)R.x.y, (int32_t)R.x.z, (int32_t)R.x.w, (int32_t)R.z};
+      uint32_t len[4];
 #pragma unroll
-      for (int q = 0; q < QPT; q++) {
-        const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
-        int32_t o5[5] = {0, 0, 0, 0, 0};
-        if (s4) {
-          const int4 a = *(const int4*)(off + L.row_base + q * 128);
-          o5[0] = a.x; o5[1] = a.y; o5[2] = a.z; o5[3] = a.w;
-          o5[4] = off[L.row_base + q * 128 + 4];
-        }
-        uint32_t len[4];
+      for (int i = 0; i < 4; i++) len[i] = ((sel >> i) & 1u) ? (uint32_t)(o5[i + 1] - o5[i]) : 0u;
+      uint32_t tot;
+      uint32_t bo = warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, tot);   // warp-local output byte offset
+      int32_t* d = o_off + o;
+      uint32_t wr = L.rank[0] - L.warp_first;   // warp-local rank
 #pragma unroll
-        for (int i = 0; i < 4; i++) len[i] = ((s4 >> i) & 1u) ? (uint32_t)(o5[i + 1] - o5[i]) : 0u;
-        uint32_t tot;
-        uint32_t bo = run + warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, tot);   // warp-local output byte offset
-        run += tot;
-        int32_t* d = o_off + (L.obase + L.rank[q]);
-        uint32_t wr = L.rank[q] - L.warp_first;   // warp-local rank
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if ((s4 >> i) & 1u) {
-            *d = (int32_t)(uint32_t)(warp_byte_base + bo);
-            d++;
-            if (chunked) { s_oo[wr] = bo; s_src[wr] = o5[i]; wr++; }
-            else if (len[i]) copy_value(o_values + warp_byte_base + bo, sv + o5[i], len[i]);
-            bo += len[i];
-          }
+      for (int i = 0; i < 4; i++) {
+        if ((sel >> i) & 1u) {
+          *d = (int32_t)(uint32_t)(warp_byte_base + bo);
+          d++;
+          if (chunked) { s_oo[wr] = bo; s_src[wr] = o5[i]; wr++; }
+          else if (len[i]) copy_value(o_values + warp_byte_base + bo, sv + o5[i], len[i]);
+          bo += len[i];
         }
       }
       if (chunked) {
@@ -1127,33 +1225,23 @@ __device__ __forceinline__ void emit_output(const KernelParams& P, const TileCtl
         copy_long_strings(sv, o_values + (warp_byte_base - mis), mis, warp_bytes, L.warp_count, s_oo, s_src, lane);
         __syncwarp();
       }
-    } else {
+    } else if (sel) {
+      if (o_width == 4) {
+        store_sel<uint32_t>((uint32_t*)o_values + o, sel, R.x.x, R.x.y, R.x.z, R.x.w);
+      } else if (o_width == 8) {
+        store_sel<uint2>((uint2*)o_values + o, sel, make_uint2(R.x.x, R.x.y), make_uint2(R.x.z, R.x.w), make_uint2(R.y.x, R.y.y),
+                         make_uint2(R.y.z, R.y.w));
+      } else if (o_width == 16) {
+        const uint4* s16 = (const uint4*)c.values + L.row_base;
+        uint4* d = (uint4*)o_values + o;
 #pragma unroll
-      for (int q = 0; q < QPT; q++) {
-        const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
-        if (!s4) continue;
-        const int64_t r = L.row_base + q * 128;
-        const uint64_t o = L.obase + L.rank[q];
-        const uint8_t* src = (const uint8_t*)c.values;
-        if (o_width == 4) {
-          const uint4 x = *(const uint4*)(src + r * 4);
-          store_sel<uint32_t>((uint32_t*)o_values + o, s4, x.x, x.y, x.z, x.w);
-        } else if (o_width == 8) {
-          const uint4 x = *(const uint4*)(src + r * 8), y = *(const uint4*)(src + r * 8 + 16);
-          store_sel<uint2>((uint2*)o_values + o, s4, make_uint2(x.x, x.y), make_uint2(x.z, x.w), make_uint2(y.x, y.y), make_uint2(y.z, y.w));
-        } else if (o_width == 16) {
-          const uint4* s16 = (const uint4*)src + r;
-          uint4* d = (uint4*)o_values + o;
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            if ((s4 >> i) & 1u) { *d = s16[i]; d++; }
-        } else if (o_width == 2) {
-          const uint2 x = *(const uint2*)(src + r * 2);
-          store_sel<uint16_t>((uint16_t*)o_values + o, s4, (uint16_t)x.x, (uint16_t)(x.x >> 16), (uint16_t)x.y, (uint16_t)(x.y >> 16));
-        } else {
-          const uint32_t x = *(const uint32_t*)(src + r);
-          store_sel<uint8_t>(o_values + o, s4, (uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24));
-        }
+        for (int i = 0; i < 4; i++)
+          if ((sel >> i) & 1u) { *d = s16[i]; d++; }
+      } else if (o_width == 2) {
+        store_sel<uint16_t>((uint16_t*)o_values + o, sel, (uint16_t)R.x.x, (uint16_t)(R.x.x >> 16), (uint16_t)R.x.y, (uint16_t)(R.x.y >> 16));
+      } else {
+        const uint32_t x = R.x.x;
+        store_sel<uint8_t>(o_values + o, sel, (uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24));
       }
     }
   }
@@ -1165,21 +1253,28 @@ __device__ __forceinline__ void emit_output(const KernelParams& P, const TileCtl
 }
 
 #ifdef CHDB_JIT
+template <int QPT, int K, int N>
+__device__ __forceinline__ void load_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx<QPT>& L, OutRegs (&R)[N > 0 ? N : 1]) {
+  if constexpr (K < N) {
+    load_output<QPT>(P, C, K, chdb_jit::kOutMeta[K], L, R[K]);
+    load_outputs_range<QPT, K + 1, N>(P, C, L, R);
+  }
+}
 template <typename V, int QPT, int K, int N>
-__device__ __forceinline__ void outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx<QPT>& L, const SharedState& sh,
-                                              uint32_t* bitstage, uint32_t* ltab, int& kb) {
+__device__ __forceinline__ void store_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx<QPT>& L, const OutRegs (&R)[N > 0 ? N : 1],
+                                                    const SharedState& sh, uint32_t* bitstage, uint32_t* ltab, int& kb) {
   if constexpr (K < N) {
     constexpr uint64_t meta = chdb_jit::kOutMeta[K];
-    emit_output<V, QPT, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, C, K, meta, L, sh, bitstage, ltab, kb);
-    outputs_range<V, QPT, K + 1, N>(P, C, L, sh, bitstage, ltab, kb);
+    store_output<V, QPT, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, C, K, meta, L, R[K], sh, bitstage, ltab, kb);
+    store_outputs_range<V, QPT, K + 1, N>(P, C, L, R, sh, bitstage, ltab, kb);
   }
 }
 #endif
 
 // The bit stage of one tile -> global bitmaps.  Stage bit (obase & 31) + r belongs to output row
 // obase + r; whole words are stored, the (at most two) words shared with neighbouring tiles are
-// merged with atomicOr (the bitmaps are zero-initialised).  Bit array kb is written by consumer
-// warp kb % kConsumerWarps, which also zeroes it for the tile after next.
+// merged with atomicOr (the bitmaps are zero-initialised).  Bit array kb is written by the group's
+// warp kb % kConsumerWarps, which also zeroes it for the group's tile after next.
 __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& sh, uint32_t* bitstage, uint64_t obase, uint32_t count,
                                            int warp, int lane) {
   const uint32_t o = (uint32_t)obase & 31u, end = o + count;
@@ -1212,7 +1307,7 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& s
         }
         if (which == 1) {
           nulls = __reduce_add_sync(FULL, nulls);
-          if (lane == 0 && nulls) sh.nulls[k] += nulls;   // array kb is always this warp's: no race
+          if (lane == 0 && nulls) atomicAdd(&sh.nulls[k], nulls);
         }
       }
       kb++;
@@ -1225,7 +1320,7 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& s
 // ------------------------------------------------------------------------------------------
 template <typename V, int QPT>
 __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
-  static_assert(4 * QPT <= 32, "selection masks are 32-bit");
+  static_assert(QPT == 1, "one quad per writer thread");
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(16) SharedState sh;
 
@@ -1233,14 +1328,15 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
   const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
   const uint32_t S = (uint32_t)P.n_stages;
   const int nq = 1 + CHDB_N_UTF8;
-  uint32_t* const bitstages = (uint32_t*)(smem + (size_t)S * P.stage_bytes);          // [2][n_bits][kBitWords]
-  uint32_t* const ltab = bitstages + 2 * P.n_bits * kBitWords;                        // long-string row tables
+  // dynamic shared memory: the stage ring | bit stages [group][2][n_bits][kBitWords] | long-string row tables
+  uint32_t* const bitstages = (uint32_t*)(smem + (size_t)S * P.stage_bytes);
+  uint32_t* const ltab = bitstages + kWriterGroups * 2 * P.n_bits * kBitWords;
 
   if (tid == 0) {
     for (uint32_t s = 0; s < S; s++) {
       mbar_init(smem_u32(&sh.full[s]), 1);
-      mbar_init(smem_u32(&sh.empty[s]), kConsumerWarps + 1);
-      mbar_init(smem_u32(&sh.aggbar[s]), 1);
+      mbar_init(smem_u32(&sh.empty[s]), kConsumerWarps);
+      mbar_init(smem_u32(&sh.aggbar[s]), kConsumerWarps);
       mbar_init(smem_u32(&sh.prebar[s]), 1);
       sh.ctl[s].arrive = 0;
     }
@@ -1256,26 +1352,32 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
   }
   for (int i = tid; i < kStrPoolBytes; i += kThreads) sh.pool[i] = (uint8_t)P.strpool[i];
   for (int i = tid; i < kMaxOutCols; i += kThreads) sh.nulls[i] = 0;
-  for (int i = tid; i < 2 * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
+  for (int i = tid; i < kWriterGroups * 2 * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
   __syncthreads();
-  // from here on the three roles only meet through mbarriers (and the consumers' named barrier)
+  // from here on the roles only meet through mbarriers (and the writers' named barriers)
 
-  if (warp == kConsumerWarps) {
+  if (warp == kWriterWarps + kConsumerWarps) {
     // =============================== producer: lane s owns input slot s ===============================
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(P.ticket, 1u);
-    tile = __shfl_sync(FULL, tile, 0);
+    PhaseClock pc;   // [8] wait for a free stage, [9] ticket + addresses + boundary offsets, [10] issue
+    pc.start(P.timing != nullptr);
+    uint32_t sentinels = 0;
     for (uint32_t n = 0;; n++) {
       const uint32_t stage = n % S, ph = (n / S) & 1u;
       mbar_wait(smem_u32(&sh.empty[stage]), ph ^ 1u);
+      pc.lap(0);
       TileCtl& C = sh.ctl[stage];
       const uint32_t full = smem_u32(&sh.full[stage]);
-      if (tile >= (uint32_t)P.num_tiles) {
+      // The ticket is taken only now that the tile can start loading at once: a tile that holds a
+      // ticket but has not published its aggregate stalls the look-back of every later tile.
+      uint32_t tile = 0;
+      if (lane == 0 && sentinels == 0) tile = atomicAdd(P.ticket, 1u);
+      tile = __shfl_sync(FULL, tile, 0);
+      if (sentinels != 0 || tile >= (uint32_t)P.num_tiles) {
+        // out of tiles: every writer group and every look-back warp must meet a stage that says so
         if (lane == 0) { C.tile = -1; mbar_arrive(full); }
-        break;
+        if (++sentinels == (uint32_t)(kWriterGroups > kLookbackWarps ? kWriterGroups : kLookbackWarps)) { pc.flush(P.timing, 8, lane); break; }
+        continue;
       }
-      uint32_t next = 0;
-      if (lane == 0) next = atomicAdd(P.ticket, 1u);
       const int64_t row0 = (int64_t)tile * kTileRows;
       const uint32_t rows = (uint32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
       uint8_t* const sg = smem + (size_t)stage * P.stage_bytes;   // generic address of the stage
@@ -1321,6 +1423,7 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
         C.cols[lane] = v;
       }
       const uint32_t tx = __reduce_add_sync(FULL, nbytes[0] + nbytes[1] + nbytes[2]);
+      pc.lap(1);
       if (lane == 0) {
         C.tile = (int32_t)tile;
         mbar_arrive_expect_tx(full, tx);
@@ -1330,28 +1433,45 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
       for (int i = 0; i < 3; i++)
         if (nbytes[i]) tma_load(dst[i], src[i], nbytes[i], full);
       if (pf_bytes) tma_prefetch_l2(pf_src, pf_bytes);
-      tile = __shfl_sync(FULL, next, 0);
+      pc.lap(2);
     }
     return;
   }
 
-  if (warp == kConsumerWarps + 1) {
-    // =============================== look-back warp ===============================
-    for (uint32_t n = 0;; n++) {
+  if (warp > kWriterWarps + kConsumerWarps) {
+    // =============================== look-back warps ===============================
+    // An L2 round trip takes a few microseconds while the memory system is busy streaming tiles, longer
+    // than a tile period: several walks are kept in flight, one per look-back warp.
+    PhaseClock pc;   // [4] wait for the tile's aggregate, [5] look-back
+    pc.start(P.timing != nullptr);
+    for (uint32_t n = (uint32_t)(warp - (kWriterWarps + kConsumerWarps + 1));; n += kLookbackWarps) {
       const uint32_t stage = n % S, ph = (n / S) & 1u;
       TileCtl& C = sh.ctl[stage];
       mbar_wait(smem_u32(&sh.full[stage]), ph);
       const int32_t tile = *(volatile int32_t*)&C.tile;
-      if (tile < 0) break;
+      if (tile < 0) { pc.flush(P.timing, 4, lane); break; }
       mbar_wait(smem_u32(&sh.aggbar[stage]), ph);
+      pc.lap(0);
       const bool last = tile == P.num_tiles - 1;
       if (has_pred) {
-        for (int qi = 0; qi < nq; qi++) {
-          const uint64_t agg = *(volatile uint64_t*)&C.agg[qi];
-          const uint64_t excl = lookback(P.tile_desc + (size_t)qi * P.num_tiles, (uint32_t)tile, agg, lane);
+        int qi = 0;
+        for (; qi + 2 <= nq; qi += 2) {   // two quantities per walk
+          const uint64_t agg[2] = {*(volatile uint64_t*)&C.agg[qi], *(volatile uint64_t*)&C.agg[qi + 1]};
+          uint64_t excl[2];
+          lookback<2>(P.tile_desc + (size_t)qi * P.num_tiles, (size_t)P.num_tiles, (uint32_t)tile, agg, lane, excl, P.timing);
           if (lane == 0) {
-            C.excl[qi] = excl;
-            if (last) P.counts[qi] = excl + agg;  // totals
+            C.excl[qi] = excl[0];
+            C.excl[qi + 1] = excl[1];
+            if (last) { P.counts[qi] = excl[0] + agg[0]; P.counts[qi + 1] = excl[1] + agg[1]; }  // totals
+          }
+        }
+        if (qi < nq) {
+          const uint64_t agg[1] = {*(volatile uint64_t*)&C.agg[qi]};
+          uint64_t excl[1];
+          lookback<1>(P.tile_desc + (size_t)qi * P.num_tiles, (size_t)P.num_tiles, (uint32_t)tile, agg, lane, excl, P.timing);
+          if (lane == 0) {
+            C.excl[qi] = excl[0];
+            if (last) P.counts[qi] = excl[0] + agg[0];
           }
         }
       } else if (lane == 0) {
@@ -1368,41 +1488,36 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(smem_u32(&sh.prebar[stage]));
-        mbar_arrive(smem_u32(&sh.empty[stage]));
-      }
+      if (lane == 0) mbar_arrive(smem_u32(&sh.prebar[stage]));
+      pc.lap(1);
     }
     return;
   }
 
-  // =============================== consumer warps ===============================
-  // phase A of tile n: selection mask of the lane's rows; returns false when the ring has run dry
-  struct TileRegs { int32_t tile; uint32_t sel, inrange; };
-  auto phase_a = [&](uint32_t n, TileRegs& t) -> bool {
-    const uint32_t stage = n % S, ph = (n / S) & 1u;
-    TileCtl& C = sh.ctl[stage];
-    mbar_wait(smem_u32(&sh.full[stage]), ph);
-    t.tile = *(volatile int32_t*)&C.tile;
-    if (t.tile < 0) return false;
-    const int64_t row0 = (int64_t)t.tile * kTileRows;
-    const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
-    const int64_t row_base = row0 + warp * kWarpRows + lane * 4;   // quad q covers rows row_base + q * 128 .. + 3
-    uint32_t inrange = 0;
-#pragma unroll
-    for (int q = 0; q < QPT; q++) {
-      const int left = tile_rows - (warp * kWarpRows + q * 128 + lane * 4);
-      inrange |= (left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u)) << (4 * q);
-    }
-    t.inrange = inrange;
-    const ColumnDesc* cols = C.cols;
-    uint32_t sel = inrange;
-    if (has_pred) {
-      sel = 0;
-#pragma unroll
-      for (int q = 0; q < QPT; q++) {
-        const int64_t qb[1] = {row_base + q * 128};
-        const uint32_t in4 = (inrange >> (4 * q)) & 0xFu;
+  if (warp >= kWriterWarps) {
+    // =============================== selector warps: phase A ===============================
+    // Run the predicate over a tile as soon as it has landed (selector warp w owns slice w): one
+    // selection nibble per lane, the slice totals, and -- by the last warp to finish -- the tile
+    // aggregate, published at once.  The gap between a tile's ticket and its aggregate is therefore
+    // one load latency plus this short phase, for every CTA alike.
+    const int slice = warp - kWriterWarps;
+    PhaseClock pc;   // [12] wait for the stage (TMA), [13] phase A
+    pc.start(P.timing != nullptr);
+    for (uint32_t n = 0;; n++) {
+      const uint32_t stage = n % S, ph = (n / S) & 1u;
+      TileCtl& C = sh.ctl[stage];
+      mbar_wait(smem_u32(&sh.full[stage]), ph);
+      pc.lap(0);
+      const int32_t tile = *(volatile int32_t*)&C.tile;
+      if (tile < 0) { if (slice == 0) pc.flush(P.timing, 12, lane); break; }
+      const int64_t row0 = (int64_t)tile * kTileRows;
+      const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
+      const ColumnDesc* cols = C.cols;
+      const int64_t qb[1] = {row0 + slice * kWarpRows + lane * 4};
+      const int left = tile_rows - (slice * kWarpRows + lane * 4);
+      const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
+      uint32_t sel4 = in4;
+      if (has_pred) {
         V acc[4];
         uint32_t accm, accv;
 #ifdef CHDB_JIT
@@ -1410,119 +1525,125 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
 #else
         run_program<V, 1>(P, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
 #endif
-        sel |= (accm & accv & in4) << (4 * q);  // NULL predicate rows are dropped (arrow-select filter)
+        sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
       }
-    }
-    t.sel = sel;
-    // per-warp totals: selected rows, selected value bytes per Utf8 output
-    const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel));
-    if (lane == 0) C.wtot[0][warp] = wrows;
-    CHDB_STATIC_UNROLL
-    for (int k = 0; k < CHDB_N_OUT; k++) {
-      const uint64_t meta = CHDB_OUT_META(P, k);
-      const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
-      if (o_utf8 == 0xFFu) continue;   // uniform branch
-      const int32_t* off = cols[o_slot].offsets;
-      uint32_t bytes = 0;
-#pragma unroll
-      for (int q = 0; q < QPT; q++) {
-        const uint32_t s4 = (sel >> (4 * q)) & 0xFu;
-        if (s4) {
-          const int4 a = *(const int4*)(off + row_base + q * 128);
-          const int a4 = off[row_base + q * 128 + 4];
-          if (s4 & 1u) bytes += (uint32_t)(a.y - a.x);
-          if (s4 & 2u) bytes += (uint32_t)(a.z - a.y);
-          if (s4 & 4u) bytes += (uint32_t)(a.w - a.z);
-          if (s4 & 8u) bytes += (uint32_t)(a4 - a.w);
+      C.sel[slice][lane] = (uint8_t)sel4;
+      const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel4));
+      if (lane == 0) C.wtot[0][slice] = wrows;
+      // selected value bytes per Utf8 output
+      CHDB_STATIC_UNROLL
+      for (int k = 0; k < CHDB_N_OUT; k++) {
+        const uint64_t meta = CHDB_OUT_META(P, k);
+        const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+        if (o_utf8 == 0xFFu) continue;   // uniform branch
+        const int32_t* off = cols[o_slot].offsets;
+        uint32_t bytes = 0;
+        if (sel4) {
+          const int4 a = *(const int4*)(off + qb[0]);
+          const int a4 = off[qb[0] + 4];
+          if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
+          if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
+          if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
+          if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
         }
+        const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+        if (lane == 0) C.wtot[1 + o_utf8][slice] = wbytes;
       }
-      const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
-      if (lane == 0) C.wtot[1 + o_utf8][warp] = wbytes;
-    }
-    // the last warp to get here publishes the tile aggregate and wakes the look-back warp
-    uint32_t is_last = 0;
-    if (lane == 0) {
-      __threadfence_block();
-      is_last = atomicAdd(&C.arrive, 1u) == (uint32_t)(kConsumerWarps - 1) ? 1u : 0u;
-      __threadfence_block();
-    }
-    is_last = __shfl_sync(FULL, is_last, 0);
-    if (is_last) {
-      if (lane < nq) {
-        uint64_t agg = 0;
-#pragma unroll
-        for (int w = 0; w < kConsumerWarps; w++) agg += *(volatile uint32_t*)&C.wtot[lane][w];
-        C.agg[lane] = agg;
-        if (has_pred) {
-          volatile uint64_t* d = P.tile_desc + (size_t)lane * P.num_tiles;
-          d[t.tile] = (t.tile == 0 ? kFlagPrefix : kFlagAgg) | agg;
-        }
-      }
+      // the last warp to get here publishes the tile aggregate
       __syncwarp();
+      uint32_t is_last = 0;
       if (lane == 0) {
-        C.arrive = 0;
-        __threadfence();
-        mbar_arrive(smem_u32(&sh.aggbar[stage]));
+        __threadfence_block();
+        is_last = atomicAdd(&C.arrive, 1u) == (uint32_t)(kConsumerWarps - 1) ? 1u : 0u;
+        __threadfence_block();
       }
+      is_last = __shfl_sync(FULL, is_last, 0);
+      if (is_last) {
+        if (lane < nq) {
+          uint64_t agg = 0;
+#pragma unroll
+          for (int w = 0; w < kConsumerWarps; w++) agg += *(volatile uint32_t*)&C.wtot[lane][w];
+          C.agg[lane] = agg;
+          if (has_pred) publish_aggregate(P.tile_desc + (size_t)lane * P.num_tiles + tile, tile == 0, agg);
+        }
+        if (lane == 0) C.arrive = 0;
+        __syncwarp();
+      }
+      if (lane == 0) mbar_arrive(smem_u32(&sh.aggbar[stage]));   // wakes the look-back warp once all slices are in
+      pc.lap(1);
     }
-    return true;
-  };
+    return;
+  }
 
-  // phase B of tile n: write every output column
-  auto phase_b = [&](uint32_t n, const TileRegs& t) {
+  // =============================== writer warps: phase B ===============================
+  const int group = warp / kConsumerWarps, slice = warp % kConsumerWarps;
+  uint32_t* const group_bits = bitstages + group * 2 * P.n_bits * kBitWords;
+  PhaseClock pc;   // [0] wait for the prefix, [1] ranks, [2] outputs, [3] bit flush + release
+  pc.start(P.timing != nullptr);
+  for (uint32_t n = group;; n += kWriterGroups) {
     const uint32_t stage = n % S, ph = (n / S) & 1u;
     TileCtl& C = sh.ctl[stage];
+    mbar_wait(smem_u32(&sh.full[stage]), ph);
+    const int32_t tile = *(volatile int32_t*)&C.tile;
+    if (tile < 0) break;
     mbar_wait(smem_u32(&sh.prebar[stage]), ph);
+    pc.lap(0);
     LaneCtx<QPT> L;
     L.lane = lane;
-    L.warp = warp;
-    L.row_base = (int64_t)t.tile * kTileRows + warp * kWarpRows + lane * 4;
-    L.inrange = t.inrange;
-    L.sel = t.sel;
+    L.warp = slice;
+    L.wid = warp;
+    const int64_t row0 = (int64_t)tile * kTileRows;
+    const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
+    L.row_base = row0 + slice * kWarpRows + lane * 4;
+    {
+      const int left = tile_rows - (slice * kWarpRows + lane * 4);
+      L.inrange = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
+    }
+    L.sel = C.sel[slice][lane];
     uint32_t rows_before = 0, tile_count = 0;
 #pragma unroll
     for (int w = 0; w < kConsumerWarps; w++) {
       const uint32_t c = C.wtot[0][w];
-      if (w < warp) rows_before += c;
+      if (w < slice) rows_before += c;
       tile_count += c;
     }
     L.warp_first = rows_before;
-    L.warp_count = C.wtot[0][warp];
+    L.warp_count = C.wtot[0][slice];
     L.obase = C.excl[0];
-    uint32_t run = rows_before;
-#pragma unroll
-    for (int q = 0; q < QPT; q++) {
+    {
       uint32_t tot;
-      L.rank[q] = run + warp_excl_scan((uint32_t)__popc((t.sel >> (4 * q)) & 0xFu), lane, tot);
-      run += tot;
+      L.rank[0] = rows_before + warp_excl_scan((uint32_t)__popc(L.sel), lane, tot);
     }
-    uint32_t* const bitstage = bitstages + (n & 1u) * P.n_bits * kBitWords;
+    pc.lap(1);
+    uint32_t* const bitstage = group_bits + ((n / kWriterGroups) & 1u) * P.n_bits * kBitWords;
     int kb = 0;
 #ifdef CHDB_JIT
-    outputs_range<V, QPT, 0, chdb_jit::kNumOut>(P, C, L, sh, bitstage, ltab, kb);
+    {
+      OutRegs R[chdb_jit::kNumOut > 0 ? chdb_jit::kNumOut : 1];
+      load_outputs_range<QPT, 0, chdb_jit::kNumOut>(P, C, L, R);
+      store_outputs_range<V, QPT, 0, chdb_jit::kNumOut>(P, C, L, R, sh, bitstage, ltab, kb);
+    }
 #else
 #pragma unroll 1
-    for (int k = 0; k < P.n_out; k++) emit_output<V, QPT>(P, C, k, CHDB_OUT_META(P, k), L, sh, bitstage, ltab, kb);
+    for (int k = 0; k < P.n_out; k++) {
+      OutRegs R;
+      const uint64_t meta = CHDB_OUT_META(P, k);
+      load_output<QPT>(P, C, k, meta, L, R);
+      store_output<V, QPT>(P, C, k, meta, L, R, sh, bitstage, ltab, kb);
+    }
 #endif
+    pc.lap(2);
     if (P.n_bits > 0) {
-      consumer_barrier();
-      flush_bits(P, sh, bitstage, L.obase, tile_count, warp, lane);
+      group_barrier(group);
+      flush_bits(P, sh, bitstage, L.obase, tile_count, slice, lane);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&sh.empty[stage]));   // this warp is done with the stage
-  };
-
-  TileRegs cur, nxt;
-  if (phase_a(0, cur)) {
-    for (uint32_t n = 0;; n++) {
-      const bool more = phase_a(n + 1, nxt);
-      phase_b(n, cur);
-      if (!more) break;
-      cur = nxt;
-    }
+    pc.lap(3);
   }
+  pc.flush(P.timing, 0, lane);
   // null counts of this CTA
-  consumer_barrier();
+  writers_barrier();
   if (tid < CHDB_N_OUT && P.out[tid].validity != nullptr && sh.nulls[tid] != 0)
     atomicAdd((unsigned long long*)(P.counts + P.out[tid].count_index), (unsigned long long)sh.nulls[tid]);
 }
@@ -1531,7 +1652,7 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
 
 #ifndef CHDB_JIT
 template <typename V, int QPT>
-__global__ void __launch_bounds__(kThreads, 3) filter_project_kernel(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) filter_project_kernel(const __grid_constant__ KernelParams P) {
   filter_project_body<V, QPT>(P);
 }
 #endif

@@ -5,6 +5,8 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -20,7 +22,7 @@ constexpr size_t kSmemPerCtaMax = 227 * 1024;
 inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 }  // namespace
 
-size_t filter_project_static_smem() { return sizeof(SharedState); }
+size_t filter_project_static_smem() { return sizeof(SharedState) + 256; }   // + what the compiler adds (alignment, its own slots)
 
 // Decides what is staged.  Every buffer of every slot is a candidate; when one stage of everything
 // does not leave room for a ring of at least two stages, the largest buffers are read from global
@@ -41,16 +43,23 @@ StagePlan plan_stages(KernelParams& kp, const int64_t* avg_utf8) {
       bufs.push_back({s, 2, c.width ? (size_t)kTileRows * c.width : (size_t)kTileRows / 8});
     }
   }
-  const size_t fixed_dyn = (size_t)2 * kp.n_bits * kBitWords * 4 +
-                           (kp.long_strings ? (size_t)kConsumerWarps * 2 * (kWarpRows + 4) * 4 : 0);
-  const size_t fixed = fixed_dyn + sizeof(SharedState) + 1024;
+  const size_t fixed_dyn = (size_t)kWriterGroups * 2 * kp.n_bits * kBitWords * 4 +
+                           (kp.long_strings ? (size_t)kWriterWarps * 2 * (kWarpRows + 4) * 4 : 0);
+  const size_t fixed = fixed_dyn + filter_project_static_smem() + 1024;
   auto stage_bytes = [&]() {
     size_t t = 0;
     for (auto& b : bufs) t += up16(b.bytes);
     return (t + 127) & ~(size_t)127;
   };
   struct Shape { int ctas, stages; };
-  const Shape shapes[] = {{3, 3}, {2, 3}, {2, 2}, {1, 3}, {1, 2}};
+  std::vector<Shape> shapes;
+  for (int c = kMinCtasPerSm; c >= 1; c--)
+    for (int st : {5, 4, 3}) shapes.push_back(Shape{c, st});
+  shapes.push_back(Shape{1, 2});
+  if (const char* e = std::getenv("CHDB_SHAPE")) {   // experiments: "ctas,stages" tried first
+    int c = 0, st = 0;
+    if (std::sscanf(e, "%d,%d", &c, &st) == 2 && c >= 1 && c <= 4 && st >= 2 && st <= kMaxStages) shapes.insert(shapes.begin(), Shape{c, st});
+  }
   Shape pick{0, 0};
   while (true) {
     const size_t sb = stage_bytes();
@@ -83,7 +92,7 @@ cudaError_t launch_filter_project(const KernelParams& p, bool has64, const Stage
   auto k32 = filter_project_kernel<uint32_t, kQuadsPerThread>;
   auto k64 = filter_project_kernel<uint64_t, kQuadsPerThread>;
   auto kern = has64 ? k64 : k32;
-  if (plan.dyn_smem > 40 * 1024) {   // opt in to the large window once per (kernel, device)
+  {   // opt in to the large dynamic window once per (kernel, device); static + dynamic may pass 48 KB for any plan
     static std::mutex mu;
     static std::map<std::pair<const void*, int>, size_t> granted;
     int dev = 0;
@@ -91,8 +100,11 @@ cudaError_t launch_filter_project(const KernelParams& p, bool has64, const Stage
     std::lock_guard<std::mutex> g(mu);
     size_t& have = granted[{(const void*)kern, dev}];
     if (have < plan.dyn_smem) {
-      const size_t want = kSmemPerCtaMax - sizeof(SharedState);
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+      cudaFuncAttributes fa;
+      cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+      if (e != cudaSuccess) return e;
+      const size_t want = kSmemPerCtaMax - fa.sharedSizeBytes;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
       if (e != cudaSuccess) return e;
       have = want;
     }

@@ -9,13 +9,25 @@
 
 namespace chdb {
 
-// CTA = kConsumerWarps consumer warps + one TMA producer warp + one look-back warp.
-constexpr int kConsumerWarps = 4;
-constexpr int kQuadsPerThread = 1;          // each consumer thread owns QPT groups of 4 consecutive rows per tile
+// A tile is kConsumerWarps slices of 128 rows.  CTA = kWriterGroups groups of kConsumerWarps writer warps
+// (phase B; group g takes the CTA's tiles g, g + kWriterGroups, ...) + kConsumerWarps selector warps
+// (phase A) + one TMA producer warp + kLookbackWarps look-back warps (warp j takes tiles j, j + kLookbackWarps, ...).
+#ifndef CHDB_CONSUMER_WARPS
+#define CHDB_CONSUMER_WARPS 8
+#endif
+#ifndef CHDB_WRITER_GROUPS
+#define CHDB_WRITER_GROUPS 2
+#endif
+constexpr int kConsumerWarps = CHDB_CONSUMER_WARPS;
+constexpr int kWriterGroups = CHDB_WRITER_GROUPS;
+constexpr int kWriterWarps = kWriterGroups * kConsumerWarps;
+constexpr int kQuadsPerThread = 1;          // each thread owns 4 consecutive rows per tile
 constexpr int kWarpRows = 32 * 4 * kQuadsPerThread;          // rows of one warp slice
-constexpr int kTileRows = kConsumerWarps * kWarpRows;        // 512 rows per tile
-constexpr int kThreads = (kConsumerWarps + 2) * 32;
-constexpr int kMaxStages = 4;               // depth of the shared-memory input ring
+constexpr int kTileRows = kConsumerWarps * kWarpRows;        // 1024 rows per tile
+constexpr int kLookbackWarps = 3;            // look-backs in flight per CTA (one L2 round trip each, ~2 us under load)
+constexpr int kThreads = (kWriterWarps + kConsumerWarps + 1 + kLookbackWarps) * 32;
+constexpr int kMinCtasPerSm = kThreads <= 512 ? 2 : 1;       // register budget the kernels are compiled for
+constexpr int kMaxStages = 6;               // depth of the shared-memory input ring
 constexpr int kMaxQuantities = 1 + kMaxOutCols;              // scanned quantities: rows + bytes per Utf8 output
 constexpr int kBitWords = kTileRows / 32 + 2;                // words of one bit-packed output stage
 constexpr uint32_t kNotStaged = 0xFFFFFFFFu;
@@ -61,6 +73,7 @@ struct KernelParams {
   uint32_t* ticket;          // dynamic tile id counter (zeroed)
   uint64_t* counts;          // see above (zeroed)
   uint64_t* error_word;      // zeroed; atomicMax(~packed)
+  uint64_t* timing;          // debug (CHDB_PHASE_TIMING=1): 16 cycle counters summed over warps, or nullptr
   int32_t num_tiles;
   int32_t n_in, n_out, n_utf8;
   int32_t pred_begin, pred_end;  // pred_begin == pred_end: no predicate (every row is kept)

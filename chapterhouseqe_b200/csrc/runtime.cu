@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -705,6 +706,14 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
 
   // Long scans run the same device code specialised for this program by NVRTC (jit.cpp); short
   // batches, or boxes without NVRTC, run the bytecode interpreter kernel.
+  // CHDB_PHASE_TIMING=1: cycles per role and phase, summed over warps, on stderr (debugging aid; synchronises)
+  Buf timing_buf;
+  const char* pt = std::getenv("CHDB_PHASE_TIMING");
+  if (pt && *pt == '1') {
+    timing_buf = dev_alloc(core, 16 * 8);
+    CUDA_CHECK(cudaMemsetAsync(timing_buf->ptr, 0, 16 * 8, core->stream));
+    kp.timing = (uint64_t*)timing_buf->ptr;
+  }
   cudaError_t le = cudaSuccess;
   const JitKernel* jk = nullptr;
   const JitMode jm = jit_mode();
@@ -720,6 +729,18 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   }
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
   core->launches++;
+  if (timing_buf) {
+    uint64_t t[16];
+    CUDA_CHECK(cudaMemcpyAsync(t, timing_buf->ptr, sizeof(t), cudaMemcpyDeviceToHost, core->stream));
+    CUDA_CHECK(cudaStreamSynchronize(core->stream));
+    const double grid = (double)std::min<int64_t>(num_tiles, (int64_t)plan.ctas_per_sm * core->sm_count);
+    const double tiles_per_cta = (double)num_tiles / grid, cw = grid * kConsumerWarps * tiles_per_cta, ow = grid * tiles_per_cta;   // (selector: warp 0 only)
+    std::fprintf(stderr, "[chdb timing] %lld tiles on %.0f CTAs (%d/SM, %d stages of %d B); mean cycles per tile -- selector: wait-stage "
+                 "%.0f, A %.0f | look-back: wait-agg %.0f, walk %.0f (%.2f hops, %.1f spins, loads %.0f, whole walk fn %.0f) | writer warp: wait-prefix %.0f, ranks %.0f, outputs %.0f, flush %.0f | "
+                 "producer: wait-free %.0f, addresses %.0f, issue %.0f\n", (long long)num_tiles, grid, plan.ctas_per_sm, kp.n_stages,
+                 kp.stage_bytes, t[12] / ow, t[13] / ow, t[4] / ow, t[5] / ow, t[6] / ow, t[7] / ow, t[14] / ow, t[15] / ow, t[0] / cw, t[1] / cw, t[2] / cw, t[3] / cw, t[8] / ow,
+                 t[9] / ow, t[10] / ow);
+  }
   CUDA_CHECK(cudaMemcpyAsync(res->host, ws, (size_t)(n_counts + 1) * 8, cudaMemcpyDeviceToHost, core->stream));
   CUDA_CHECK(cudaEventRecord(res->done, core->stream));
   out->result = res;
