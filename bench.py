@@ -388,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
     value = all_rows * args.steps / secs
     per_gpu_gbs = total_rows * args.steps * bytes_per_row / secs / 1e9
     peak, peak_src = measured_peak()
-    avg_launch_us = elapsed_ms * 1e3 / max(launches, 1)
+    avg_launch_us = elapsed_ms * 1e3 / max(launches_per_step * args.steps, 1)   # one batch = select + scan + gather
     algo_bytes_per_launch = total_rows * bytes_per_row / launches_per_step
 
     line = {
@@ -401,13 +401,14 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks, "gpu_launches": int(all_launches), "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
         "specialised_launches": int(jit_launches),
         "roofline": {"bound": "hbm",
-                     "kernel": ("chdb_jit_kernel (device_code.cuh specialised for the program by NVRTC)" if jit_launches
-                                else "filter_project_kernel<uint64_t,4> (bytecode interpreter)"),
+                     "kernel": ("chdb_jit_select + scan_kernel + chdb_jit_gather per batch (device_code.cuh specialised for the "
+                                "program by NVRTC); gather dominates" if jit_launches
+                                else "select_kernel + scan_kernel + gather_kernel per batch (bytecode interpreter)"),
                      "achieved": per_gpu_gbs, "peak": peak,
                      "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": measured_traffic(args.batch_rows),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
-                     "avg_launch_us": avg_launch_us, "launches_per_step": launches_per_step},
+                     "avg_batch_us": avg_launch_us, "batches_per_step": launches_per_step, "kernels_per_batch": 3},
     }
 
     # ---- materialize-side gather (N > 1): every rank's compacted batches travel to rank 0 over NVLink ----

@@ -1,32 +1,26 @@
-// Fused WHERE-evaluation -> selection -> decoupled-look-back scan -> compaction kernel (sm_100a).
+// Filter / projection / compaction on sm_100a: three kernels per batch.
 //
-// Persistent, warp-specialised CTAs.  A tile is kTileRows consecutive rows; tiles are handed out by
-// an atomic ticket, so a tile's predecessors are always resident or finished.
+//   select   streams the predicate's columns through a TMA-fed ring of shared-memory stages, runs the
+//            predicate bytecode (accumulator in registers, 128-bit shared-memory loads) and writes the
+//            selection bitmap (1 bit per row) plus, per 128-row slice, the number of selected rows and
+//            the selected value bytes of every Utf8 output.                         [compute_value.rs]
+//   scan     exclusive prefix sums of the slice counts: block scans chained by a decoupled look-back
+//            over 64-bit {flag | value} descriptors.
+//   gather   streams every column an output needs through the same kind of ring, together with the
+//            tile's selection bits and slice prefixes, and writes the selected rows straight to their
+//            final positions (neighbouring lanes hit neighbouring addresses); validity / Boolean bits
+//            are assembled per warp in shared memory and written as words; Utf8 offsets restart at 0;
+//            projection expressions are evaluated here, under the selection mask, so checked-integer
+//            errors are raised for surviving rows only.                 [filter_record.rs:37, record_projection.rs]
 //
-//   producer warp (one lane)   takes tickets and streams each tile's slice of every staged input
-//                              buffer (values, validity bitmaps, Utf8 offsets and short-string
-//                              bytes) into a ring of shared-memory stages with TMA bulk copies
-//                              (cp.async.bulk + mbarrier complete_tx); buffers that are not staged
-//                              get a bulk L2 prefetch instead.  HBM requests for the next tiles are
-//                              therefore in flight while the current ones are being processed.
-//   consumer warps             phase A(t): run the predicate bytecode over the staged tile (128-bit
-//                              shared-memory loads, accumulator in registers) -> selection mask;
-//                              per-warp totals (rows, value bytes per Utf8 output); the last warp
-//                              to arrive publishes the tile aggregate.     [compute_value.rs]
-//                              phase B(t): rank the selected rows, then for every output column write
-//                              the selected values straight to their final position (neighbouring
-//                              lanes hit neighbouring addresses); bit-packed outputs (validity,
-//                              Boolean) are assembled in shared memory and written as whole words;
-//                              Utf8 offsets restart at 0.                  [filter_record.rs:37]
-//                              Software-pipelined: A(t+1) runs before B(t), so a tile's aggregate is
-//                              public one phase before anybody needs its prefix.
-//   look-back warp             turns tile aggregates into exclusive prefixes with a decoupled
-//                              look-back over 64-bit {flag | value} descriptors while the consumers
-//                              are busy with A(t+1).
-//
-// HBM traffic is each referenced input byte once and each output byte once.
-// Projection expressions are evaluated in phase B under the selection mask, so checked-integer
-// errors are raised for surviving rows only (the reference projects after filtering).
+// Why not one fused single-pass kernel: with the memory system busy streaming tiles an L2 round trip
+// costs ~3 000 cycles, and a per-tile look-back puts at least one such round trip (plus the polling for
+// neighbours that are a little late) on every tile's critical path; measured, that capped the fused
+// kernel at 25-30 % of HBM peak.  Here no tile ever waits for another CTA, both streaming kernels are
+// plain persistent pipelines (producer warp -> mbarrier ring -> compute warps), and the predicate
+// columns the gather kernel re-reads were streamed by the select kernel moments earlier: they are
+// served by the 126 MB L2 for batches of a few million rows, so HBM traffic stays at each referenced
+// input byte once and each output byte once (+ 1 bit and ~0.1 byte of counts per row).
 //
 // Accumulator convention: for 8/16/32-bit integers and Float32 only the low 32 bits of the
 // container are meaningful (integers sign-/zero-extended to 32 bits); 64-bit types use all of it.
@@ -788,98 +782,57 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
   return v;
 }
 
-// Decoupled look-back (Merrill & Garland) on packed {flag:2 | value:62} descriptors; executed by
-// one full warp.  The tile's own descriptor already holds its aggregate (published by the consumer
-// warps).  Tiles are numbered by an atomic ticket, so every predecessor is resident or finished and
-// publishes its aggregate without waiting for anybody: the spin always terminates.
-constexpr uint64_t kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
+// Decoupled look-back (Merrill & Garland) on packed {flag:2 | value:62} descriptors.
 // Aggregates are published with a fire-and-forget red.max: {PREFIX | v} > {AGG | v} > 0 as unsigned
 // numbers, so a descriptor can only move forward whatever order the updates reach L2 in, and the
 // publisher needs no fence (the word carries its own flag; nothing else is read through it).
-__device__ __forceinline__ void publish_aggregate(uint64_t* d, bool first_tile, uint64_t agg) {
-  const uint64_t v = (first_tile ? kFlagPrefix : kFlagAgg) | agg;
+constexpr uint64_t kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
+__device__ __forceinline__ void publish_descriptor(uint64_t* d, uint64_t flag, uint64_t value) {
+  const uint64_t v = flag | value;
   asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(d), "l"(v) : "memory");
 }
-// Descriptor loads are relaxed, gpu-scope loads served by L2.  (Not `volatile`: strong system-scope loads
-// complete one at a time, which turned a 16-load hop into sixteen L2 round trips.)
+// Relaxed, gpu-scope loads served by L2 (not `volatile`: strong system-scope loads complete one at a time).
 __device__ __forceinline__ uint64_t load_descriptor(const uint64_t* p) {
   uint64_t v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-constexpr int kLookBackPerLane = 8;   // 256 predecessors per hop, all loads of a hop in flight together
-// NQ quantities (separate descriptor arrays, num_tiles apart) are walked together, so the L2 round
-// trips of a hop are paid once.
-template <int NQ>
-__device__ __forceinline__ void lookback(uint64_t* desc, size_t num_tiles, uint32_t tile, const uint64_t (&agg)[NQ], int lane,
-                                         uint64_t (&excl)[NQ], uint64_t* timing) {
-#pragma unroll
-  for (int qi = 0; qi < NQ; qi++) excl[qi] = 0;
-  if (tile == 0) return;
-  uint64_t* d = desc;
-  bool done[NQ];
-#pragma unroll
-  for (int qi = 0; qi < NQ; qi++) done[qi] = false;
-  int64_t base = (int64_t)tile - 1;
-  uint32_t dbg_hops = 0, dbg_spins = 0;
-  long long dbg_t0 = clock64(), dbg_load = 0;
+// Exclusive prefix of chunk `chunk`, by one full warp; the chunk's own aggregate is already public.
+constexpr int kLookBackPerLane = 4;   // 128 predecessors per hop, all loads of a hop in flight together
+__device__ __forceinline__ uint64_t lookback(uint64_t* d, uint32_t chunk, uint64_t agg, int lane) {
+  if (chunk == 0) return 0;
+  uint64_t excl = 0;
+  int64_t base = (int64_t)chunk - 1;
   while (true) {
-    dbg_hops++;
-    const long long dbg_h0 = clock64();
-    // each lane inspects kLookBackPerLane consecutive predecessors (nearest first)
-    uint64_t v[NQ][kLookBackPerLane];
+    uint64_t v[kLookBackPerLane];
 #pragma unroll
-    for (int qi = 0; qi < NQ; qi++) {
+    for (int j = 0; j < kLookBackPerLane; j++) {
+      const int64_t idx = base - (lane * kLookBackPerLane + j);
+      v[j] = 2ull << 62;   // chunks "before 0" contribute an inclusive prefix of 0
+      if (idx >= 0) v[j] = load_descriptor(d + idx);
+    }
+    uint64_t part = 0;
+    bool found = false;
 #pragma unroll
-      for (int j = 0; j < kLookBackPerLane; j++) {
+    for (int j = 0; j < kLookBackPerLane; j++) {
+      if (!found) {
         const int64_t idx = base - (lane * kLookBackPerLane + j);
-        v[qi][j] = 2ull << 62;   // tiles "before 0" contribute an inclusive prefix of 0
-        if (idx >= 0 && !done[qi]) v[qi][j] = load_descriptor(d + (size_t)qi * num_tiles + idx);
+        while ((v[j] >> 62) == 0) { __nanosleep(40); v[j] = load_descriptor(d + idx); }
+        part += v[j] & kValueMask;
+        found = (v[j] >> 62) == 2;
       }
     }
-    if (timing != nullptr) { dbg_load += (long long)(v[0][0] & 1) + (long long)(v[NQ - 1][kLookBackPerLane - 1] & 1) + clock64() - dbg_h0; }
-    bool all_done = true;
-#pragma unroll
-    for (int qi = 0; qi < NQ; qi++) {
-      if (done[qi]) continue;   // warp-uniform
-      uint64_t part = 0;
-      bool found = false;
-#pragma unroll
-      for (int j = 0; j < kLookBackPerLane; j++) {
-        if (!found) {
-          const int64_t idx = base - (lane * kLookBackPerLane + j);
-          while ((v[qi][j] >> 62) == 0) { dbg_spins++; __nanosleep(40); v[qi][j] = load_descriptor(d + (size_t)qi * num_tiles + idx); }
-          part += v[qi][j] & kValueMask;
-          found = (v[qi][j] >> 62) == 2;
-        }
-      }
-      const uint32_t pm = __ballot_sync(FULL, found);
-      if (pm) {
-        const int first = __ffs(pm) - 1;  // lane holding the nearest predecessor that already knows its prefix
-        excl[qi] += warp_sum64(lane <= first ? part : 0);
-        done[qi] = true;
-      } else {
-        excl[qi] += warp_sum64(part);
-        all_done = false;
-      }
+    const uint32_t pm = __ballot_sync(FULL, found);
+    if (pm) {
+      const int first = __ffs(pm) - 1;  // lane holding the nearest predecessor that already knows its prefix
+      excl += warp_sum64(lane <= first ? part : 0);
+      break;
     }
-    if (all_done) break;
+    excl += warp_sum64(part);
     base -= 32 * kLookBackPerLane;
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int qi = 0; qi < NQ; qi++)
-      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(d + (size_t)qi * num_tiles + tile), "l"(kFlagPrefix | (excl[qi] + agg[qi])) : "memory");
-  }
-  if (timing != nullptr) {   // debugging aid: hops and spin iterations (max over lanes) per walk
-    const uint32_t ms = __reduce_max_sync(FULL, dbg_spins);
-    if (lane == 0) {
-      atomicAdd((unsigned long long*)&timing[6], (unsigned long long)dbg_hops);
-      atomicAdd((unsigned long long*)&timing[7], (unsigned long long)ms);
-      atomicAdd((unsigned long long*)&timing[14], (unsigned long long)dbg_load);
-      atomicAdd((unsigned long long*)&timing[15], (unsigned long long)(clock64() - dbg_t0));
-    }
-  }
+  if (lane == 0) publish_descriptor(d + chunk, kFlagPrefix, excl + agg);
+  return excl;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -897,9 +850,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// The suspend-time hint lets the hardware park the waiting warp until the phase completes (or ~10 ms
-// pass) instead of returning after the short default limit: waiting warps then cost no issue slots
-// and no shared-memory pipeline traffic.
+// The suspend-time hint lets the hardware park the waiting warp until the phase completes.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -919,12 +870,8 @@ __device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32
 __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-// named barriers: 1 + g for writer group g, 15 for all writer warps
-__device__ __forceinline__ void group_barrier(int group) {
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kConsumerWarps * 32) : "memory");
-}
-__device__ __forceinline__ void writers_barrier() {
-  asm volatile("bar.sync 15, %0;" ::"n"(kWriterWarps * 32) : "memory");
+__device__ __forceinline__ void compute_warps_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
 }
 
 // Role profile (debugging aid, CHDB_PHASE_TIMING=1): lane 0 of every warp accumulates the cycles it
@@ -942,70 +889,300 @@ struct PhaseClock {
 
 // Everything one tile needs besides its staged bytes; one per stage of the ring.
 struct TileCtl {
-  int32_t tile;                                   // ticket, or -1: no more tiles
-  uint32_t arrive;                                // selector warps that finished their slice
-  uint8_t sel[kConsumerWarps][32];                // selection nibble of (slice, lane): its 4 rows
-  uint32_t wtot[kMaxQuantities][kConsumerWarps];  // per-warp totals: [0] rows, [1 + u] bytes of Utf8 output u
-  uint64_t agg[kMaxQuantities];                   // tile totals
-  uint64_t excl[kMaxQuantities];                  // exclusive prefixes from the look-back
+  int32_t tile;                                   // tile index, or -1: no more tiles
+  int32_t pad;
   ColumnDesc cols[kMaxInCols];                    // the input columns as seen by this tile: pointers are biased so that
                                                   // indexing with the ABSOLUTE row lands in the stage (or in global memory)
 };
 struct SharedState {
-  uint64_t full[kMaxStages], empty[kMaxStages], aggbar[kMaxStages], prebar[kMaxStages];
+  uint64_t full[kMaxStages], empty[kMaxStages];
   TileCtl ctl[kMaxStages];
   uint32_t nulls[kMaxOutCols];
   uint8_t pext4[256];                             // [sel4 << 4 | bits4] -> the selected bits, packed
   uint8_t pool[kStrPoolBytes];
 };
 
-// ------------------------------------------------------------------------------------------
-// phase B: writing the selected rows
-// ------------------------------------------------------------------------------------------
-// What a lane knows about its rows of the current tile once the prefixes are in.
-template <int QPT>
-struct LaneCtx {
-  int64_t row_base;       // absolute row of the lane's quad 0; quad q starts at row_base + q * 128
-  uint32_t inrange;       // rows that exist (tail tile), 4 bits per quad
-  uint32_t sel;           // selected rows, 4 bits per quad
-  uint32_t rank[QPT];     // tile-local rank of the first selected row of each quad
-  uint64_t obase;         // output row of the tile's first selected row
-  uint32_t warp_first;    // tile-local rank of the warp's first selected row
-  uint32_t warp_count;    // selected rows of this warp
-  int lane, warp;         // warp: slice of the tile this warp owns
-  int wid;                // writer warp index in the CTA (its private long-string tables)
-};
-
-// Drops the selected bits of the lane's rows into the tile's bit stage (zero-initialised): bit for
-// output row obase + r sits at stage bit (obase & 31) + r.
-template <int QPT>
-__device__ __forceinline__ void put_bits(uint32_t bits, const LaneCtx<QPT>& L, uint32_t* sb, const uint8_t* pext4) {
-  const uint32_t o = (uint32_t)L.obase & 31u;
-#pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    const uint32_t s4 = (L.sel >> (4 * q)) & 0xFu, b4 = (bits >> (4 * q)) & 0xFu & s4;
-    if (b4) {
-      const uint32_t c = pext4[(s4 << 4) | b4];
-      const uint32_t p = o + L.rank[q], sh = p & 31u;
-      atomicOr(&sb[p >> 5], c << sh);
-      if (sh > 28u && (c >> (32u - sh))) atomicOr(&sb[(p >> 5) + 1], c >> (32u - sh));
+__device__ __forceinline__ void init_shared(const KernelParams& P, const KernelStage& ST, SharedState& sh, int tid) {
+  if (tid == 0) {
+    for (int s = 0; s < ST.n_stages; s++) {
+      mbar_init(smem_u32(&sh.full[s]), 1);
+      mbar_init(smem_u32(&sh.empty[s]), kSlices);
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < 256; i += kThreads) {
+    const uint32_t s = (uint32_t)i >> 4, v = (uint32_t)i & 15u;
+    uint32_t out = 0, n = 0;
+    for (int j = 0; j < 4; j++)
+      if ((s >> j) & 1u) { out |= ((v >> j) & 1u) << n; n++; }
+    sh.pext4[i] = (uint8_t)out;
+  }
+  for (int i = tid; i < kStrPoolBytes; i += kThreads) sh.pool[i] = (uint8_t)P.strpool[i];
+  for (int i = tid; i < kMaxOutCols; i += kThreads) sh.nulls[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// the producer warp (both streaming kernels): tile n of this CTA is tile blockIdx.x + n * gridDim.x.
+// Lane s owns input slot s: it copies the tile's slice of each buffer the kernel uses into the stage
+// with TMA bulk copies (completion is counted in bytes on the stage's `full` mbarrier) and leaves the
+// column's biased pointers in the stage's table; buffers that are used but not staged get a bulk L2
+// prefetch.  GATHER: lane 31 also brings the tile's selection bits and slice prefixes.
+// ------------------------------------------------------------------------------------------
+template <bool GATHER>
+__device__ __forceinline__ void producer_loop(const KernelParams& P, const KernelStage& ST, SharedState& sh, uint8_t* smem, int lane) {
+  const uint32_t S = (uint32_t)ST.n_stages;
+  const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
+  const int nq = 1 + CHDB_N_UTF8;
+  PhaseClock pc;   // [8] wait for a free stage, [9] addresses + boundary offsets, [10] issue
+  pc.start(P.timing != nullptr);
+  uint32_t sentinels = 0;
+  for (uint32_t n = 0;; n++) {
+    const uint32_t stage = n % S, ph = (n / S) & 1u;
+    mbar_wait(smem_u32(&sh.empty[stage]), ph ^ 1u);
+    pc.lap(0);
+    TileCtl& C = sh.ctl[stage];
+    const uint32_t full = smem_u32(&sh.full[stage]);
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)n * gridDim.x;
+    if (tile >= P.num_tiles) {
+      // out of tiles: every compute group must meet a stage that says so
+      if (lane == 0) { C.tile = -1; mbar_arrive(full); }
+      if (++sentinels == (uint32_t)kComputeGroups) { pc.flush(P.timing, 8, lane); break; }
+      continue;
+    }
+    const int64_t row0 = tile * kTileRows;
+    const uint32_t rows = (uint32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
+    uint8_t* const sg = smem + (size_t)stage * ST.stage_bytes;   // generic address of the stage
+    const uint32_t ss = smem_u32(sg);
+    // what this lane copies: up to three buffers of its slot
+    const void* src[3] = {nullptr, nullptr, nullptr};
+    uint32_t dst[3] = {0, 0, 0}, nbytes[3] = {0, 0, 0};
+    const void* pf_src = nullptr;   // used but not staged: bulk L2 prefetch instead
+    uint32_t pf_bytes = 0;
+    if (lane < CHDB_N_IN) {
+      const ColumnDesc g = P.in[lane];
+      const StageSlot sl = ST.slot[lane];
+      const uint32_t use = ST.use[lane];
+      ColumnDesc v = g;
+      const uint32_t bit_bytes = (((rows + 7u) >> 3) + 15u) & ~15u;
+      if ((use & USE_VALIDITY) && g.validity != nullptr && sl.validity != kNotStaged) {
+        src[0] = g.validity + (row0 >> 3); dst[0] = ss + sl.validity; nbytes[0] = bit_bytes;
+        v.validity = sg + sl.validity - (row0 >> 3);
+      }
+      if (g.type == T_UTF8) {
+        if ((use & USE_OFFSETS) && sl.offsets != kNotStaged) {
+          src[1] = g.offsets + row0; dst[1] = ss + sl.offsets; nbytes[1] = ((rows + 1u) * 4u + 15u) & ~15u;
+          v.offsets = (const int32_t*)(sg + sl.offsets) - row0;
+        }
+        if (use & USE_VALUES) {
+          const uint32_t o0 = (uint32_t)g.offsets[row0], o1 = (uint32_t)g.offsets[row0 + rows];
+          const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
+          if (sl.values != kNotStaged && len <= sl.values_cap) {
+            src[2] = (const uint8_t*)g.values + lo; dst[2] = ss + sl.values; nbytes[2] = len;
+            v.values = sg + sl.values - lo;
+          } else {
+            pf_src = (const uint8_t*)g.values + lo; pf_bytes = len;
+          }
+        }
+      } else if (use & USE_VALUES) {
+        const uint32_t w = g.width;
+        const uint32_t vb = w ? (rows * w + 15u) & ~15u : bit_bytes;
+        const int64_t first = w ? row0 * (int64_t)w : (row0 >> 3);
+        if (sl.values != kNotStaged) {
+          src[2] = (const uint8_t*)g.values + first; dst[2] = ss + sl.values; nbytes[2] = vb;
+          v.values = sg + sl.values - first;
+        } else {
+          pf_src = (const uint8_t*)g.values + first; pf_bytes = vb;
+        }
+      }
+      C.cols[lane] = v;
+    }
+    uint32_t extra = 0;
+    if (GATHER && has_pred && lane == 31) extra = kTileRows / 8 + (uint32_t)nq * kSlices * 8;
+    const uint32_t tx = __reduce_add_sync(FULL, nbytes[0] + nbytes[1] + nbytes[2] + extra);
+    pc.lap(1);
+    if (lane == 0) {
+      C.tile = (int32_t)tile;
+      mbar_arrive_expect_tx(full, tx);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      if (nbytes[i]) tma_load(dst[i], src[i], nbytes[i], full);
+    if (pf_bytes) tma_prefetch_l2(pf_src, pf_bytes);
+    if (extra) {
+      tma_load(ss + ST.sel_off, P.sel_bits + tile * (kTileRows / 32), kTileRows / 8, full);
+      for (int qi = 0; qi < nq; qi++)
+        tma_load(ss + ST.prefix_off + qi * kSlices * 8, P.slice_prefix + (size_t)qi * P.slice_pitch + tile * kSlices, kSlices * 8, full);
+    }
+    pc.lap(2);
   }
 }
 
-template <int QPT>
-__device__ __forceinline__ uint32_t load_bits_all(const uint8_t* __restrict__ bits, int64_t row_base, uint32_t need) {
-  if (bits == nullptr) return FULL;
-  uint32_t m = 0;
+// ------------------------------------------------------------------------------------------
+// select: predicate -> selection bitmap + per-slice counts
+// ------------------------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ void select_body(const KernelParams& P, const KernelStage& ST) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) SharedState sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t S = (uint32_t)ST.n_stages;
+  init_shared(P, ST, sh, tid);
+  __syncthreads();
+  // from here on the producer and the compute warps only meet through the stages' mbarriers
+  if (warp == kComputeWarps) {
+    producer_loop<false>(P, ST, sh, smem, lane);
+    return;
+  }
+  const int group = warp / kSlices, slice = warp % kSlices;
+  PhaseClock pc;   // [0] wait for the stage (TMA), [1] predicate + counts
+  pc.start(P.timing != nullptr);
+  for (uint32_t n = group;; n += kComputeGroups) {
+    const uint32_t stage = n % S, ph = (n / S) & 1u;
+    TileCtl& C = sh.ctl[stage];
+    mbar_wait(smem_u32(&sh.full[stage]), ph);
+    pc.lap(0);
+    const int32_t tile = *(volatile int32_t*)&C.tile;
+    if (tile < 0) break;
+    const int64_t row0 = (int64_t)tile * kTileRows;
+    const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
+    const ColumnDesc* cols = C.cols;
+    const int64_t qb[1] = {row0 + slice * kWarpRows + lane * 4};
+    const int left = tile_rows - (slice * kWarpRows + lane * 4);
+    const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
+    V acc[4];
+    uint32_t accm, accv;
+#ifdef CHDB_JIT
+    run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
+#else
+    run_program<V, 1>(P, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
+#endif
+    const uint32_t sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
+    // selection bits: 8 lanes make one word, 4 words per slice
+    uint32_t word = sel4 << (4 * (lane & 7));
+    word |= __shfl_xor_sync(FULL, word, 1);
+    word |= __shfl_xor_sync(FULL, word, 2);
+    word |= __shfl_xor_sync(FULL, word, 4);
+    const int64_t sg = (int64_t)tile * kSlices + slice;   // slice index in the batch
+    if ((lane & 7) == 0) P.sel_bits[sg * 4 + (lane >> 3)] = word;
+    const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel4));
+    if (lane == 0) P.slice_counts[sg] = wrows;
+    // selected value bytes per Utf8 output
+    CHDB_STATIC_UNROLL
+    for (int k = 0; k < CHDB_N_OUT; k++) {
+      const uint64_t meta = CHDB_OUT_META(P, k);
+      const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+      if (o_utf8 == 0xFFu) continue;   // uniform branch
+      const int32_t* off = cols[o_slot].offsets;
+      uint32_t bytes = 0;
+      if (sel4) {
+        const int4 a = *(const int4*)(off + qb[0]);
+        const int a4 = off[qb[0] + 4];
+        if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
+        if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
+        if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
+        if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
+      }
+      const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+      if (lane == 0) P.slice_counts[(size_t)(1 + o_utf8) * P.slice_pitch + sg] = wbytes;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&sh.empty[stage]));   // this warp is done with the stage
+    pc.lap(1);
+  }
+  pc.flush(P.timing, 0, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// scan: slice counts -> exclusive slice prefixes.  Grid (chunks, quantities); each CTA scans
+// kScanChunk slices (8 per thread) and chains to its predecessors with a decoupled look-back.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scan_body(const KernelParams& P) {
+  __shared__ uint64_t s_warp[kScanThreads / 32];
+  __shared__ uint64_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t chunk = blockIdx.x, qi = blockIdx.y;
+  const uint32_t* counts = P.slice_counts + (size_t)qi * P.slice_pitch;
+  uint64_t* prefix = P.slice_prefix + (size_t)qi * P.slice_pitch;
+  uint64_t* desc = P.chunk_desc + (size_t)qi * P.num_chunks;
+  const int64_t i0 = (int64_t)chunk * kScanChunk + tid * 8;   // slice_pitch is a multiple of 8: all or nothing
+  uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (i0 < P.slice_pitch) {
+    const uint4 a = *(const uint4*)(counts + i0), b = *(const uint4*)(counts + i0 + 4);
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+  }
+  uint64_t mine = 0;
 #pragma unroll
-  for (int q = 0; q < QPT; q++) {
-    if ((need >> (4 * q)) & 0xFu) {
-      const int64_t r = row_base + q * 128;
-      const uint32_t byte = bits[r >> 3];
-      m |= ((byte >> (uint32_t)(r & 4)) & 0xFu) << (4 * q);
+  for (int j = 0; j < 8; j++) mine += c[j];
+  // block-wide exclusive scan of the thread sums
+  uint64_t x = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t y = __shfl_up_sync(FULL, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  uint64_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; w++) {
+    const uint64_t t = s_warp[w];
+    if (w < warp) before += t;
+    total += t;
+  }
+  if (warp == 0) {
+    if (lane == 0) publish_descriptor(desc + chunk, chunk == 0 ? kFlagPrefix : kFlagAgg, total);
+    const uint64_t excl = lookback(desc, chunk, total, lane);
+    if (lane == 0) {
+      s_base = excl;
+      if (chunk == (uint32_t)P.num_chunks - 1) P.counts[qi] = excl + total;   // totals
     }
   }
-  return m;
+  __syncthreads();
+  uint64_t run = s_base + before + (x - mine);
+  if (i0 < P.slice_pitch) {
+    uint64_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { o[j] = run; run += c[j]; }
+    ulonglong2* dst = (ulonglong2*)(prefix + i0);
+#pragma unroll
+    for (int j = 0; j < 4; j++) dst[j] = make_ulonglong2(o[2 * j], o[2 * j + 1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather: writing the selected rows
+// ------------------------------------------------------------------------------------------
+// What a lane knows about its rows of the current slice.
+struct LaneCtx {
+  int64_t row_base;       // absolute row of the lane's first row
+  uint32_t inrange;       // rows that exist (tail tile), 4 bits
+  uint32_t sel;           // selected rows, 4 bits
+  uint32_t rank;          // slice-local rank of the lane's first selected row
+  uint32_t count;         // selected rows of the slice
+  uint64_t obase;         // output row of the slice's first selected row
+  const uint64_t* prefix; // the tile's slice prefixes [quantity][kSlices] (staged), or nullptr without a predicate
+  int lane, slice;
+  int wid;                // compute warp index in the CTA (its private bit stage / long-string tables)
+};
+
+// Drops the selected bits of the lane's rows into the warp's bit stage (zero-initialised): the bit of
+// output row obase + r sits at stage bit (obase & 31) + r.
+__device__ __forceinline__ void put_bits(uint32_t bits, const LaneCtx& L, uint32_t* sb, const uint8_t* pext4) {
+  const uint32_t s4 = L.sel, b4 = bits & 0xFu & s4;
+  if (b4) {
+    const uint32_t c = pext4[(s4 << 4) | b4];
+    const uint32_t p = ((uint32_t)L.obase & 31u) + L.rank, sh = p & 31u;
+    atomicOr(&sb[p >> 5], c << sh);
+    if (sh > 28u && (c >> (32u - sh))) atomicOr(&sb[(p >> 5) + 1], c >> (32u - sh));
+  }
+}
+
+__device__ __forceinline__ uint32_t load_bits4(const uint8_t* __restrict__ bits, int64_t r, uint32_t need) {
+  if (bits == nullptr) return FULL;
+  if (!need) return 0;
+  return ((uint32_t)bits[r >> 3] >> (uint32_t)(r & 4)) & 0xFu;
 }
 
 // Stores the selected elements of one quad at consecutive output positions.
@@ -1073,7 +1250,7 @@ __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, u
       const uint32_t mid = (lo_r + hi_r) >> 1;
       if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
     }
-    uint32_t r = lo_r - 1;  // row holding byte x (never an empty string)
+    uint32_t r = lo_r - 1;  // row holding byte x (empty strings are skipped by the search)
     const bool full = (t - s) == 16u;
     if (full && x + 16u <= s_oo[r + 1]) {
       *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
@@ -1104,7 +1281,7 @@ __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, u
   }
 }
 
-// Phase B handles an output column in two steps so that, with the program known at compile time
+// An output column is handled in two steps so that, with the program known at compile time
 // (CHDB_JIT), the loads of ALL pass-through columns are issued before the first store: the
 // shared-memory latencies overlap instead of adding up column by column.
 struct OutRegs {
@@ -1114,9 +1291,8 @@ struct OutRegs {
 };
 
 // `meta` packs the eight small OutDesc fields; under CHDB_JIT it is a compile-time constant.
-template <int QPT>
 __device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
-                                            const LaneCtx<QPT>& L, OutRegs& R) {
+                                            const LaneCtx& L, OutRegs& R) {
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu;
   R.x = make_uint4(0, 0, 0, 0);
@@ -1127,11 +1303,11 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl
   const ColumnDesc& c = C.cols[o_slot];
   const uint32_t sel = L.sel;
   const int64_t r = L.row_base;
-  if (P.out[k].validity != nullptr) R.vbits = load_bits_all<QPT>(c.validity, r, sel);
+  if (P.out[k].validity != nullptr) R.vbits = load_bits4(c.validity, r, sel);
   if (!sel) return;
   const uint8_t* src = (const uint8_t*)c.values;
   if (o_type == T_BOOL) {
-    R.z = load_bits_all<QPT>(src, r, sel);
+    R.z = load_bits4(src, r, sel);
   } else if (o_type == T_UTF8) {
     const int4 a = *(const int4*)(c.offsets + r);
     R.x = make_uint4((uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w);
@@ -1151,11 +1327,10 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl
 
 // Writes output column k for this lane's rows.  BEGIN/END: the expression's instruction range when known at
 // compile time.  kb: running index of the bit-packed outputs (Boolean values, validity bitmaps) in the bit stage.
-template <typename V, int QPT, int BEGIN = -1, int END = -1>
+template <typename V, int BEGIN = -1, int END = -1>
 __device__ __forceinline__ void store_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
-                                             const LaneCtx<QPT>& L, const OutRegs& R, const SharedState& sh, uint32_t* bitstage,
+                                             const LaneCtx& L, const OutRegs& R, const SharedState& sh, uint32_t* bitstage,
                                              uint32_t* ltab, int& kb) {
-  static_assert(QPT == 1, "one quad per writer thread");
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
   const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu;
@@ -1164,7 +1339,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
   const uint32_t sel = L.sel;
   const int lane = L.lane;
   const ColumnDesc* cols = C.cols;
-  const uint64_t o = L.obase + L.rank[0];   // output row of the lane's first selected row
+  const uint64_t o = L.obase + L.rank;   // output row of the lane's first selected row
   uint32_t vbits = R.vbits;  // validity of this output for the lane's rows
   if (o_kind == OUT_EXPR) {
     uint32_t accm = 0;
@@ -1180,49 +1355,44 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
       else if (o_width == 2) store_sel<uint16_t>((uint16_t*)o_values + o, sel, (uint16_t)a4[0], (uint16_t)a4[1], (uint16_t)a4[2], (uint16_t)a4[3]);
       else store_sel<uint8_t>((uint8_t*)o_values + o, sel, (uint8_t)a4[0], (uint8_t)a4[1], (uint8_t)a4[2], (uint8_t)a4[3]);
     }
-    if (o_type == T_BOOL) { put_bits<QPT>(accm, L, bitstage + kb * kBitWords, sh.pext4); kb++; }
+    if (o_type == T_BOOL) { put_bits(accm, L, bitstage + kb * kBitWords, sh.pext4); kb++; }
   } else {
     const ColumnDesc& c = cols[o_slot];
     if (o_type == T_BOOL) {
-      put_bits<QPT>(R.z, L, bitstage + kb * kBitWords, sh.pext4);
+      put_bits(R.z, L, bitstage + kb * kBitWords, sh.pext4);
       kb++;
     } else if (o_type == T_UTF8) {
       // offsets: running sum of the selected lengths, restarted at 0 for the output
       const uint8_t* sv = (const uint8_t*)c.values;
-      uint32_t bytes_before = 0;
-#pragma unroll
-      for (int w = 0; w < kConsumerWarps; w++)
-        if (w < L.warp) bytes_before += C.wtot[1 + o_utf8][w];
-      const uint32_t warp_bytes = C.wtot[1 + o_utf8][L.warp];
-      const uint64_t warp_byte_base = C.excl[1 + o_utf8] + bytes_before;   // output byte offset of this warp's first value
+      const uint64_t byte_base = L.prefix[(1 + o_utf8) * kSlices + L.slice];   // output byte offset of this slice's first value
       int32_t* const o_off = P.out[k].offsets;
-      // long values are copied by the whole warp, chunk-centric; short ones by the lane that owns the row
-      const bool chunked = P.long_strings != 0 && warp_bytes > 24u * L.warp_count;
-      uint32_t* s_oo = ltab + L.wid * (2 * (kWarpRows + 4));
-      int32_t* s_src = (int32_t*)(s_oo + kWarpRows + 4);
       const int32_t o5[5] = {(int32_t)R.x.x, (int32_t)R.x.y, (int32_t)R.x.z, (int32_t)R.x.w, (int32_t)R.z};
       uint32_t len[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) len[i] = ((sel >> i) & 1u) ? (uint32_t)(o5[i + 1] - o5[i]) : 0u;
-      uint32_t tot;
-      uint32_t bo = warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, tot);   // warp-local output byte offset
+      uint32_t slice_bytes;
+      uint32_t bo = warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, slice_bytes);   // slice-local output byte offset
+      // long values are copied by the whole warp, chunk-centric; short ones by the lane that owns the row
+      const bool chunked = P.long_strings != 0 && slice_bytes > 24u * L.count;
+      uint32_t* s_oo = ltab + L.wid * (2 * (kWarpRows + 4));
+      int32_t* s_src = (int32_t*)(s_oo + kWarpRows + 4);
       int32_t* d = o_off + o;
-      uint32_t wr = L.rank[0] - L.warp_first;   // warp-local rank
+      uint32_t wr = L.rank;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         if ((sel >> i) & 1u) {
-          *d = (int32_t)(uint32_t)(warp_byte_base + bo);
+          *d = (int32_t)(uint32_t)(byte_base + bo);
           d++;
           if (chunked) { s_oo[wr] = bo; s_src[wr] = o5[i]; wr++; }
-          else if (len[i]) copy_value(o_values + warp_byte_base + bo, sv + o5[i], len[i]);
+          else if (len[i]) copy_value(o_values + byte_base + bo, sv + o5[i], len[i]);
           bo += len[i];
         }
       }
       if (chunked) {
-        if (lane == 0) s_oo[L.warp_count] = warp_bytes;
+        if (lane == 0) s_oo[L.count] = slice_bytes;
         __syncwarp();
-        const uint32_t mis = (uint32_t)(warp_byte_base & 15u);
-        copy_long_strings(sv, o_values + (warp_byte_base - mis), mis, warp_bytes, L.warp_count, s_oo, s_src, lane);
+        const uint32_t mis = (uint32_t)(byte_base & 15u);
+        copy_long_strings(sv, o_values + (byte_base - mis), mis, slice_bytes, L.count, s_oo, s_src, lane);
         __syncwarp();
       }
     } else if (sel) {
@@ -1247,36 +1417,34 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
   }
   if (o_has_validity) {
     // nulls are the rare case: the stage collects the NULL bits (most lanes have nothing to add)
-    put_bits<QPT>(~vbits, L, bitstage + kb * kBitWords, sh.pext4);
+    put_bits(~vbits, L, bitstage + kb * kBitWords, sh.pext4);
     kb++;
   }
 }
 
 #ifdef CHDB_JIT
-template <int QPT, int K, int N>
-__device__ __forceinline__ void load_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx<QPT>& L, OutRegs (&R)[N > 0 ? N : 1]) {
+template <int K, int N>
+__device__ __forceinline__ void load_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx& L, OutRegs (&R)[N > 0 ? N : 1]) {
   if constexpr (K < N) {
-    load_output<QPT>(P, C, K, chdb_jit::kOutMeta[K], L, R[K]);
-    load_outputs_range<QPT, K + 1, N>(P, C, L, R);
+    load_output(P, C, K, chdb_jit::kOutMeta[K], L, R[K]);
+    load_outputs_range<K + 1, N>(P, C, L, R);
   }
 }
-template <typename V, int QPT, int K, int N>
-__device__ __forceinline__ void store_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx<QPT>& L, const OutRegs (&R)[N > 0 ? N : 1],
+template <typename V, int K, int N>
+__device__ __forceinline__ void store_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx& L, const OutRegs (&R)[N > 0 ? N : 1],
                                                     const SharedState& sh, uint32_t* bitstage, uint32_t* ltab, int& kb) {
   if constexpr (K < N) {
     constexpr uint64_t meta = chdb_jit::kOutMeta[K];
-    store_output<V, QPT, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, C, K, meta, L, R[K], sh, bitstage, ltab, kb);
-    store_outputs_range<V, QPT, K + 1, N>(P, C, L, R, sh, bitstage, ltab, kb);
+    store_output<V, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, C, K, meta, L, R[K], sh, bitstage, ltab, kb);
+    store_outputs_range<V, K + 1, N>(P, C, L, R, sh, bitstage, ltab, kb);
   }
 }
 #endif
 
-// The bit stage of one tile -> global bitmaps.  Stage bit (obase & 31) + r belongs to output row
-// obase + r; whole words are stored, the (at most two) words shared with neighbouring tiles are
-// merged with atomicOr (the bitmaps are zero-initialised).  Bit array kb is written by the group's
-// warp kb % kConsumerWarps, which also zeroes it for the group's tile after next.
-__device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& sh, uint32_t* bitstage, uint64_t obase, uint32_t count,
-                                           int warp, int lane) {
+// The warp's bit stage -> global bitmaps.  Stage bit (obase & 31) + r belongs to output row obase + r;
+// whole words are stored, the (at most two) words shared with neighbouring slices are merged with
+// atomicOr (the bitmaps are zero-initialised).  The stage is left zeroed for the warp's next slice.
+__device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& sh, uint32_t* bitstage, uint64_t obase, uint32_t count, int lane) {
   const uint32_t o = (uint32_t)obase & 31u, end = o + count;
   const uint32_t nwords = (end + 31u) >> 5;
   const uint64_t g0 = obase >> 5;
@@ -1289,308 +1457,71 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& s
 #pragma unroll
     for (int which = 0; which < 2; which++) {   // 0: Boolean values, 1: validity
       if (which == 0 ? !is_bool : validity == nullptr) continue;
-      if (kb % kConsumerWarps == warp) {
-        uint32_t* sb = bitstage + kb * kBitWords;
-        uint32_t* g = (uint32_t*)(which == 0 ? (uint8_t*)P.out[k].values : validity);
-        uint32_t nulls = 0;
-        for (uint32_t w = lane; w < (uint32_t)kBitWords; w += 32) {
-          uint32_t word = sb[w];
-          sb[w] = 0;
-          if (w < nwords) {
-            const uint32_t lo = w == 0 ? o : 0u, hi = 32 * w + 32 > end ? end - 32 * w : 32u;
-            const uint32_t mask = (hi >= 32 ? FULL : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-            if (which == 1) { nulls += (uint32_t)__popc(word & mask); word = ~word; }
-            word &= mask;
-            if (mask == FULL) g[g0 + w] = word;
-            else if (word) atomicOr(&g[g0 + w], word);
-          }
+      uint32_t* sb = bitstage + kb * kBitWords;
+      uint32_t* g = (uint32_t*)(which == 0 ? (uint8_t*)P.out[k].values : validity);
+      uint32_t nulls = 0;
+      if (lane < kBitWords) {
+        const uint32_t w = (uint32_t)lane;
+        uint32_t word = sb[w];
+        sb[w] = 0;
+        if (w < nwords) {
+          const uint32_t lo = w == 0 ? o : 0u, hi = 32 * w + 32 > end ? end - 32 * w : 32u;
+          const uint32_t mask = (hi >= 32 ? FULL : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+          if (which == 1) { nulls = (uint32_t)__popc(word & mask); word = ~word; }
+          word &= mask;
+          if (mask == FULL) g[g0 + w] = word;
+          else if (word) atomicOr(&g[g0 + w], word);
         }
-        if (which == 1) {
-          nulls = __reduce_add_sync(FULL, nulls);
-          if (lane == 0 && nulls) atomicAdd(&sh.nulls[k], nulls);
-        }
+      }
+      if (which == 1) {
+        nulls = __reduce_add_sync(FULL, nulls);
+        if (lane == 0 && nulls) atomicAdd(&sh.nulls[k], nulls);
       }
       kb++;
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// the kernel
-// ------------------------------------------------------------------------------------------
-template <typename V, int QPT>
-__device__ __forceinline__ void filter_project_body(const KernelParams& P) {
-  static_assert(QPT == 1, "one quad per writer thread");
+template <typename V>
+__device__ __forceinline__ void gather_body(const KernelParams& P, const KernelStage& ST) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(16) SharedState sh;
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
-  const uint32_t S = (uint32_t)P.n_stages;
-  const int nq = 1 + CHDB_N_UTF8;
-  // dynamic shared memory: the stage ring | bit stages [group][2][n_bits][kBitWords] | long-string row tables
-  uint32_t* const bitstages = (uint32_t*)(smem + (size_t)S * P.stage_bytes);
-  uint32_t* const ltab = bitstages + kWriterGroups * 2 * P.n_bits * kBitWords;
-
-  if (tid == 0) {
-    for (uint32_t s = 0; s < S; s++) {
-      mbar_init(smem_u32(&sh.full[s]), 1);
-      mbar_init(smem_u32(&sh.empty[s]), kConsumerWarps);
-      mbar_init(smem_u32(&sh.aggbar[s]), kConsumerWarps);
-      mbar_init(smem_u32(&sh.prebar[s]), 1);
-      sh.ctl[s].arrive = 0;
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  for (int i = tid; i < 256; i += kThreads) {
-    const uint32_t s = (uint32_t)i >> 4, v = (uint32_t)i & 15u;
-    uint32_t out = 0, n = 0;
-    for (int j = 0; j < 4; j++)
-      if ((s >> j) & 1u) { out |= ((v >> j) & 1u) << n; n++; }
-    sh.pext4[i] = (uint8_t)out;
-  }
-  for (int i = tid; i < kStrPoolBytes; i += kThreads) sh.pool[i] = (uint8_t)P.strpool[i];
-  for (int i = tid; i < kMaxOutCols; i += kThreads) sh.nulls[i] = 0;
-  for (int i = tid; i < kWriterGroups * 2 * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
+  const uint32_t S = (uint32_t)ST.n_stages;
+  // dynamic shared memory: the stage ring | bit stages [compute warp][n_bits][kBitWords] | long-string row tables
+  uint32_t* const bitstages = (uint32_t*)(smem + (size_t)S * ST.stage_bytes);
+  uint32_t* const ltab = bitstages + kComputeWarps * P.n_bits * kBitWords;
+  init_shared(P, ST, sh, tid);
+  for (int i = tid; i < kComputeWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
   __syncthreads();
-  // from here on the roles only meet through mbarriers (and the writers' named barriers)
-
-  if (warp == kWriterWarps + kConsumerWarps) {
-    // =============================== producer: lane s owns input slot s ===============================
-    PhaseClock pc;   // [8] wait for a free stage, [9] ticket + addresses + boundary offsets, [10] issue
-    pc.start(P.timing != nullptr);
-    uint32_t sentinels = 0;
-    for (uint32_t n = 0;; n++) {
-      const uint32_t stage = n % S, ph = (n / S) & 1u;
-      mbar_wait(smem_u32(&sh.empty[stage]), ph ^ 1u);
-      pc.lap(0);
-      TileCtl& C = sh.ctl[stage];
-      const uint32_t full = smem_u32(&sh.full[stage]);
-      // The ticket is taken only now that the tile can start loading at once: a tile that holds a
-      // ticket but has not published its aggregate stalls the look-back of every later tile.
-      uint32_t tile = 0;
-      if (lane == 0 && sentinels == 0) tile = atomicAdd(P.ticket, 1u);
-      tile = __shfl_sync(FULL, tile, 0);
-      if (sentinels != 0 || tile >= (uint32_t)P.num_tiles) {
-        // out of tiles: every writer group and every look-back warp must meet a stage that says so
-        if (lane == 0) { C.tile = -1; mbar_arrive(full); }
-        if (++sentinels == (uint32_t)(kWriterGroups > kLookbackWarps ? kWriterGroups : kLookbackWarps)) { pc.flush(P.timing, 8, lane); break; }
-        continue;
-      }
-      const int64_t row0 = (int64_t)tile * kTileRows;
-      const uint32_t rows = (uint32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
-      uint8_t* const sg = smem + (size_t)stage * P.stage_bytes;   // generic address of the stage
-      const uint32_t ss = smem_u32(sg);
-      // what this lane copies: up to three buffers of its slot
-      const void* src[3] = {nullptr, nullptr, nullptr};
-      uint32_t dst[3] = {0, 0, 0}, nbytes[3] = {0, 0, 0};
-      const void* pf_src = nullptr;   // not staged: bulk L2 prefetch instead
-      uint32_t pf_bytes = 0;
-      if (lane < CHDB_N_IN) {
-        const ColumnDesc g = P.in[lane];
-        const StageSlot sl = P.stage[lane];
-        ColumnDesc v = g;
-        const uint32_t bit_bytes = (((rows + 7u) >> 3) + 15u) & ~15u;
-        if (g.validity != nullptr && sl.validity != kNotStaged) {
-          src[0] = g.validity + (row0 >> 3); dst[0] = ss + sl.validity; nbytes[0] = bit_bytes;
-          v.validity = sg + sl.validity - (row0 >> 3);
-        }
-        if (g.type == T_UTF8) {
-          if (sl.offsets != kNotStaged) {
-            src[1] = g.offsets + row0; dst[1] = ss + sl.offsets; nbytes[1] = ((rows + 1u) * 4u + 15u) & ~15u;
-            v.offsets = (const int32_t*)(sg + sl.offsets) - row0;
-          }
-          const uint32_t o0 = (uint32_t)g.offsets[row0], o1 = (uint32_t)g.offsets[row0 + rows];
-          const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
-          if (sl.values != kNotStaged && len <= sl.values_cap) {
-            src[2] = (const uint8_t*)g.values + lo; dst[2] = ss + sl.values; nbytes[2] = len;
-            v.values = sg + sl.values - lo;
-          } else {
-            pf_src = (const uint8_t*)g.values + lo; pf_bytes = len;
-          }
-        } else {
-          const uint32_t w = g.width;
-          const uint32_t vb = w ? (rows * w + 15u) & ~15u : bit_bytes;
-          const int64_t first = w ? row0 * (int64_t)w : (row0 >> 3);
-          if (sl.values != kNotStaged) {
-            src[2] = (const uint8_t*)g.values + first; dst[2] = ss + sl.values; nbytes[2] = vb;
-            v.values = sg + sl.values - first;
-          } else {
-            pf_src = (const uint8_t*)g.values + first; pf_bytes = vb;
-          }
-        }
-        C.cols[lane] = v;
-      }
-      const uint32_t tx = __reduce_add_sync(FULL, nbytes[0] + nbytes[1] + nbytes[2]);
-      pc.lap(1);
-      if (lane == 0) {
-        C.tile = (int32_t)tile;
-        mbar_arrive_expect_tx(full, tx);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-        if (nbytes[i]) tma_load(dst[i], src[i], nbytes[i], full);
-      if (pf_bytes) tma_prefetch_l2(pf_src, pf_bytes);
-      pc.lap(2);
-    }
+  // from here on the producer and the compute warps only meet through the stages' mbarriers
+  if (warp == kComputeWarps) {
+    producer_loop<true>(P, ST, sh, smem, lane);
     return;
   }
-
-  if (warp > kWriterWarps + kConsumerWarps) {
-    // =============================== look-back warps ===============================
-    // An L2 round trip takes a few microseconds while the memory system is busy streaming tiles, longer
-    // than a tile period: several walks are kept in flight, one per look-back warp.
-    PhaseClock pc;   // [4] wait for the tile's aggregate, [5] look-back
-    pc.start(P.timing != nullptr);
-    for (uint32_t n = (uint32_t)(warp - (kWriterWarps + kConsumerWarps + 1));; n += kLookbackWarps) {
-      const uint32_t stage = n % S, ph = (n / S) & 1u;
-      TileCtl& C = sh.ctl[stage];
-      mbar_wait(smem_u32(&sh.full[stage]), ph);
-      const int32_t tile = *(volatile int32_t*)&C.tile;
-      if (tile < 0) { pc.flush(P.timing, 4, lane); break; }
-      mbar_wait(smem_u32(&sh.aggbar[stage]), ph);
-      pc.lap(0);
-      const bool last = tile == P.num_tiles - 1;
-      if (has_pred) {
-        int qi = 0;
-        for (; qi + 2 <= nq; qi += 2) {   // two quantities per walk
-          const uint64_t agg[2] = {*(volatile uint64_t*)&C.agg[qi], *(volatile uint64_t*)&C.agg[qi + 1]};
-          uint64_t excl[2];
-          lookback<2>(P.tile_desc + (size_t)qi * P.num_tiles, (size_t)P.num_tiles, (uint32_t)tile, agg, lane, excl, P.timing);
-          if (lane == 0) {
-            C.excl[qi] = excl[0];
-            C.excl[qi + 1] = excl[1];
-            if (last) { P.counts[qi] = excl[0] + agg[0]; P.counts[qi + 1] = excl[1] + agg[1]; }  // totals
-          }
-        }
-        if (qi < nq) {
-          const uint64_t agg[1] = {*(volatile uint64_t*)&C.agg[qi]};
-          uint64_t excl[1];
-          lookback<1>(P.tile_desc + (size_t)qi * P.num_tiles, (size_t)P.num_tiles, (uint32_t)tile, agg, lane, excl, P.timing);
-          if (lane == 0) {
-            C.excl[qi] = excl[0];
-            if (last) P.counts[qi] = excl[0] + agg[0];
-          }
-        }
-      } else if (lane == 0) {
-        C.excl[0] = (uint64_t)tile * kTileRows;
-        if (last) P.counts[0] = (uint64_t)P.num_rows;
-      }
-      __syncwarp();
-      if (last && has_pred) {
-        // closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
-        const uint64_t total_rows = C.excl[0] + C.agg[0];
-        for (int k = lane; k < CHDB_N_OUT; k += 32) {
-          const OutDesc& o = P.out[k];
-          if (o.utf8_index != 0xFFu) o.offsets[total_rows] = (int32_t)(C.excl[1 + o.utf8_index] + C.agg[1 + o.utf8_index]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sh.prebar[stage]));
-      pc.lap(1);
+  if (has_pred && blockIdx.x == 0 && warp == 0) {
+    // closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
+    for (int k = lane; k < CHDB_N_OUT; k += 32) {
+      const OutDesc& o = P.out[k];
+      if (o.utf8_index != 0xFFu) o.offsets[P.counts[0]] = (int32_t)P.counts[1 + o.utf8_index];
     }
-    return;
   }
-
-  if (warp >= kWriterWarps) {
-    // =============================== selector warps: phase A ===============================
-    // Run the predicate over a tile as soon as it has landed (selector warp w owns slice w): one
-    // selection nibble per lane, the slice totals, and -- by the last warp to finish -- the tile
-    // aggregate, published at once.  The gap between a tile's ticket and its aggregate is therefore
-    // one load latency plus this short phase, for every CTA alike.
-    const int slice = warp - kWriterWarps;
-    PhaseClock pc;   // [12] wait for the stage (TMA), [13] phase A
-    pc.start(P.timing != nullptr);
-    for (uint32_t n = 0;; n++) {
-      const uint32_t stage = n % S, ph = (n / S) & 1u;
-      TileCtl& C = sh.ctl[stage];
-      mbar_wait(smem_u32(&sh.full[stage]), ph);
-      pc.lap(0);
-      const int32_t tile = *(volatile int32_t*)&C.tile;
-      if (tile < 0) { if (slice == 0) pc.flush(P.timing, 12, lane); break; }
-      const int64_t row0 = (int64_t)tile * kTileRows;
-      const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
-      const ColumnDesc* cols = C.cols;
-      const int64_t qb[1] = {row0 + slice * kWarpRows + lane * 4};
-      const int left = tile_rows - (slice * kWarpRows + lane * 4);
-      const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
-      uint32_t sel4 = in4;
-      if (has_pred) {
-        V acc[4];
-        uint32_t accm, accv;
-#ifdef CHDB_JIT
-        run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
-#else
-        run_program<V, 1>(P, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
-#endif
-        sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
-      }
-      C.sel[slice][lane] = (uint8_t)sel4;
-      const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel4));
-      if (lane == 0) C.wtot[0][slice] = wrows;
-      // selected value bytes per Utf8 output
-      CHDB_STATIC_UNROLL
-      for (int k = 0; k < CHDB_N_OUT; k++) {
-        const uint64_t meta = CHDB_OUT_META(P, k);
-        const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
-        if (o_utf8 == 0xFFu) continue;   // uniform branch
-        const int32_t* off = cols[o_slot].offsets;
-        uint32_t bytes = 0;
-        if (sel4) {
-          const int4 a = *(const int4*)(off + qb[0]);
-          const int a4 = off[qb[0] + 4];
-          if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
-          if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
-          if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
-          if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
-        }
-        const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
-        if (lane == 0) C.wtot[1 + o_utf8][slice] = wbytes;
-      }
-      // the last warp to get here publishes the tile aggregate
-      __syncwarp();
-      uint32_t is_last = 0;
-      if (lane == 0) {
-        __threadfence_block();
-        is_last = atomicAdd(&C.arrive, 1u) == (uint32_t)(kConsumerWarps - 1) ? 1u : 0u;
-        __threadfence_block();
-      }
-      is_last = __shfl_sync(FULL, is_last, 0);
-      if (is_last) {
-        if (lane < nq) {
-          uint64_t agg = 0;
-#pragma unroll
-          for (int w = 0; w < kConsumerWarps; w++) agg += *(volatile uint32_t*)&C.wtot[lane][w];
-          C.agg[lane] = agg;
-          if (has_pred) publish_aggregate(P.tile_desc + (size_t)lane * P.num_tiles + tile, tile == 0, agg);
-        }
-        if (lane == 0) C.arrive = 0;
-        __syncwarp();
-      }
-      if (lane == 0) mbar_arrive(smem_u32(&sh.aggbar[stage]));   // wakes the look-back warp once all slices are in
-      pc.lap(1);
-    }
-    return;
-  }
-
-  // =============================== writer warps: phase B ===============================
-  const int group = warp / kConsumerWarps, slice = warp % kConsumerWarps;
-  uint32_t* const group_bits = bitstages + group * 2 * P.n_bits * kBitWords;
-  PhaseClock pc;   // [0] wait for the prefix, [1] ranks, [2] outputs, [3] bit flush + release
+  const int group = warp / kSlices, slice = warp % kSlices;
+  uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
+  PhaseClock pc;   // [0] wait for the stage (TMA), [1] ranks, [2] outputs, [3] bit flush + release
   pc.start(P.timing != nullptr);
-  for (uint32_t n = group;; n += kWriterGroups) {
+  for (uint32_t n = group;; n += kComputeGroups) {
     const uint32_t stage = n % S, ph = (n / S) & 1u;
     TileCtl& C = sh.ctl[stage];
     mbar_wait(smem_u32(&sh.full[stage]), ph);
+    pc.lap(0);
     const int32_t tile = *(volatile int32_t*)&C.tile;
     if (tile < 0) break;
-    mbar_wait(smem_u32(&sh.prebar[stage]), ph);
-    pc.lap(0);
-    LaneCtx<QPT> L;
+    const uint8_t* sg = smem + (size_t)stage * ST.stage_bytes;
+    LaneCtx L;
     L.lane = lane;
-    L.warp = slice;
+    L.slice = slice;
     L.wid = warp;
     const int64_t row0 = (int64_t)tile * kTileRows;
     const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
@@ -1599,51 +1530,44 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
       const int left = tile_rows - (slice * kWarpRows + lane * 4);
       L.inrange = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
     }
-    L.sel = C.sel[slice][lane];
-    uint32_t rows_before = 0, tile_count = 0;
-#pragma unroll
-    for (int w = 0; w < kConsumerWarps; w++) {
-      const uint32_t c = C.wtot[0][w];
-      if (w < slice) rows_before += c;
-      tile_count += c;
+    if (has_pred) {
+      const uint32_t word = ((const uint32_t*)(sg + ST.sel_off))[slice * 4 + (lane >> 3)];
+      L.sel = (word >> (4 * (lane & 7))) & 0xFu;
+      L.prefix = (const uint64_t*)(sg + ST.prefix_off);
+      L.obase = L.prefix[slice];
+    } else {
+      L.sel = L.inrange;
+      L.prefix = nullptr;
+      L.obase = (uint64_t)(row0 + slice * kWarpRows);
     }
-    L.warp_first = rows_before;
-    L.warp_count = C.wtot[0][slice];
-    L.obase = C.excl[0];
-    {
-      uint32_t tot;
-      L.rank[0] = rows_before + warp_excl_scan((uint32_t)__popc(L.sel), lane, tot);
-    }
+    L.rank = warp_excl_scan((uint32_t)__popc(L.sel), lane, L.count);
     pc.lap(1);
-    uint32_t* const bitstage = group_bits + ((n / kWriterGroups) & 1u) * P.n_bits * kBitWords;
     int kb = 0;
 #ifdef CHDB_JIT
     {
       OutRegs R[chdb_jit::kNumOut > 0 ? chdb_jit::kNumOut : 1];
-      load_outputs_range<QPT, 0, chdb_jit::kNumOut>(P, C, L, R);
-      store_outputs_range<V, QPT, 0, chdb_jit::kNumOut>(P, C, L, R, sh, bitstage, ltab, kb);
+      load_outputs_range<0, chdb_jit::kNumOut>(P, C, L, R);
+      store_outputs_range<V, 0, chdb_jit::kNumOut>(P, C, L, R, sh, bitstage, ltab, kb);
     }
 #else
 #pragma unroll 1
     for (int k = 0; k < P.n_out; k++) {
       OutRegs R;
       const uint64_t meta = CHDB_OUT_META(P, k);
-      load_output<QPT>(P, C, k, meta, L, R);
-      store_output<V, QPT>(P, C, k, meta, L, R, sh, bitstage, ltab, kb);
+      load_output(P, C, k, meta, L, R);
+      store_output<V>(P, C, k, meta, L, R, sh, bitstage, ltab, kb);
     }
 #endif
     pc.lap(2);
-    if (P.n_bits > 0) {
-      group_barrier(group);
-      flush_bits(P, sh, bitstage, L.obase, tile_count, slice, lane);
-    }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&sh.empty[stage]));   // this warp is done with the stage
+    if (P.n_bits > 0) flush_bits(P, sh, bitstage, L.obase, L.count, lane);
+    __syncwarp();
     pc.lap(3);
   }
   pc.flush(P.timing, 0, lane);
   // null counts of this CTA
-  writers_barrier();
+  compute_warps_barrier();
   if (tid < CHDB_N_OUT && P.out[tid].validity != nullptr && sh.nulls[tid] != 0)
     atomicAdd((unsigned long long*)(P.counts + P.out[tid].count_index), (unsigned long long)sh.nulls[tid]);
 }
@@ -1651,17 +1575,25 @@ __device__ __forceinline__ void filter_project_body(const KernelParams& P) {
 }  // namespace
 
 #ifndef CHDB_JIT
-template <typename V, int QPT>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) filter_project_kernel(const __grid_constant__ KernelParams P) {
-  filter_project_body<V, QPT>(P);
+template <typename V>
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) select_kernel(const __grid_constant__ KernelParams P, const __grid_constant__ KernelStage ST) {
+  select_body<V>(P, ST);
 }
+template <typename V>
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) gather_kernel(const __grid_constant__ KernelParams P, const __grid_constant__ KernelStage ST) {
+  gather_body<V>(P, ST);
+}
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(const __grid_constant__ KernelParams P) { scan_body(P); }
 #endif
 
 }  // namespace chdb
 
 #ifdef CHDB_JIT
-// one specialised kernel per NVRTC module, found by its unmangled name
-extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_kernel(const __grid_constant__ chdb::KernelParams P) {
-  chdb::filter_project_body<chdb_jit::Container, chdb::kQuadsPerThread>(P);
+// the two specialised streaming kernels of one NVRTC module, found by their unmangled names
+extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_select(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::KernelStage ST) {
+  chdb::select_body<chdb_jit::Container>(P, ST);
+}
+extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_gather(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::KernelStage ST) {
+  chdb::gather_body<chdb_jit::Container>(P, ST);
 }
 #endif

@@ -659,30 +659,41 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     return out;
   }
 
-  // ---- launch ----
+  // ---- launch: select -> scan -> gather (gather alone when there is no predicate) ----
   const int64_t num_tiles = (n + kTileRows - 1) / kTileRows;
   if (num_tiles > INT32_MAX) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "batch too large");
   const int nq = 1 + n_utf8;
-  // workspace: counts[n_counts] | error word | ticket (8 bytes) | tile descriptors
-  const size_t ws_counts = (size_t)(n_counts + 2) * 8;
-  const size_t ws_bytes = ws_counts + (compact ? (size_t)nq * (size_t)num_tiles * 8 : 0);
+  const int64_t slice_pitch = num_tiles * kSlices;
+  const int64_t num_chunks = (slice_pitch + kScanChunk - 1) / kScanChunk;
+  // workspace: counts[n_counts] | error word | pad | chunk descriptors   (zeroed)
+  //            | selection bits | slice counts | slice prefixes            (written before they are read)
+  const size_t ws_counts = round_up((size_t)(n_counts + 2) * 8, 128);
+  const size_t ws_desc = compact ? round_up((size_t)nq * (size_t)num_chunks * 8, 128) : 0;
+  const size_t ws_sel = compact ? (size_t)num_tiles * (kTileRows / 8) : 0;
+  const size_t ws_cnt = compact ? round_up((size_t)nq * (size_t)slice_pitch * 4, 128) : 0;
+  const size_t ws_pre = compact ? (size_t)nq * (size_t)slice_pitch * 8 : 0;
   auto res = std::make_shared<RunResult>();
   res->core = core;
   res->n_counts = n_counts;
-  res->workspace = dev_alloc(core, ws_bytes);
+  res->workspace = dev_alloc(core, ws_counts + ws_desc + ws_sel + ws_cnt + ws_pre);
   if ((size_t)(n_counts + 1) * 8 > CtxCore::kPinnedBlock) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "too many counted outputs");
   res->host = (uint64_t*)core->pinned_get();
   CUDA_CHECK(cudaEventCreateWithFlags(&res->done, cudaEventDisableTiming));
   uint8_t* ws = (uint8_t*)res->workspace->ptr;
-  CUDA_CHECK(cudaMemsetAsync(ws, 0, ws_bytes, core->stream));
+  CUDA_CHECK(cudaMemsetAsync(ws, 0, ws_counts + ws_desc, core->stream));
   for (auto& z : to_zero) CUDA_CHECK(cudaMemsetAsync(z.first, 0, z.second, core->stream));
 
   kp.num_rows = n;
+  kp.num_slices = (n + kWarpRows - 1) / kWarpRows;
+  kp.slice_pitch = slice_pitch;
   kp.counts = (uint64_t*)ws;
   kp.error_word = (uint64_t*)ws + n_counts;
-  kp.ticket = (uint32_t*)((uint64_t*)ws + n_counts + 1);
-  kp.tile_desc = (uint64_t*)(ws + ws_counts);
+  kp.chunk_desc = (uint64_t*)(ws + ws_counts);
+  kp.sel_bits = (uint32_t*)(ws + ws_counts + ws_desc);
+  kp.slice_counts = (uint32_t*)(ws + ws_counts + ws_desc + ws_sel);
+  kp.slice_prefix = (uint64_t*)(ws + ws_counts + ws_desc + ws_sel + ws_cnt);
   kp.num_tiles = (int32_t)num_tiles;
+  kp.num_chunks = (int32_t)num_chunks;
   kp.n_out = ko;
   kp.n_utf8 = n_utf8;
   kp.pred_begin = compact ? p.pred_begin : 0;
@@ -693,7 +704,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   kp.n_bits = 0;
   for (int k = 0; k < ko; k++) kp.n_bits += (kp.out[k].type == T_BOOL ? 1 : 0) + (kp.out[k].validity != nullptr ? 1 : 0);
   kp.long_strings = avg_utf8 > 16 ? 1 : 0;
-  // what is staged in shared memory: every buffer the kernel reads, budget permitting
+  if (!compact) kp.counts = (uint64_t*)ws;
   int64_t slot_avg[kMaxInCols];
   for (size_t s = 0; s < p.slot_to_col.size(); s++) {
     const DeviceColumn& c = in->cols[p.slot_to_col[s]];
@@ -702,18 +713,44 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     if ((((uintptr_t)c.values | (uintptr_t)c.validity | (uintptr_t)c.offsets) & 15u) != 0)
       throw Error(CHDB_ERR_INVALID_ARGUMENT, "device buffers must be 16-byte aligned");
   }
-  const StagePlan plan = plan_stages(kp, slot_avg);
+  // which buffers each streaming kernel touches
+  KernelStage st_select, st_gather;
+  std::memset(&st_select, 0, sizeof(st_select));
+  std::memset(&st_gather, 0, sizeof(st_gather));
+  auto mark_instrs = [&](KernelStage& st, int begin, int end) {
+    for (int i = begin; i < end; i++) {
+      const Instr& ins = kp.instrs[i];
+      if (ins.op == OP_CMP_UTF8) {
+        if (ins.slot != 0xFF) st.use[ins.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
+        const uint8_t sb = (uint8_t)(ins.imm >> 56);
+        if (sb != 0xFF) st.use[sb] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
+      } else if (ins.src == SRC_COL) {
+        st.use[ins.slot] |= USE_VALUES | USE_VALIDITY;
+      }
+    }
+  };
+  mark_instrs(st_select, kp.pred_begin, kp.pred_end);
+  for (int k = 0; k < ko; k++) {
+    const OutDesc& od = kp.out[k];
+    if (od.kind == OUT_EXPR) {
+      mark_instrs(st_gather, od.begin, od.end);
+    } else {
+      st_gather.use[od.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
+      if (od.type == T_UTF8) st_select.use[od.slot] |= USE_OFFSETS;   // selected value bytes per slice
+    }
+  }
+  const StagePlan plan_gather = plan_stages(kp, st_gather, slot_avg, true);
+  const StagePlan plan_select = compact ? plan_stages(kp, st_select, slot_avg, false) : StagePlan{0, 1};
 
-  // Long scans run the same device code specialised for this program by NVRTC (jit.cpp); short
-  // batches, or boxes without NVRTC, run the bytecode interpreter kernel.
   // CHDB_PHASE_TIMING=1: cycles per role and phase, summed over warps, on stderr (debugging aid; synchronises)
   Buf timing_buf;
   const char* pt = std::getenv("CHDB_PHASE_TIMING");
   if (pt && *pt == '1') {
-    timing_buf = dev_alloc(core, 16 * 8);
-    CUDA_CHECK(cudaMemsetAsync(timing_buf->ptr, 0, 16 * 8, core->stream));
-    kp.timing = (uint64_t*)timing_buf->ptr;
+    timing_buf = dev_alloc(core, 32 * 8);
+    CUDA_CHECK(cudaMemsetAsync(timing_buf->ptr, 0, 32 * 8, core->stream));
   }
+  // Long scans run the same device code specialised for this program by NVRTC (jit.cpp); short
+  // batches, or boxes without NVRTC, run the bytecode interpreter kernels.
   cudaError_t le = cudaSuccess;
   const JitKernel* jk = nullptr;
   const JitMode jm = jit_mode();
@@ -721,25 +758,32 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     std::string why;
     jk = jit_get(kp, p.has64, &why);
   }
-  if (jk) {
-    le = jit_launch(jk, kp, plan, core->sm_count, core->stream);
-    core->jit_launches++;
-  } else {
-    le = launch_filter_project(kp, p.has64, plan, core->sm_count, core->stream);
+  if (compact) {
+    kp.timing = timing_buf ? (uint64_t*)timing_buf->ptr : nullptr;
+    le = jk ? jit_launch_select(jk, kp, st_select, plan_select, core->sm_count, core->stream)
+            : launch_select(kp, st_select, p.has64, plan_select, core->sm_count, core->stream);
+    if (le == cudaSuccess) le = launch_scan(kp, core->stream);
+    core->launches += 2;
   }
+  if (le == cudaSuccess) {
+    kp.timing = timing_buf ? (uint64_t*)timing_buf->ptr + 16 : nullptr;
+    le = jk ? jit_launch_gather(jk, kp, st_gather, plan_gather, core->sm_count, core->stream)
+            : launch_gather(kp, st_gather, p.has64, plan_gather, core->sm_count, core->stream);
+    core->launches++;
+  }
+  if (jk) core->jit_launches++;
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
-  core->launches++;
   if (timing_buf) {
-    uint64_t t[16];
+    uint64_t t[32];
     CUDA_CHECK(cudaMemcpyAsync(t, timing_buf->ptr, sizeof(t), cudaMemcpyDeviceToHost, core->stream));
     CUDA_CHECK(cudaStreamSynchronize(core->stream));
-    const double grid = (double)std::min<int64_t>(num_tiles, (int64_t)plan.ctas_per_sm * core->sm_count);
-    const double tiles_per_cta = (double)num_tiles / grid, cw = grid * kConsumerWarps * tiles_per_cta, ow = grid * tiles_per_cta;   // (selector: warp 0 only)
-    std::fprintf(stderr, "[chdb timing] %lld tiles on %.0f CTAs (%d/SM, %d stages of %d B); mean cycles per tile -- selector: wait-stage "
-                 "%.0f, A %.0f | look-back: wait-agg %.0f, walk %.0f (%.2f hops, %.1f spins, loads %.0f, whole walk fn %.0f) | writer warp: wait-prefix %.0f, ranks %.0f, outputs %.0f, flush %.0f | "
-                 "producer: wait-free %.0f, addresses %.0f, issue %.0f\n", (long long)num_tiles, grid, plan.ctas_per_sm, kp.n_stages,
-                 kp.stage_bytes, t[12] / ow, t[13] / ow, t[4] / ow, t[5] / ow, t[6] / ow, t[7] / ow, t[14] / ow, t[15] / ow, t[0] / cw, t[1] / cw, t[2] / cw, t[3] / cw, t[8] / ow,
-                 t[9] / ow, t[10] / ow);
+    const double tiles = (double)num_tiles, cw = tiles * kSlices;
+    std::fprintf(stderr, "[chdb timing] %lld tiles; mean cycles per tile -- select (%d/SM, %d stages of %d B): compute warp wait-stage %.0f, "
+                 "predicate %.0f | producer wait-free %.0f, addresses %.0f, issue %.0f -- gather (%d/SM, %d stages of %d B): compute warp "
+                 "wait-stage %.0f, ranks %.0f, outputs %.0f, flush %.0f | producer wait-free %.0f, addresses %.0f, issue %.0f\n",
+                 (long long)num_tiles, plan_select.ctas_per_sm, st_select.n_stages, st_select.stage_bytes, t[0] / cw, t[1] / cw,
+                 t[8] / tiles, t[9] / tiles, t[10] / tiles, plan_gather.ctas_per_sm, st_gather.n_stages, st_gather.stage_bytes,
+                 t[16] / cw, t[17] / cw, t[18] / cw, t[19] / cw, t[24] / tiles, t[25] / tiles, t[26] / tiles);
   }
   CUDA_CHECK(cudaMemcpyAsync(res->host, ws, (size_t)(n_counts + 1) * 8, cudaMemcpyDeviceToHost, core->stream));
   CUDA_CHECK(cudaEventRecord(res->done, core->stream));
