@@ -905,7 +905,7 @@ struct SharedState {
 __device__ __forceinline__ void init_shared(const KernelParams& P, const KernelStage& ST, SharedState& sh, int tid) {
   if (tid == 0) {
     for (int s = 0; s < ST.n_stages; s++) {
-      mbar_init(smem_u32(&sh.full[s]), 1);
+      mbar_init(smem_u32(&sh.full[s]), kProducerWarps);
       mbar_init(smem_u32(&sh.empty[s]), kSlices);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -920,103 +920,138 @@ __device__ __forceinline__ void init_shared(const KernelParams& P, const KernelS
   }
   for (int i = tid; i < kStrPoolBytes; i += kThreads) sh.pool[i] = (uint8_t)P.strpool[i];
   for (int i = tid; i < kMaxOutCols; i += kThreads) sh.nulls[i] = 0;
+  // the tiles' column tables: types and widths never change, the producers fill in the pointers per tile
+  for (int i = tid; i < ST.n_stages * CHDB_N_IN; i += kThreads) sh.ctl[i / CHDB_N_IN].cols[i % CHDB_N_IN] = P.in[i % CHDB_N_IN];
 }
 
 // ------------------------------------------------------------------------------------------
-// the producer warp (both streaming kernels): tile n of this CTA is tile blockIdx.x + n * gridDim.x.
-// Lane s owns input slot s: it copies the tile's slice of each buffer the kernel uses into the stage
-// with TMA bulk copies (completion is counted in bytes on the stage's `full` mbarrier) and leaves the
-// column's biased pointers in the stage's table; buffers that are used but not staged get a bulk L2
-// prefetch.  GATHER: lane 31 also brings the tile's selection bits and slice prefixes.
+// the producer warps (both streaming kernels): tile n of this CTA is tile blockIdx.x + n * gridDim.x.
+// The three warps walk the same tile sequence; warp `kind` brings one kind of buffer (0: validity
+// bitmaps, 1: Utf8 offsets, 2: values), lane s for input slot s: the tile's slice goes into the stage
+// with a TMA bulk copy (completion is counted in bytes on the stage's `full` mbarrier, on which every
+// producer warp arrives once) and the column's biased pointer into the stage's table; buffers that
+// are used but not staged get a bulk L2 prefetch.  GATHER: lane 31 of warp 0 also brings the tile's
+// selection bits and slice prefixes.  Issuing a bulk copy costs the issuing warp ~100 cycles, which is
+// why the ~10 copies of a tile are spread over three warps.
 // ------------------------------------------------------------------------------------------
 template <bool GATHER>
-__device__ __forceinline__ void producer_loop(const KernelParams& P, const KernelStage& ST, SharedState& sh, uint8_t* smem, int lane) {
-  const uint32_t S = (uint32_t)ST.n_stages;
+__device__ __forceinline__ void producer_loop(const KernelParams& P, const KernelStage& ST, SharedState& sh, uint8_t* smem, int lane, int kind) {
+  const int32_t S = ST.n_stages;
   const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
   const int nq = 1 + CHDB_N_UTF8;
-  PhaseClock pc;   // [8] wait for a free stage, [9] addresses + boundary offsets, [10] issue
+  PhaseClock pc;   // [8] wait for a free stage, [9] addresses, [10] issue
   pc.start(P.timing != nullptr);
-  uint32_t sentinels = 0;
-  for (uint32_t n = 0;; n++) {
-    const uint32_t stage = n % S, ph = (n / S) & 1u;
+  // this CTA's tiles: blockIdx.x + n * gridDim.x for n < n_mine; then one "no more tiles" stage per compute group
+  const int64_t n_mine = (int64_t)blockIdx.x < P.num_tiles ? (P.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t last_tile = P.num_tiles - 1;
+  const uint32_t last_rows = (uint32_t)(P.num_rows - last_tile * kTileRows);
+  // What this lane brings is fixed for the whole launch: one buffer, a fixed number of bytes further per
+  // tile -- except Utf8 value bytes.
+  const uint8_t* gsrc = nullptr;   // global base of the buffer
+  uint32_t stride = 0;             // bytes per tile
+  uint32_t soff = 0;               // offset in the stage
+  uint32_t full_bytes = 0, tail_bytes = 0;   // copy sizes: whole tile / last tile
+  bool used = false, staged = false, utf8_values = false;
+  uint32_t values_cap = 0;
+  const int32_t* goff = nullptr;
+  if (lane < CHDB_N_IN) {
+    const ColumnDesc g = P.in[lane];
+    const StageSlot sl = ST.slot[lane];
+    const uint32_t use = ST.use[lane];
+    const uint32_t tail_bits = (((last_rows + 7u) >> 3) + 15u) & ~15u;
+    if (kind == 0) {
+      gsrc = g.validity;
+      if ((use & USE_VALIDITY) && g.validity != nullptr) {
+        used = true; staged = sl.validity != kNotStaged; stride = kTileRows / 8; soff = sl.validity;
+        full_bytes = kTileRows / 8; tail_bytes = tail_bits;
+      }
+    } else if (kind == 1) {
+      gsrc = (const uint8_t*)g.offsets;
+      if (g.type == T_UTF8 && (use & USE_OFFSETS)) {
+        used = true; staged = sl.offsets != kNotStaged; stride = kTileRows * 4; soff = sl.offsets;
+        full_bytes = ((kTileRows + 1u) * 4u + 15u) & ~15u; tail_bytes = ((last_rows + 1u) * 4u + 15u) & ~15u;
+      }
+    } else {
+      gsrc = (const uint8_t*)g.values;
+      if (use & USE_VALUES) {
+        used = true; staged = sl.values != kNotStaged; soff = sl.values;
+        if (g.type == T_UTF8) {
+          utf8_values = true; goff = g.offsets; values_cap = sl.values_cap;
+        } else {
+          const uint32_t w = g.width;
+          stride = w ? kTileRows * w : kTileRows / 8;
+          full_bytes = stride; tail_bytes = w ? (last_rows * w + 15u) & ~15u : tail_bits;
+        }
+      }
+    }
+  }
+  // Utf8 value bytes of a tile start at offsets[row0]: fetched three tiles ahead (an L2 round trip takes
+  // longer than issuing a tile)
+  uint32_t b0[3] = {0, 0, 0}, b1[3] = {0, 0, 0};
+  auto fetch_bounds = [&](int64_t n, uint32_t& o0, uint32_t& o1) {
+    if (utf8_values && n < n_mine) {
+      const int64_t tile = (int64_t)blockIdx.x + n * gridDim.x;
+      const int64_t row0 = tile * kTileRows;
+      o0 = (uint32_t)goff[row0];
+      o1 = (uint32_t)goff[row0 + (tile == last_tile ? last_rows : kTileRows)];
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < 3; j++) fetch_bounds(j, b0[j], b1[j]);
+  int32_t stage = 0;
+  uint32_t ph = 0;
+  for (int64_t n = 0; n < n_mine + kComputeGroups; n++) {
     mbar_wait(smem_u32(&sh.empty[stage]), ph ^ 1u);
     pc.lap(0);
     TileCtl& C = sh.ctl[stage];
     const uint32_t full = smem_u32(&sh.full[stage]);
-    const int64_t tile = (int64_t)blockIdx.x + (int64_t)n * gridDim.x;
-    if (tile >= P.num_tiles) {
-      // out of tiles: every compute group must meet a stage that says so
-      if (lane == 0) { C.tile = -1; mbar_arrive(full); }
-      if (++sentinels == (uint32_t)kComputeGroups) { pc.flush(P.timing, 8, lane); break; }
-      continue;
-    }
-    const int64_t row0 = tile * kTileRows;
-    const uint32_t rows = (uint32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
-    uint8_t* const sg = smem + (size_t)stage * ST.stage_bytes;   // generic address of the stage
-    const uint32_t ss = smem_u32(sg);
-    // what this lane copies: up to three buffers of its slot
-    const void* src[3] = {nullptr, nullptr, nullptr};
-    uint32_t dst[3] = {0, 0, 0}, nbytes[3] = {0, 0, 0};
-    const void* pf_src = nullptr;   // used but not staged: bulk L2 prefetch instead
-    uint32_t pf_bytes = 0;
-    if (lane < CHDB_N_IN) {
-      const ColumnDesc g = P.in[lane];
-      const StageSlot sl = ST.slot[lane];
-      const uint32_t use = ST.use[lane];
-      ColumnDesc v = g;
-      const uint32_t bit_bytes = (((rows + 7u) >> 3) + 15u) & ~15u;
-      if ((use & USE_VALIDITY) && g.validity != nullptr && sl.validity != kNotStaged) {
-        src[0] = g.validity + (row0 >> 3); dst[0] = ss + sl.validity; nbytes[0] = bit_bytes;
-        v.validity = sg + sl.validity - (row0 >> 3);
+    if (n >= n_mine) {
+      if (lane == 0) { if (kind == 0) C.tile = -1; mbar_arrive(full); }
+    } else {
+      const int64_t tile = (int64_t)blockIdx.x + n * gridDim.x;
+      const bool last = tile == last_tile;
+      uint8_t* const sg = smem + (size_t)stage * ST.stage_bytes;   // generic address of the stage
+      const uint32_t ss = smem_u32(sg);
+      const int64_t adv = tile * (int64_t)stride;
+      const uint8_t* src = gsrc + adv;
+      uint32_t nbytes = used && staged ? (last ? tail_bytes : full_bytes) : 0u;
+      const uint8_t* vptr = used && staged ? sg + soff - adv : gsrc;   // biased: indexing with the absolute row lands in the stage
+      uint32_t pf_bytes = used && !staged ? (last ? tail_bytes : full_bytes) : 0u;   // used but not staged: bulk L2 prefetch
+      if (utf8_values) {
+        const uint32_t lo = b0[0] & ~15u, len = (b1[0] - lo + 15u) & ~15u;
+        src = gsrc + lo;
+        if (staged && len <= values_cap) { nbytes = len; vptr = sg + soff - lo; pf_bytes = 0; }
+        else { nbytes = 0; vptr = gsrc; pf_bytes = len; }
+        // rotate the bounds queue and refill its tail
+        b0[0] = b0[1]; b1[0] = b1[1]; b0[1] = b0[2]; b1[1] = b1[2];
+        fetch_bounds(n + 3, b0[2], b1[2]);
       }
-      if (g.type == T_UTF8) {
-        if ((use & USE_OFFSETS) && sl.offsets != kNotStaged) {
-          src[1] = g.offsets + row0; dst[1] = ss + sl.offsets; nbytes[1] = ((rows + 1u) * 4u + 15u) & ~15u;
-          v.offsets = (const int32_t*)(sg + sl.offsets) - row0;
-        }
-        if (use & USE_VALUES) {
-          const uint32_t o0 = (uint32_t)g.offsets[row0], o1 = (uint32_t)g.offsets[row0 + rows];
-          const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
-          if (sl.values != kNotStaged && len <= sl.values_cap) {
-            src[2] = (const uint8_t*)g.values + lo; dst[2] = ss + sl.values; nbytes[2] = len;
-            v.values = sg + sl.values - lo;
-          } else {
-            pf_src = (const uint8_t*)g.values + lo; pf_bytes = len;
-          }
-        }
-      } else if (use & USE_VALUES) {
-        const uint32_t w = g.width;
-        const uint32_t vb = w ? (rows * w + 15u) & ~15u : bit_bytes;
-        const int64_t first = w ? row0 * (int64_t)w : (row0 >> 3);
-        if (sl.values != kNotStaged) {
-          src[2] = (const uint8_t*)g.values + first; dst[2] = ss + sl.values; nbytes[2] = vb;
-          v.values = sg + sl.values - first;
-        } else {
-          pf_src = (const uint8_t*)g.values + first; pf_bytes = vb;
-        }
+      if (lane < CHDB_N_IN) {
+        if (kind == 0) C.cols[lane].validity = vptr;
+        else if (kind == 1) C.cols[lane].offsets = (const int32_t*)vptr;
+        else C.cols[lane].values = vptr;
       }
-      C.cols[lane] = v;
+      uint32_t extra = 0;
+      if (GATHER && has_pred && kind == 0 && lane == 31) extra = kTileRows / 8 + (uint32_t)nq * kSlices * 8;
+      const uint32_t tx = __reduce_add_sync(FULL, nbytes + extra);
+      pc.lap(1);
+      if (lane == 0) {
+        if (kind == 0) C.tile = (int32_t)tile;
+        mbar_arrive_expect_tx(full, tx);
+      }
+      __syncwarp();
+      if (nbytes) tma_load(ss + soff, src, nbytes, full);
+      if (pf_bytes) tma_prefetch_l2(src, pf_bytes);
+      if (extra) {
+        tma_load(ss + ST.sel_off, P.sel_bits + tile * (kTileRows / 32), kTileRows / 8, full);
+        for (int qi = 0; qi < nq; qi++)
+          tma_load(ss + ST.prefix_off + qi * kSlices * 8, P.slice_prefix + (size_t)qi * P.slice_pitch + tile * kSlices, kSlices * 8, full);
+      }
+      pc.lap(2);
     }
-    uint32_t extra = 0;
-    if (GATHER && has_pred && lane == 31) extra = kTileRows / 8 + (uint32_t)nq * kSlices * 8;
-    const uint32_t tx = __reduce_add_sync(FULL, nbytes[0] + nbytes[1] + nbytes[2] + extra);
-    pc.lap(1);
-    if (lane == 0) {
-      C.tile = (int32_t)tile;
-      mbar_arrive_expect_tx(full, tx);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-      if (nbytes[i]) tma_load(dst[i], src[i], nbytes[i], full);
-    if (pf_bytes) tma_prefetch_l2(pf_src, pf_bytes);
-    if (extra) {
-      tma_load(ss + ST.sel_off, P.sel_bits + tile * (kTileRows / 32), kTileRows / 8, full);
-      for (int qi = 0; qi < nq; qi++)
-        tma_load(ss + ST.prefix_off + qi * kSlices * 8, P.slice_prefix + (size_t)qi * P.slice_pitch + tile * kSlices, kSlices * 8, full);
-    }
-    pc.lap(2);
+    if (++stage == S) { stage = 0; ph ^= 1u; }
   }
+  if (kind == 2) pc.flush(P.timing, 8, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1031,15 +1066,15 @@ __device__ __forceinline__ void select_body(const KernelParams& P, const KernelS
   init_shared(P, ST, sh, tid);
   __syncthreads();
   // from here on the producer and the compute warps only meet through the stages' mbarriers
-  if (warp == kComputeWarps) {
-    producer_loop<false>(P, ST, sh, smem, lane);
+  if (warp >= kComputeWarps) {
+    producer_loop<false>(P, ST, sh, smem, lane, warp - kComputeWarps);
     return;
   }
   const int group = warp / kSlices, slice = warp % kSlices;
   PhaseClock pc;   // [0] wait for the stage (TMA), [1] predicate + counts
   pc.start(P.timing != nullptr);
-  for (uint32_t n = group;; n += kComputeGroups) {
-    const uint32_t stage = n % S, ph = (n / S) & 1u;
+  uint32_t stage = (uint32_t)group % S, ph = ((uint32_t)group / S) & 1u;
+  for (;;) {
     TileCtl& C = sh.ctl[stage];
     mbar_wait(smem_u32(&sh.full[stage]), ph);
     pc.lap(0);
@@ -1090,6 +1125,8 @@ __device__ __forceinline__ void select_body(const KernelParams& P, const KernelS
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&sh.empty[stage]));   // this warp is done with the stage
     pc.lap(1);
+    stage += kComputeGroups;
+    while (stage >= S) { stage -= S; ph ^= 1u; }
   }
   pc.flush(P.timing, 0, lane);
 }
@@ -1496,8 +1533,8 @@ __device__ __forceinline__ void gather_body(const KernelParams& P, const KernelS
   for (int i = tid; i < kComputeWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
   __syncthreads();
   // from here on the producer and the compute warps only meet through the stages' mbarriers
-  if (warp == kComputeWarps) {
-    producer_loop<true>(P, ST, sh, smem, lane);
+  if (warp >= kComputeWarps) {
+    producer_loop<true>(P, ST, sh, smem, lane, warp - kComputeWarps);
     return;
   }
   if (has_pred && blockIdx.x == 0 && warp == 0) {
@@ -1511,8 +1548,8 @@ __device__ __forceinline__ void gather_body(const KernelParams& P, const KernelS
   uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
   PhaseClock pc;   // [0] wait for the stage (TMA), [1] ranks, [2] outputs, [3] bit flush + release
   pc.start(P.timing != nullptr);
-  for (uint32_t n = group;; n += kComputeGroups) {
-    const uint32_t stage = n % S, ph = (n / S) & 1u;
+  uint32_t stage = (uint32_t)group % S, ph = ((uint32_t)group / S) & 1u;
+  for (;;) {
     TileCtl& C = sh.ctl[stage];
     mbar_wait(smem_u32(&sh.full[stage]), ph);
     pc.lap(0);
@@ -1564,6 +1601,8 @@ __device__ __forceinline__ void gather_body(const KernelParams& P, const KernelS
     if (P.n_bits > 0) flush_bits(P, sh, bitstage, L.obase, L.count, lane);
     __syncwarp();
     pc.lap(3);
+    stage += kComputeGroups;
+    while (stage >= S) { stage -= S; ph ^= 1u; }
   }
   pc.flush(P.timing, 0, lane);
   // null counts of this CTA

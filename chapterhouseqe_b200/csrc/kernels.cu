@@ -58,10 +58,10 @@ StagePlan plan_stages(const KernelParams& kp, KernelStage& st, const int64_t* av
   struct Shape { int ctas, stages; };
   std::vector<Shape> shapes;
   for (int c = kMinCtasPerSm; c >= 1; c--)
-    for (int n = kMaxStages; n >= 2; n--) shapes.push_back(Shape{c, n});
+    for (int n = kMaxStages; n > kComputeGroups; n--) shapes.push_back(Shape{c, n});   // the parity waits need a ring deeper than the groups
   if (const char* e = std::getenv(gather ? "CHDB_SHAPE" : "CHDB_SHAPE_SELECT")) {   // experiments: "ctas,stages" tried first
     int c = 0, n = 0;
-    if (std::sscanf(e, "%d,%d", &c, &n) == 2 && c >= 1 && c <= 4 && n >= 2 && n <= kMaxStages) shapes.insert(shapes.begin(), Shape{c, n});
+    if (std::sscanf(e, "%d,%d", &c, &n) == 2 && c >= 1 && c <= 4 && n > kComputeGroups && n <= kMaxStages) shapes.insert(shapes.begin(), Shape{c, n});
   }
   Shape pick{0, 0};
   while (true) {
@@ -74,7 +74,7 @@ StagePlan plan_stages(const KernelParams& kp, KernelStage& st, const int64_t* av
     auto big = std::max_element(bufs.begin(), bufs.end(), [](const Buf& a, const Buf& b) { return a.bytes < b.bytes; });
     bufs.erase(big);
   }
-  if (!pick.ctas) pick = Shape{1, 2};
+  if (!pick.ctas) pick = Shape{1, kComputeGroups + 1};
   size_t off = 0;
   for (auto& b : bufs) {
     StageSlot& sl = st.slot[b.slot];

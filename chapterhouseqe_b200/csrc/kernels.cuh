@@ -10,7 +10,7 @@
 namespace chdb {
 
 // A tile is kSlices slices of 128 rows; a slice is the unit one warp works on (4 rows per lane).
-// Both streaming kernels are persistent: one TMA producer warp feeds a ring of shared-memory stages,
+// Both streaming kernels are persistent: kProducerWarps TMA producer warps feed a ring of shared-memory stages,
 // kComputeGroups groups of kSlices compute warps drain it (group g takes the CTA's tiles g, g + kComputeGroups, ...).
 #ifndef CHDB_SLICES
 #define CHDB_SLICES 8
@@ -23,7 +23,8 @@ constexpr int kComputeGroups = CHDB_COMPUTE_GROUPS;
 constexpr int kComputeWarps = kComputeGroups * kSlices;
 constexpr int kWarpRows = 128;                        // rows of one slice
 constexpr int kTileRows = kSlices * kWarpRows;        // 1024 rows per tile
-constexpr int kThreads = (kComputeWarps + 1) * 32;
+constexpr int kProducerWarps = 3;           // one per kind of buffer: validity bitmaps, Utf8 offsets, values
+constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
 constexpr int kMinCtasPerSm = kThreads <= 512 ? 2 : 1;       // register budget the kernels are compiled for
 constexpr int kMaxStages = 8;               // depth of the shared-memory input ring
 constexpr int kMaxQuantities = 1 + kMaxOutCols;              // scanned quantities: rows + bytes per Utf8 output
