@@ -152,6 +152,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        # NVML queries take driver locks that kernel launches and allocations also need: sample sparsely
+        self.period = float(os.environ.get("CHDB_BENCH_CLOCK_PERIOD", "0.05"))
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -180,7 +182,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop_evt.wait(0.004)
+            self._stop_evt.wait(self.period)
 
     def stop(self):
         self._stop_evt.set()
@@ -358,10 +360,23 @@ def run_ours(args, rank, world, local_rank):
     ev0.record(stream)
     prev = None
     t_host0 = time.perf_counter()
+    trace = [] if os.environ.get("CHDB_BENCH_TRACE") else None
     for _ in range(args.steps):
-        cur = one_step()
-        prev = cur   # the previous step's outputs are released here (cudaFreeAsync on the same stream)
+        if trace is not None:
+            cur = []
+            for b in dev_batches:
+                t0 = time.perf_counter()
+                cur.append(b.run(prog))
+                trace.append(("run", (time.perf_counter() - t0) * 1e6))
+            t0 = time.perf_counter()
+            prev = cur
+            trace.append(("release", (time.perf_counter() - t0) * 1e6))
+        else:
+            cur = one_step()
+            prev = cur   # the previous step's outputs are released here (they go back to the ctx's block cache)
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
+    if trace is not None:
+        sys.stderr.write("[bench trace] " + " ".join(f"{k}:{v:.0f}" for k, v in trace) + "\n")
     ev1.record(stream)
     ctx.synchronize()
     torch.cuda.synchronize(device)

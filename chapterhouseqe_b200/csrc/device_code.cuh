@@ -850,17 +850,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// The suspend-time hint lets the hardware park the waiting warp until the phase completes.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// try_wait with the default (short) time limit, and a back-off between failed tries.  (With an explicit
+// suspend-time hint of milliseconds, launches now and then took milliseconds: a waiter parked just as its
+// phase completed seems to sleep the hint out.)
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 // global -> shared bulk copy (TMA, 1-D); dst, src and bytes are multiples of 16
 __device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar) {
@@ -870,6 +874,12 @@ __device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32
 __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+// Programmatic dependent launch: the three kernels of a batch are launched back to back with
+// programmatic stream serialisation, so a kernel's CTAs are scheduled (and run their prologue) while its
+// predecessor drains; grid_dependency_wait() returns once the predecessor has completed and its writes
+// are visible.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void compute_warps_barrier() {
   asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
 }
@@ -1064,11 +1074,24 @@ __device__ __forceinline__ void select_body(const KernelParams& P, const KernelS
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t S = (uint32_t)ST.n_stages;
   init_shared(P, ST, sh, tid);
+  grid_launch_dependents();   // the scan kernel may be scheduled as soon as SMs free up (it waits for this grid to finish)
   __syncthreads();
   // from here on the producer and the compute warps only meet through the stages' mbarriers
   if (warp >= kComputeWarps) {
     producer_loop<false>(P, ST, sh, smem, lane, warp - kComputeWarps);
     return;
+  }
+  // The gather kernel merges the edge words of bit-packed outputs (validity, Boolean) with atomicOr:
+  // they are zeroed here, by the whole grid, instead of by one memset per buffer on the stream.
+  if (P.n_bits > 0) {
+    const int64_t words = (P.num_rows + 31) >> 5;
+    const int64_t first = (int64_t)blockIdx.x * (kComputeWarps * 32) + tid, step = (int64_t)gridDim.x * (kComputeWarps * 32);
+    for (int k = 0; k < P.n_out; k++) {
+      uint32_t* bits[2] = {P.out[k].type == T_BOOL ? (uint32_t*)P.out[k].values : nullptr, (uint32_t*)P.out[k].validity};
+      for (int j = 0; j < 2; j++)
+        if (bits[j] != nullptr)
+          for (int64_t i = first; i < words; i += step) bits[j][i] = 0;
+    }
   }
   const int group = warp / kSlices, slice = warp % kSlices;
   PhaseClock pc;   // [0] wait for the stage (TMA), [1] predicate + counts
@@ -1139,6 +1162,8 @@ __device__ __forceinline__ void scan_body(const KernelParams& P) {
   __shared__ uint64_t s_warp[kScanThreads / 32];
   __shared__ uint64_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  grid_launch_dependents();
+  grid_dependency_wait();     // the select kernel's slice counts
   const uint32_t chunk = blockIdx.x, qi = blockIdx.y;
   const uint32_t* counts = P.slice_counts + (size_t)qi * P.slice_pitch;
   uint64_t* prefix = P.slice_prefix + (size_t)qi * P.slice_pitch;
@@ -1531,6 +1556,7 @@ __device__ __forceinline__ void gather_body(const KernelParams& P, const KernelS
   uint32_t* const ltab = bitstages + kComputeWarps * P.n_bits * kBitWords;
   init_shared(P, ST, sh, tid);
   for (int i = tid; i < kComputeWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
+  grid_dependency_wait();     // the scan kernel's prefixes (and, through it, the select kernel's selection bits)
   __syncthreads();
   // from here on the producer and the compute warps only meet through the stages' mbarriers
   if (warp >= kComputeWarps) {

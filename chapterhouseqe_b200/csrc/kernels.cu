@@ -93,6 +93,8 @@ StagePlan plan_stages(const KernelParams& kp, KernelStage& st, const int64_t* av
   return plan;
 }
 
+bool pdl_enabled();
+
 cudaError_t launch_streaming(const void* kernel, const KernelParams& p, const KernelStage& st, const StagePlan& plan, int sm_count,
                              size_t* granted, cudaStream_t stream) {
   if (*granted == 0) {   // opt in to the large dynamic window once per kernel; static + dynamic may pass 48 KB for any plan
@@ -107,7 +109,22 @@ cudaError_t launch_streaming(const void* kernel, const KernelParams& p, const Ke
   const int64_t resident = (int64_t)plan.ctas_per_sm * sm_count;
   const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, resident);
   void* args[] = {const_cast<KernelParams*>(&p), const_cast<KernelStage*>(&st)};
-  return cudaLaunchKernel(kernel, dim3(grid), dim3(kThreads), args, plan.dyn_smem, stream);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = plan.dyn_smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("CHDB_PDL"); return !(e && *e == '0'); }();
+  return on;
 }
 
 namespace {
@@ -132,8 +149,17 @@ cudaError_t launch_gather(const KernelParams& p, const KernelStage& st, bool has
 }
 
 cudaError_t launch_scan(const KernelParams& p, cudaStream_t stream) {
-  scan_kernel<<<dim3((unsigned)p.num_chunks, (unsigned)(1 + p.n_utf8)), dim3(kScanThreads), 0, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p.num_chunks, (unsigned)(1 + p.n_utf8));
+  cfg.blockDim = dim3(kScanThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  void* args[] = {const_cast<KernelParams*>(&p)};
+  return cudaLaunchKernelExC(&cfg, (const void*)scan_kernel, args);
 }
 
 }  // namespace chdb

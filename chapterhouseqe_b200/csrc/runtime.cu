@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,9 +48,19 @@ struct CtxCore {
   // size-class cache of pinned host buffers: downloaded batches land in page-locked memory so the
   // D2H copies run at PCIe speed; ArrowArray.release hands the blocks back here.
   std::map<size_t, std::vector<void*>> host_free;
+  // Device blocks released by finished batches, by size: steady-state batches of one shape reuse them
+  // without going back to cudaMallocAsync / cudaFreeAsync (which cost a dozen driver calls per batch and
+  // now and then take the allocator's millisecond slow path).  Reuse is safe because everything this
+  // library does with a block is ordered on the ctx's one stream.
+  std::map<size_t, std::vector<void*>> dev_free;
+  size_t dev_cached = 0;
+  static constexpr size_t kDevCacheCap = (size_t)24 << 30;   // beyond this, released blocks go back to the pool
 
   ~CtxCore() {
     cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& kv : dev_free)
+      for (void* p : kv.second) cudaFreeAsync(p, stream);
     if (stream) cudaStreamSynchronize(stream);
     for (void* p : pinned_free) cudaFreeHost(p);
     for (auto& kv : host_free)
@@ -108,10 +119,17 @@ struct DevBuf {
   void* ptr = nullptr;
   size_t bytes = 0;
   ~DevBuf() {
-    if (ptr) {
-      cudaSetDevice(core->device);
-      cudaFreeAsync(ptr, core->stream);
+    if (!ptr) return;
+    {
+      std::lock_guard<std::mutex> g(core->mu);
+      if (core->dev_cached + bytes <= CtxCore::kDevCacheCap) {
+        core->dev_free[bytes].push_back(ptr);
+        core->dev_cached += bytes;
+        return;
+      }
     }
+    cudaSetDevice(core->device);
+    cudaFreeAsync(ptr, core->stream);
   }
 };
 using Buf = std::shared_ptr<DevBuf>;
@@ -120,6 +138,16 @@ static Buf dev_alloc(const Core& core, size_t bytes) {
   auto b = std::make_shared<DevBuf>();
   b->core = core;
   b->bytes = round_up(bytes + kPad, 256);
+  {
+    std::lock_guard<std::mutex> g(core->mu);
+    auto it = core->dev_free.find(b->bytes);
+    if (it != core->dev_free.end() && !it->second.empty()) {
+      b->ptr = it->second.back();
+      it->second.pop_back();
+      core->dev_cached -= b->bytes;
+      return b;
+    }
+  }
   CUDA_CHECK(cudaMallocAsync(&b->ptr, b->bytes, core->stream));
   return b;
 }
@@ -494,7 +522,33 @@ static DeviceColumn const_column(const Core& core, const OutputColumn& o) {
   return dc;
 }
 
+// CHDB_HOST_TIMING=1: where the host spends its time inside execute() (debugging aid): calls that take
+// longer than 300 us report their phases on stderr.
+struct HostClock {
+  bool on;
+  std::chrono::steady_clock::time_point t0, t;
+  double ph[4] = {0, 0, 0, 0};
+  HostClock() {
+    static const bool enabled = [] { const char* e = std::getenv("CHDB_HOST_TIMING"); return e && *e == '1'; }();
+    on = enabled;
+    if (on) t0 = t = std::chrono::steady_clock::now();
+  }
+  void lap(int i) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    ph[i] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  ~HostClock() {
+    if (!on) return;
+    const double total = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    if (total > 300) std::fprintf(stderr, "[chdb host] execute %.0f us: allocate outputs %.0f, workspace+memset %.0f, plan+launch %.0f, read-back %.0f\n",
+                                  total, ph[0], ph[1], ph[2], ph[3]);
+  }
+};
+
 static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in_orig) {
+  HostClock hc;
   const Core& core = ctx->core;
   CUDA_CHECK(cudaSetDevice(core->device));
   if (in_orig->core->device != core->device)
@@ -659,6 +713,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     return out;
   }
 
+  hc.lap(0);
   // ---- launch: select -> scan -> gather (gather alone when there is no predicate) ----
   const int64_t num_tiles = (n + kTileRows - 1) / kTileRows;
   if (num_tiles > INT32_MAX) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "batch too large");
@@ -681,8 +736,10 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   CUDA_CHECK(cudaEventCreateWithFlags(&res->done, cudaEventDisableTiming));
   uint8_t* ws = (uint8_t*)res->workspace->ptr;
   CUDA_CHECK(cudaMemsetAsync(ws, 0, ws_counts + ws_desc, core->stream));
-  for (auto& z : to_zero) CUDA_CHECK(cudaMemsetAsync(z.first, 0, z.second, core->stream));
+  if (!compact)   // (with a predicate the select kernel zeroes them)
+    for (auto& z : to_zero) CUDA_CHECK(cudaMemsetAsync(z.first, 0, z.second, core->stream));
 
+  hc.lap(1);
   kp.num_rows = n;
   kp.num_slices = (n + kWarpRows - 1) / kWarpRows;
   kp.slice_pitch = slice_pitch;
@@ -785,10 +842,12 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
                  t[8] / tiles, t[9] / tiles, t[10] / tiles, plan_gather.ctas_per_sm, st_gather.n_stages, st_gather.stage_bytes,
                  t[16] / cw, t[17] / cw, t[18] / cw, t[19] / cw, t[24] / tiles, t[25] / tiles, t[26] / tiles);
   }
+  hc.lap(2);
   CUDA_CHECK(cudaMemcpyAsync(res->host, ws, (size_t)(n_counts + 1) * 8, cudaMemcpyDeviceToHost, core->stream));
   CUDA_CHECK(cudaEventRecord(res->done, core->stream));
   out->result = res;
   out->num_rows = compact ? -1 : n;
+  hc.lap(3);
   return out;
 }
 

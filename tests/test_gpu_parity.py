@@ -311,3 +311,22 @@ def test_round_trip_properties_at_scale():
     # idempotence: filtering the result again with the same predicate changes nothing
     again = C.filter_record(out, [[], [], []], sp.parse_expr("id % 2 = 0"))
     assert again.equals(out)
+
+
+@pytest.mark.parametrize("jit", ["0", "always"])
+def test_many_tiles_per_cta(jit, monkeypatch):
+    """700k rows = 684 tiles on at most 148 persistent CTAs: every CTA walks its shared-memory ring several
+    times (stage reuse, mbarrier phase flips), with nulls, Utf8 and a fused projection, against the oracle."""
+    monkeypatch.setenv("CHDB_JIT", jit)
+    rb = make_mixed_batch(700_000, seed=991)
+    al = [[] for _ in rb.schema]
+    expr = sp.parse_expr("(id % 2 = 0 and value2 > 10.0) or d < 0.5")
+    want = O.filter_record(O.batch_from_arrow(rb), al, expr)
+    ok, why = O.batches_equal(O.batch_from_arrow(C.filter_record(rb, al, expr)), want)
+    assert ok, why
+    sel = sp.parse_select(PROJECTIONS[1] + " where id % 3 = 0")
+    b = O.batch_from_arrow(rb)
+    want = O.project_record(sel["projection"], O.filter_record(b, al, sel["selection"]), al)
+    got = O.batch_from_arrow(C.filter_project_record(sel["selection"], sel["projection"], rb, al))
+    ok, why = O.batches_equal(got, want)
+    assert ok, why
