@@ -765,6 +765,12 @@ __device__ __forceinline__ void run_program(const KernelParams& P, const ColumnD
 // ------------------------------------------------------------------------------------------
 // scans
 // ------------------------------------------------------------------------------------------
+// Waits are bounded: a wait that lasts about a second is a bug (or a lost dependency), and a diagnostic plus a
+// trapped launch (the host sees a CUDA error) beats a hung stream.
+__device__ __noinline__ void wait_timed_out(const char* what, uint32_t a, uint32_t b) {
+  printf("[chdb] %s timed out: block %d warp %d (%u, %u)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5), a, b);
+  __trap();
+}
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
   uint32_t x = v;
 #pragma unroll
@@ -817,7 +823,12 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* d, uint32_t chunk, uint64
     for (int j = 0; j < kLookBackPerLane; j++) {
       if (!found) {
         const int64_t idx = base - (lane * kLookBackPerLane + j);
-        while ((v[j] >> 62) == 0) { __nanosleep(40); v[j] = load_descriptor(d + idx); }
+        uint32_t spins = 0;
+        while ((v[j] >> 62) == 0) {
+          __nanosleep(40);
+          v[j] = load_descriptor(d + idx);
+          if (++spins > (1u << 22)) wait_timed_out("look-back", chunk, (uint32_t)idx);
+        }
         part += v[j] & kValueMask;
         found = (v[j] >> 62) == 2;
       }
@@ -864,7 +875,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 22)) wait_timed_out("mbarrier wait", bar, parity);
+  }
 }
 // global -> shared bulk copy (TMA, 1-D); dst, src and bytes are multiples of 16
 __device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar) {
@@ -886,6 +901,7 @@ __device__ __forceinline__ void compute_warps_barrier() {
 
 // Role profile (debugging aid, CHDB_PHASE_TIMING=1): lane 0 of every warp accumulates the cycles it
 // spends in each phase and adds them to P.timing[] when it leaves.
+#ifdef CHDB_TIMING
 struct PhaseClock {
   long long t, acc[4];
   bool on;
@@ -896,6 +912,13 @@ struct PhaseClock {
       for (int i = 0; i < 4; i++) atomicAdd((unsigned long long*)&timing[base + i], (unsigned long long)acc[i]);
   }
 };
+#else
+struct PhaseClock {   // compiled out (the run-time specialised kernels get it with CHDB_PHASE_TIMING=1)
+  __device__ __forceinline__ void start(bool) {}
+  __device__ __forceinline__ void lap(int) {}
+  __device__ __forceinline__ void flush(uint64_t*, int, int) {}
+};
+#endif
 
 // Everything one tile needs besides its staged bytes; one per stage of the ring.
 struct TileCtl {
@@ -1250,10 +1273,11 @@ __device__ __forceinline__ uint32_t load_bits4(const uint8_t* __restrict__ bits,
 // Stores the selected elements of one quad at consecutive output positions.
 template <typename E>
 __device__ __forceinline__ void store_sel(E* d, uint32_t s4, const E& e0, const E& e1, const E& e2, const E& e3) {
-  if (s4 & 1u) { *d = e0; d++; }
-  if (s4 & 2u) { *d = e1; d++; }
-  if (s4 & 4u) { *d = e2; d++; }
-  if (s4 & 8u) { *d = e3; }
+  const uint32_t i1 = s4 & 1u, i2 = i1 + ((s4 >> 1) & 1u), i3 = i2 + ((s4 >> 2) & 1u);
+  if (s4 & 1u) d[0] = e0;
+  if (s4 & 2u) d[i1] = e1;
+  if (s4 & 4u) d[i2] = e2;
+  if (s4 & 8u) d[i3] = e3;
 }
 
 // 16 / 4 bytes from an arbitrarily aligned address (buffers are padded, so the aligned words around
@@ -1357,16 +1381,15 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl
                                             const LaneCtx& L, OutRegs& R) {
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu;
-  R.x = make_uint4(0, 0, 0, 0);
-  R.y = make_uint4(0, 0, 0, 0);
-  R.z = 0;
+  // Only what the column's type needs is loaded, and nothing is cleared first: fields the stores never
+  // look at stay undefined (clearing ten registers per output cost more instructions than the loads).
   R.vbits = FULL;
   if (o_kind != OUT_PASS) return;
   const ColumnDesc& c = C.cols[o_slot];
   const uint32_t sel = L.sel;
   const int64_t r = L.row_base;
   if (P.out[k].validity != nullptr) R.vbits = load_bits4(c.validity, r, sel);
-  if (!sel) return;
+  if (!L.inrange) return;   // (a tail tile's missing rows: nothing to read, nothing will be stored)
   const uint8_t* src = (const uint8_t*)c.values;
   if (o_type == T_BOOL) {
     R.z = load_bits4(src, r, sel);
@@ -1479,7 +1502,10 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
   }
   if (o_has_validity) {
     // nulls are the rare case: the stage collects the NULL bits (most lanes have nothing to add)
-    put_bits(~vbits, L, bitstage + kb * kBitWords, sh.pext4);
+    const uint32_t nulls = sel & ~vbits & 0xFu;
+    if (nulls) put_bits(nulls, L, bitstage + kb * kBitWords, sh.pext4);
+    const uint32_t slice_nulls = __reduce_add_sync(FULL, (uint32_t)__popc(nulls));
+    if (lane == 0 && slice_nulls) atomicAdd(const_cast<uint32_t*>(&sh.nulls[k]), slice_nulls);
     kb++;
   }
 }
@@ -1521,7 +1547,6 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& s
       if (which == 0 ? !is_bool : validity == nullptr) continue;
       uint32_t* sb = bitstage + kb * kBitWords;
       uint32_t* g = (uint32_t*)(which == 0 ? (uint8_t*)P.out[k].values : validity);
-      uint32_t nulls = 0;
       if (lane < kBitWords) {
         const uint32_t w = (uint32_t)lane;
         uint32_t word = sb[w];
@@ -1529,15 +1554,11 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& s
         if (w < nwords) {
           const uint32_t lo = w == 0 ? o : 0u, hi = 32 * w + 32 > end ? end - 32 * w : 32u;
           const uint32_t mask = (hi >= 32 ? FULL : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-          if (which == 1) { nulls = (uint32_t)__popc(word & mask); word = ~word; }
+          if (which == 1) word = ~word;
           word &= mask;
           if (mask == FULL) g[g0 + w] = word;
           else if (word) atomicOr(&g[g0 + w], word);
         }
-      }
-      if (which == 1) {
-        nulls = __reduce_add_sync(FULL, nulls);
-        if (lane == 0 && nulls) atomicAdd(&sh.nulls[k], nulls);
       }
       kb++;
     }

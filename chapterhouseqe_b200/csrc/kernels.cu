@@ -96,7 +96,7 @@ StagePlan plan_stages(const KernelParams& kp, KernelStage& st, const int64_t* av
 bool pdl_enabled();
 
 cudaError_t launch_streaming(const void* kernel, const KernelParams& p, const KernelStage& st, const StagePlan& plan, int sm_count,
-                             size_t* granted, cudaStream_t stream) {
+                             size_t* granted, bool after_kernel, cudaStream_t stream) {
   if (*granted == 0) {   // opt in to the large dynamic window once per kernel; static + dynamic may pass 48 KB for any plan
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
@@ -118,7 +118,9 @@ cudaError_t launch_streaming(const void* kernel, const KernelParams& p, const Ke
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  // only a kernel that follows another kernel of the same batch (and waits for it with griddepcontrol.wait) may start
+  // early; the select kernel follows the workspace memset and must not overtake it
+  cfg.numAttrs = after_kernel && pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
@@ -140,12 +142,12 @@ size_t* granted_slot(const void* kern) {
 
 cudaError_t launch_select(const KernelParams& p, const KernelStage& st, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream) {
   const void* kern = has64 ? (const void*)select_kernel<uint64_t> : (const void*)select_kernel<uint32_t>;
-  return launch_streaming(kern, p, st, plan, sm_count, granted_slot(kern), stream);
+  return launch_streaming(kern, p, st, plan, sm_count, granted_slot(kern), false, stream);
 }
 
 cudaError_t launch_gather(const KernelParams& p, const KernelStage& st, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream) {
   const void* kern = has64 ? (const void*)gather_kernel<uint64_t> : (const void*)gather_kernel<uint32_t>;
-  return launch_streaming(kern, p, st, plan, sm_count, granted_slot(kern), stream);
+  return launch_streaming(kern, p, st, plan, sm_count, granted_slot(kern), p.pred_end > p.pred_begin, stream);
 }
 
 cudaError_t launch_scan(const KernelParams& p, cudaStream_t stream) {

@@ -115,7 +115,7 @@ cudaError_t launch_scan(const KernelParams& p, cudaStream_t stream);
 cudaError_t launch_gather(const KernelParams& p, const KernelStage& st, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream);
 // shared by the ahead-of-time and the run-time compiled kernels
 cudaError_t launch_streaming(const void* kernel, const KernelParams& p, const KernelStage& st, const StagePlan& plan, int sm_count,
-                             size_t* granted, cudaStream_t stream);
+                             size_t* granted, bool after_kernel, cudaStream_t stream);
 #endif
 
 }  // namespace chdb

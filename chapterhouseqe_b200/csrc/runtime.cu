@@ -54,6 +54,7 @@ struct CtxCore {
   // library does with a block is ordered on the ctx's one stream.
   std::map<size_t, std::vector<void*>> dev_free;
   size_t dev_cached = 0;
+  std::vector<cudaEvent_t> events_free;   // recycled: creating / destroying an event is a driver resource call
   static constexpr size_t kDevCacheCap = (size_t)24 << 30;   // beyond this, released blocks go back to the pool
 
   ~CtxCore() {
@@ -61,6 +62,7 @@ struct CtxCore {
     if (stream) cudaStreamSynchronize(stream);
     for (auto& kv : dev_free)
       for (void* p : kv.second) cudaFreeAsync(p, stream);
+    for (cudaEvent_t e : events_free) cudaEventDestroy(e);
     if (stream) cudaStreamSynchronize(stream);
     for (void* p : pinned_free) cudaFreeHost(p);
     for (auto& kv : host_free)
@@ -110,6 +112,23 @@ struct CtxCore {
   void pinned_put(void* p) {
     std::lock_guard<std::mutex> g(mu);
     pinned_free.push_back(p);
+  }
+  cudaEvent_t event_get() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (!events_free.empty()) {
+        cudaEvent_t e = events_free.back();
+        events_free.pop_back();
+        return e;
+      }
+    }
+    cudaEvent_t e = nullptr;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return e;
+  }
+  void event_put(cudaEvent_t e) {
+    std::lock_guard<std::mutex> g(mu);
+    events_free.push_back(e);
   }
 };
 using Core = std::shared_ptr<CtxCore>;
@@ -161,8 +180,7 @@ struct RunResult {
   bool waited = false;
   Buf workspace;
   ~RunResult() {
-    cudaSetDevice(core->device);
-    if (done) cudaEventDestroy(done);
+    if (done) core->event_put(done);
     if (host) core->pinned_put(host);
   }
   void wait() {
@@ -733,7 +751,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   res->workspace = dev_alloc(core, ws_counts + ws_desc + ws_sel + ws_cnt + ws_pre);
   if ((size_t)(n_counts + 1) * 8 > CtxCore::kPinnedBlock) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "too many counted outputs");
   res->host = (uint64_t*)core->pinned_get();
-  CUDA_CHECK(cudaEventCreateWithFlags(&res->done, cudaEventDisableTiming));
+  res->done = core->event_get();
   uint8_t* ws = (uint8_t*)res->workspace->ptr;
   CUDA_CHECK(cudaMemsetAsync(ws, 0, ws_counts + ws_desc, core->stream));
   if (!compact)   // (with a predicate the select kernel zeroes them)
