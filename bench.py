@@ -292,7 +292,7 @@ def workload_config(args, sample_rows=None):
     cfg = {"workload": "C2 large_simple-shaped synthetic: " + SQL, "rows_per_gpu": args.rows,
            "batch_rows": args.batch_rows, "schema": "id i32 | k i64 | value2 f32 (10% null) | d f64 (5% null) | value1 utf8[8]",
            "null_semantics": "non-Kleene (arrow compute::and/or)", "parallelism": f"shard-by-batch x{args.gpus}, no collective",
-           "l2": "inputs (3.6 GB per GPU) exceed the 126 MB L2; no flush needed"}
+           "l2": "inputs (3.6 GB per GPU, 152 MB per batch) exceed the 126 MB L2; no flush needed"}
     if sample_rows is not None:
         cfg["sample_rows_per_step"] = sample_rows
     return cfg
