@@ -35,6 +35,11 @@ STR_LEN = 8
 IN_BYTES_PER_ROW = 4 + 8 + (4 + 0.125) + (8 + 0.125) + (4 + STR_LEN)
 
 
+if os.environ.get("CHDB_BENCH_WATCHDOG"):   # debugging aid: dump every thread's stack if the run is still going after N seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ["CHDB_BENCH_WATCHDOG"]), exit=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,7 +170,7 @@ class ClockSampler(threading.Thread):
             self.nv = None
 
     def run(self):
-        if self.nv is None:
+        if self.nv is None or os.environ.get("CHDB_BENCH_NO_CLOCKS"):
             return
         nv = self.nv
         names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",

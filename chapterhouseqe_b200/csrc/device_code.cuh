@@ -1087,6 +1087,38 @@ __device__ __forceinline__ void producer_loop(const KernelParams& P, const Kerne
   if (kind == 2) pc.flush(P.timing, 8, lane);
 }
 
+// How a compute group walks the ring.  A parity wait on an mbarrier is only sound if the waiter has seen the
+// barrier's previous phase complete: with groups taking every kComputeGroups-th tile, a group that simply
+// waited for its next tile could find that stage still in the phase of the tile before (its bytes not
+// landed yet) -- which looks exactly like "already complete".  So every group observes EVERY tile's
+// `full` barrier, in order: the tiles before its first one at the start, and the kComputeGroups - 1
+// tiles after each of its own before it releases that one (while it holds a stage the producers cannot
+// run more than a ring ahead, so nothing it has yet to observe can complete twice).
+struct RingCursor {
+  uint32_t stage, ph;
+  __device__ __forceinline__ void next(uint32_t S) { if (++stage == S) { stage = 0; ph ^= 1u; } }
+};
+// Waits for the tile at `c`; false when it is the "no more tiles" marker.
+__device__ __forceinline__ bool observe_tile(SharedState& sh, const RingCursor& c) {
+  mbar_wait(smem_u32(&sh.full[c.stage]), c.ph);
+  return *(volatile int32_t*)&sh.ctl[c.stage].tile >= 0;
+}
+// After a group's tile: observe the tiles of the other groups that follow it, then release the stage.
+// Leaves `c` at the group's next tile; false when the ring has run dry.
+__device__ __forceinline__ bool release_and_advance(SharedState& sh, RingCursor& c, uint32_t S, int lane) {
+  const uint32_t mine = c.stage;
+  bool more = true;
+#pragma unroll
+  for (int j = 1; j < kComputeGroups; j++) {
+    c.next(S);
+    if (more && !observe_tile(sh, c)) more = false;
+  }
+  c.next(S);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(smem_u32(&sh.empty[mine]));   // this warp is done with the stage
+  return more;
+}
+
 // ------------------------------------------------------------------------------------------
 // select: predicate -> selection bitmap + per-slice counts
 // ------------------------------------------------------------------------------------------
@@ -1119,13 +1151,15 @@ __device__ __forceinline__ void select_body(const KernelParams& P, const KernelS
   const int group = warp / kSlices, slice = warp % kSlices;
   PhaseClock pc;   // [0] wait for the stage (TMA), [1] predicate + counts
   pc.start(P.timing != nullptr);
-  uint32_t stage = (uint32_t)group % S, ph = ((uint32_t)group / S) & 1u;
-  for (;;) {
+  RingCursor cur{0, 0};
+  bool more = true;
+  for (int j = 0; j < group && more; j++) { more = observe_tile(sh, cur); cur.next(S); }   // the tiles before this group's first
+  while (more) {
+    const uint32_t stage = cur.stage;
     TileCtl& C = sh.ctl[stage];
-    mbar_wait(smem_u32(&sh.full[stage]), ph);
+    if (!observe_tile(sh, cur)) break;
     pc.lap(0);
     const int32_t tile = *(volatile int32_t*)&C.tile;
-    if (tile < 0) break;
     const int64_t row0 = (int64_t)tile * kTileRows;
     const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
     const ColumnDesc* cols = C.cols;
@@ -1168,11 +1202,8 @@ __device__ __forceinline__ void select_body(const KernelParams& P, const KernelS
       const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
       if (lane == 0) P.slice_counts[(size_t)(1 + o_utf8) * P.slice_pitch + sg] = wbytes;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&sh.empty[stage]));   // this warp is done with the stage
+    more = release_and_advance(sh, cur, S, lane);
     pc.lap(1);
-    stage += kComputeGroups;
-    while (stage >= S) { stage -= S; ph ^= 1u; }
   }
   pc.flush(P.timing, 0, lane);
 }
@@ -1595,13 +1626,15 @@ __device__ __forceinline__ void gather_body(const KernelParams& P, const KernelS
   uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
   PhaseClock pc;   // [0] wait for the stage (TMA), [1] ranks, [2] outputs, [3] bit flush + release
   pc.start(P.timing != nullptr);
-  uint32_t stage = (uint32_t)group % S, ph = ((uint32_t)group / S) & 1u;
-  for (;;) {
+  RingCursor cur{0, 0};
+  bool more = true;
+  for (int j = 0; j < group && more; j++) { more = observe_tile(sh, cur); cur.next(S); }   // the tiles before this group's first
+  while (more) {
+    const uint32_t stage = cur.stage;
     TileCtl& C = sh.ctl[stage];
-    mbar_wait(smem_u32(&sh.full[stage]), ph);
+    if (!observe_tile(sh, cur)) break;
     pc.lap(0);
     const int32_t tile = *(volatile int32_t*)&C.tile;
-    if (tile < 0) break;
     const uint8_t* sg = smem + (size_t)stage * ST.stage_bytes;
     LaneCtx L;
     L.lane = lane;
@@ -1643,13 +1676,10 @@ __device__ __forceinline__ void gather_body(const KernelParams& P, const KernelS
     }
 #endif
     pc.lap(2);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&sh.empty[stage]));   // this warp is done with the stage
+    more = release_and_advance(sh, cur, S, lane);
     if (P.n_bits > 0) flush_bits(P, sh, bitstage, L.obase, L.count, lane);
     __syncwarp();
     pc.lap(3);
-    stage += kComputeGroups;
-    while (stage >= S) { stage -= S; ph ^= 1u; }
   }
   pc.flush(P.timing, 0, lane);
   // null counts of this CTA
