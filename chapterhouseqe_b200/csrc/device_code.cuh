@@ -96,7 +96,6 @@ __device__ __forceinline__ void report_rows(const KernelParams& P, const Instr& 
 // ------------------------------------------------------------------------------------------
 // loads
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int QPT>
 __device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ bits, const int64_t (&qbase)[QPT], uint32_t need) {
