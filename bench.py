@@ -43,7 +43,7 @@ if os.environ.get("CHDB_BENCH_WATCHDOG"):   # debugging aid: dump every thread's
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
@@ -151,26 +151,33 @@ def batch_nbytes(rb) -> int:
 # ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+class ClockSampler:
+    """SM clock and throttle reasons of one GPU during the timed region (NVML).
+
+    An NVML query -- from a thread of this process or from `nvidia-smi -lms` next to it -- stalls this process's
+    CUDA calls for milliseconds to tens of milliseconds now and then (measured: host enqueue time per step 0.8 ms
+    -> 2-13 ms with a 20 ms sampling period), which starves the GPU in a timed region that is itself only tens
+    of milliseconds long.  So the samples are taken by the benchmark thread itself after it has enqueued all
+    timed steps and before it synchronises: the GPU is still working through the queue (under load, inside the
+    timed region) and the host has nothing left to enqueue that a stall could delay."""
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        # NVML queries take driver locks that kernel launches and allocations also need: sample sparsely
-        self.period = float(os.environ.get("CHDB_BENCH_CLOCK_PERIOD", "0.05"))
-        self._stop_evt = threading.Event()
+        self.samples, self.reasons, self.max_mhz, self.nv = [], set(), None, None
+        if os.environ.get("CHDB_BENCH_NO_CLOCKS"):
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)   # first query (slow) outside the timed region
         except Exception:  # noqa: BLE001
             self.nv = None
 
-    def run(self):
-        if self.nv is None or os.environ.get("CHDB_BENCH_NO_CLOCKS"):
+    def sample_while(self, busy, max_samples: int = 64):
+        """Samples until busy() turns false (at least once)."""
+        if self.nv is None:
             return
         nv = self.nv
         names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
@@ -178,7 +185,7 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
                  nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-        while not self._stop_evt.is_set():
+        while True:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -187,13 +194,14 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop_evt.wait(self.period)
+            if len(self.samples) >= max_samples or not busy():
+                break
+            time.sleep(0.002)
 
-    def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
+    def result(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "sampled": "NVML, by the benchmark thread between enqueueing the last timed step and synchronising"}
 
 
 def measured_traffic(batch_rows: int):
@@ -345,6 +353,7 @@ def run_ours(args, rank, world, local_rank):
     def one_step():
         return [b.run(prog) for b in dev_batches]
 
+    sampler = ClockSampler(local_rank)   # NVML initialised (and queried once) before the warm-up
     outs = None
     for _ in range(max(args.warmup, 0)):
         outs = one_step()
@@ -356,12 +365,15 @@ def run_ours(args, rank, world, local_rank):
         o.check()
     outs = None
 
-    sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0, jit0 = ctx.launch_count, ctx.jit_launch_count
     barrier()
     torch.cuda.synchronize(device)
-    sampler.start()
+    # a cyclic-GC pause in the middle of the enqueue loop (tens of ms with torch / pyarrow loaded) starves the GPU,
+    # which is only a few ms behind the host: collect now, not during the timed region
+    import gc
+    gc.collect()
+    gc.disable()
     ev0.record(stream)
     prev = None
     t_host0 = time.perf_counter()
@@ -383,10 +395,12 @@ def run_ours(args, rank, world, local_rank):
     if trace is not None:
         sys.stderr.write("[bench trace] " + " ".join(f"{k}:{v:.0f}" for k, v in trace) + "\n")
     ev1.record(stream)
+    sampler.sample_while(lambda: not ev1.query())   # the GPU is still inside the timed region, the host is done enqueueing
     ctx.synchronize()
     torch.cuda.synchronize(device)
     barrier()
-    clocks = sampler.stop()
+    gc.enable()
+    clocks = sampler.result()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
     jit_launches = ctx.jit_launch_count - jit0

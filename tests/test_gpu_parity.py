@@ -330,3 +330,25 @@ def test_many_tiles_per_cta(jit, monkeypatch):
     got = O.batch_from_arrow(C.filter_project_record(sel["selection"], sel["projection"], rb, al))
     ok, why = O.batches_equal(got, want)
     assert ok, why
+
+
+@pytest.mark.parametrize("jit", ["0", "always"])
+def test_schema_wider_than_the_stage_ring(jit, monkeypatch):
+    """20 Int64 columns (+ validity on half of them) need 164 KB per 1024-row stage: a ring of at least four stages does
+    not fit in shared memory, so the planner leaves the largest buffers in global memory (read through the same
+    column table, prefetched into L2 by the producer warps).  Results must not depend on what is staged."""
+    monkeypatch.setenv("CHDB_JIT", jit)
+    rng = np.random.default_rng(5)
+    n = 150_000
+    cols, fields = [], []
+    for c in range(20):
+        v = rng.integers(-1000, 1000, n, dtype=np.int64)
+        nullable = c % 2 == 1
+        cols.append(pa.array(v, mask=(rng.random(n) < 0.2) if nullable else None))
+        fields.append(pa.field(f"c{c}", pa.int64(), nullable))
+    rb = pa.RecordBatch.from_arrays(cols, schema=pa.schema(fields))
+    al = [[] for _ in rb.schema]
+    expr = sp.parse_expr("c0 % 3 = 0 or c1 > 10")
+    want = O.filter_record(O.batch_from_arrow(rb), al, expr)
+    ok, why = O.batches_equal(O.batch_from_arrow(C.filter_record(rb, al, expr)), want)
+    assert ok, why
