@@ -1352,105 +1352,34 @@ __device__ __forceinline__ void copy_value(uint8_t* dst, const uint8_t* src, uin
 // 16-byte output chunks, finding the source row of a byte by binary search over the warp's
 // selected rows (s_oo: warp-local output byte offsets, s_src: source byte offsets).
 __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, uint8_t* gal, uint32_t mis, uint32_t nbytes, uint32_t nrows,
-                                               const uint32_t* s_oo, const int32_t* s_src, uint32_t uniform_len, int lane) {
-  // uniform_len != 0: every selected value of the slice has that length (the reference's generator writes 8- or 100-byte
-  // strings, create_sample_data.rs:165-189): the row of an output byte is a division, not a search
-  const uint32_t UL = uniform_len;
-  auto oo = [&](uint32_t r) -> uint32_t { return UL ? r * UL : s_oo[r]; };
+                                               const uint32_t* s_oo, const int32_t* s_src, int lane) {
   const uint32_t end = mis + nbytes;
   const uint32_t nchunks = (end + 15u) >> 4;
-  uint32_t first = (uint32_t)lane;
-  if (UL) {
-    // Four chunks per trip, their loads in flight together (one chunk at a time the loop is a chain of L2 round
-    // trips); chunks that are partial or straddle two values are left to the general loop below.
-    const uint32_t quads = nchunks / 128u;   // whole trips of 4 x 32 chunks
 #pragma unroll 1
-    for (uint32_t q = 0; q < quads; q++) {
-      uint4 v[4];
-      bool simple[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t ch = q * 128u + (uint32_t)j * 32u + (uint32_t)lane;
-        const uint32_t lo = ch << 4;
-        simple[j] = false;
-        if (lo >= mis && lo + 16u <= end) {
-          const uint32_t x = lo - mis, r = x / UL, in = x - r * UL;
-          if (in + 16u <= UL) {
-            simple[j] = true;
-            v[j] = load16_unaligned(sv + s_src[r] + in);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t ch = q * 128u + (uint32_t)j * 32u + (uint32_t)lane;
-        if (simple[j]) *(uint4*)(gal + (ch << 4)) = v[j];
-      }
-      // the others of this trip: the general way, one by one
-#pragma unroll 1
-      for (int j = 0; j < 4; j++) {
-        if (simple[j]) continue;
-        const uint32_t ch = q * 128u + (uint32_t)j * 32u + (uint32_t)lane;
-        const uint32_t lo = ch << 4, hi = lo + 16;
-        const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
-        if (s >= t) continue;
-        uint32_t r = (s - mis) / UL;
-        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-#pragma unroll 1
-        for (uint32_t b = s; b < t;) {
-          const uint32_t xb = b - mis;
-          while (xb >= (r + 1) * UL) r++;
-          const uint8_t* sp = sv + s_src[r] + (xb - r * UL);
-          uint32_t piece, step;
-          if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= (r + 1) * UL) { piece = load4_unaligned(sp); step = 4; }
-          else { piece = (uint32_t)*sp << (8u * (b & 3u)); step = 1; }
-          const uint32_t wi = (b - lo) >> 2;
-          if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
-          b += step;
-        }
-        if (t - s == 16u) {
-          *(uint4*)(gal + lo) = make_uint4(w0, w1, w2, w3);
-        } else {
-          for (uint32_t b = s; b < t; b++) {
-            const uint32_t wi = (b - lo) >> 2;
-            const uint32_t word = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
-            gal[b] = (uint8_t)(word >> (8u * (b & 3u)));
-          }
-        }
-      }
-    }
-    first = quads * 128u + (uint32_t)lane;
-  }
-#pragma unroll 1
-  for (uint32_t ch = first; ch < nchunks; ch += 32) {
+  for (uint32_t ch = lane; ch < nchunks; ch += 32) {
     const uint32_t lo = ch << 4, hi = lo + 16;
     const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
     if (s >= t) continue;
     const uint32_t x = s - mis;  // warp-local output byte index of the first byte produced
-    uint32_t r;
-    if (UL) {
-      r = x / UL;
-    } else {
-      uint32_t lo_r = 0, hi_r = nrows;  // first r in (0, nrows] with s_oo[r] > x
-      while (lo_r < hi_r) {
-        const uint32_t mid = (lo_r + hi_r) >> 1;
-        if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
-      }
-      r = lo_r - 1;  // row holding byte x (empty strings are skipped by the search)
+    uint32_t lo_r = 0, hi_r = nrows;  // first r in (0, nrows] with s_oo[r] > x
+    while (lo_r < hi_r) {
+      const uint32_t mid = (lo_r + hi_r) >> 1;
+      if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
     }
+    uint32_t r = lo_r - 1;  // row holding byte x (empty strings are skipped by the search)
     const bool full = (t - s) == 16u;
-    if (full && x + 16u <= oo(r + 1)) {
-      *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - oo(r)));
+    if (full && x + 16u <= s_oo[r + 1]) {
+      *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
       continue;
     }
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll 1
     for (uint32_t b = s; b < t;) {
       const uint32_t xb = b - mis;
-      while (xb >= oo(r + 1)) r++;
-      const uint8_t* sp = sv + s_src[r] + (xb - oo(r));
+      while (xb >= s_oo[r + 1]) r++;
+      const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
       uint32_t piece, step;
-      if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= oo(r + 1)) { piece = load4_unaligned(sp); step = 4; }
+      if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) { piece = load4_unaligned(sp); step = 4; }
       else { piece = (uint32_t)*sp << (8u * (b & 3u)); step = 1; }
       const uint32_t wi = (b - lo) >> 2;
       if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
@@ -1576,16 +1505,9 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
       }
       if (chunked) {
         if (lane == 0) s_oo[L.count] = slice_bytes;
-        // all selected values of the slice equally long?
-        const uint32_t ul = slice_bytes / L.count;   // (chunked implies count != 0)
-        bool same = ul * L.count == slice_bytes;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-          if ((sel >> i) & 1u) same = same && len[i] == ul;
-        const uint32_t uniform_len = __all_sync(FULL, same) ? ul : 0u;
         __syncwarp();
         const uint32_t mis = (uint32_t)(byte_base & 15u);
-        copy_long_strings(sv, o_values + (byte_base - mis), mis, slice_bytes, L.count, s_oo, s_src, uniform_len, lane);
+        copy_long_strings(sv, o_values + (byte_base - mis), mis, slice_bytes, L.count, s_oo, s_src, lane);
         __syncwarp();
       }
     } else if (sel) {
