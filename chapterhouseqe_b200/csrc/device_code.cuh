@@ -53,6 +53,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 #define CHDB_COL_TYPE(P, s) chdb_jit::kColType[s]
 #define CHDB_COL_WIDTH(P, s) chdb_jit::kColWidth[s]
 #define CHDB_OUT_META(P, k) chdb_jit::kOutMeta[k]
+#define CHDB_LONG_STRINGS(P) (chdb_jit::kLongStrings != 0)
 #else
 #define CHDB_STATIC_UNROLL _Pragma("unroll 1")
 #define CHDB_N_IN P.n_in
@@ -64,6 +65,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 #define CHDB_COL_WIDTH(P, s) P.in[s].width
 // the eight small fields of OutDesc arrive as one 64-bit constant load
 #define CHDB_OUT_META(P, k) (reinterpret_cast<const uint64_t*>(&P.out[k])[3])
+#define CHDB_LONG_STRINGS(P) (P.long_strings != 0)
 #endif
 
 template <typename V> struct Cont;
@@ -767,7 +769,9 @@ __device__ __forceinline__ void run_program(const KernelParams& P, const ColumnD
 // Waits are bounded: a wait that lasts about a second is a bug (or a lost dependency), and a diagnostic plus a
 // trapped launch (the host sees a CUDA error) beats a hung stream.
 __device__ __noinline__ void wait_timed_out(const char* what, uint32_t a, uint32_t b) {
+#ifndef CHDB_JIT   // (the run-time specialised kernels only trap: a printf call site costs them registers on the hot path)
   printf("[chdb] %s timed out: block %d warp %d (%u, %u)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5), a, b);
+#endif
   __trap();
 }
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
@@ -1488,7 +1492,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
       uint32_t slice_bytes;
       uint32_t bo = warp_excl_scan(len[0] + len[1] + len[2] + len[3], lane, slice_bytes);   // slice-local output byte offset
       // long values are copied by the whole warp, chunk-centric; short ones by the lane that owns the row
-      const bool chunked = P.long_strings != 0 && slice_bytes > 24u * L.count;
+      const bool chunked = CHDB_LONG_STRINGS(P) && slice_bytes > 24u * L.count;
       uint32_t* s_oo = ltab + L.wid * (2 * (kWarpRows + 4));
       int32_t* s_src = (int32_t*)(s_oo + kWarpRows + 4);
       int32_t* d = o_off + o;
