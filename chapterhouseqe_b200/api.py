@@ -285,7 +285,7 @@ class Program:
         return int(n.value), log.value.decode(errors="replace")
 
     def run(self, rb: pa.RecordBatch, ctx: Context | None = None) -> pa.RecordBatch:
-        """Host batch in, host batch out (upload -> fused kernel -> download)."""
+        """Host batch in, host batch out (upload -> select, scan, gather kernels -> download)."""
         L = load_library()
         ctx = ctx or default_context()
         a, s = _export_batch(rb)

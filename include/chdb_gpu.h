@@ -128,7 +128,7 @@ int64_t chdb_ctx_launch_count(chdb_ctx* ctx);
 int64_t chdb_ctx_jit_launch_count(chdb_ctx* ctx);
 
 /* ---- run-time specialisation ----
- * Long scans run the fused kernel's own source compiled by NVRTC with the program's bytecode baked
+ * Long scans run the kernels' own source compiled by NVRTC with the program's bytecode baked
  * in as constants (same code, dispatch folded away).  Controlled by the CHDB_JIT environment
  * variable: "0" interpreter kernel only, unset / "1" batches of >= 2^18 rows, "always" every launch.
  * Without libnvrtc the interpreter kernel is used; results are identical either way. */
