@@ -54,6 +54,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 #define CHDB_COL_WIDTH(P, s) chdb_jit::kColWidth[s]
 #define CHDB_OUT_META(P, k) chdb_jit::kOutMeta[k]
 #define CHDB_LONG_STRINGS(P) (chdb_jit::kLongStrings != 0)
+#define CHDB_OUT_HAS_VALIDITY(P, k) (chdb_jit::kOutHasValidity[k] != 0)
 #else
 #define CHDB_STATIC_UNROLL _Pragma("unroll 1")
 #define CHDB_N_IN P.n_in
@@ -66,6 +67,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 // the eight small fields of OutDesc arrive as one 64-bit constant load
 #define CHDB_OUT_META(P, k) (reinterpret_cast<const uint64_t*>(&P.out[k])[3])
 #define CHDB_LONG_STRINGS(P) (P.long_strings != 0)
+#define CHDB_OUT_HAS_VALIDITY(P, k) (P.out[k].validity != nullptr)
 #endif
 
 template <typename V> struct Cont;
@@ -1422,7 +1424,7 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl
   const ColumnDesc& c = C.cols[o_slot];
   const uint32_t sel = L.sel;
   const int64_t r = L.row_base;
-  if (P.out[k].validity != nullptr) R.vbits = load_bits4(c.validity, r, sel);
+  if (CHDB_OUT_HAS_VALIDITY(P, k)) R.vbits = load_bits4(c.validity, r, sel);
   if (!L.inrange) return;   // (a tail tile's missing rows: nothing to read, nothing will be stored)
   const uint8_t* src = (const uint8_t*)c.values;
   if (o_type == T_BOOL) {
@@ -1454,7 +1456,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
   const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu;
   uint8_t* const o_values = (uint8_t*)P.out[k].values;
-  const bool o_has_validity = P.out[k].validity != nullptr;
+  const bool o_has_validity = CHDB_OUT_HAS_VALIDITY(P, k);
   const uint32_t sel = L.sel;
   const int lane = L.lane;
   const ColumnDesc* cols = C.cols;
@@ -1578,7 +1580,7 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& s
     uint8_t* const validity = P.out[k].validity;
 #pragma unroll
     for (int which = 0; which < 2; which++) {   // 0: Boolean values, 1: validity
-      if (which == 0 ? !is_bool : validity == nullptr) continue;
+      if (which == 0 ? !is_bool : !CHDB_OUT_HAS_VALIDITY(P, k)) continue;
       uint32_t* sb = bitstage + kb * kBitWords;
       uint32_t* g = (uint32_t*)(which == 0 ? (uint8_t*)P.out[k].values : validity);
       if (lane < kBitWords) {
