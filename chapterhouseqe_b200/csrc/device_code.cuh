@@ -1613,13 +1613,18 @@ __device__ __forceinline__ void gather_body(const KernelParams& P, const KernelS
   uint32_t* const ltab = bitstages + kComputeWarps * P.n_bits * kBitWords;
   init_shared(P, ST, sh, tid);
   for (int i = tid; i < kComputeWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
-  grid_dependency_wait();     // the scan kernel's prefixes (and, through it, the select kernel's selection bits)
   __syncthreads();
   // from here on the producer and the compute warps only meet through the stages' mbarriers
   if (warp >= kComputeWarps) {
+    // The input columns do not depend on the select and scan kernels: the producer warps that bring Utf8
+    // offsets and values start filling the ring while those kernels are still running (programmatic dependent
+    // launch).  Only the warp that also brings the selection bits and the slice prefixes waits for them, and
+    // no tile is `full` before that warp has arrived on its barrier.
+    if (warp == kComputeWarps) grid_dependency_wait();
     producer_loop<true>(P, ST, sh, smem, lane, warp - kComputeWarps);
     return;
   }
+  grid_dependency_wait();     // compute warps: the scan kernel's totals, the bitmaps the select kernel zeroed
   if (has_pred && blockIdx.x == 0 && warp == 0) {
     // closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
     for (int k = lane; k < CHDB_N_OUT; k += 32) {
