@@ -524,9 +524,8 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL's own output (its version banner at NCCL_DEBUG >= VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
