@@ -1,26 +1,22 @@
-// Filter / projection / compaction on sm_100a: three kernels per batch.
+// Filter / projection / compaction on sm_100a: one fused single-pass kernel per batch.
 //
-//   select   streams the predicate's columns through a TMA-fed ring of shared-memory stages, runs the
-//            predicate bytecode (accumulator in registers, 128-bit shared-memory loads) and writes the
-//            selection bitmap (1 bit per row) plus, per 128-row slice, the number of selected rows and
-//            the selected value bytes of every Utf8 output.                         [compute_value.rs]
-//   scan     exclusive prefix sums of the slice counts: block scans chained by a decoupled look-back
-//            over 64-bit {flag | value} descriptors.
-//   gather   streams every column an output needs through the same kind of ring, together with the
-//            tile's selection bits and slice prefixes, and writes the selected rows straight to their
-//            final positions (neighbouring lanes hit neighbouring addresses); validity / Boolean bits
-//            are assembled per warp in shared memory and written as words; Utf8 offsets restart at 0;
-//            projection expressions are evaluated here, under the selection mask, so checked-integer
-//            errors are raised for surviving rows only.                 [filter_record.rs:37, record_projection.rs]
+// A CTA owns one tile of 1024 rows.  Warp 0 brings the tile's slice of every column the program touches
+// into shared memory with TMA bulk copies; every warp then evaluates the predicate bytecode on its
+// slices (accumulator in registers, 128-bit shared-memory loads; compute_value.rs), keeps the
+// selection bits in registers and posts the slice counts; one warp per scanned quantity (selected
+// rows, selected value bytes per Utf8 output) publishes the tile's aggregate and obtains the tile's
+// batch-wide exclusive prefix by decoupled look-back over its predecessors' descriptors; finally every
+// warp writes the selected rows of its slices straight to their final positions (neighbouring lanes
+// hit neighbouring addresses); validity / Boolean bits are assembled per warp in shared memory and
+// written as words; Utf8 offsets restart at 0; projection expressions are evaluated under the
+// selection mask, so checked-integer errors are raised for surviving rows only
+// (filter_record.rs:37, record_projection.rs).
 //
-// Why not one fused single-pass kernel: with the memory system busy streaming tiles an L2 round trip
-// costs ~3 000 cycles, and a per-tile look-back puts at least one such round trip (plus the polling for
-// neighbours that are a little late) on every tile's critical path; measured, that capped the fused
-// kernel at 25-30 % of HBM peak.  Here no tile ever waits for another CTA, both streaming kernels are
-// plain persistent pipelines (producer warp -> mbarrier ring -> compute warps), and the predicate
-// columns the gather kernel re-reads were streamed by the select kernel moments earlier: they are
-// served by the 126 MB L2 for batches of a few million rows, so HBM traffic stays at each referenced
-// input byte once and each output byte once (+ 1 bit and ~0.1 byte of counts per row).
+// Every input byte is read from HBM once and every output byte written once.  Latency (the tile's
+// loads, the look-back's L2 round trips) is hidden the way GPUs hide latency: by 5-6 other tiles
+// resident on the same SM, each in a different phase.  (Round 1 ran one persistent CTA per SM, first
+// with a per-tile look-back on its critical path -- 29 % of HBM peak -- then as three kernels with a
+// second read of the predicate columns -- 45 %.)
 //
 // Accumulator convention: for 8/16/32-bit integers and Float32 only the low 32 bits of the
 // container are meaningful (integers sign-/zero-extended to 32 bits); 64-bit types use all of it.
@@ -79,7 +75,7 @@ template <> struct Cont<uint64_t> { static constexpr bool k64 = true; };
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void report_error(const KernelParams& P, uint32_t order, int64_t row, uint32_t code) {
   unsigned long long packed = ((unsigned long long)order << 56) | (((unsigned long long)row & 0xFFFFFFFFFFFFull) << 8) | code;
-  atomicMax((unsigned long long*)P.error_word, ~packed);
+  atomicMax((unsigned long long*)P.b.error_word, ~packed);
 }
 
 // bad / divz: per-thread row masks of failing rows (already restricted to evaluated rows)
@@ -851,8 +847,9 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* d, uint32_t chunk, uint64
   return excl;
 }
 
+
 // ------------------------------------------------------------------------------------------
-// shared-memory plumbing: mbarriers, TMA bulk copies, named barriers
+// shared-memory plumbing: mbarriers, TMA bulk copies, programmatic dependent launch
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { uint64_t a;
   asm("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
@@ -860,15 +857,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { uint64_t a;
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// try_wait with the default (short) time limit, and a back-off between failed tries.  (With an explicit
-// suspend-time hint of milliseconds, launches now and then took milliseconds: a waiter parked just as its
-// phase completed seems to sleep the hint out.)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -882,7 +876,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(128);
+    __nanosleep(64);
     if (++spins > (1u << 22)) wait_timed_out("mbarrier wait", bar, parity);
   }
 }
@@ -894,384 +888,90 @@ __device__ __forceinline__ void tma_load(uint32_t dst_s, const void* src, uint32
 __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-// Programmatic dependent launch: the three kernels of a batch are launched back to back with
-// programmatic stream serialisation, so a kernel's CTAs are scheduled (and run their prologue) while its
-// predecessor drains; grid_dependency_wait() returns once the predecessor has completed and its writes
-// are visible.
+// Programmatic dependent launch: the stream kernel is launched as the programmatic dependent of the small
+// kernel that zeroes its workspace, so its CTAs are scheduled (and run their prologue) while that kernel --
+// and the previous batch's stream kernel before it -- drain; grid_dependency_wait() returns once the
+// predecessor has completed and its writes are visible.
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void compute_warps_barrier() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
-}
 
-// Role profile (debugging aid, CHDB_PHASE_TIMING=1): lane 0 of every warp accumulates the cycles it
-// spends in each phase and adds them to P.timing[] when it leaves.
-#ifdef CHDB_TIMING
-struct PhaseClock {
-  long long t, acc[4];
-  bool on;
-  __device__ __forceinline__ void start(bool enabled) { on = enabled; acc[0] = acc[1] = acc[2] = acc[3] = 0; if (on) t = clock64(); }
-  __device__ __forceinline__ void lap(int i) { if (on) { const long long now = clock64(); acc[i] += now - t; t = now; } }
-  __device__ __forceinline__ void flush(uint64_t* timing, int base, int lane) {
-    if (on && lane == 0)
-      for (int i = 0; i < 4; i++) atomicAdd((unsigned long long*)&timing[base + i], (unsigned long long)acc[i]);
-  }
+// What the output code needs from the CTA's shared memory besides the tile itself.
+struct TileShared {
+  const uint8_t* pool;      // string literals (kernel parameter space)
+  const uint8_t* pext4;     // [sel4 << 4 | bits4] -> the selected bits, packed
+  uint32_t* nulls;          // [n_out] NULLs written by this CTA
 };
-#else
-struct PhaseClock {   // compiled out (the run-time specialised kernels get it with CHDB_PHASE_TIMING=1)
-  __device__ __forceinline__ void start(bool) {}
-  __device__ __forceinline__ void lap(int) {}
-  __device__ __forceinline__ void flush(uint64_t*, int, int) {}
-};
-#endif
-
-// Everything one tile needs besides its staged bytes; one per stage of the ring.
-struct TileCtl {
-  int32_t tile;                                   // tile index, or -1: no more tiles
-  int32_t pad;
-  ColumnDesc cols[kMaxInCols];                    // the input columns as seen by this tile: pointers are biased so that
-                                                  // indexing with the ABSOLUTE row lands in the stage (or in global memory)
-};
-struct SharedState {
-  uint64_t full[kMaxStages], empty[kMaxStages];
-  TileCtl ctl[kMaxStages];
-  uint32_t nulls[kMaxOutCols];
-  uint8_t pext4[256];                             // [sel4 << 4 | bits4] -> the selected bits, packed
-  uint8_t pool[kStrPoolBytes];
-};
-
-__device__ __forceinline__ void init_shared(const KernelParams& P, const KernelStage& ST, SharedState& sh, int tid) {
-  if (tid == 0) {
-    for (int s = 0; s < ST.n_stages; s++) {
-      mbar_init(smem_u32(&sh.full[s]), kProducerWarps);
-      mbar_init(smem_u32(&sh.empty[s]), kSlices);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  for (int i = tid; i < 256; i += kThreads) {
-    const uint32_t s = (uint32_t)i >> 4, v = (uint32_t)i & 15u;
-    uint32_t out = 0, n = 0;
-    for (int j = 0; j < 4; j++)
-      if ((s >> j) & 1u) { out |= ((v >> j) & 1u) << n; n++; }
-    sh.pext4[i] = (uint8_t)out;
-  }
-  for (int i = tid; i < kStrPoolBytes; i += kThreads) sh.pool[i] = (uint8_t)P.strpool[i];
-  for (int i = tid; i < kMaxOutCols; i += kThreads) sh.nulls[i] = 0;
-  // the tiles' column tables: types and widths never change, the producers fill in the pointers per tile
-  for (int i = tid; i < ST.n_stages * CHDB_N_IN; i += kThreads) sh.ctl[i / CHDB_N_IN].cols[i % CHDB_N_IN] = P.in[i % CHDB_N_IN];
-}
 
 // ------------------------------------------------------------------------------------------
-// the producer warps (both streaming kernels): tile n of this CTA is tile blockIdx.x + n * gridDim.x.
-// The three warps walk the same tile sequence; warp `kind` brings one kind of buffer (0: validity
-// bitmaps, 1: Utf8 offsets, 2: values), lane s for input slot s: the tile's slice goes into the stage
-// with a TMA bulk copy (completion is counted in bytes on the stage's `full` mbarrier, on which every
-// producer warp arrives once) and the column's biased pointer into the stage's table; buffers that
-// are used but not staged get a bulk L2 prefetch.  GATHER: lane 31 of warp 0 also brings the tile's
-// selection bits and slice prefixes.  Issuing a bulk copy costs the issuing warp ~100 cycles, which is
-// why the ~10 copies of a tile are spread over three warps.
+// Loading the tile: warp 0, lane s for input slot s.  The tile's slice of every staged buffer goes into
+// the stage with a TMA bulk copy (completion is counted in bytes on the `full` mbarrier) and the
+// column's biased pointer into the tile's column table; buffers that are used but not staged get a
+// bulk L2 prefetch.  Utf8 value bytes start at offsets[row0]: those copies are issued in a second
+// step (the two bounds are a global load away), after the fixed-size ones are already in flight.
 // ------------------------------------------------------------------------------------------
-template <bool GATHER>
-__device__ __forceinline__ void producer_loop(const KernelParams& P, const KernelStage& ST, SharedState& sh, uint8_t* smem, int lane, int kind) {
-  const int32_t S = ST.n_stages;
-  const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
-  const int nq = 1 + CHDB_N_UTF8;
-  PhaseClock pc;   // [8] wait for a free stage, [9] addresses, [10] issue
-  pc.start(P.timing != nullptr);
-  // this CTA's tiles: blockIdx.x + n * gridDim.x for n < n_mine; then one "no more tiles" stage per compute group
-  const int64_t n_mine = (int64_t)blockIdx.x < P.num_tiles ? (P.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t last_tile = P.num_tiles - 1;
-  const uint32_t last_rows = (uint32_t)(P.num_rows - last_tile * kTileRows);
-  // What this lane brings is fixed for the whole launch: one buffer, a fixed number of bytes further per
-  // tile -- except Utf8 value bytes.
-  const uint8_t* gsrc = nullptr;   // global base of the buffer
-  uint32_t stride = 0;             // bytes per tile
-  uint32_t soff = 0;               // offset in the stage
-  uint32_t full_bytes = 0, tail_bytes = 0;   // copy sizes: whole tile / last tile
-  bool used = false, staged = false, utf8_values = false;
-  uint32_t values_cap = 0;
-  const int32_t* goff = nullptr;
+__device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan& TP, ColumnDesc* cols, uint8_t* stage, uint32_t full,
+                                          int64_t row0, uint32_t tile_rows, int lane) {
+  const uint32_t ss = smem_u32(stage);
+  const uint32_t bits_bytes = (((tile_rows + 7u) >> 3) + 15u) & ~15u;
+  uint32_t nb[3] = {0, 0, 0}, so[3] = {0, 0, 0}, pf[3] = {0, 0, 0};   // 0: validity, 1: offsets, 2: values
+  const uint8_t* src[3] = {nullptr, nullptr, nullptr};
+  bool utf8_values = false;
+  uint32_t cap = 0, vso = 0;
+  ColumnDesc c;
+  c.values = nullptr; c.validity = nullptr; c.offsets = nullptr; c.type = 0; c.width = 0;
   if (lane < CHDB_N_IN) {
-    const ColumnDesc g = P.in[lane];
-    const StageSlot sl = ST.slot[lane];
-    const uint32_t use = ST.use[lane];
-    const uint32_t tail_bits = (((last_rows + 7u) >> 3) + 15u) & ~15u;
-    if (kind == 0) {
-      gsrc = g.validity;
-      if ((use & USE_VALIDITY) && g.validity != nullptr) {
-        used = true; staged = sl.validity != kNotStaged; stride = kTileRows / 8; soff = sl.validity;
-        full_bytes = kTileRows / 8; tail_bytes = tail_bits;
-      }
-    } else if (kind == 1) {
-      gsrc = (const uint8_t*)g.offsets;
-      if (g.type == T_UTF8 && (use & USE_OFFSETS)) {
-        used = true; staged = sl.offsets != kNotStaged; stride = kTileRows * 4; soff = sl.offsets;
-        full_bytes = ((kTileRows + 1u) * 4u + 15u) & ~15u; tail_bytes = ((last_rows + 1u) * 4u + 15u) & ~15u;
-      }
-    } else {
-      gsrc = (const uint8_t*)g.values;
-      if (use & USE_VALUES) {
-        used = true; staged = sl.values != kNotStaged; soff = sl.values;
-        if (g.type == T_UTF8) {
-          utf8_values = true; goff = g.offsets; values_cap = sl.values_cap;
-        } else {
-          const uint32_t w = g.width;
-          stride = w ? kTileRows * w : kTileRows / 8;
-          full_bytes = stride; tail_bytes = w ? (last_rows * w + 15u) & ~15u : tail_bits;
-        }
-      }
+    c = P.in[lane];
+    const StageSlot sl = TP.slot[lane];
+    const uint32_t use = TP.use[lane];
+    ColumnDesc t = c;   // this tile's view
+    if ((use & USE_VALIDITY) && c.validity != nullptr) {
+      src[0] = c.validity + (row0 >> 3);
+      if (sl.validity != kNotStaged) { nb[0] = bits_bytes; so[0] = sl.validity; t.validity = stage + sl.validity - (row0 >> 3); }
+      else pf[0] = bits_bytes;
     }
-  }
-  // Utf8 value bytes of a tile start at offsets[row0]: fetched three tiles ahead (an L2 round trip takes
-  // longer than issuing a tile)
-  uint32_t b0[3] = {0, 0, 0}, b1[3] = {0, 0, 0};
-  auto fetch_bounds = [&](int64_t n, uint32_t& o0, uint32_t& o1) {
-    if (utf8_values && n < n_mine) {
-      const int64_t tile = (int64_t)blockIdx.x + n * gridDim.x;
-      const int64_t row0 = tile * kTileRows;
-      o0 = (uint32_t)goff[row0];
-      o1 = (uint32_t)goff[row0 + (tile == last_tile ? last_rows : kTileRows)];
+    if (c.type == T_UTF8) {
+      if (use & USE_OFFSETS) {
+        src[1] = (const uint8_t*)(c.offsets + row0);
+        const uint32_t bytes = ((tile_rows + 1u) * 4u + 15u) & ~15u;
+        if (sl.offsets != kNotStaged) { nb[1] = bytes; so[1] = sl.offsets; t.offsets = (const int32_t*)(stage + sl.offsets) - row0; }
+        else pf[1] = bytes;
+      }
+      if (use & USE_VALUES) { utf8_values = true; cap = sl.values != kNotStaged ? sl.values_cap : 0u; vso = sl.values; }
+    } else if (use & USE_VALUES) {
+      const uint32_t w = c.width;
+      const uint32_t bytes = w ? (tile_rows * w + 15u) & ~15u : bits_bytes;
+      const int64_t adv = w ? row0 * (int64_t)w : (row0 >> 3);
+      src[2] = (const uint8_t*)c.values + adv;
+      if (sl.values != kNotStaged) { nb[2] = bytes; so[2] = sl.values; t.values = stage + sl.values - adv; }
+      else pf[2] = bytes;
     }
-  };
-#pragma unroll
-  for (int j = 0; j < 3; j++) fetch_bounds(j, b0[j], b1[j]);
-  int32_t stage = 0;
-  uint32_t ph = 0;
-  for (int64_t n = 0; n < n_mine + kComputeGroups; n++) {
-    mbar_wait(smem_u32(&sh.empty[stage]), ph ^ 1u);
-    pc.lap(0);
-    TileCtl& C = sh.ctl[stage];
-    const uint32_t full = smem_u32(&sh.full[stage]);
-    if (n >= n_mine) {
-      if (lane == 0) { if (kind == 0) C.tile = -1; mbar_arrive(full); }
-    } else {
-      const int64_t tile = (int64_t)blockIdx.x + n * gridDim.x;
-      const bool last = tile == last_tile;
-      uint8_t* const sg = smem + (size_t)stage * ST.stage_bytes;   // generic address of the stage
-      const uint32_t ss = smem_u32(sg);
-      const int64_t adv = tile * (int64_t)stride;
-      const uint8_t* src = gsrc + adv;
-      uint32_t nbytes = used && staged ? (last ? tail_bytes : full_bytes) : 0u;
-      const uint8_t* vptr = used && staged ? sg + soff - adv : gsrc;   // biased: indexing with the absolute row lands in the stage
-      uint32_t pf_bytes = used && !staged ? (last ? tail_bytes : full_bytes) : 0u;   // used but not staged: bulk L2 prefetch
-      if (utf8_values) {
-        const uint32_t lo = b0[0] & ~15u, len = (b1[0] - lo + 15u) & ~15u;
-        src = gsrc + lo;
-        if (staged && len <= values_cap) { nbytes = len; vptr = sg + soff - lo; pf_bytes = 0; }
-        else { nbytes = 0; vptr = gsrc; pf_bytes = len; }
-        // rotate the bounds queue and refill its tail
-        b0[0] = b0[1]; b1[0] = b1[1]; b0[1] = b0[2]; b1[1] = b1[2];
-        fetch_bounds(n + 3, b0[2], b1[2]);
-      }
-      if (lane < CHDB_N_IN) {
-        if (kind == 0) C.cols[lane].validity = vptr;
-        else if (kind == 1) C.cols[lane].offsets = (const int32_t*)vptr;
-        else C.cols[lane].values = vptr;
-      }
-      uint32_t extra = 0;
-      if (GATHER && has_pred && kind == 0 && lane == 31) extra = kTileRows / 8 + (uint32_t)nq * kSlices * 8;
-      const uint32_t tx = __reduce_add_sync(FULL, nbytes + extra);
-      pc.lap(1);
-      if (lane == 0) {
-        if (kind == 0) C.tile = (int32_t)tile;
-        mbar_arrive_expect_tx(full, tx);
-      }
-      __syncwarp();
-      if (nbytes) tma_load(ss + soff, src, nbytes, full);
-      if (pf_bytes) tma_prefetch_l2(src, pf_bytes);
-      if (extra) {
-        tma_load(ss + ST.sel_off, P.sel_bits + tile * (kTileRows / 32), kTileRows / 8, full);
-        for (int qi = 0; qi < nq; qi++)
-          tma_load(ss + ST.prefix_off + qi * kSlices * 8, P.slice_prefix + (size_t)qi * P.slice_pitch + tile * kSlices, kSlices * 8, full);
-      }
-      pc.lap(2);
-    }
-    if (++stage == S) { stage = 0; ph ^= 1u; }
+    cols[lane] = t;
   }
-  if (kind == 2) pc.flush(P.timing, 8, lane);
-}
-
-// How a compute group walks the ring.  A parity wait on an mbarrier is only sound if the waiter has seen the
-// barrier's previous phase complete: with groups taking every kComputeGroups-th tile, a group that simply
-// waited for its next tile could find that stage still in the phase of the tile before (its bytes not
-// landed yet) -- which looks exactly like "already complete".  So every group observes EVERY tile's
-// `full` barrier, in order: the tiles before its first one at the start, and the kComputeGroups - 1
-// tiles after each of its own before it releases that one (while it holds a stage the producers cannot
-// run more than a ring ahead, so nothing it has yet to observe can complete twice).
-struct RingCursor {
-  uint32_t stage, ph;
-  __device__ __forceinline__ void next(uint32_t S) { if (++stage == S) { stage = 0; ph ^= 1u; } }
-};
-// Waits for the tile at `c`; false when it is the "no more tiles" marker.
-__device__ __forceinline__ bool observe_tile(SharedState& sh, const RingCursor& c) {
-  mbar_wait(smem_u32(&sh.full[c.stage]), c.ph);
-  return *(volatile int32_t*)&sh.ctl[c.stage].tile >= 0;
-}
-// After a group's tile: observe the tiles of the other groups that follow it, then release the stage.
-// Leaves `c` at the group's next tile; false when the ring has run dry.
-__device__ __forceinline__ bool release_and_advance(SharedState& sh, RingCursor& c, uint32_t S, int lane) {
-  const uint32_t mine = c.stage;
-  bool more = true;
-#pragma unroll
-  for (int j = 1; j < kComputeGroups; j++) {
-    c.next(S);
-    if (more && !observe_tile(sh, c)) more = false;
-  }
-  c.next(S);
+  // Utf8 bounds: in flight while the fixed-size copies are issued
+  uint32_t o0 = 0, o1 = 0;
+  if (utf8_values) { o0 = (uint32_t)c.offsets[row0]; o1 = (uint32_t)c.offsets[row0 + tile_rows]; }
+  const uint32_t tx = __reduce_add_sync(FULL, nb[0] + nb[1] + nb[2]);
+  if (lane == 0) mbar_expect_tx(full, tx);
   __syncwarp();
-  if (lane == 0) mbar_arrive(smem_u32(&sh.empty[mine]));   // this warp is done with the stage
-  return more;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (nb[i]) tma_load(ss + so[i], src[i], nb[i], full);
+    if (pf[i]) tma_prefetch_l2(src[i], pf[i]);
+  }
+  uint32_t vbytes = 0;
+  const uint8_t* vsrc = nullptr;
+  if (utf8_values) {
+    const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
+    vsrc = (const uint8_t*)c.values + lo;
+    if (cap != 0 && len <= cap) { vbytes = len; cols[lane].values = stage + vso - lo; }
+    else if (len) tma_prefetch_l2(vsrc, len);
+  }
+  const uint32_t tx2 = __reduce_add_sync(FULL, vbytes);
+  __syncwarp();   // the column table is complete before the arrival that publishes it
+  if (lane == 0) mbar_arrive_expect_tx(full, tx2);
+  __syncwarp();
+  if (vbytes) tma_load(ss + vso, vsrc, vbytes, full);
 }
-
-// ------------------------------------------------------------------------------------------
-// select: predicate -> selection bitmap + per-slice counts
-// ------------------------------------------------------------------------------------------
-template <typename V>
-__device__ __forceinline__ void select_body(const KernelParams& P, const KernelStage& ST) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(16) SharedState sh;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t S = (uint32_t)ST.n_stages;
-  init_shared(P, ST, sh, tid);
-  grid_launch_dependents();   // the scan kernel may be scheduled as soon as SMs free up (it waits for this grid to finish)
-  __syncthreads();
-  // from here on the producer and the compute warps only meet through the stages' mbarriers
-  if (warp >= kComputeWarps) {
-    producer_loop<false>(P, ST, sh, smem, lane, warp - kComputeWarps);
-    return;
-  }
-  // The gather kernel merges the edge words of bit-packed outputs (validity, Boolean) with atomicOr:
-  // they are zeroed here, by the whole grid, instead of by one memset per buffer on the stream.
-  if (P.n_bits > 0) {
-    const int64_t words = (P.num_rows + 31) >> 5;
-    const int64_t first = (int64_t)blockIdx.x * (kComputeWarps * 32) + tid, step = (int64_t)gridDim.x * (kComputeWarps * 32);
-    for (int k = 0; k < P.n_out; k++) {
-      uint32_t* bits[2] = {P.out[k].type == T_BOOL ? (uint32_t*)P.out[k].values : nullptr, (uint32_t*)P.out[k].validity};
-      for (int j = 0; j < 2; j++)
-        if (bits[j] != nullptr)
-          for (int64_t i = first; i < words; i += step) bits[j][i] = 0;
-    }
-  }
-  const int group = warp / kSlices, slice = warp % kSlices;
-  PhaseClock pc;   // [0] wait for the stage (TMA), [1] predicate + counts
-  pc.start(P.timing != nullptr);
-  RingCursor cur{0, 0};
-  bool more = true;
-  for (int j = 0; j < group && more; j++) { more = observe_tile(sh, cur); cur.next(S); }   // the tiles before this group's first
-  while (more) {
-    const uint32_t stage = cur.stage;
-    TileCtl& C = sh.ctl[stage];
-    if (!observe_tile(sh, cur)) break;
-    pc.lap(0);
-    const int32_t tile = *(volatile int32_t*)&C.tile;
-    const int64_t row0 = (int64_t)tile * kTileRows;
-    const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
-    const ColumnDesc* cols = C.cols;
-    const int64_t qb[1] = {row0 + slice * kWarpRows + lane * 4};
-    const int left = tile_rows - (slice * kWarpRows + lane * 4);
-    const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
-    V acc[4];
-    uint32_t accm, accv;
-#ifdef CHDB_JIT
-    run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
-#else
-    run_program<V, 1>(P, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
-#endif
-    const uint32_t sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
-    // selection bits: 8 lanes make one word, 4 words per slice
-    uint32_t word = sel4 << (4 * (lane & 7));
-    word |= __shfl_xor_sync(FULL, word, 1);
-    word |= __shfl_xor_sync(FULL, word, 2);
-    word |= __shfl_xor_sync(FULL, word, 4);
-    const int64_t sg = (int64_t)tile * kSlices + slice;   // slice index in the batch
-    if ((lane & 7) == 0) P.sel_bits[sg * 4 + (lane >> 3)] = word;
-    const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel4));
-    if (lane == 0) P.slice_counts[sg] = wrows;
-    // selected value bytes per Utf8 output
-    CHDB_STATIC_UNROLL
-    for (int k = 0; k < CHDB_N_OUT; k++) {
-      const uint64_t meta = CHDB_OUT_META(P, k);
-      const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
-      if (o_utf8 == 0xFFu) continue;   // uniform branch
-      const int32_t* off = cols[o_slot].offsets;
-      uint32_t bytes = 0;
-      if (sel4) {
-        const int4 a = *(const int4*)(off + qb[0]);
-        const int a4 = off[qb[0] + 4];
-        if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
-        if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
-        if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
-        if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
-      }
-      const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
-      if (lane == 0) P.slice_counts[(size_t)(1 + o_utf8) * P.slice_pitch + sg] = wbytes;
-    }
-    more = release_and_advance(sh, cur, S, lane);
-    pc.lap(1);
-  }
-  pc.flush(P.timing, 0, lane);
-}
-
-// ------------------------------------------------------------------------------------------
-// scan: slice counts -> exclusive slice prefixes.  Grid (chunks, quantities); each CTA scans
-// kScanChunk slices (8 per thread) and chains to its predecessors with a decoupled look-back.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void scan_body(const KernelParams& P) {
-  __shared__ uint64_t s_warp[kScanThreads / 32];
-  __shared__ uint64_t s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  grid_launch_dependents();
-  grid_dependency_wait();     // the select kernel's slice counts
-  const uint32_t chunk = blockIdx.x, qi = blockIdx.y;
-  const uint32_t* counts = P.slice_counts + (size_t)qi * P.slice_pitch;
-  uint64_t* prefix = P.slice_prefix + (size_t)qi * P.slice_pitch;
-  uint64_t* desc = P.chunk_desc + (size_t)qi * P.num_chunks;
-  const int64_t i0 = (int64_t)chunk * kScanChunk + tid * 8;   // slice_pitch is a multiple of 8: all or nothing
-  uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (i0 < P.slice_pitch) {
-    const uint4 a = *(const uint4*)(counts + i0), b = *(const uint4*)(counts + i0 + 4);
-    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-  }
-  uint64_t mine = 0;
-#pragma unroll
-  for (int j = 0; j < 8; j++) mine += c[j];
-  // block-wide exclusive scan of the thread sums
-  uint64_t x = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint64_t y = __shfl_up_sync(FULL, x, d);
-    if (lane >= d) x += y;
-  }
-  if (lane == 31) s_warp[warp] = x;
-  __syncthreads();
-  uint64_t before = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < kScanThreads / 32; w++) {
-    const uint64_t t = s_warp[w];
-    if (w < warp) before += t;
-    total += t;
-  }
-  if (warp == 0) {
-    if (lane == 0) publish_descriptor(desc + chunk, chunk == 0 ? kFlagPrefix : kFlagAgg, total);
-    const uint64_t excl = lookback(desc, chunk, total, lane);
-    if (lane == 0) {
-      s_base = excl;
-      if (chunk == (uint32_t)P.num_chunks - 1) P.counts[qi] = excl + total;   // totals
-    }
-  }
-  __syncthreads();
-  uint64_t run = s_base + before + (x - mine);
-  if (i0 < P.slice_pitch) {
-    uint64_t o[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { o[j] = run; run += c[j]; }
-    ulonglong2* dst = (ulonglong2*)(prefix + i0);
-#pragma unroll
-    for (int j = 0; j < 4; j++) dst[j] = make_ulonglong2(o[2 * j], o[2 * j + 1]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // gather: writing the selected rows
 // ------------------------------------------------------------------------------------------
@@ -1283,7 +983,7 @@ struct LaneCtx {
   uint32_t rank;          // slice-local rank of the lane's first selected row
   uint32_t count;         // selected rows of the slice
   uint64_t obase;         // output row of the slice's first selected row
-  const uint64_t* prefix; // the tile's slice prefixes [quantity][kSlices] (staged), or nullptr without a predicate
+  const uint64_t* prefix; // the tile's slice prefixes [quantity][kTileSlices], or nullptr without a predicate
   int lane, slice;
   int wid;                // compute warp index in the CTA (its private bit stage / long-string tables)
 };
@@ -1413,7 +1113,7 @@ struct OutRegs {
 };
 
 // `meta` packs the eight small OutDesc fields; under CHDB_JIT it is a compile-time constant.
-__device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
+__device__ __forceinline__ void load_output(const KernelParams& P, const ColumnDesc* cols, const int k, const uint64_t meta,
                                             const LaneCtx& L, OutRegs& R) {
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu;
@@ -1421,7 +1121,7 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl
   // look at stay undefined (clearing ten registers per output cost more instructions than the loads).
   R.vbits = FULL;
   if (o_kind != OUT_PASS) return;
-  const ColumnDesc& c = C.cols[o_slot];
+  const ColumnDesc& c = cols[o_slot];
   const uint32_t sel = L.sel;
   const int64_t r = L.row_base;
   if (CHDB_OUT_HAS_VALIDITY(P, k)) R.vbits = load_bits4(c.validity, r, sel);
@@ -1449,8 +1149,8 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const TileCtl
 // Writes output column k for this lane's rows.  BEGIN/END: the expression's instruction range when known at
 // compile time.  kb: running index of the bit-packed outputs (Boolean values, validity bitmaps) in the bit stage.
 template <typename V, int BEGIN = -1, int END = -1>
-__device__ __forceinline__ void store_output(const KernelParams& P, const TileCtl& C, const int k, const uint64_t meta,
-                                             const LaneCtx& L, const OutRegs& R, const SharedState& sh, uint32_t* bitstage,
+__device__ __forceinline__ void store_output(const KernelParams& P, const ColumnDesc* cols, const int k, const uint64_t meta,
+                                             const LaneCtx& L, const OutRegs& R, const TileShared& sh, uint32_t* bitstage,
                                              uint32_t* ltab, int& kb) {
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
@@ -1459,7 +1159,6 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
   const bool o_has_validity = CHDB_OUT_HAS_VALIDITY(P, k);
   const uint32_t sel = L.sel;
   const int lane = L.lane;
-  const ColumnDesc* cols = C.cols;
   const uint64_t o = L.obase + L.rank;   // output row of the lane's first selected row
   uint32_t vbits = R.vbits;  // validity of this output for the lane's rows
   if (o_kind == OUT_EXPR) {
@@ -1485,7 +1184,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
     } else if (o_type == T_UTF8) {
       // offsets: running sum of the selected lengths, restarted at 0 for the output
       const uint8_t* sv = (const uint8_t*)c.values;
-      const uint64_t byte_base = L.prefix[(1 + o_utf8) * kSlices + L.slice];   // output byte offset of this slice's first value
+      const uint64_t byte_base = L.prefix[(1 + o_utf8) * kTileSlices + L.slice];   // output byte offset of this slice's first value
       int32_t* const o_off = P.out[k].offsets;
       const int32_t o5[5] = {(int32_t)R.x.x, (int32_t)R.x.y, (int32_t)R.x.z, (int32_t)R.x.w, (int32_t)R.z};
       uint32_t len[4];
@@ -1541,26 +1240,26 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const TileCt
     const uint32_t nulls = sel & ~vbits & 0xFu;
     if (nulls) put_bits(nulls, L, bitstage + kb * kBitWords, sh.pext4);
     const uint32_t slice_nulls = __reduce_add_sync(FULL, (uint32_t)__popc(nulls));
-    if (lane == 0 && slice_nulls) atomicAdd(const_cast<uint32_t*>(&sh.nulls[k]), slice_nulls);
+    if (lane == 0 && slice_nulls) atomicAdd(&sh.nulls[k], slice_nulls);
     kb++;
   }
 }
 
 #ifdef CHDB_JIT
 template <int K, int N>
-__device__ __forceinline__ void load_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx& L, OutRegs (&R)[N > 0 ? N : 1]) {
+__device__ __forceinline__ void load_outputs_range(const KernelParams& P, const ColumnDesc* cols, const LaneCtx& L, OutRegs (&R)[N > 0 ? N : 1]) {
   if constexpr (K < N) {
-    load_output(P, C, K, chdb_jit::kOutMeta[K], L, R[K]);
-    load_outputs_range<K + 1, N>(P, C, L, R);
+    load_output(P, cols, K, chdb_jit::kOutMeta[K], L, R[K]);
+    load_outputs_range<K + 1, N>(P, cols, L, R);
   }
 }
 template <typename V, int K, int N>
-__device__ __forceinline__ void store_outputs_range(const KernelParams& P, const TileCtl& C, const LaneCtx& L, const OutRegs (&R)[N > 0 ? N : 1],
-                                                    const SharedState& sh, uint32_t* bitstage, uint32_t* ltab, int& kb) {
+__device__ __forceinline__ void store_outputs_range(const KernelParams& P, const ColumnDesc* cols, const LaneCtx& L, const OutRegs (&R)[N > 0 ? N : 1],
+                                                    const TileShared& sh, uint32_t* bitstage, uint32_t* ltab, int& kb) {
   if constexpr (K < N) {
     constexpr uint64_t meta = chdb_jit::kOutMeta[K];
-    store_output<V, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, C, K, meta, L, R[K], sh, bitstage, ltab, kb);
-    store_outputs_range<V, K + 1, N>(P, C, L, R, sh, bitstage, ltab, kb);
+    store_output<V, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, cols, K, meta, L, R[K], sh, bitstage, ltab, kb);
+    store_outputs_range<V, K + 1, N>(P, cols, L, R, sh, bitstage, ltab, kb);
   }
 }
 #endif
@@ -1568,7 +1267,7 @@ __device__ __forceinline__ void store_outputs_range(const KernelParams& P, const
 // The warp's bit stage -> global bitmaps.  Stage bit (obase & 31) + r belongs to output row obase + r;
 // whole words are stored, the (at most two) words shared with neighbouring slices are merged with
 // atomicOr (the bitmaps are zero-initialised).  The stage is left zeroed for the warp's next slice.
-__device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& sh, uint32_t* bitstage, uint64_t obase, uint32_t count, int lane) {
+__device__ __forceinline__ void flush_bits(const KernelParams& P, uint32_t* bitstage, uint64_t obase, uint32_t count, int lane) {
   const uint32_t o = (uint32_t)obase & 31u, end = o + count;
   const uint32_t nwords = (end + 31u) >> 5;
   const uint64_t g0 = obase >> 5;
@@ -1601,125 +1300,249 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, SharedState& s
   }
 }
 
-template <typename V>
-__device__ __forceinline__ void gather_body(const KernelParams& P, const KernelStage& ST) {
+
+// ------------------------------------------------------------------------------------------
+// The stream kernel: one CTA per tile of kTileRows rows.
+//   1. warp 0 brings the tile's slice of every column the program touches into shared memory (TMA);
+//   2. every warp evaluates the predicate on its slices: selection bits and ranks stay in registers, the
+//      slice counts (selected rows; selected value bytes per Utf8 output) go to shared memory;
+//   3. warp q turns quantity q's slice counts into batch-wide exclusive prefixes: it publishes the tile's
+//      aggregate and walks back over its predecessors' descriptors (decoupled look-back) -- the other
+//      resident CTAs of the SM keep the memory system busy meanwhile;
+//   4. every warp writes the selected rows of its slices to their final positions.
+// Without a predicate steps 2-3 fall away (every row is kept, output row = input row).
+// MANY: one launch over several batches of one schema: the CTA first fetches its batch's record.
+// ------------------------------------------------------------------------------------------
+template <typename V, bool MANY>
+__device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePlan& TP) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(16) SharedState sh;
+  __shared__ __align__(8) uint64_t s_full;
+  __shared__ uint32_t s_nulls[kMaxOutCols];
+  __shared__ uint32_t s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
-  const uint32_t S = (uint32_t)ST.n_stages;
-  // dynamic shared memory: the stage ring | bit stages [compute warp][n_bits][kBitWords] | long-string row tables
-  uint32_t* const bitstages = (uint32_t*)(smem + (size_t)S * ST.stage_bytes);
-  uint32_t* const ltab = bitstages + kComputeWarps * P.n_bits * kBitWords;
-  init_shared(P, ST, sh, tid);
-  for (int i = tid; i < kComputeWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
-  __syncthreads();
-  // from here on the producer and the compute warps only meet through the stages' mbarriers
-  if (warp >= kComputeWarps) {
-    // The input columns do not depend on the select and scan kernels: the producer warps that bring Utf8
-    // offsets and values start filling the ring while those kernels are still running (programmatic dependent
-    // launch).  Only the warp that also brings the selection bits and the slice prefixes waits for them, and
-    // no tile is `full` before that warp has arrived on its barrier.
-    if (warp == kComputeWarps) grid_dependency_wait();
-    producer_loop<true>(P, ST, sh, smem, lane, warp - kComputeWarps);
-    return;
+  int64_t tile = blockIdx.x;
+  if (MANY) {
+    // this tile's parameter block: the program part from the launch parameters, the batch part from its record
+    KernelParams* mine = (KernelParams*)(smem + TP.params_off);
+    const int32_t k = PP.many_tile_batch[blockIdx.x];   // (one entry per tile: the batch it belongs to)
+    const uint8_t* rec = PP.many + (size_t)k * (size_t)PP.many_stride;
+    uint32_t* d32 = (uint32_t*)mine;
+    const uint32_t* s32 = (const uint32_t*)&PP;
+    for (int i = tid; i < (int)(sizeof(KernelParams) / 4); i += kThreads) d32[i] = s32[i];
+    __syncthreads();
+    const int n_in = PP.n_in, n_out = PP.n_out;
+    const uint32_t* r32 = (const uint32_t*)rec;
+    uint32_t* hb = (uint32_t*)&mine->b;
+    for (int i = tid; i < (int)(sizeof(BatchHeader) / 4); i += kThreads) hb[i] = r32[i];
+    uint32_t* hi = (uint32_t*)mine->in;
+    for (int i = tid; i < n_in * 8; i += kThreads) hi[i] = r32[sizeof(BatchHeader) / 4 + i];
+    uint32_t* ho = (uint32_t*)mine->out;
+    for (int i = tid; i < n_out * 8; i += kThreads) ho[i] = r32[sizeof(BatchHeader) / 4 + n_in * 8 + i];
+    __syncthreads();
+    tile -= mine->b.first_tile;
   }
-  grid_dependency_wait();     // compute warps: the scan kernel's totals, the bitmaps the select kernel zeroed
-  if (has_pred && blockIdx.x == 0 && warp == 0) {
-    // closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
-    for (int k = lane; k < CHDB_N_OUT; k += 32) {
-      const OutDesc& o = P.out[k];
-      if (o.utf8_index != 0xFFu) o.offsets[P.counts[0]] = (int32_t)P.counts[1 + o.utf8_index];
+  const KernelParams& P = MANY ? *(const KernelParams*)(smem + TP.params_off) : PP;
+  const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
+  const int nq = 1 + CHDB_N_UTF8;
+  uint8_t* const stage = smem;
+  ColumnDesc* const cols = (ColumnDesc*)(smem + TP.cols_off);
+  uint32_t* const s_cnt = (uint32_t*)(smem + TP.cnt_off);
+  uint64_t* const s_pre = (uint64_t*)(smem + TP.pre_off);
+  uint64_t* const s_tot = (uint64_t*)(smem + TP.tot_off);
+  uint32_t* const bitstages = (uint32_t*)(smem + TP.bits_off);
+  uint32_t* const ltab = (uint32_t*)(smem + TP.ltab_off);
+  uint8_t* const pext4 = smem + TP.pext_off;
+  const uint32_t full = smem_u32(&s_full);
+  if (tid == 0) {
+    mbar_init(full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (P.n_bits > 0) {
+    for (int i = tid; i < 256; i += kThreads) {
+      const uint32_t s = (uint32_t)i >> 4, v = (uint32_t)i & 15u;
+      uint32_t out = 0, n = 0;
+      for (int j = 0; j < 4; j++)
+        if ((s >> j) & 1u) { out |= ((v >> j) & 1u) << n; n++; }
+      pext4[i] = (uint8_t)out;
+    }
+    for (int i = tid; i < kWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
+  }
+  if (tid < kMaxOutCols) s_nulls[tid] = 0;
+  const int64_t row0 = tile * kTileRows;
+  const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.b.num_rows ? kTileRows : P.b.num_rows - row0);
+  const bool last_tile = tile == (int64_t)P.b.num_tiles - 1;
+  __syncthreads();
+  grid_launch_dependents();
+  grid_dependency_wait();     // the zeroed workspace; inputs an earlier kernel on this stream may still be writing
+  if (warp == 0) load_tile(P, TP, cols, stage, full, row0, (uint32_t)tile_rows, lane);
+  mbar_wait(full, 0);
+
+  TileShared sh;
+  sh.pool = (const uint8_t*)P.strpool;
+  sh.pext4 = pext4;
+  sh.nulls = s_nulls;
+
+  // ---- 2. predicate -> selection bits, ranks, slice counts ----
+  uint32_t sels = 0;        // 4 selection bits per slice of this warp
+  uint32_t ranks[kSpw];     // slice-local rank of the lane's first selected row
+#pragma unroll
+  for (int j = 0; j < kSpw; j++) {
+    const int slice = warp * kSpw + j;
+    const int64_t qb[1] = {row0 + slice * kWarpRows + lane * 4};
+    const int left = tile_rows - (slice * kWarpRows + lane * 4);
+    const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
+    uint32_t sel4 = in4;
+    if (has_pred) {
+      V acc[4];
+      uint32_t accm, accv;
+#ifdef CHDB_JIT
+      run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
+#else
+      run_program<V, 1>(P, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
+#endif
+      sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
+    }
+    uint32_t wrows;
+    ranks[j] = warp_excl_scan((uint32_t)__popc(sel4), lane, wrows);
+    sels |= sel4 << (4 * j);
+    if (lane == 0) s_cnt[slice] = wrows;
+    if (has_pred) {
+      // selected value bytes per Utf8 output
+      CHDB_STATIC_UNROLL
+      for (int k = 0; k < CHDB_N_OUT; k++) {
+        const uint64_t meta = CHDB_OUT_META(P, k);
+        const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+        if (o_utf8 == 0xFFu) continue;   // uniform branch
+        const int32_t* off = cols[o_slot].offsets;
+        uint32_t bytes = 0;
+        if (sel4) {
+          const int4 a = *(const int4*)(off + qb[0]);
+          const int a4 = off[qb[0] + 4];
+          if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
+          if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
+          if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
+          if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
+        }
+        const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+        if (lane == 0) s_cnt[(1 + o_utf8) * kTileSlices + slice] = wbytes;
+      }
     }
   }
-  const int group = warp / kSlices, slice = warp % kSlices;
+
+  // ---- 3. slice counts -> batch-wide exclusive prefixes ----
+  if (has_pred) {
+    __syncthreads();
+    for (int q = warp; q < nq; q += kWarps) {
+      const uint32_t c = lane < kTileSlices ? s_cnt[q * kTileSlices + lane] : 0u;
+      uint32_t agg;
+      const uint32_t before = warp_excl_scan(c, lane, agg);
+      uint64_t* desc = P.b.desc + (size_t)q * (size_t)P.b.num_tiles;
+      if (lane == 0) publish_descriptor(desc + tile, tile == 0 ? kFlagPrefix : kFlagAgg, agg);
+      const uint64_t excl = lookback(desc, (uint32_t)tile, agg, lane);
+      if (lane < kTileSlices) s_pre[q * kTileSlices + lane] = excl + before;
+      if (lane == 0) s_tot[q] = excl + agg;
+    }
+    __syncthreads();
+    if (last_tile) {
+      // batch totals, and the closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
+      if (tid < nq) P.b.counts[tid] = s_tot[tid];
+      if (tid < CHDB_N_OUT) {
+        const OutDesc& o = P.out[tid];
+        if (o.utf8_index != 0xFFu) o.offsets[s_tot[0]] = (int32_t)s_tot[1 + o.utf8_index];
+      }
+    }
+  }
+
+  // ---- 4. the selected rows, to their final positions ----
   uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
-  PhaseClock pc;   // [0] wait for the stage (TMA), [1] ranks, [2] outputs, [3] bit flush + release
-  pc.start(P.timing != nullptr);
-  RingCursor cur{0, 0};
-  bool more = true;
-  for (int j = 0; j < group && more; j++) { more = observe_tile(sh, cur); cur.next(S); }   // the tiles before this group's first
-  while (more) {
-    const uint32_t stage = cur.stage;
-    TileCtl& C = sh.ctl[stage];
-    if (!observe_tile(sh, cur)) break;
-    pc.lap(0);
-    const int32_t tile = *(volatile int32_t*)&C.tile;
-    const uint8_t* sg = smem + (size_t)stage * ST.stage_bytes;
+#pragma unroll
+  for (int j = 0; j < kSpw; j++) {
+    const int slice = warp * kSpw + j;
+    if (slice * kWarpRows >= tile_rows) break;   // (tail tile)
     LaneCtx L;
     L.lane = lane;
     L.slice = slice;
     L.wid = warp;
-    const int64_t row0 = (int64_t)tile * kTileRows;
-    const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.num_rows ? kTileRows : P.num_rows - row0);
     L.row_base = row0 + slice * kWarpRows + lane * 4;
     {
       const int left = tile_rows - (slice * kWarpRows + lane * 4);
       L.inrange = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
     }
+    L.sel = (sels >> (4 * j)) & 0xFu;
+    L.rank = ranks[j];
+    L.count = s_cnt[slice];
     if (has_pred) {
-      const uint32_t word = ((const uint32_t*)(sg + ST.sel_off))[slice * 4 + (lane >> 3)];
-      L.sel = (word >> (4 * (lane & 7))) & 0xFu;
-      L.prefix = (const uint64_t*)(sg + ST.prefix_off);
-      L.obase = L.prefix[slice];
+      L.prefix = s_pre;
+      L.obase = s_pre[slice];
     } else {
-      L.sel = L.inrange;
       L.prefix = nullptr;
       L.obase = (uint64_t)(row0 + slice * kWarpRows);
     }
-    L.rank = warp_excl_scan((uint32_t)__popc(L.sel), lane, L.count);
-    pc.lap(1);
     int kb = 0;
 #ifdef CHDB_JIT
     {
       OutRegs R[chdb_jit::kNumOut > 0 ? chdb_jit::kNumOut : 1];
-      load_outputs_range<0, chdb_jit::kNumOut>(P, C, L, R);
-      store_outputs_range<V, 0, chdb_jit::kNumOut>(P, C, L, R, sh, bitstage, ltab, kb);
+      load_outputs_range<0, chdb_jit::kNumOut>(P, cols, L, R);
+      store_outputs_range<V, 0, chdb_jit::kNumOut>(P, cols, L, R, sh, bitstage, ltab, kb);
     }
 #else
 #pragma unroll 1
     for (int k = 0; k < P.n_out; k++) {
       OutRegs R;
       const uint64_t meta = CHDB_OUT_META(P, k);
-      load_output(P, C, k, meta, L, R);
-      store_output<V>(P, C, k, meta, L, R, sh, bitstage, ltab, kb);
+      load_output(P, cols, k, meta, L, R);
+      store_output<V>(P, cols, k, meta, L, R, sh, bitstage, ltab, kb);
     }
 #endif
-    pc.lap(2);
-    more = release_and_advance(sh, cur, S, lane);
-    if (P.n_bits > 0) flush_bits(P, sh, bitstage, L.obase, L.count, lane);
-    __syncwarp();
-    pc.lap(3);
+    if (P.n_bits > 0) {
+      __syncwarp();
+      flush_bits(P, bitstage, L.obase, L.count, lane);
+      __syncwarp();
+    }
   }
-  pc.flush(P.timing, 0, lane);
-  // null counts of this CTA
-  compute_warps_barrier();
-  if (tid < CHDB_N_OUT && P.out[tid].validity != nullptr && sh.nulls[tid] != 0)
-    atomicAdd((unsigned long long*)(P.counts + P.out[tid].count_index), (unsigned long long)sh.nulls[tid]);
+
+  // ---- null counts; the last CTA to finish mirrors the counts into pinned host memory ----
+  __syncthreads();
+  if (tid < CHDB_N_OUT && P.out[tid].validity != nullptr && s_nulls[tid] != 0)
+    atomicAdd((unsigned long long*)(P.b.counts + P.out[tid].count_index), (unsigned long long)s_nulls[tid]);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(P.b.done, 1u) == (uint32_t)P.b.num_tiles - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = tid; i <= P.n_counts; i += kThreads) P.b.host_counts[i] = __ldcg((const unsigned long long*)P.b.counts + i);
+  }
 }
 
 }  // namespace
 
+// Zeroes the workspace of one launch (look-back descriptors, counts, error word, bit-packed outputs).
+__device__ __forceinline__ void zero_body(uint4* p, size_t n16) {
+  grid_launch_dependents();
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += step) p[i] = make_uint4(0, 0, 0, 0);
+}
+
 #ifndef CHDB_JIT
-template <typename V>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) select_kernel(const __grid_constant__ KernelParams P, const __grid_constant__ KernelStage ST) {
-  select_body<V>(P, ST);
+template <typename V, bool MANY>
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) stream_kernel(const __grid_constant__ KernelParams P, const __grid_constant__ TilePlan TP) {
+  stream_body<V, MANY>(P, TP);
 }
-template <typename V>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) gather_kernel(const __grid_constant__ KernelParams P, const __grid_constant__ KernelStage ST) {
-  gather_body<V>(P, ST);
-}
-__global__ void __launch_bounds__(kScanThreads) scan_kernel(const __grid_constant__ KernelParams P) { scan_body(P); }
+__global__ void __launch_bounds__(kZeroThreads) zero_kernel(uint4* p, size_t n16) { zero_body(p, n16); }
 #endif
 
 }  // namespace chdb
 
 #ifdef CHDB_JIT
-// the two specialised streaming kernels of one NVRTC module, found by their unmangled names
-extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_select(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::KernelStage ST) {
-  chdb::select_body<chdb_jit::Container>(P, ST);
+// the specialised kernels of one NVRTC module, found by their unmangled names
+extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_stream(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::TilePlan TP) {
+  chdb::stream_body<chdb_jit::Container, false>(P, TP);
 }
-extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_gather(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::KernelStage ST) {
-  chdb::gather_body<chdb_jit::Container>(P, ST);
+extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_stream_many(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::TilePlan TP) {
+  chdb::stream_body<chdb_jit::Container, true>(P, TP);
 }
 #endif

@@ -16,19 +16,17 @@ enum class JitMode { Never, Auto, Always };
 JitMode jit_mode();
 constexpr int64_t kJitAutoRows = 1 << 18;
 
-struct JitKernel {   // one NVRTC module: the select and the gather kernel specialised for one program
+struct JitKernel {   // one NVRTC module: the stream kernel (single-batch and many-batch entry points) specialised for one program
   std::vector<char> cubin;
   cudaLibrary_t library = nullptr;
-  cudaKernel_t select = nullptr, gather = nullptr;
-  size_t select_granted = 0, gather_granted = 0;   // dynamic shared memory opted in to so far (single device per process rank)
+  cudaKernel_t stream = nullptr, stream_many = nullptr;
 };
 
 bool jit_available(std::string* why);
 std::string jit_prologue(const KernelParams& kp, bool has64, int min_blocks);
 // Cached; returns nullptr (and the reason) when specialisation is impossible -> use the interpreter.
-const JitKernel* jit_get(const KernelParams& kp, bool has64, std::string* err);
-cudaError_t jit_launch_select(const JitKernel* k, const KernelParams& p, const KernelStage& st, const StagePlan& plan, int sm_count, cudaStream_t stream);
-cudaError_t jit_launch_gather(const JitKernel* k, const KernelParams& p, const KernelStage& st, const StagePlan& plan, int sm_count, cudaStream_t stream);
+const JitKernel* jit_get(const KernelParams& kp, bool has64, int min_blocks, std::string* err);
+cudaError_t jit_launch_stream(const JitKernel* k, const KernelParams& p, const TilePlan& tp, unsigned grid, cudaStream_t stream);
 void jit_stats(int64_t* compiles, double* seconds);
 std::vector<char> jit_compile_offline(const KernelParams& kp, bool has64, std::string* log);
 

@@ -12,6 +12,9 @@
 #include <utility>
 #include <vector>
 
+namespace chdb {
+constexpr int kMinCtasPerSm = 4;   // register budget the interpreter kernels are compiled for
+}
 #include "device_code.cuh"
 
 namespace chdb {
@@ -19,22 +22,22 @@ namespace chdb {
 namespace {
 constexpr size_t kSmemPerSm = 228 * 1024;        // B200: 228 KB per SM, 1 KB of it reserved per resident CTA
 constexpr size_t kSmemPerCtaMax = 227 * 1024;
+constexpr size_t kStaticSmem = 256;              // s_full, s_nulls, s_last + what the compiler adds
 inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
-// static shared memory of the streaming kernels + what the compiler adds (alignment, its own slots)
-constexpr size_t kStaticSmem = sizeof(SharedState) + 256;
+inline size_t up128(size_t x) { return (x + 127) & ~(size_t)127; }
 }  // namespace
 
-// Decides what is staged.  Every buffer the kernel uses is a candidate; when one stage of everything
-// does not leave room for a ring of at least two stages, the largest buffers are read from global
-// memory instead (the producer then prefetches their slices into L2).  Utf8 value bytes are staged
-// only when the values are short (long values are copied global -> global by whole warps).
-StagePlan plan_stages(const KernelParams& kp, KernelStage& st, const int64_t* avg_utf8, bool gather) {
+// Decides what is staged.  Every buffer the kernel uses is a candidate; when the tile's slice of everything
+// would leave room for fewer than kWantCtas CTAs per SM, the largest buffers are read from global memory instead
+// (the loading warp then prefetches their slices into L2).  Utf8 value bytes are staged only when the values
+// are short (long values are copied global -> global by whole warps).
+int plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many) {
   struct Buf { int slot; int kind; size_t bytes; };   // kind 0: validity, 1: offsets, 2: values
   std::vector<Buf> bufs;
   for (int s = 0; s < kp.n_in; s++) {
-    st.slot[s] = StageSlot{kNotStaged, kNotStaged, kNotStaged, 0};
+    tp.slot[s] = StageSlot{kNotStaged, kNotStaged, kNotStaged, 0};
     const ColumnDesc& c = kp.in[s];
-    const uint8_t use = st.use[s];
+    const uint8_t use = tp.use[s];
     if ((use & USE_VALIDITY) && c.validity != nullptr) bufs.push_back({s, 0, (size_t)kTileRows / 8});
     if (c.type == T_UTF8) {
       if (use & USE_OFFSETS) bufs.push_back({s, 1, (size_t)(kTileRows + 4) * 4});
@@ -44,124 +47,107 @@ StagePlan plan_stages(const KernelParams& kp, KernelStage& st, const int64_t* av
       bufs.push_back({s, 2, c.width ? (size_t)kTileRows * c.width : (size_t)kTileRows / 8});
     }
   }
-  const bool has_pred = kp.pred_end > kp.pred_begin;
-  const size_t extras = gather && has_pred ? (size_t)kTileRows / 8 + (size_t)(1 + kp.n_utf8) * kSlices * 8 : 0;
-  const size_t fixed_dyn = gather ? (size_t)kComputeWarps * kp.n_bits * kBitWords * 4 +
-                                        (kp.long_strings ? (size_t)kComputeWarps * 2 * (kWarpRows + 4) * 4 : 0)
-                                  : 0;
-  const size_t fixed = fixed_dyn + kStaticSmem + 1024;
+  const int nq = 1 + kp.n_utf8;
+  // the tables behind the stage
+  size_t tables = 0;
+  auto table = [&](size_t bytes) { const size_t at = tables; tables += up16(bytes); return at; };
+  const size_t t_cols = table((size_t)std::max(kp.n_in, 1) * sizeof(ColumnDesc));
+  const size_t t_cnt = table((size_t)nq * kTileSlices * 4);
+  const size_t t_pre = table((size_t)nq * kTileSlices * 8);
+  const size_t t_tot = table((size_t)nq * 8);
+  const size_t t_bits = table((size_t)kWarps * kp.n_bits * kBitWords * 4);
+  const size_t t_ltab = table(kp.long_strings ? (size_t)kWarps * 2 * (kWarpRows + 4) * 4 : 0);
+  const size_t t_pext = table(kp.n_bits > 0 ? 256 : 0);
+  const size_t t_params = table(many ? sizeof(KernelParams) : 0);
   auto stage_bytes = [&]() {
-    size_t t = extras;
+    size_t t = 0;
     for (auto& b : bufs) t += up16(b.bytes);
-    return (t + 127) & ~(size_t)127;
+    return up128(t);
   };
-  struct Shape { int ctas, stages; };
-  std::vector<Shape> shapes;
-  for (int c = kMinCtasPerSm; c >= 1; c--)
-    for (int n = kMaxStages; n > kComputeGroups; n--) shapes.push_back(Shape{c, n});   // the parity waits need a ring deeper than the groups
-  if (const char* e = std::getenv(gather ? "CHDB_SHAPE" : "CHDB_SHAPE_SELECT")) {   // experiments: "ctas,stages" tried first
-    int c = 0, n = 0;
-    if (std::sscanf(e, "%d,%d", &c, &n) == 2 && c >= 1 && c <= 4 && n > kComputeGroups && n <= kMaxStages) shapes.insert(shapes.begin(), Shape{c, n});
-  }
-  Shape pick{0, 0};
-  while (true) {
-    const size_t sb = stage_bytes();
-    for (const Shape& sh : shapes) {
-      const size_t per_cta = fixed + (size_t)sh.stages * sb;
-      if (per_cta * sh.ctas <= kSmemPerSm && per_cta - 1024 <= kSmemPerCtaMax) { pick = sh; break; }
-    }
-    if (pick.ctas || bufs.empty()) break;
+  int want = 4;   // fewer resident tiles than this and the loads / look-backs stop overlapping
+  if (const char* e = std::getenv("CHDB_WANT_CTAS")) want = std::max(1, std::min(16, std::atoi(e)));
+  auto ctas_for = [&](size_t dyn) { return (int)std::min<size_t>(16, kSmemPerSm / (dyn + kStaticSmem + 1024)); };
+  while (!bufs.empty()) {
+    const size_t dyn = stage_bytes() + tables;
+    if (dyn + kStaticSmem <= kSmemPerCtaMax && ctas_for(dyn) >= want) break;
     auto big = std::max_element(bufs.begin(), bufs.end(), [](const Buf& a, const Buf& b) { return a.bytes < b.bytes; });
     bufs.erase(big);
   }
-  if (!pick.ctas) pick = Shape{1, kComputeGroups + 1};
   size_t off = 0;
   for (auto& b : bufs) {
-    StageSlot& sl = st.slot[b.slot];
+    StageSlot& sl = tp.slot[b.slot];
     if (b.kind == 0) sl.validity = (uint32_t)off;
     else if (b.kind == 1) sl.offsets = (uint32_t)off;
     else { sl.values = (uint32_t)off; sl.values_cap = (uint32_t)b.bytes; }
     off += up16(b.bytes);
   }
-  st.sel_off = (uint32_t)off;
-  st.prefix_off = (uint32_t)(off + kTileRows / 8);
-  st.stage_bytes = (int32_t)stage_bytes();
-  st.n_stages = pick.stages;
-  StagePlan plan;
-  plan.dyn_smem = (size_t)pick.stages * (size_t)st.stage_bytes + fixed_dyn;
-  plan.ctas_per_sm = pick.ctas;
-  return plan;
+  const size_t sb = stage_bytes();
+  tp.cols_off = (uint32_t)(sb + t_cols);
+  tp.cnt_off = (uint32_t)(sb + t_cnt);
+  tp.pre_off = (uint32_t)(sb + t_pre);
+  tp.tot_off = (uint32_t)(sb + t_tot);
+  tp.bits_off = (uint32_t)(sb + t_bits);
+  tp.ltab_off = (uint32_t)(sb + t_ltab);
+  tp.pext_off = (uint32_t)(sb + t_pext);
+  tp.params_off = (uint32_t)(sb + t_params);
+  tp.dyn_smem = (uint32_t)(sb + tables);
+  return std::max(1, ctas_for(tp.dyn_smem));
 }
 
-bool pdl_enabled();
-
-cudaError_t launch_streaming(const void* kernel, const KernelParams& p, const KernelStage& st, const StagePlan& plan, int sm_count,
-                             size_t* granted, bool after_kernel, cudaStream_t stream) {
-  if (*granted == 0) {   // opt in to the large dynamic window once per kernel; static + dynamic may pass 48 KB for any plan
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
-    if (e != cudaSuccess) return e;
-    const size_t want = kSmemPerCtaMax - fa.sharedSizeBytes;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-    if (e != cudaSuccess) return e;
-    *granted = want;
-  }
-  const int64_t resident = (int64_t)plan.ctas_per_sm * sm_count;
-  const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, resident);
-  void* args[] = {const_cast<KernelParams*>(&p), const_cast<KernelStage*>(&st)};
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = plan.dyn_smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  // only a kernel that follows another kernel of the same batch (and waits for it with griddepcontrol.wait) may start
-  // early; the select kernel follows the workspace memset and must not overtake it
-  cfg.numAttrs = after_kernel && pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelExC(&cfg, kernel, args);
-}
-
+namespace {
 bool pdl_enabled() {
   static const bool on = [] { const char* e = std::getenv("CHDB_PDL"); return !(e && *e == '0'); }();
   return on;
 }
-
-namespace {
-size_t* granted_slot(const void* kern) {
+// the large dynamic shared-memory window is opted in to once per (kernel, device)
+cudaError_t grant_smem(const void* kern) {
   static std::mutex mu;
-  static std::map<std::pair<const void*, int>, size_t> granted;
+  static std::map<std::pair<const void*, int>, bool> granted;
   int dev = 0;
-  cudaGetDevice(&dev);
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> g(mu);
-  return &granted[{kern, dev}];
+  bool& ok = granted[{kern, dev}];
+  if (ok) return cudaSuccess;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerCtaMax - fa.sharedSizeBytes));
+  if (e != cudaSuccess) return e;
+  ok = true;
+  return cudaSuccess;
 }
 }  // namespace
 
-cudaError_t launch_select(const KernelParams& p, const KernelStage& st, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream) {
-  const void* kern = has64 ? (const void*)select_kernel<uint64_t> : (const void*)select_kernel<uint32_t>;
-  return launch_streaming(kern, p, st, plan, sm_count, granted_slot(kern), false, stream);
-}
-
-cudaError_t launch_gather(const KernelParams& p, const KernelStage& st, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream) {
-  const void* kern = has64 ? (const void*)gather_kernel<uint64_t> : (const void*)gather_kernel<uint32_t>;
-  return launch_streaming(kern, p, st, plan, sm_count, granted_slot(kern), p.pred_end > p.pred_begin, stream);
-}
-
-cudaError_t launch_scan(const KernelParams& p, cudaStream_t stream) {
+cudaError_t launch_stream_kernel(const void* kernel, const KernelParams& p, const TilePlan& tp, unsigned grid, cudaStream_t stream) {
+  cudaError_t e = grant_smem(kernel);
+  if (e != cudaSuccess) return e;
+  void* args[] = {const_cast<KernelParams*>(&p), const_cast<TilePlan*>(&tp)};
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)p.num_chunks, (unsigned)(1 + p.n_utf8));
-  cfg.blockDim = dim3(kScanThreads);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = tp.dyn_smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  void* args[] = {const_cast<KernelParams*>(&p)};
-  return cudaLaunchKernelExC(&cfg, (const void*)scan_kernel, args);
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;   // (always follows launch_zero's kernel)
+  return cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
+cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, unsigned grid, cudaStream_t stream) {
+  const bool many = p.many != nullptr;
+  const void* kern = has64 ? (many ? (const void*)stream_kernel<uint64_t, true> : (const void*)stream_kernel<uint64_t, false>)
+                           : (many ? (const void*)stream_kernel<uint32_t, true> : (const void*)stream_kernel<uint32_t, false>);
+  return launch_stream_kernel(kern, p, tp, grid, stream);
+}
+
+cudaError_t launch_zero(void* p, size_t bytes, cudaStream_t stream) {
+  const size_t n16 = bytes / 16;
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(592, (n16 + kZeroThreads - 1) / kZeroThreads));
+  zero_kernel<<<grid, kZeroThreads, 0, stream>>>((uint4*)p, n16);
+  return cudaGetLastError();
 }
 
 }  // namespace chdb

@@ -1,4 +1,4 @@
-// Kernel parameter block of the select -> scan -> gather kernels.
+// Kernel parameter block of the fused filter / project / compact kernel ("stream" kernel).
 #pragma once
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
@@ -9,29 +9,28 @@
 
 namespace chdb {
 
-// A tile is kSlices slices of 128 rows; a slice is the unit one warp works on (4 rows per lane).
-// Both streaming kernels are persistent: kProducerWarps TMA producer warps feed a ring of shared-memory stages,
-// kComputeGroups groups of kSlices compute warps drain it (group g takes the CTA's tiles g, g + kComputeGroups, ...).
-#ifndef CHDB_SLICES
-#define CHDB_SLICES 8
+// One CTA works on one tile.  A tile is kTileSlices slices of 128 rows; a slice is the unit one warp
+// works on at a time (4 consecutive rows per lane, so every column access is a 128-bit load); warp w
+// owns slices [w * kSpw, (w + 1) * kSpw) of its tile.  Many small CTAs (instead of one persistent CTA
+// per SM) let the hardware hide one tile's load and look-back latency behind its neighbours' work:
+// 5-6 tiles are resident per SM, each with its input landing in (or being read from) shared memory.
+#ifndef CHDB_WARPS
+#define CHDB_WARPS 4
 #endif
-#ifndef CHDB_COMPUTE_GROUPS
-#define CHDB_COMPUTE_GROUPS 3
+#ifndef CHDB_SPW
+#define CHDB_SPW 2
 #endif
-constexpr int kSlices = CHDB_SLICES;
-constexpr int kComputeGroups = CHDB_COMPUTE_GROUPS;
-constexpr int kComputeWarps = kComputeGroups * kSlices;
+constexpr int kWarps = CHDB_WARPS;
+constexpr int kSpw = CHDB_SPW;                        // slices per warp
+constexpr int kTileSlices = kWarps * kSpw;
 constexpr int kWarpRows = 128;                        // rows of one slice
-constexpr int kTileRows = kSlices * kWarpRows;        // 1024 rows per tile
-constexpr int kProducerWarps = 3;           // one per kind of buffer: validity bitmaps, Utf8 offsets, values
-constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
-constexpr int kMinCtasPerSm = kThreads <= 512 ? 2 : 1;       // register budget the kernels are compiled for
-constexpr int kMaxStages = 8;               // depth of the shared-memory input ring
-constexpr int kMaxQuantities = 1 + kMaxOutCols;              // scanned quantities: rows + bytes per Utf8 output
-constexpr int kBitWords = kWarpRows / 32 + 2;                // words of one slice's bit-packed output stage
+constexpr int kTileRows = kTileSlices * kWarpRows;    // 1024 rows per tile
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxQuantities = 1 + kMaxOutCols;       // scanned quantities: rows + bytes per Utf8 output
+constexpr int kBitWords = kWarpRows / 32 + 2;         // words of one slice's bit-packed output stage
 constexpr uint32_t kNotStaged = 0xFFFFFFFFu;
-constexpr int kScanThreads = 256;
-constexpr int kScanChunk = kScanThreads * 8;  // slices per CTA of the scan kernel
+constexpr int kZeroThreads = 256;
+static_assert(kTileSlices <= 32, "a warp scans the tile's slice counts in one go");
 
 struct ColumnDesc {          // one input column slot (32 bytes)
   const void* values;        // fixed width: values; Boolean: bit-packed values; Utf8: value bytes
@@ -42,9 +41,9 @@ struct ColumnDesc {          // one input column slot (32 bytes)
   uint8_t pad[6];
 };
 
-// Where a column's slice of one tile sits inside a shared-memory stage (byte offsets from the stage
-// base, 16-byte aligned), or kNotStaged when the kernel reads that buffer from global memory (or not
-// at all).
+// Where a column's slice of the tile sits inside the CTA's shared-memory stage (byte offsets from the
+// stage base, 16-byte aligned), or kNotStaged when the kernel reads that buffer from global memory
+// (or not at all).
 struct StageSlot {
   uint32_t values;           // fixed width: kTileRows * width bytes; Boolean: kTileRows / 8; Utf8: values_cap bytes
   uint32_t validity;         // kTileRows / 8 bytes
@@ -53,12 +52,19 @@ struct StageSlot {
 };
 enum SlotUse : uint8_t { USE_VALUES = 1, USE_VALIDITY = 2, USE_OFFSETS = 4 };
 
-// One streaming kernel's view of the input: which buffers it touches and where they are staged.
-struct KernelStage {
-  int32_t n_stages;              // depth of the input ring (2 .. kMaxStages)
-  int32_t stage_bytes;           // bytes of one stage (multiple of 128)
-  uint32_t sel_off;              // gather: the tile's selection bits (kTileRows / 8 bytes), then ...
-  uint32_t prefix_off;           // ... its slice prefixes: [quantity][kSlices] uint64
+// The CTA's dynamic shared memory: the stage (the tile's slice of every staged buffer, brought in by TMA
+// bulk copies) followed by the small per-tile tables.
+struct TilePlan {
+  uint32_t cols_off;             // ColumnDesc[n_in]: the input columns as seen by this tile (pointers biased so that
+                                 // indexing with the ABSOLUTE row lands in the stage, or in global memory)
+  uint32_t cnt_off;              // uint32[quantity][kTileSlices]: per-slice counts
+  uint32_t pre_off;              // uint64[quantity][kTileSlices]: per-slice exclusive prefixes (batch-wide)
+  uint32_t tot_off;              // uint64[quantity]: batch totals (valid in the last tile)
+  uint32_t bits_off;             // uint32[warp][n_bits][kBitWords]: per-warp bit stages
+  uint32_t ltab_off;             // long strings: per-warp row tables
+  uint32_t pext_off;             // uint8[256] bit-compaction table (only with bit-packed outputs)
+  uint32_t params_off;           // MANY: this tile's KernelParams copy
+  uint32_t dyn_smem;             // total
   uint8_t use[kMaxInCols];       // SlotUse mask per input slot
   StageSlot slot[kMaxInCols];
 };
@@ -78,44 +84,50 @@ struct OutDesc {             // one output column that goes through the kernel (
   uint8_t count_index;       // index into counts[] for this column's null count
 };
 
+// What differs from batch to batch (pointers and sizes).  A launch over many small batches reads one of
+// these per batch from global memory (packed: header, then n_in ColumnDesc, then n_out OutDesc).
+struct BatchHeader {
+  int64_t num_rows;
+  uint64_t* desc;            // [quantity][num_tiles] decoupled look-back descriptors (zeroed)
+  uint64_t* counts;          // see below (zeroed)
+  uint64_t* error_word;      // zeroed; atomicMax(~packed)
+  uint64_t* host_counts;     // pinned host mirror of counts[] + error word, written by the last CTA to finish
+  uint32_t* done;            // zeroed; CTAs that have finished
+  int32_t num_tiles;
+  int32_t first_tile;        // MANY: blockIdx.x of this batch's tile 0
+};
+
 // counts[] layout (uint64 each): [0] output rows, [1 .. 1+n_utf8) output value bytes per Utf8
 // output, [1+n_utf8 ..) null count per kernel output, last: error word.
 struct KernelParams {
-  int64_t num_rows;
-  int64_t num_slices;        // ceil(num_rows / 128)
-  int64_t slice_pitch;       // num_slices rounded up to a whole number of tiles
-  uint32_t* sel_bits;        // select -> gather: one bit per row (kTileRows / 8 bytes per tile, every tile complete)
-  uint32_t* slice_counts;    // select -> scan: [quantity][slice_pitch] selected rows / selected value bytes per slice
-  uint64_t* slice_prefix;    // scan -> gather: [quantity][slice_pitch] exclusive prefixes
-  uint64_t* chunk_desc;      // scan: [quantity][num_chunks] decoupled look-back descriptors (zeroed)
-  uint64_t* counts;          // see above (zeroed)
-  uint64_t* error_word;      // zeroed; atomicMax(~packed)
-  uint64_t* timing;          // debug (CHDB_PHASE_TIMING=1): 16 cycle counters summed over warps, or nullptr
-  int32_t num_tiles, num_chunks;
+  BatchHeader b;
   int32_t n_in, n_out, n_utf8;
-  int32_t pred_begin, pred_end;  // pred_begin == pred_end: no predicate (every row is kept; gather only)
+  int32_t pred_begin, pred_end;  // pred_begin == pred_end: no predicate (every row is kept)
   int32_t n_bits;                // bit-packed outputs (Boolean values + validity bitmaps)
   int32_t long_strings;          // 1: per-warp row tables for the chunk-centric long-string copy are allocated
+  int32_t n_counts;              // entries of counts[] before the error word
+  // MANY (one launch over several batches of one schema and shape): packed per-batch records in global memory
+  const uint8_t* many;           // nullptr: single batch (everything is in this block)
+  const int32_t* many_tile_batch;  // [grid] batch index of every tile
+  int32_t many_batches, many_stride;
   ColumnDesc in[kMaxInCols];
   OutDesc out[kMaxOutCols];
   Instr instrs[kMaxInstr];
   char strpool[kStrPoolBytes];
 };
-static_assert(sizeof(KernelParams) + sizeof(KernelStage) <= 4096, "kernel parameters must fit 4 KB");
+static_assert(sizeof(KernelParams) + sizeof(TilePlan) <= 4096, "kernel parameters must fit 4 KB");
 
 #ifndef __CUDACC_RTC__
-// Fills `st` for one of the streaming kernels (st.use[] set by the caller; needs kp.in[], kp.n_*):
-// decides which buffers are staged in shared memory.  avg_utf8[s]: mean value length of Utf8 slot s
-// (or < 0).  Returns the dynamic shared memory the launch needs and the CTAs per SM it was sized for.
-struct StagePlan { size_t dyn_smem; int ctas_per_sm; };
-StagePlan plan_stages(const KernelParams& kp, KernelStage& st, const int64_t* avg_utf8, bool gather);
+// Fills `tp` (tp.use[] set by the caller; needs kp.in[], kp.n_*): decides which buffers are staged in
+// shared memory.  avg_utf8[s]: mean value length of Utf8 slot s (or < 0).  Returns the CTAs per SM the
+// plan leaves room for.
+int plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many);
 // has64: the program touches 64-bit types (selects the 64-bit accumulator container).
-cudaError_t launch_select(const KernelParams& p, const KernelStage& st, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream);
-cudaError_t launch_scan(const KernelParams& p, cudaStream_t stream);
-cudaError_t launch_gather(const KernelParams& p, const KernelStage& st, bool has64, const StagePlan& plan, int sm_count, cudaStream_t stream);
+cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, unsigned grid, cudaStream_t stream);
+// Zeroes `bytes` (a multiple of 16) at p; the stream kernel that follows is launched as its programmatic dependent.
+cudaError_t launch_zero(void* p, size_t bytes, cudaStream_t stream);
 // shared by the ahead-of-time and the run-time compiled kernels
-cudaError_t launch_streaming(const void* kernel, const KernelParams& p, const KernelStage& st, const StagePlan& plan, int sm_count,
-                             size_t* granted, bool after_kernel, cudaStream_t stream);
+cudaError_t launch_stream_kernel(const void* kernel, const KernelParams& p, const TilePlan& tp, unsigned grid, cudaStream_t stream);
 #endif
 
 }  // namespace chdb

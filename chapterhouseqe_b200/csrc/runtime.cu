@@ -560,7 +560,7 @@ struct HostClock {
   ~HostClock() {
     if (!on) return;
     const double total = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-    if (total > 300) std::fprintf(stderr, "[chdb host] execute %.0f us: allocate outputs %.0f, workspace+memset %.0f, plan+launch %.0f, read-back %.0f\n",
+    if (total > 300) std::fprintf(stderr, "[chdb host] execute %.0f us: allocate outputs %.0f, workspace+zero %.0f, plan+launch %.0f, event %.0f\n",
                                   total, ph[0], ph[1], ph[2], ph[3]);
   }
 };
@@ -599,7 +599,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     any_const |= o.kind == OutputColumn::CONST;
     all_const &= o.kind == OutputColumn::CONST;
   }
-  if (any_const && !all_const && n != 1)
+  if (any_const && !all_const && !use_pred && n != 1)   // (under a predicate the surviving rows count: checked after the launch)
     throw Error(CHDB_ERR_INVALID_ARGUMENT, "Invalid argument error: all columns in a record batch must have the same length");
 
   // which outputs go through the kernel
@@ -613,7 +613,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
 
   KernelParams kp;
   std::memset(&kp, 0, sizeof(kp));
-  int n_utf8 = 0, n_counts = 1, max_w = 4;
+  int n_utf8 = 0, n_counts = 1;
   if (launch) {
     for (size_t s = 0; s < p.slot_to_col.size(); s++) {
       const DeviceColumn& c = in->cols[p.slot_to_col[s]];
@@ -645,7 +645,10 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
 
   int utf8_seen = 0, ko = 0;
   int64_t avg_utf8 = -1;  // mean value length of the longest Utf8 output (sizes the staging area); -1: none
-  std::vector<std::pair<void*, size_t>> to_zero;
+  // Bit-packed outputs (Boolean values, validity bitmaps) are merged into with atomicOr at slice edges, so they start
+  // zeroed: they live, with the look-back descriptors and the counts, in ONE region that one small kernel zeroes.
+  struct ZeroReq { size_t col; int ko; bool validity; size_t bytes; size_t at; };
+  std::vector<ZeroReq> zero_reqs;
   for (size_t k = 0; k < p.outputs.size(); k++) {
     const OutputColumn& o = p.outputs[k];
     DeviceColumn dc;
@@ -680,7 +683,6 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
         od.begin = (uint8_t)o.begin;
         od.end = (uint8_t)o.end;
         od.utf8_index = 0xFF;
-        max_w = std::max(max_w, o.width);
         bool nullable = false;
         if (o.kind == OutputColumn::PASS) {
           if (o.slot < 0) throw Error(CHDB_ERR_INVALID_ARGUMENT, "internal: pass-through column without a kernel slot");
@@ -701,19 +703,17 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
           dc.value_bytes = -1;
           dc.bytes_index = 1 + utf8_seen;
           utf8_seen++;
+          dc.values = dc.values_buf->ptr;
+          od.values = dc.values_buf->ptr;
         } else if (o.type == T_BOOL) {
-          dc.values_buf = dev_alloc(core, round_up(bitmap_bytes(n), 4));
-          to_zero.push_back({dc.values_buf->ptr, round_up(bitmap_bytes(n), 4)});
+          zero_reqs.push_back({k, ko, false, round_up(bitmap_bytes(n), 4), 0});
         } else {
           dc.values_buf = dev_alloc(core, (size_t)n * (size_t)o.width);
+          dc.values = dc.values_buf->ptr;
+          od.values = dc.values_buf->ptr;
         }
-        dc.values = dc.values_buf->ptr;
-        od.values = dc.values_buf->ptr;
         if (nullable) {
-          dc.validity_buf = dev_alloc(core, round_up(bitmap_bytes(n), 4));
-          to_zero.push_back({dc.validity_buf->ptr, round_up(bitmap_bytes(n), 4)});
-          dc.validity = (const uint8_t*)dc.validity_buf->ptr;
-          od.validity = (uint8_t*)dc.validity_buf->ptr;
+          zero_reqs.push_back({k, ko, true, round_up(bitmap_bytes(n), 4), 0});
           od.count_index = (uint8_t)n_counts;
           dc.null_count = -1;
           dc.count_index = n_counts;
@@ -726,49 +726,57 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   }
 
   if (!launch) {
+    if (any_const && !all_const && compact)   // n == 0: nothing survives next to len-1 literal columns
+      throw Error(CHDB_ERR_INVALID_ARGUMENT, "Invalid argument error: all columns in a record batch must have the same length");
     out->num_rows = all_const ? 1 : n;
-    if (compact) out->num_rows = 0;   // n == 0
+    if (compact && !all_const) out->num_rows = 0;   // n == 0
     return out;
   }
 
   hc.lap(0);
-  // ---- launch: select -> scan -> gather (gather alone when there is no predicate) ----
+  // ---- one launch of the stream kernel (preceded by the kernel that zeroes its workspace) ----
   const int64_t num_tiles = (n + kTileRows - 1) / kTileRows;
   if (num_tiles > INT32_MAX) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "batch too large");
   const int nq = 1 + n_utf8;
-  const int64_t slice_pitch = num_tiles * kSlices;
-  const int64_t num_chunks = (slice_pitch + kScanChunk - 1) / kScanChunk;
-  // workspace: counts[n_counts] | error word | pad | chunk descriptors   (zeroed)
-  //            | selection bits | slice counts | slice prefixes            (written before they are read)
+  // zeroed region: counts[n_counts] | error word | done | pad || look-back descriptors || bit-packed outputs
   const size_t ws_counts = round_up((size_t)(n_counts + 2) * 8, 128);
-  const size_t ws_desc = compact ? round_up((size_t)nq * (size_t)num_chunks * 8, 128) : 0;
-  const size_t ws_sel = compact ? (size_t)num_tiles * (kTileRows / 8) : 0;
-  const size_t ws_cnt = compact ? round_up((size_t)nq * (size_t)slice_pitch * 4, 128) : 0;
-  const size_t ws_pre = compact ? (size_t)nq * (size_t)slice_pitch * 8 : 0;
+  const size_t ws_desc = compact ? round_up((size_t)nq * (size_t)num_tiles * 8, 128) : 0;
+  size_t ws_total = ws_counts + ws_desc;
+  for (auto& z : zero_reqs) { z.at = ws_total; ws_total += round_up(z.bytes, 128); }
   auto res = std::make_shared<RunResult>();
   res->core = core;
   res->n_counts = n_counts;
-  res->workspace = dev_alloc(core, ws_counts + ws_desc + ws_sel + ws_cnt + ws_pre);
+  res->workspace = dev_alloc(core, ws_total);
   if ((size_t)(n_counts + 1) * 8 > CtxCore::kPinnedBlock) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "too many counted outputs");
   res->host = (uint64_t*)core->pinned_get();
   res->done = core->event_get();
   uint8_t* ws = (uint8_t*)res->workspace->ptr;
-  CUDA_CHECK(cudaMemsetAsync(ws, 0, ws_counts + ws_desc, core->stream));
-  if (!compact)   // (with a predicate the select kernel zeroes them)
-    for (auto& z : to_zero) CUDA_CHECK(cudaMemsetAsync(z.first, 0, z.second, core->stream));
+  for (auto& z : zero_reqs) {
+    DeviceColumn& dc = out->cols[z.col];
+    OutDesc& od = kp.out[z.ko];
+    if (z.validity) {
+      dc.validity_buf = res->workspace;
+      dc.validity = ws + z.at;
+      od.validity = ws + z.at;
+    } else {
+      dc.values_buf = res->workspace;
+      dc.values = ws + z.at;
+      od.values = ws + z.at;
+    }
+  }
+  CUDA_CHECK(launch_zero(ws, ws_total, core->stream));
+  core->launches++;
 
   hc.lap(1);
-  kp.num_rows = n;
-  kp.num_slices = (n + kWarpRows - 1) / kWarpRows;
-  kp.slice_pitch = slice_pitch;
-  kp.counts = (uint64_t*)ws;
-  kp.error_word = (uint64_t*)ws + n_counts;
-  kp.chunk_desc = (uint64_t*)(ws + ws_counts);
-  kp.sel_bits = (uint32_t*)(ws + ws_counts + ws_desc);
-  kp.slice_counts = (uint32_t*)(ws + ws_counts + ws_desc + ws_sel);
-  kp.slice_prefix = (uint64_t*)(ws + ws_counts + ws_desc + ws_sel + ws_cnt);
-  kp.num_tiles = (int32_t)num_tiles;
-  kp.num_chunks = (int32_t)num_chunks;
+  kp.b.num_rows = n;
+  kp.b.counts = (uint64_t*)ws;
+  kp.b.error_word = (uint64_t*)ws + n_counts;
+  kp.b.done = (uint32_t*)((uint64_t*)ws + n_counts + 1);
+  kp.b.desc = (uint64_t*)(ws + ws_counts);
+  kp.b.host_counts = res->host;
+  kp.b.num_tiles = (int32_t)num_tiles;
+  kp.b.first_tile = 0;
+  kp.n_counts = n_counts;
   kp.n_out = ko;
   kp.n_utf8 = n_utf8;
   kp.pred_begin = compact ? p.pred_begin : 0;
@@ -779,7 +787,6 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   kp.n_bits = 0;
   for (int k = 0; k < ko; k++) kp.n_bits += (kp.out[k].type == T_BOOL ? 1 : 0) + (kp.out[k].validity != nullptr ? 1 : 0);
   kp.long_strings = avg_utf8 > 16 ? 1 : 0;
-  if (!compact) kp.counts = (uint64_t*)ws;
   int64_t slot_avg[kMaxInCols];
   for (size_t s = 0; s < p.slot_to_col.size(); s++) {
     const DeviceColumn& c = in->cols[p.slot_to_col[s]];
@@ -788,42 +795,29 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     if ((((uintptr_t)c.values | (uintptr_t)c.validity | (uintptr_t)c.offsets) & 15u) != 0)
       throw Error(CHDB_ERR_INVALID_ARGUMENT, "device buffers must be 16-byte aligned");
   }
-  // which buffers each streaming kernel touches
-  KernelStage st_select, st_gather;
-  std::memset(&st_select, 0, sizeof(st_select));
-  std::memset(&st_gather, 0, sizeof(st_gather));
-  auto mark_instrs = [&](KernelStage& st, int begin, int end) {
+  // which buffers the kernel touches
+  TilePlan tp;
+  std::memset(&tp, 0, sizeof(tp));
+  auto mark_instrs = [&](int begin, int end) {
     for (int i = begin; i < end; i++) {
       const Instr& ins = kp.instrs[i];
       if (ins.op == OP_CMP_UTF8) {
-        if (ins.slot != 0xFF) st.use[ins.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
+        if (ins.slot != 0xFF) tp.use[ins.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
         const uint8_t sb = (uint8_t)(ins.imm >> 56);
-        if (sb != 0xFF) st.use[sb] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
+        if (sb != 0xFF) tp.use[sb] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
       } else if (ins.src == SRC_COL) {
-        st.use[ins.slot] |= USE_VALUES | USE_VALIDITY;
+        tp.use[ins.slot] |= USE_VALUES | USE_VALIDITY;
       }
     }
   };
-  mark_instrs(st_select, kp.pred_begin, kp.pred_end);
+  mark_instrs(kp.pred_begin, kp.pred_end);
   for (int k = 0; k < ko; k++) {
     const OutDesc& od = kp.out[k];
-    if (od.kind == OUT_EXPR) {
-      mark_instrs(st_gather, od.begin, od.end);
-    } else {
-      st_gather.use[od.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
-      if (od.type == T_UTF8) st_select.use[od.slot] |= USE_OFFSETS;   // selected value bytes per slice
-    }
+    if (od.kind == OUT_EXPR) mark_instrs(od.begin, od.end);
+    else tp.use[od.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
   }
-  const StagePlan plan_gather = plan_stages(kp, st_gather, slot_avg, true);
-  const StagePlan plan_select = compact ? plan_stages(kp, st_select, slot_avg, false) : StagePlan{0, 1};
+  const int ctas_per_sm = plan_tile(kp, tp, slot_avg, false);
 
-  // CHDB_PHASE_TIMING=1: cycles per role and phase, summed over warps, on stderr (debugging aid; synchronises)
-  Buf timing_buf;
-  const char* pt = std::getenv("CHDB_PHASE_TIMING");
-  if (pt && *pt == '1') {
-    timing_buf = dev_alloc(core, 32 * 8);
-    CUDA_CHECK(cudaMemsetAsync(timing_buf->ptr, 0, 32 * 8, core->stream));
-  }
   // Long scans run the same device code specialised for this program by NVRTC (jit.cpp); short
   // batches, or boxes without NVRTC, run the bytecode interpreter kernels.
   cudaError_t le = cudaSuccess;
@@ -831,40 +825,26 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   const JitMode jm = jit_mode();
   if (jm == JitMode::Always || (jm == JitMode::Auto && n >= kJitAutoRows)) {
     std::string why;
-    jk = jit_get(kp, p.has64, &why);
+    jk = jit_get(kp, p.has64, std::min(ctas_per_sm, 8), &why);
   }
-  if (compact) {
-    kp.timing = timing_buf ? (uint64_t*)timing_buf->ptr : nullptr;
-    le = jk ? jit_launch_select(jk, kp, st_select, plan_select, core->sm_count, core->stream)
-            : launch_select(kp, st_select, p.has64, plan_select, core->sm_count, core->stream);
-    if (le == cudaSuccess) le = launch_scan(kp, core->stream);
-    core->launches += 2;
-  }
-  if (le == cudaSuccess) {
-    kp.timing = timing_buf ? (uint64_t*)timing_buf->ptr + 16 : nullptr;
-    le = jk ? jit_launch_gather(jk, kp, st_gather, plan_gather, core->sm_count, core->stream)
-            : launch_gather(kp, st_gather, p.has64, plan_gather, core->sm_count, core->stream);
-    core->launches++;
-  }
+  le = jk ? jit_launch_stream(jk, kp, tp, (unsigned)num_tiles, core->stream)
+          : launch_stream(kp, tp, p.has64, (unsigned)num_tiles, core->stream);
+  core->launches++;
   if (jk) core->jit_launches++;
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
-  if (timing_buf) {
-    uint64_t t[32];
-    CUDA_CHECK(cudaMemcpyAsync(t, timing_buf->ptr, sizeof(t), cudaMemcpyDeviceToHost, core->stream));
-    CUDA_CHECK(cudaStreamSynchronize(core->stream));
-    const double tiles = (double)num_tiles, cw = tiles * kSlices;
-    std::fprintf(stderr, "[chdb timing] %lld tiles; mean cycles per tile -- select (%d/SM, %d stages of %d B): compute warp wait-stage %.0f, "
-                 "predicate %.0f | producer wait-free %.0f, addresses %.0f, issue %.0f -- gather (%d/SM, %d stages of %d B): compute warp "
-                 "wait-stage %.0f, ranks %.0f, outputs %.0f, flush %.0f | producer wait-free %.0f, addresses %.0f, issue %.0f\n",
-                 (long long)num_tiles, plan_select.ctas_per_sm, st_select.n_stages, st_select.stage_bytes, t[0] / cw, t[1] / cw,
-                 t[8] / tiles, t[9] / tiles, t[10] / tiles, plan_gather.ctas_per_sm, st_gather.n_stages, st_gather.stage_bytes,
-                 t[16] / cw, t[17] / cw, t[18] / cw, t[19] / cw, t[24] / tiles, t[25] / tiles, t[26] / tiles);
-  }
   hc.lap(2);
-  CUDA_CHECK(cudaMemcpyAsync(res->host, ws, (size_t)(n_counts + 1) * 8, cudaMemcpyDeviceToHost, core->stream));
-  CUDA_CHECK(cudaEventRecord(res->done, core->stream));
+  CUDA_CHECK(cudaEventRecord(res->done, core->stream));   // the counts arrive in res->host with the kernel's last CTA
   out->result = res;
   out->num_rows = compact ? -1 : n;
+  if (all_const) {
+    out->num_rows = 1;   // record_projection.rs:73 over len-1 arrays, whatever the filter kept (the launch only raises the predicate's errors)
+  } else if (any_const && compact) {
+    // literal columns are len 1: RecordBatch::try_new accepts them only next to exactly one surviving row
+    check_run_error(out.get());
+    resolve(out.get());
+    if (out->num_rows != 1)
+      throw Error(CHDB_ERR_INVALID_ARGUMENT, "Invalid argument error: all columns in a record batch must have the same length");
+  }
   hc.lap(3);
   return out;
 }
@@ -981,7 +961,7 @@ size_t chdb_program_jit_source(const chdb_program* prog, char* buf, size_t cap) 
   if (!prog) return 0;
   KernelParams kp;
   shape_params(*prog->p, kp);
-  std::string s = jit_prologue(kp, prog->p->has64, prog->p->has64 ? 3 : 4);
+  std::string s = jit_prologue(kp, prog->p->has64, 5);
   if (buf && cap) {
     size_t n = std::min(cap - 1, s.size());
     std::memcpy(buf, s.data(), n);
