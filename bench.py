@@ -1,15 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- filter + project + compaction throughput on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, device-resident + e2e)
-  python bench.py --impl reference [...]                         the CPU restatement on all host threads
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3|C4|C4H|C5|C2S]   our arm (CUDA)
+  python bench.py --impl reference [...]                                          the CPU restatement, all host threads
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): large_simple.sql-shaped synthetic rows,
-100 M rows per GPU, columns id Int32 | k Int64 | value2 Float32 (10 % null) | d Float64 (5 % null) |
-value1 Utf8 (8 bytes), predicate `(id % 2 = 0 AND value2 > 10.0) OR d < 0.5` with the reference's
-non-Kleene null semantics, `select *`, in device-native batches of 2^22 rows.  One step = one pass of
-the fused kernel over every batch.  Multi-GPU: one process per GPU (torchrun), batches shard by
-file / row group, so there is no collective on the data path ("weak" scaling: 100 M rows per GPU).
+Workloads (BASELINE.json configs).  Every input column is referenced in every config.
+  C2  (default, the configuration the metric is quoted on): large_simple.sql-shaped, 100 M rows per GPU,
+      id Int32 | k Int64 | value2 Float32 (10 % null) | d Float64 (5 % null) | value1 Utf8[8],
+      `select * where (id % 2 = 0 AND value2 > 10.0) OR d < 0.5` (the reference's non-Kleene AND/OR), 2^22-row batches.
+  C2S same data in the reference's native 10 000-row batches (physical_planner.rs:323), processed through the
+      many-batch entry point (one launch set per 512 records).
+  C3  simple.sql query 4: 7-column projection with arithmetic and implicit casts over `where id > 25 + 0.0`
+      (fused filter + project), base schema, 16 M rows.
+  C4  only_wide_strings_query.sql: base schema with 100-byte strings, `select * where id > 25`, 10 M rows;
+  C4H the same data with `where id % 2 = 0`.
+  C5  huge_simple.sql scaled: base schema (id Int32 | value1 Utf8[8] | value2 Float32), `select * where id % 2 = 0`,
+      500 M rows per GPU (4 B rows at 8 GPUs), sharded by file / row group.
+One step = `--passes` passes of the hot path over the GPU's resident rows (default: enough for >= 50 ms per step).
+Multi-GPU: one process per GPU (torchrun), records shard by record_id, no collective on the data path ("weak").
 """
 from __future__ import annotations
 
@@ -18,22 +26,38 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PREDICATE = "(id % 2 = 0 and value2 > 10.0) or d < 0.5"
-SQL = f"select * from read_files('large_simple/*.parquet') where {PREDICATE}"
 METRIC = "filter_project_rows_per_s"
 UNIT = "rows/s"
-SEED = 0xC4DB0002
-NULL_V2, NULL_D = 0.10, 0.05
-STR_LEN = 8
-# algorithmic bytes per input row: id 4 + k 8 + value2 (4 + 1/8) + d (8 + 1/8) + value1 (4 offset + 8 bytes)
-IN_BYTES_PER_ROW = 4 + 8 + (4 + 0.125) + (8 + 0.125) + (4 + STR_LEN)
 
+BASE_COLS = lambda L: [("id", "i32", "seq", 0.0), ("value1", "utf8", L, 0.0), ("value2", "f32", "u100", 0.0)]  # noqa: E731
+CONFIGS = {
+    "C2": dict(seed=0xC4DB0002, rows=100_000_000, batch_rows=1 << 22, passes=24,
+               cols=[("id", "i32", "seq", 0.0), ("k", "i64", "u31", 0.0), ("value2", "f32", "u100", 0.10),
+                     ("d", "f64", "normal", 0.05), ("value1", "utf8", 8, 0.0)],
+               sql="select * from read_files('large_simple/*.parquet') where (id % 2 = 0 and value2 > 10.0) or d < 0.5",
+               title="C2 large_simple-shaped synthetic"),
+    "C3": dict(seed=0xC4DB0003, rows=16_000_000, batch_rows=1 << 22, passes=96, cols=BASE_COLS(8), id_mod=46340,
+               sql="select id, value1, id + 10.0 as id_plus_10, (value2 + 10) / 100 as value2, 1.0 / id as value3, "
+                   "1.0 / (id * id) as value4, id * id as value5 from read_files('simple/*.parquet') where id > 25 + 0.0",
+               title="C3 simple.sql q4-shaped projection with arithmetic and casts (ids in [1, 46340])"),
+    "C4": dict(seed=0xC4DB0004, rows=10_000_000, batch_rows=1 << 21, passes=24, cols=BASE_COLS(100),
+               sql="select * from read_files('simple_wide_string/*.parquet') where id > 25",
+               title="C4 only_wide_strings-shaped (100-byte strings), ~100 % selected"),
+    "C4H": dict(seed=0xC4DB0004, rows=10_000_000, batch_rows=1 << 21, passes=24, cols=BASE_COLS(100),
+                sql="select * from read_files('simple_wide_string/*.parquet') where id % 2 = 0",
+                title="C4 only_wide_strings-shaped (100-byte strings), 50 % selected"),
+    "C5": dict(seed=0xC4DB0005, rows=500_000_000, batch_rows=1 << 22, passes=6, cols=BASE_COLS(8),
+               sql="select * from read_files('huge_simple/*.parquet') where id % 2 = 0",
+               title="C5 huge_simple-scaled (4 B rows at 8 GPUs)"),
+}
+CONFIGS["C2S"] = dict(CONFIGS["C2"], batch_rows=10_000, rows=20_000_000, passes=8, many=512,
+                      title="C2 in reference-native 10 000-row records (many-batch launches of 512 records)")
+WIDTH = {"i32": 4, "i64": 8, "f32": 4, "f64": 8}
 
 if os.environ.get("CHDB_BENCH_WATCHDOG"):   # debugging aid: dump every thread's stack if the run is still going after N seconds
     import faulthandler
@@ -43,19 +67,27 @@ if os.environ.get("CHDB_BENCH_WATCHDOG"):   # debugging aid: dump every thread's
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
-    ap.add_argument("--batch-rows", type=int, default=1 << 22)
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="C2")
+    ap.add_argument("--rows", type=int, default=None, help="rows per GPU (default: the config's)")
+    ap.add_argument("--batch-rows", type=int, default=None)
+    ap.add_argument("--passes", type=int, default=None, help="passes over the resident rows per step")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-instances", type=int, default=3, help="filter operator instances (ctx + stream each) for e2e")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the single-thread cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget for each cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the N>1 materialize-gather measurement")
     ap.add_argument("--gather-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of three benchmarked batches")
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    a.rows = a.rows or cfg["rows"]
+    a.batch_rows = a.batch_rows or cfg["batch_rows"]
+    a.passes = a.passes or cfg["passes"]
+    return a
 
 
 # ---------------------------------------------------------------------------------------------
@@ -70,8 +102,9 @@ def batch_sizes(rows: int, batch_rows: int):
     return out
 
 
-def gen_batch_torch(start: int, n: int, seed: int, device):
-    """One batch as torch tensors (values padded so every buffer is readable 64 bytes past its end)."""
+def gen_batch_torch(cfg, start: int, n: int, seed: int, device):
+    """One batch as torch tensors per column: {"name": (values, validity | None, offsets | None, nulls)}; every
+    buffer is readable 64 bytes past its logical end (TMA bulk copies move whole 16-byte units)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -85,63 +118,88 @@ def gen_batch_torch(start: int, n: int, seed: int, device):
         packed = (valid.view(-1, 8).to(torch.int32) * w).sum(dim=1).to(torch.uint8)
         out = torch.zeros(n8 // 8 + pad, dtype=torch.uint8, device=device)
         out[: n8 // 8] = packed
-        return out, int(valid.sum().item())
+        return out, n - int(valid.sum().item())
 
-    ids = torch.zeros(n + pad, dtype=torch.int32, device=device)
-    ids[:n] = torch.arange(start, start + n, dtype=torch.int64, device=device).to(torch.int32)
-    k = torch.zeros(n + pad, dtype=torch.int64, device=device)
-    k[:n] = torch.randint(-2**31, 2**31, (n,), generator=g, device=device, dtype=torch.int64)
-    v2 = torch.zeros(n + pad, dtype=torch.float32, device=device)
-    v2[:n] = torch.rand(n, generator=g, device=device) * 100.0
-    v2_valid, v2_nvalid = bitmap(NULL_V2)
-    d = torch.zeros(n + pad, dtype=torch.float64, device=device)
-    d[:n] = torch.randn(n, generator=g, device=device, dtype=torch.float64)
-    d_valid, d_nvalid = bitmap(NULL_D)
-    s = torch.zeros(n * STR_LEN + pad, dtype=torch.uint8, device=device)
-    s[: n * STR_LEN] = torch.randint(97, 123, (n * STR_LEN,), generator=g, device=device, dtype=torch.int64).to(torch.uint8)
-    offs = torch.zeros(n + 1 + pad, dtype=torch.int32, device=device)
-    offs[: n + 1] = torch.arange(0, (n + 1) * STR_LEN, STR_LEN, dtype=torch.int64, device=device).to(torch.int32)
-    return dict(n=n, id=ids, k=k, value2=v2, value2_valid=v2_valid, value2_nulls=n - v2_nvalid, d=d, d_valid=d_valid,
-                d_nulls=n - d_nvalid, value1=s, value1_offsets=offs)
+    cols = {}
+    for name, typ, dist, p_null in cfg["cols"]:
+        offsets = None
+        if typ == "utf8":
+            L = int(dist)
+            vals = torch.zeros(n * L + pad, dtype=torch.uint8, device=device)
+            vals[: n * L] = torch.randint(97, 123, (n * L,), generator=g, device=device, dtype=torch.int64).to(torch.uint8)
+            offsets = torch.zeros(n + 1 + pad, dtype=torch.int32, device=device)
+            offsets[: n + 1] = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device=device).to(torch.int32)
+        else:
+            dt = {"i32": torch.int32, "i64": torch.int64, "f32": torch.float32, "f64": torch.float64}[typ]
+            vals = torch.zeros(n + pad, dtype=dt, device=device)
+            if dist == "seq":
+                ids = torch.arange(start, start + n, dtype=torch.int64, device=device)
+                if cfg.get("id_mod"):
+                    ids = ids % cfg["id_mod"] + 1
+                vals[:n] = ids.to(dt)
+            elif dist == "u31":
+                vals[:n] = torch.randint(-2**31, 2**31, (n,), generator=g, device=device, dtype=torch.int64).to(dt)
+            elif dist == "u100":
+                vals[:n] = (torch.rand(n, generator=g, device=device) * 100.0).to(dt)
+            elif dist == "normal":
+                vals[:n] = torch.randn(n, generator=g, device=device, dtype=dt)
+            else:
+                raise ValueError(dist)
+        validity, nulls = (None, 0)
+        if p_null > 0:
+            validity, nulls = bitmap(p_null)
+        cols[name] = (vals, validity, offsets, nulls)
+    return dict(n=n, cols=cols)
 
 
-def schema():
+def schema(cfg):
     import pyarrow as pa
-    return pa.schema([pa.field("id", pa.int32(), False), pa.field("k", pa.int64(), False),
-                      pa.field("value2", pa.float32(), True), pa.field("d", pa.float64(), True),
-                      pa.field("value1", pa.utf8(), False)])
+    t = {"i32": pa.int32(), "i64": pa.int64(), "f32": pa.float32(), "f64": pa.float64(), "utf8": pa.utf8()}
+    return pa.schema([pa.field(name, t[typ], p_null > 0) for name, typ, _, p_null in cfg["cols"]])
 
 
-def to_host_batch(t, pin: bool):
+def in_bytes_per_row(cfg) -> float:
+    """Algorithmic input bytes per row: value bytes (Utf8: 4-byte offset + string bytes) + 1/8 per
+    validity bitmap, every referenced column once (all columns are referenced in every config)."""
+    b = 0.0
+    for _, typ, dist, p_null in cfg["cols"]:
+        b += (4 + int(dist)) if typ == "utf8" else WIDTH[typ]
+        b += 0.125 if p_null > 0 else 0.0
+    return b
+
+
+def wrap_device_batch(C, cfg, t, ctx):
+    vals, vald, offs = [], [], []
+    for name, *_ in cfg["cols"]:
+        v, val, off, _ = t["cols"][name]
+        vals.append(v.data_ptr())
+        vald.append(val.data_ptr() if val is not None else 0)
+        offs.append(off.data_ptr() if off is not None else 0)
+    return C.DeviceBatch.wrap(schema(cfg), t["n"], vals, vald, offs, ctx=ctx, keepalive=t)
+
+
+def to_host_batch(cfg, t, pin: bool):
     """torch tensors -> pyarrow RecordBatch over (optionally pinned) host memory, zero-copy."""
     import pyarrow as pa
     import torch
     n = t["n"]
+    keep, arrays = [], []
 
     def host(x, count):
         h = torch.empty(count, dtype=x.dtype, pin_memory=pin)
         h.copy_(x[:count])
-        return h
+        keep.append(h)
+        return pa.py_buffer(h.numpy())
 
-    keep = {}
-    keep["id"] = host(t["id"], n)
-    keep["k"] = host(t["k"], n)
-    keep["value2"] = host(t["value2"], n)
-    keep["d"] = host(t["d"], n)
-    keep["value1"] = host(t["value1"], n * STR_LEN)
-    keep["offs"] = host(t["value1_offsets"], n + 1)
-    keep["v2v"] = host(t["value2_valid"], (n + 7) // 8)
-    keep["dv"] = host(t["d_valid"], (n + 7) // 8)
-    buf = lambda h: pa.py_buffer(h.numpy())  # noqa: E731
-    arrays = [
-        pa.Array.from_buffers(pa.int32(), n, [None, buf(keep["id"])]),
-        pa.Array.from_buffers(pa.int64(), n, [None, buf(keep["k"])]),
-        pa.Array.from_buffers(pa.float32(), n, [buf(keep["v2v"]), buf(keep["value2"])], null_count=t["value2_nulls"]),
-        pa.Array.from_buffers(pa.float64(), n, [buf(keep["dv"]), buf(keep["d"])], null_count=t["d_nulls"]),
-        pa.Array.from_buffers(pa.utf8(), n, [None, buf(keep["offs"]), buf(keep["value1"])]),
-    ]
-    rb = pa.RecordBatch.from_arrays(arrays, schema=schema())
-    return rb, keep
+    sch = schema(cfg)
+    for f, (name, typ, dist, _) in zip(sch, cfg["cols"]):
+        v, val, off, nulls = t["cols"][name]
+        vb = host(val, (n + 7) // 8) if val is not None else None
+        if typ == "utf8":
+            arrays.append(pa.Array.from_buffers(f.type, n, [vb, host(off, n + 1), host(v, n * int(dist))], null_count=nulls))
+        else:
+            arrays.append(pa.Array.from_buffers(f.type, n, [vb, host(v, n)], null_count=nulls))
+    return pa.RecordBatch.from_arrays(arrays, schema=sch), keep
 
 
 def batch_nbytes(rb) -> int:
@@ -155,11 +213,9 @@ class ClockSampler:
     """SM clock and throttle reasons of one GPU during the timed region (NVML).
 
     An NVML query -- from a thread of this process or from `nvidia-smi -lms` next to it -- stalls this process's
-    CUDA calls for milliseconds to tens of milliseconds now and then (measured: host enqueue time per step 0.8 ms
-    -> 2-13 ms with a 20 ms sampling period), which starves the GPU in a timed region that is itself only tens
-    of milliseconds long.  So the samples are taken by the benchmark thread itself after it has enqueued all
-    timed steps and before it synchronises: the GPU is still working through the queue (under load, inside the
-    timed region) and the host has nothing left to enqueue that a stall could delay."""
+    CUDA calls for milliseconds now and then, which starves the GPU in a timed region, so the samples are taken
+    by the benchmark thread itself after it has enqueued all timed steps and before it synchronises: the GPU is
+    still working through the queue (under load, inside the timed region)."""
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz, self.nv = [], set(), None, None
@@ -196,7 +252,7 @@ class ClockSampler:
                 pass
             if len(self.samples) >= max_samples or not busy():
                 break
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def result(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -204,13 +260,12 @@ class ClockSampler:
                 "sampled": "NVML, by the benchmark thread between enqueueing the last timed step and synchronising"}
 
 
-def measured_traffic(batch_rows: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same workload (profiles/traffic.json); None if never captured."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
+def measured_traffic(config: str, batch_rows: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stream kernel from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json: {config: {batch_rows, dram_bytes_per_launch}}); None if never captured."""
     try:
-        t = json.load(open(p))
-        if int(t.get("batch_rows", -1)) == int(batch_rows):
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(config)
+        if t and int(t.get("batch_rows", -1)) == int(batch_rows):
             return t["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
@@ -230,30 +285,80 @@ def measured_peak():
 # ---------------------------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / baseline here, never the product path)
 # ---------------------------------------------------------------------------------------------
-def cpu_filter(rb, expr):
+def oracle_step_fn(sel):
+    """The reference's per-record work (filter_record, then project_record when the query has a select list other
+    than `*`) on an already converted oracle Batch: the reference receives an Arc<RecordBatch> by pointer
+    (exchange_operator.rs:621-667), so the Arrow -> oracle-array conversion stays outside every timed loop."""
     from oracle import compute_value as O
-    b = O.batch_from_arrow(rb)
-    return O.filter_record(b, [[] for _ in b.fields], expr)
+    star = len(sel["projection"]) == 1 and "Wildcard" in sel["projection"][0]
+
+    def run(b):
+        al = [[] for _ in b.fields]
+        out = O.filter_record(b, al, sel["selection"])
+        if not star:
+            out = O.project_record(sel["projection"], out, al)
+        return out
+    return run
 
 
-def cpu_baseline_single_thread(host_batches, expr, budget_s: float):
+def pyarrow_step_fn(config: str):
+    """Independent SIMD CPU reference (Arrow C++ through pyarrow.compute).  `%` has no pyarrow kernel:
+    x % 2 is computed as x - (x / 2) * 2 (truncating integer division, same result)."""
+    import pyarrow.compute as pc
+
+    def mod2_is_0(x):
+        return pc.equal(pc.subtract(x, pc.multiply(pc.divide(x, 2), 2)), 0)
+
+    if config in ("C2", "C2S"):
+        return lambda rb: rb.filter(pc.or_(pc.and_(mod2_is_0(rb["id"]), pc.greater(rb["value2"], 10.0)),
+                                           pc.less(rb["d"], 0.5)))
+    if config in ("C4H", "C5"):
+        return lambda rb: rb.filter(mod2_is_0(rb["id"]))
+    if config == "C4":
+        return lambda rb: rb.filter(pc.greater(rb["id"], 25))
+    return None
+
+
+def timed_sample(fn, items, budget_s: float):
     t0 = time.perf_counter()
-    rows = 0
-    used = 0
-    for rb in host_batches:
-        cpu_filter(rb, expr)
-        rows += rb.num_rows
+    rows = used = 0
+    for it, n in items:
+        fn(it)
+        rows += n
         used += 1
         if time.perf_counter() - t0 >= budget_s:
             break
     dt = time.perf_counter() - t0
-    return {"value": rows / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{used} batch(es) = {rows} rows of the same workload, oracle/arrow_kernels.c + tree walk, 1 thread, {dt:.2f} s"}
+    return rows / dt, used, rows, dt
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Rust reference cannot be built
-    here) on all host threads, one batch per thread like N filter instances pulling from one exchange."""
+def cpu_baselines(args, cfg, sel, host_batches):
+    """Single-thread oracle (mirrors the reference's one inline filter instance, filter_task.rs:99) and single-thread
+    pyarrow.compute, each on a bounded sample of the same workload."""
+    from oracle import compute_value as O
+    O.lib()
+    fn = oracle_step_fn(sel)
+    conv = [(O.batch_from_arrow(rb), rb.num_rows) for rb in host_batches]   # outside the timed region
+    fn(conv[0][0])
+    v, used, rows, dt = timed_sample(fn, conv, args.cpu_seconds)
+    out = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{used} record(s) = {rows} rows of the same workload, oracle (arrow_kernels.c + tree walk) on 1 thread, "
+                     f"{dt:.2f} s; Arrow->oracle conversion outside the timed loop"}
+    pa_fn = pyarrow_step_fn(args.config)
+    if pa_fn is not None:
+        import pyarrow as pa
+        pa.set_cpu_count(1)
+        pa_fn(host_batches[0])
+        v2, used2, rows2, dt2 = timed_sample(pa_fn, [(rb, rb.num_rows) for rb in host_batches], args.cpu_seconds)
+        out["pyarrow_compute"] = {"value": v2, "unit": UNIT, "cores": 1,
+                                  "sample": f"{used2} record(s) = {rows2} rows, pyarrow {pa.__version__} compute + RecordBatch.filter, "
+                                            f"1 thread, {dt2:.2f} s"}
+    return out
+
+
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Rust reference cannot be built here) on all
+    host threads, one record per thread at a time -- N filter instances pulling from one exchange."""
     if rank != 0:
         return
     import concurrent.futures as cf
@@ -263,22 +368,24 @@ def run_reference(args, rank, world):
     from chapterhouseqe_b200 import sqlparser_lite as sp
     from oracle import compute_value as O
     O.lib()
-    expr = sp.parse_expr(PREDICATE)
+    sel = sp.parse_select(cfg["sql"])
+    fn = oracle_step_fn(sel)
     cores = os.cpu_count() or 1
-    # bounded sample of the workload: 2 batches per thread (at least 8), generated like our arm's data
-    n_batches = min(len(batch_sizes(args.rows, args.batch_rows)), max(8, 2 * cores))
+    # bounded sample of the workload: >= 2 records per thread, at most ~64 M rows, generated like our arm's data
+    sizes = batch_sizes(args.rows, args.batch_rows)
+    n_batches = min(len(sizes), max(8, 2 * cores, min(4096, (32_000_000 // args.batch_rows))))
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
-    host = []
-    for i, (start, n) in enumerate(batch_sizes(args.rows, args.batch_rows)[:n_batches]):
-        t = gen_batch_torch(start, n, SEED + i, dev)
-        rb, keep = to_host_batch(t, pin=False)
-        host.append((rb, keep))
-        del t
-    sample_rows = sum(rb.num_rows for rb, _ in host)
+    conv = []
+    for i, (start, n) in enumerate(sizes[:n_batches]):
+        t = gen_batch_torch(cfg, start, n, cfg["seed"] + i, dev)
+        rb, keep = to_host_batch(cfg, t, pin=False)
+        conv.append(O.batch_from_arrow(rb))   # the reference holds RecordBatches already: converted once, outside the timed loop
+        del t, rb, keep
+    sample_rows = sum(b.num_rows for b in conv)
     pool = cf.ThreadPoolExecutor(max_workers=cores)
 
     def step():
-        list(pool.map(lambda x: cpu_filter(x[0], expr), host))
+        list(pool.map(fn, conv))
 
     for _ in range(args.warmup):
         step()
@@ -291,30 +398,31 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32/f32/f64", "data": "synthetic",
-        "config": workload_config(args, sample_rows=sample_rows),
+        "config": workload_config(args, cfg),
+        "sample_rows_per_step": sample_rows,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_batches} batches = {sample_rows} rows per step, one batch per thread on {cores} threads "
-                                   "(oracle port of the arrow-rs path; the Rust reference cannot be built in this image)"},
+                         "sample": f"{n_batches} records = {sample_rows} rows per step, one record per thread on {cores} threads, "
+                                   "inputs already in memory as arrays (no conversion in the timed loop); oracle port of the "
+                                   "arrow-rs path -- the Rust reference cannot be built in this image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, sample_rows=None):
-    cfg = {"workload": "C2 large_simple-shaped synthetic: " + SQL, "rows_per_gpu": args.rows,
-           "batch_rows": args.batch_rows, "schema": "id i32 | k i64 | value2 f32 (10% null) | d f64 (5% null) | value1 utf8[8]",
-           "null_semantics": "non-Kleene (arrow compute::and/or)", "parallelism": f"shard-by-batch x{args.gpus}, no collective",
-           "l2": "inputs (3.6 GB per GPU, 152 MB per batch) exceed the 126 MB L2; no flush needed"}
-    if sample_rows is not None:
-        cfg["sample_rows_per_step"] = sample_rows
-    return cfg
+def workload_config(args, cfg):
+    cols = " | ".join(f"{n} {t}" + (f"[{d}]" if t == "utf8" else "") + (f" ({int(p * 100)}% null)" if p else "")
+                      for n, t, d, p in cfg["cols"])
+    return {"workload": f"{cfg['title']}: {cfg['sql']}", "name": args.config, "rows_per_gpu": args.rows,
+            "batch_rows": args.batch_rows, "passes_per_step": args.passes, "schema": cols,
+            "null_semantics": "non-Kleene (arrow compute::and/or)", "parallelism": f"shard-by-record x{args.gpus}, no collective",
+            "l2": "resident inputs per GPU exceed the 126 MB L2 and every pass streams all of them; no flush needed"}
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
+def run_ours(args, cfg, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
@@ -329,20 +437,21 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     ctx = C.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
-    sel = sp.parse_select(SQL)
-    prog = C.Program.compile_filter(sel["selection"], schema())
+    sel = sp.parse_select(cfg["sql"])
+    star = len(sel["projection"]) == 1 and "Wildcard" in sel["projection"][0]
+    sch = schema(cfg)
+    prog = (C.Program.compile_filter(sel["selection"], sch) if star
+            else C.Program.compile_filter_project(sel["selection"], sel["projection"], sch))
+    many = int(cfg.get("many", 0))
 
     # ---- resident inputs ----
     sizes = batch_sizes(args.rows, args.batch_rows)
     base_row = rank * args.rows
     tensors, dev_batches = [], []
     for i, (start, n) in enumerate(sizes):
-        t = gen_batch_torch(base_row + start, n, SEED + rank * 100003 + i, device)
+        t = gen_batch_torch(cfg, base_row + start, n, cfg["seed"] + rank * 100003 + i, device)
         tensors.append(t)
-        vals = [t["id"].data_ptr(), t["k"].data_ptr(), t["value2"].data_ptr(), t["d"].data_ptr(), t["value1"].data_ptr()]
-        vald = [0, 0, t["value2_valid"].data_ptr(), t["d_valid"].data_ptr(), 0]
-        offs = [0, 0, 0, 0, t["value1_offsets"].data_ptr()]
-        dev_batches.append(C.DeviceBatch.wrap(schema(), n, vals, vald, offs, ctx=ctx, keepalive=t))
+        dev_batches.append(wrap_device_batch(C, cfg, t, ctx))
     torch.cuda.synchronize(device)
     total_rows = sum(n for _, n in sizes)
 
@@ -350,19 +459,45 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    def one_step():
-        return [b.run(prog) for b in dev_batches]
+    if many:
+        groups = [dev_batches[i:i + many] for i in range(0, len(dev_batches), many)]
+
+        def one_pass():
+            out = []
+            for g in groups:
+                out.extend(C.DeviceBatch.run_many(prog, g))
+            return out
+    else:
+        def one_pass():
+            return [b.run(prog) for b in dev_batches]
 
     sampler = ClockSampler(local_rank)   # NVML initialised (and queried once) before the warm-up
     outs = None
-    for _ in range(max(args.warmup, 0)):
-        outs = one_step()
+    for _ in range(max(args.warmup, 1)):
+        outs = one_pass()
     ctx.synchronize()
     torch.cuda.synchronize(device)
-    rows_out = sum(o.num_rows for o in outs) if outs else 0
-    bytes_out = sum(o.nbytes for o in outs) if outs else 0
-    for o in outs or []:
+    rows_out = sum(o.num_rows for o in outs)
+    bytes_out = sum(o.nbytes for o in outs)
+    for o in outs:
         o.check()
+
+    # ---- the benchmarked configuration against the oracle: first, middle and last record of this rank ----
+    parity = None
+    if not args.no_parity and rank == 0:
+        from oracle import compute_value as O
+        O.lib()
+        fn = oracle_step_fn(sel)
+        checked = []
+        for i in sorted({0, len(dev_batches) // 2, len(dev_batches) - 1}):
+            got = O.batch_from_arrow(outs[i].download())
+            want = fn(O.batch_from_arrow(to_host_batch(cfg, tensors[i], pin=False)[0]))
+            ok, why = O.batches_equal(got, want)
+            if not ok:
+                raise SystemExit(f"bench.py: record {i} of the benchmarked run differs from the oracle: {why}")
+            checked.append(i)
+        parity = {"parity_checked_batches": len(checked), "records": checked, "rows_each": [sizes[i][1] for i in checked],
+                  "against": "oracle (bit-exact: values, validity, offsets, schema)"}
     outs = None
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -377,23 +512,10 @@ def run_ours(args, rank, world, local_rank):
     ev0.record(stream)
     prev = None
     t_host0 = time.perf_counter()
-    trace = [] if os.environ.get("CHDB_BENCH_TRACE") else None
-    for _ in range(args.steps):
-        if trace is not None:
-            cur = []
-            for b in dev_batches:
-                t0 = time.perf_counter()
-                cur.append(b.run(prog))
-                trace.append(("run", (time.perf_counter() - t0) * 1e6))
-            t0 = time.perf_counter()
-            prev = cur
-            trace.append(("release", (time.perf_counter() - t0) * 1e6))
-        else:
-            cur = one_step()
-            prev = cur   # the previous step's outputs are released here (they go back to the ctx's block cache)
+    for _ in range(args.steps * args.passes):
+        cur = one_pass()
+        prev = cur   # the previous pass's outputs are released here (they go back to the ctx's block cache)
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
-    if trace is not None:
-        sys.stderr.write("[bench trace] " + " ".join(f"{k}:{v:.0f}" for k, v in trace) + "\n")
     ev1.record(stream)
     sampler.sample_while(lambda: not ev1.query())   # the GPU is still inside the timed region, the host is done enqueueing
     ctx.synchronize()
@@ -404,9 +526,9 @@ def run_ours(args, rank, world, local_rank):
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
     jit_launches = ctx.jit_launch_count - jit0
-    if rows_out == 0 and prev:
-        rows_out = sum(o.num_rows for o in prev)
-        bytes_out = sum(o.nbytes for o in prev)
+    for o in prev:   # the LAST timed pass's outputs: device error word + row counts must match the warm-up's
+        o.check()
+    assert sum(o.num_rows for o in prev) == rows_out, "timed pass produced a different row count than the warm-up"
     prev = None
 
     # whole-job numbers: MAX over ranks of the device time, SUM of rows / launches (no data-path collective)
@@ -414,44 +536,50 @@ def run_ours(args, rank, world, local_rank):
         elapsed_ms, [total_rows, rows_out, launches, jit_launches], device)
 
     selectivity = rows_out / total_rows
-    # algorithmic bytes: every referenced input byte once + every output byte once
-    out_bytes_per_row = IN_BYTES_PER_ROW   # select *: same columns (output validity kept: nulls survive)
-    bytes_per_row = IN_BYTES_PER_ROW + selectivity * out_bytes_per_row
-    launches_per_step = len(sizes)
+    # algorithmic bytes: every referenced input byte once + every output byte once (the output bytes are
+    # what the result batches hold: values + offsets + validity of the surviving rows)
+    bytes_per_row = in_bytes_per_row(cfg) + bytes_out / total_rows
+    n_passes = args.steps * args.passes
+    records = len(sizes)
     secs = elapsed_ms / 1e3
-    value = all_rows * args.steps / secs
-    per_gpu_gbs = total_rows * args.steps * bytes_per_row / secs / 1e9
+    value = all_rows * n_passes / secs
+    per_gpu_gbs = total_rows * n_passes * bytes_per_row / secs / 1e9
     peak, peak_src = measured_peak()
-    avg_launch_us = elapsed_ms * 1e3 / max(launches_per_step * args.steps, 1)   # one batch = select + scan + gather
-    algo_bytes_per_launch = total_rows * bytes_per_row / launches_per_step
+    stream_launches_per_pass = len(groups) if many else records
+    avg_launch_us = elapsed_ms * 1e3 / max(stream_launches_per_pass * n_passes, 1)
+    algo_bytes_per_launch = total_rows * bytes_per_row / stream_launches_per_pass
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "i32/f32/f64", "data": "synthetic (torch Philox on device, seed 0xC4DB0002+rank)",
-        "config": workload_config(args),
-        "selectivity": selectivity, "rows_out_per_step": all_rows_out,
+        "dtype": "i32/f32/f64", "data": f"synthetic (torch Philox on device, seed {cfg['seed']:#x}+rank)",
+        "config": workload_config(args, cfg),
+        "selectivity": selectivity, "rows_out_per_pass": all_rows_out,
         "hbm_gbs_per_gpu": per_gpu_gbs, "pct_of_8TBs": per_gpu_gbs / 8000.0 * 100.0,
         "clocks": clocks, "gpu_launches": int(all_launches), "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
         "specialised_launches": int(jit_launches),
         "roofline": {"bound": "hbm",
-                     "kernel": ("chdb_jit_select + scan_kernel + chdb_jit_gather per batch (device_code.cuh specialised for the "
-                                "program by NVRTC); gather dominates" if jit_launches
-                                else "select_kernel + scan_kernel + gather_kernel per batch (bytecode interpreter)"),
-                     "achieved": per_gpu_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": measured_traffic(args.batch_rows),
+                     "kernel": ("chdb_jit_stream" + ("_many" if many else "") + " (device_code.cuh specialised for the program by "
+                                "NVRTC), one launch per " + (f"{many} records" if many else "record") + ", preceded by zero_kernel"
+                                if jit_launches else "stream_kernel (bytecode interpreter) preceded by zero_kernel"),
+                     "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
+                     "traffic": measured_traffic(args.config, args.batch_rows),
+                     "traffic_note": "DRAM read+write bytes of one stream-kernel launch under ncu (cold L2; part of the output is "
+                                     "still dirty in L2 when the kernel ends, so it can read below the algorithmic bytes)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
-                     "avg_batch_us": avg_launch_us, "batches_per_step": launches_per_step, "kernels_per_batch": 3},
+                     "avg_launch_us": avg_launch_us, "stream_launches_per_pass": stream_launches_per_pass,
+                     "timing": "CUDA events on the ctx stream around all timed passes (zero_kernel + stream kernel per launch)"},
     }
+    if parity:
+        line.update(parity)
 
     # ---- materialize-side gather (N > 1): every rank's compacted batches travel to rank 0 over NVLink ----
     if world > 1 and not args.no_gather:
         def gather_step():
-            outs_ = one_step()
-            bufs = [t_ for o in outs_ for t_ in multigpu.device_batch_buffers(o)]
+            outs_ = one_pass()
             torch.cuda.current_stream(device).wait_stream(stream)
-            got = multigpu.gather_buffers(bufs, dst=0)
+            got = multigpu.gather_batches(outs_, dst=0)
             return outs_, got
         gather_step()
         barrier()
@@ -462,17 +590,21 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(device)
         barrier()
         dtg = time.perf_counter() - t0
+        gathered = multigpu.gathered_bytes(keep[1]) if rank == 0 else 0
         del keep
-        dtg_ms, _ = multigpu.reduce_step(dtg * 1e3, [0.0], device)
+        dtg_ms, (gathered,) = multigpu.reduce_step(dtg * 1e3, [gathered], device)
         line["gather"] = {"value": all_rows * args.gather_steps / (dtg_ms / 1e3), "unit": UNIT, "steps": args.gather_steps,
-                          "to_rank": 0, "transport": "torch.distributed isend/irecv (NCCL p2p over NVLink)",
-                          "note": "filter + variable-size gather of every output buffer to rank 0; the reference's per-record "
-                                  "result files allow per-GPU materialize instead, which is what `value` measures"}
+                          "to_rank": 0, "ingest_gbs_rank0": gathered / (dtg_ms / 1e3) / 1e9 / max(args.gather_steps, 1) * args.gather_steps,
+                          "transport": multigpu.GATHER_TRANSPORT,
+                          "note": "one pass of filter + variable-size gather of every result buffer to rank 0; the reference's "
+                                  "per-record result files allow per-GPU materialize instead, which is what `value` measures"}
 
     # ---- e2e: host batches (pinned) -> chdb_filter_record -> host batches, copies inside the timed region ----
     if not args.no_e2e:
         import concurrent.futures as cf
-        host = [to_host_batch(t, pin=True) for t in tensors]
+        e2e_records = min(len(tensors), max(8, 100_000_000 // args.batch_rows // 4 if many else len(tensors)))
+        host = [to_host_batch(cfg, t, pin=True) for t in tensors[:e2e_records]]
+        e2e_rows = sum(rb.num_rows for rb, _ in host)
         n_inst = max(1, args.e2e_instances)
         ctxs = [ctx] + [C.Context(local_rank) for _ in range(n_inst - 1)]
         pool = cf.ThreadPoolExecutor(max_workers=n_inst)
@@ -499,17 +631,17 @@ def run_ours(args, rank, world, local_rank):
             _, d2h = e2e_step()
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
-        dt = multigpu.reduce_step(dt * 1e3, [0.0], device)[0] / 1e3
+        dt, (all_e2e_rows,) = multigpu.reduce_step(dt * 1e3, [e2e_rows], device)
         h2d = sum(batch_nbytes(rb) for rb, _ in host)
-        line["e2e"] = {"value": all_rows * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "instances": n_inst,
+        line["e2e"] = {"value": all_e2e_rows * args.e2e_steps / (dt / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "instances": n_inst, "rows_per_step": e2e_rows,
                        "path": "Program.run -> chdb_filter_record (Arrow C Data Interface, pinned host buffers)"}
         if rank == 0 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_single_thread([rb for rb, _ in host], sel["selection"], args.cpu_seconds)
+            line["cpu_baseline"] = cpu_baselines(args, cfg, sel, [rb for rb, _ in host])
         pool.shutdown()
     elif rank == 0 and not args.no_cpu:
-        host = [to_host_batch(t, pin=False)[0] for t in tensors[:4]]
-        line["cpu_baseline"] = cpu_baseline_single_thread(host, sel["selection"], args.cpu_seconds)
+        host = [to_host_batch(cfg, t, pin=False)[0] for t in tensors[:max(4, 32_000_000 // args.batch_rows // 64)]]
+        line["cpu_baseline"] = cpu_baselines(args, cfg, sel, host)
 
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -517,11 +649,12 @@ def run_ours(args, rank, world, local_rank):
 
 def main():
     args = parse_args()
+    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank, world)
         return
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own output (its version banner at NCCL_DEBUG >= VERSION) goes to stderr
@@ -531,7 +664,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        run_ours(args, cfg, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -99,6 +99,13 @@ def load_library():
     sig("chdb_upload", i32, vp, vp, vp, pvp, stp)
     sig("chdb_device_batch_wrap", i32, vp, vp, i64, pvp, pvp, pvp, pvp, stp)
     sig("chdb_run_device", i32, vp, vp, vp, pvp, stp)
+    sig("chdb_run_device_many", i32, vp, vp, pvp, i32, pvp, stp)
+    sig("chdb_device_batch_ready", i32, vp, vp, stp)
+    sig("chdb_filter_record_async", i32, vp, vp, vp, vp, pvp, stp)
+    sig("chdb_project_record_async", i32, vp, vp, vp, vp, pvp, stp)
+    sig("chdb_poll", i32, vp, stp)
+    sig("chdb_pending_result", i32, vp, vp, vp, stp)
+    sig("chdb_pending_release", None, vp)
     sig("chdb_device_batch_status", i32, vp, vp, stp)
     sig("chdb_device_batch_num_rows", i64, vp, vp, stp)
     sig("chdb_device_batch_num_columns", i32, vp)
@@ -119,7 +126,9 @@ EXPORTED_SYMBOLS = [
     "chdb_program_compile_project", "chdb_program_compile_filter_project", "chdb_program_release",
     "chdb_program_disassemble", "chdb_program_num_instructions", "chdb_filter_record", "chdb_project_record",
     "chdb_filter_record_expr", "chdb_project_record_items", "chdb_compute_value", "chdb_upload",
-    "chdb_device_batch_wrap", "chdb_run_device", "chdb_device_batch_status", "chdb_device_batch_num_rows",
+    "chdb_device_batch_wrap", "chdb_run_device", "chdb_run_device_many", "chdb_device_batch_ready",
+    "chdb_filter_record_async", "chdb_project_record_async", "chdb_poll", "chdb_pending_result", "chdb_pending_release",
+    "chdb_device_batch_status", "chdb_device_batch_num_rows",
     "chdb_device_batch_num_columns", "chdb_device_batch_column", "chdb_device_batch_nbytes", "chdb_download",
     "chdb_peer_copy",
     "chdb_device_batch_release",
@@ -300,10 +309,70 @@ class Program:
         _check(rc, st)
         return _import_batch(oa, os_)
 
+    def run_async(self, rb: pa.RecordBatch, ctx: Context | None = None) -> "Pending":
+        """Enqueues upload + kernels and returns at once (chdb_filter_record_async); poll() / result() on the handle."""
+        L = load_library()
+        ctx = ctx or default_context()
+        a, s = _export_batch(rb)
+        h, st = ctypes.c_void_p(), _Status()
+        try:
+            rc = L.chdb_filter_record_async(ctx._h, self._h, ctypes.addressof(a), ctypes.addressof(s), ctypes.byref(h),
+                                            ctypes.byref(st))
+        except BaseException:
+            if a.release:
+                a.release(ctypes.byref(a))
+            _release_schema(s)
+            raise
+        if rc != 0:
+            if a.release:
+                a.release(ctypes.byref(a))
+            _release_schema(s)
+        _check(rc, st)
+        return Pending(h, a, s, rb)
+
     def close(self):
         if getattr(self, "_h", None):
             load_library().chdb_program_release(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Pending:
+    """A host-batch call in flight (chdb_filter_record_async): the input batch stays borrowed until poll() is true."""
+
+    def __init__(self, handle, arr, sch, keep):
+        self._h, self._a, self._s, self._keep = handle, arr, sch, keep
+
+    def poll(self) -> bool:
+        """Never blocks. True once the result can be taken."""
+        st = _Status()
+        r = load_library().chdb_poll(self._h, ctypes.byref(st))
+        if r < 0:
+            _check(-r, st)
+        return r == 1
+
+    def result(self) -> pa.RecordBatch:
+        L = load_library()
+        oa, os_, st = _ArrowArray(), _ArrowSchema(), _Status()
+        rc = L.chdb_pending_result(self._h, ctypes.addressof(oa), ctypes.addressof(os_), ctypes.byref(st))
+        _check(rc, st)
+        out = _import_batch(oa, os_)
+        self.close()
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().chdb_pending_release(self._h)
+            self._h = None
+            if self._a.release:
+                self._a.release(ctypes.byref(self._a))
+            _release_schema(self._s)
+            self._keep = None
 
     def __del__(self):
         try:
@@ -361,6 +430,29 @@ class DeviceBatch:
         h, st = ctypes.c_void_p(), _Status()
         _check(L.chdb_run_device(self.ctx._h, prog._h, self._h, ctypes.byref(h), ctypes.byref(st)), st)
         return DeviceBatch(h, self.ctx, (self, self._keepalive))
+
+    @staticmethod
+    def run_many(prog: Program, batches: list["DeviceBatch"]) -> list["DeviceBatch"]:
+        """ONE launch set over many batches of one schema (chdb_run_device_many); one output batch per input."""
+        if not batches:
+            return []
+        L = load_library()
+        ctx = batches[0].ctx
+        n = len(batches)
+        arr = ctypes.c_void_p * n
+        ins = arr(*[b._h for b in batches])
+        outs = arr()
+        st = _Status()
+        _check(L.chdb_run_device_many(ctx._h, prog._h, ins, n, outs, ctypes.byref(st)), st)
+        return [DeviceBatch(ctypes.c_void_p(outs[i]), ctx, batches[i]) for i in range(n)]
+
+    @property
+    def ready(self) -> bool:
+        """Whether the run producing this batch has finished (never blocks)."""
+        st = _Status()
+        r = load_library().chdb_device_batch_ready(self.ctx._h, self._h, ctypes.byref(st))
+        _check(st.code, st)
+        return r == 1
 
     def check(self):
         st = _Status()

@@ -171,17 +171,19 @@ static Buf dev_alloc(const Core& core, size_t bytes) {
   return b;
 }
 
-// Counts of one kernel run, read back asynchronously into pinned memory.
-struct RunResult {
+// One launch set (zero kernel + stream kernel): what its output batches share.  The counts of the run are mirrored
+// into pinned host memory by the kernel's last CTA; `done` fires when the launch has finished.
+struct LaunchShared {
   Core core;
-  uint64_t* host = nullptr;   // [n_counts] counts then [n_counts] = error word
-  int n_counts = 0;
   cudaEvent_t done = nullptr;
   bool waited = false;
-  Buf workspace;
-  ~RunResult() {
+  Buf workspace;              // counts, look-back descriptors, tickets, bit-packed outputs
+  Buf params;                 // many-batch launches: per-batch records + tile table
+  void* host = nullptr;       // pinned: count mirrors (+ staging of the records)
+  size_t host_cls = 0;
+  ~LaunchShared() {
     if (done) core->event_put(done);
-    if (host) core->pinned_put(host);
+    if (host) core->host_put(host, host_cls);
   }
   void wait() {
     if (waited) return;
@@ -189,6 +191,22 @@ struct RunResult {
     CUDA_CHECK(cudaEventSynchronize(done));
     waited = true;
   }
+  bool ready() {
+    if (waited) return true;
+    CUDA_CHECK(cudaSetDevice(core->device));
+    const cudaError_t e = cudaEventQuery(done);
+    if (e == cudaErrorNotReady) return false;
+    CUDA_CHECK(e);
+    waited = true;
+    return true;
+  }
+};
+// One batch's share of it.
+struct RunResult {
+  std::shared_ptr<LaunchShared> launch;
+  uint64_t* host = nullptr;   // [n_counts] counts then [n_counts] = error word
+  int n_counts = 0;
+  void wait() { launch->wait(); }
 };
 
 struct DeviceColumn {
@@ -393,39 +411,48 @@ static void* host_alloc(ExportedArray* ex, size_t bytes) {
   return p;
 }
 
-static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchema* out_schema) {
+// Value bytes of a Utf8 column; wrapped columns learn it from their offsets on first use (two 4-byte reads).
+static int64_t utf8_value_bytes(const DeviceColumn& c, int64_t n) {
+  if (c.value_bytes != -3) return c.value_bytes;
+  DeviceColumn& m = const_cast<DeviceColumn&>(c);
+  int32_t ends[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpy(&ends[0], c.offsets, 4, cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaMemcpy(&ends[1], c.offsets + n, 4, cudaMemcpyDeviceToHost));
+  m.first_offset = ends[0];
+  m.value_bytes = ends[1] - ends[0];
+  return m.value_bytes;
+}
+
+// A download in two steps, so that a caller can do something else (or poll) while the copies run:
+// download_begin() needs the run's counts (it waits for the launch unless it has finished) and enqueues every
+// device -> pinned host copy on the ctx stream; download_end() runs after those copies have completed.
+struct Download {
+  std::unique_ptr<ExportedArray> top;
+  std::vector<ExportedArray*> exs;
+  std::vector<int64_t> first;   // Utf8: offsets[0] of the copied offsets (rebased to 0 in download_end)
+  int64_t n = 0;
+};
+
+static void download_begin(chdb_device_batch* b, Download& d) {
   const Core& core = b->core;
   CUDA_CHECK(cudaSetDevice(core->device));
   check_run_error(b);
   resolve(b);
-  const int64_t n = b->num_rows;
-  auto* top = new ExportedArray;
+  const int64_t n = d.n = b->num_rows;
+  d.top.reset(new ExportedArray);
+  ExportedArray* top = d.top.get();
   top->core = core;
-  std::unique_ptr<ExportedArray> top_guard(top);
   top->child_storage.resize(b->cols.size());
   for (auto& c : top->child_storage) std::memset(&c, 0, sizeof(c));
-  // pass 1: offsets (needed to size Utf8 value copies of shared / sliced columns)
-  std::vector<int32_t*> host_offsets(b->cols.size(), nullptr);
-  std::vector<ExportedArray*> exs(b->cols.size(), nullptr);
+  d.exs.assign(b->cols.size(), nullptr);
+  d.first.assign(b->cols.size(), 0);
   for (size_t ci = 0; ci < b->cols.size(); ci++) {
-    exs[ci] = new ExportedArray;
-    exs[ci]->core = core;
+    ExportedArray* ex = d.exs[ci] = new ExportedArray;
+    ex->core = core;
     ::ArrowArray& a = top->child_storage[ci];
-    a.private_data = exs[ci];
+    a.private_data = ex;
     a.release = release_array;
     DeviceColumn& c = b->cols[ci];
-    if (c.meta.type == T_UTF8) {
-      int32_t* ho = (int32_t*)host_alloc(exs[ci], (size_t)(n + 1) * 4);
-      ho[0] = 0;
-      if (n) CUDA_CHECK(cudaMemcpyAsync(ho, c.offsets, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, core->stream));
-      host_offsets[ci] = ho;
-    }
-  }
-  CUDA_CHECK(cudaStreamSynchronize(core->stream));
-  // pass 2: values + validity
-  for (size_t ci = 0; ci < b->cols.size(); ci++) {
-    DeviceColumn& c = b->cols[ci];
-    ExportedArray* ex = exs[ci];
     void* hv = nullptr;
     uint8_t* hval = nullptr;
     if (c.validity != nullptr && c.null_count != 0 && n) {
@@ -433,13 +460,24 @@ static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchem
       CUDA_CHECK(cudaMemcpyAsync(hval, c.validity, bitmap_bytes(n), cudaMemcpyDeviceToHost, core->stream));
     }
     if (c.meta.type == T_UTF8) {
-      int32_t* ho = host_offsets[ci];
-      const int64_t first = n ? ho[0] : 0, last = n ? ho[n] : 0;
+      int32_t* ho = (int32_t*)host_alloc(ex, (size_t)(n + 1) * 4);
+      ho[0] = 0;
+      if (n) CUDA_CHECK(cudaMemcpyAsync(ho, c.offsets, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, core->stream));
+      int64_t first = 0, last = 0;
+      if (n) {
+        if (utf8_value_bytes(c, n) >= 0 && c.first_offset >= 0) {
+          first = c.first_offset;
+          last = first + c.value_bytes;
+        } else {   // a sliced view: the extent is in the offsets themselves
+          CUDA_CHECK(cudaStreamSynchronize(core->stream));
+          first = ho[0];
+          last = ho[n];
+        }
+      }
+      d.first[ci] = first;
       hv = host_alloc(ex, (size_t)(last - first));
       if (last > first)
         CUDA_CHECK(cudaMemcpyAsync(hv, (const uint8_t*)c.values + first, (size_t)(last - first), cudaMemcpyDeviceToHost, core->stream));
-      if (first != 0)
-        for (int64_t i = 0; i <= n; i++) ho[i] -= (int32_t)first;
       ex->buffers = {hval, ho, hv};
     } else if (c.meta.type == T_BOOL) {
       hv = host_alloc(ex, bitmap_bytes(n));
@@ -452,12 +490,20 @@ static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchem
       ex->buffers = {hval, hv};
     }
   }
-  CUDA_CHECK(cudaStreamSynchronize(core->stream));
+}
+
+static void download_end(chdb_device_batch* b, Download& d, ::ArrowArray* out, ::ArrowSchema* out_schema) {
+  const int64_t n = d.n;
+  ExportedArray* top = d.top.get();
   make_schema(out_schema, "+s", "", 0, b->cols.size());
   for (size_t ci = 0; ci < b->cols.size(); ci++) {
     DeviceColumn& c = b->cols[ci];
-    ExportedArray* ex = exs[ci];
+    ExportedArray* ex = d.exs[ci];
     ::ArrowArray& a = top->child_storage[ci];
+    if (c.meta.type == T_UTF8 && d.first[ci] != 0) {
+      int32_t* ho = (int32_t*)ex->buffers[1];
+      for (int64_t i = 0; i <= n; i++) ho[i] -= (int32_t)d.first[ci];
+    }
     int64_t nulls = c.null_count;
     if (nulls < 0) {  // unknown (sliced view): count what was copied
       const uint8_t* hval = (const uint8_t*)ex->buffers[0];
@@ -484,8 +530,29 @@ static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchem
   out->n_children = (int64_t)top->children.size();
   out->children = top->children.data();
   out->release = release_array;
-  out->private_data = top_guard.release();
+  out->private_data = d.top.release();
 }
+
+static void download_batch(chdb_device_batch* b, ::ArrowArray* out, ::ArrowSchema* out_schema) {
+  Download d;
+  download_begin(b, d);
+  CUDA_CHECK(cudaStreamSynchronize(b->core->stream));
+  download_end(b, d, out, out_schema);
+}
+
+}  // namespace chdb
+
+// A host-batch call in flight (chdb_filter_record_async): 0 kernels running, 1 device -> host copies running,
+// 2 ready, 3 result taken.
+struct chdb_pending {
+  chdb::Core core;
+  std::unique_ptr<chdb_device_batch> dev_in, dev_out;
+  chdb::Download dl;
+  int stage = 0;
+  cudaEvent_t copied = nullptr;
+};
+
+namespace chdb {
 
 // ------------------------------------------------------------------------------------------
 // executor
@@ -540,35 +607,53 @@ static DeviceColumn const_column(const Core& core, const OutputColumn& o) {
   return dc;
 }
 
-// CHDB_HOST_TIMING=1: where the host spends its time inside execute() (debugging aid): calls that take
-// longer than 300 us report their phases on stderr.
-struct HostClock {
-  bool on;
-  std::chrono::steady_clock::time_point t0, t;
-  double ph[4] = {0, 0, 0, 0};
-  HostClock() {
-    static const bool enabled = [] { const char* e = std::getenv("CHDB_HOST_TIMING"); return e && *e == '1'; }();
-    on = enabled;
-    if (on) t0 = t = std::chrono::steady_clock::now();
-  }
-  void lap(int i) {
-    if (!on) return;
-    const auto now = std::chrono::steady_clock::now();
-    ph[i] += std::chrono::duration<double, std::micro>(now - t).count();
-    t = now;
-  }
-  ~HostClock() {
-    if (!on) return;
-    const double total = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-    if (total > 300) std::fprintf(stderr, "[chdb host] execute %.0f us: allocate outputs %.0f, workspace+zero %.0f, plan+launch %.0f, event %.0f\n",
-                                  total, ph[0], ph[1], ph[2], ph[3]);
+// Output buffers of one launch over many batches come out of one slab (one allocation per launch, not per column
+// and batch).
+struct Slab {
+  Buf buf;
+  size_t used = 0;
+  void* take(size_t bytes) {
+    const size_t at = used;
+    used += round_up(bytes + kPad, 256);
+    if (used > buf->bytes) throw Error(CHDB_ERR_CUDA, "internal: output slab overflow");
+    return (uint8_t*)buf->ptr + at;
   }
 };
 
-static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in_orig) {
-  HostClock hc;
+// Everything execute() decides about one batch before anything is launched.
+struct ZeroReq { size_t col; int ko; bool validity; size_t bytes; size_t at; };
+struct Prepared {
+  const chdb_device_batch* in = nullptr;
+  std::unique_ptr<chdb_device_batch> view;
+  std::unique_ptr<chdb_device_batch> out;
+  bool launch = false, compact = false, any_const = false, all_const = false;
+  int64_t n = 0;
+  int ko = 0, n_utf8 = 0, n_counts = 1;
+  int64_t avg_utf8 = -1;   // mean value length of the longest Utf8 output (sizes the staging area); -1: none
+  uint64_t shape = 0;      // which input slots / outputs carry validity: batches of one launch must agree
+  std::vector<ZeroReq> zero_reqs;
+  ColumnDesc in_desc[kMaxInCols];
+  OutDesc out_desc[kMaxOutCols];
+};
+
+// Bytes of output capacity prepare() will ask the allocator for (upper bound), for sizing a slab.
+static size_t output_capacity(const Program& p, const chdb_device_batch* in) {
+  const int64_t n = in->num_rows < 0 ? 0 : in->num_rows;
+  size_t t = 0;
+  for (auto& o : p.outputs) {
+    if (o.kind == OutputColumn::CONST) continue;
+    if (o.type == T_UTF8) {
+      const int64_t vb = o.in_col >= 0 ? std::max<int64_t>(in->cols[o.in_col].value_bytes, 0) : 0;
+      t += round_up((size_t)vb + kPad, 256) + round_up((size_t)(n + 1) * 4 + kPad, 256);
+    } else if (o.type != T_BOOL) {
+      t += round_up((size_t)n * (size_t)o.width + kPad, 256);
+    }
+  }
+  return t + 1024;
+}
+
+static void prepare(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in_orig, Slab* slab, Prepared& P) {
   const Core& core = ctx->core;
-  CUDA_CHECK(cudaSetDevice(core->device));
   if (in_orig->core->device != core->device)
     throw Error(CHDB_ERR_INVALID_ARGUMENT, "batch lives on another device than the ctx");
   check_schema(p, in_orig);
@@ -576,7 +661,6 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   if (in_orig->result) check_run_error(in_orig);
 
   const chdb_device_batch* in = in_orig;
-  std::unique_ptr<chdb_device_batch> view;
   bool use_pred = p.has_pred;
   if (p.requires_single_row && in->num_rows != 1) throw Error(p.single_row_code, p.single_row_msg);
   if (p.has_pred && p.pred_const) {
@@ -584,48 +668,56 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     if (in->num_rows < 1)
       throw Error(CHDB_ERR_INVALID_ARGUMENT,
                   "Invalid argument error: Filter predicate of length 1 is larger than target array of length 0");
-    view = view_rows(in, p.pred_const_value ? 1 : 0);
-    in = view.get();
+    P.view = view_rows(in, p.pred_const_value ? 1 : 0);
+    in = P.view.get();
     use_pred = false;
   }
-  const int64_t n = in->num_rows;
+  P.in = in;
+  const int64_t n = P.n = in->num_rows;
+  auto alloc = [&](size_t bytes, Buf* keep) -> void* {
+    if (slab) { *keep = slab->buf; return slab->take(bytes); }
+    *keep = dev_alloc(core, bytes);
+    return (*keep)->ptr;
+  };
 
-  std::unique_ptr<chdb_device_batch> out(new chdb_device_batch);
+  P.out.reset(new chdb_device_batch);
+  chdb_device_batch* out = P.out.get();
   out->core = core;
 
   // len-1 constant outputs (record_projection.rs:73: RecordBatch::try_new checks equal lengths)
-  bool any_const = false, all_const = !p.outputs.empty();
+  P.any_const = false;
+  P.all_const = !p.outputs.empty();
   for (auto& o : p.outputs) {
-    any_const |= o.kind == OutputColumn::CONST;
-    all_const &= o.kind == OutputColumn::CONST;
+    P.any_const |= o.kind == OutputColumn::CONST;
+    P.all_const &= o.kind == OutputColumn::CONST;
   }
-  if (any_const && !all_const && !use_pred && n != 1)   // (under a predicate the surviving rows count: checked after the launch)
+  if (P.any_const && !P.all_const && !use_pred && n != 1)   // (under a predicate the surviving rows count: checked after the launch)
     throw Error(CHDB_ERR_INVALID_ARGUMENT, "Invalid argument error: all columns in a record batch must have the same length");
 
   // which outputs go through the kernel
-  const bool compact = use_pred;
-  std::vector<int> kernel_outs;
-  for (size_t k = 0; k < p.outputs.size(); k++) {
-    const OutputColumn& o = p.outputs[k];
-    if (o.kind == OutputColumn::EXPR || (o.kind == OutputColumn::PASS && compact)) kernel_outs.push_back((int)k);
-  }
-  const bool launch = n > 0 && (!kernel_outs.empty() || compact);
+  const bool compact = P.compact = use_pred;
+  bool any_kernel_out = false;
+  for (auto& o : p.outputs) any_kernel_out |= o.kind == OutputColumn::EXPR || (o.kind == OutputColumn::PASS && compact);
+  const bool launch = P.launch = n > 0 && (any_kernel_out || compact);
 
-  KernelParams kp;
-  std::memset(&kp, 0, sizeof(kp));
+  std::memset(P.in_desc, 0, sizeof(P.in_desc));
+  std::memset(P.out_desc, 0, sizeof(P.out_desc));
   int n_utf8 = 0, n_counts = 1;
   if (launch) {
     for (size_t s = 0; s < p.slot_to_col.size(); s++) {
       const DeviceColumn& c = in->cols[p.slot_to_col[s]];
-      kp.in[s].values = c.values;
-      kp.in[s].validity = c.validity;
-      kp.in[s].offsets = c.offsets;
-      kp.in[s].type = c.meta.type;
-      kp.in[s].width = (uint8_t)c.meta.width;
+      P.in_desc[s].values = c.values;
+      P.in_desc[s].validity = c.validity;
+      P.in_desc[s].offsets = c.offsets;
+      P.in_desc[s].type = c.meta.type;
+      P.in_desc[s].width = (uint8_t)c.meta.width;
+      if (c.validity) P.shape |= 1ull << s;
+      // TMA bulk copies move 16-byte units
+      if ((((uintptr_t)c.values | (uintptr_t)c.validity | (uintptr_t)c.offsets) & 15u) != 0)
+        throw Error(CHDB_ERR_INVALID_ARGUMENT, "device buffers must be 16-byte aligned");
     }
-    kp.n_in = (int)p.slot_to_col.size();
-    for (int k : kernel_outs)
-      if (p.outputs[k].type == T_UTF8) n_utf8++;
+    for (auto& o : p.outputs)
+      if ((o.kind == OutputColumn::EXPR || (o.kind == OutputColumn::PASS && compact)) && o.type == T_UTF8) n_utf8++;
     n_counts = 1 + n_utf8;
   }
 
@@ -644,11 +736,9 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   };
 
   int utf8_seen = 0, ko = 0;
-  int64_t avg_utf8 = -1;  // mean value length of the longest Utf8 output (sizes the staging area); -1: none
   // Bit-packed outputs (Boolean values, validity bitmaps) are merged into with atomicOr at slice edges, so they start
   // zeroed: they live, with the look-back descriptors and the counts, in ONE region that one small kernel zeroes.
-  struct ZeroReq { size_t col; int ko; bool validity; size_t bytes; size_t at; };
-  std::vector<ZeroReq> zero_reqs;
+  out->cols.reserve(p.outputs.size());
   for (size_t k = 0; k < p.outputs.size(); k++) {
     const OutputColumn& o = p.outputs[k];
     DeviceColumn dc;
@@ -675,7 +765,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
           dc.offsets = (const int32_t*)dc.offsets_buf->ptr;
         }
       } else {
-        OutDesc& od = kp.out[ko];
+        OutDesc& od = P.out_desc[ko];
         od.kind = o.kind == OutputColumn::EXPR ? OUT_EXPR : OUT_PASS;
         od.type = o.type;
         od.width = (uint8_t)o.width;
@@ -692,111 +782,115 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
         }
         if (o.type == T_UTF8) {
           const DeviceColumn& src = in->cols[o.in_col];
-          int64_t vb = src.value_bytes;
+          const int64_t vb = utf8_value_bytes(src, n);
           if (vb < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "filtering a sliced Utf8 view");
-          avg_utf8 = std::max<int64_t>(avg_utf8, (vb + n - 1) / n);
-          dc.values_buf = dev_alloc(core, (size_t)vb);
-          dc.offsets_buf = dev_alloc(core, (size_t)(n + 1) * 4);
-          dc.offsets = (const int32_t*)dc.offsets_buf->ptr;
-          od.offsets = (int32_t*)dc.offsets_buf->ptr;
+          P.avg_utf8 = std::max<int64_t>(P.avg_utf8, (vb + n - 1) / n);
+          dc.values = alloc((size_t)vb, &dc.values_buf);
+          dc.offsets = (const int32_t*)alloc((size_t)(n + 1) * 4, &dc.offsets_buf);
+          od.offsets = (int32_t*)dc.offsets;
           od.utf8_index = (uint8_t)utf8_seen;
           dc.value_bytes = -1;
           dc.bytes_index = 1 + utf8_seen;
           utf8_seen++;
-          dc.values = dc.values_buf->ptr;
-          od.values = dc.values_buf->ptr;
+          od.values = (void*)dc.values;
         } else if (o.type == T_BOOL) {
-          zero_reqs.push_back({k, ko, false, round_up(bitmap_bytes(n), 4), 0});
+          P.zero_reqs.push_back({k, ko, false, round_up(bitmap_bytes(n), 4), 0});
         } else {
-          dc.values_buf = dev_alloc(core, (size_t)n * (size_t)o.width);
-          dc.values = dc.values_buf->ptr;
-          od.values = dc.values_buf->ptr;
+          dc.values = alloc((size_t)n * (size_t)o.width, &dc.values_buf);
+          od.values = (void*)dc.values;
         }
         if (nullable) {
-          zero_reqs.push_back({k, ko, true, round_up(bitmap_bytes(n), 4), 0});
+          P.zero_reqs.push_back({k, ko, true, round_up(bitmap_bytes(n), 4), 0});
           od.count_index = (uint8_t)n_counts;
           dc.null_count = -1;
           dc.count_index = n_counts;
           n_counts++;
+          P.shape |= 1ull << (32 + ko);
         }
         ko++;
       }
     }
     out->cols.push_back(std::move(dc));
   }
-
+  P.ko = ko;
+  P.n_utf8 = n_utf8;
+  P.n_counts = n_counts;
   if (!launch) {
-    if (any_const && !all_const && compact)   // n == 0: nothing survives next to len-1 literal columns
+    if (P.any_const && !P.all_const && compact)   // n == 0: nothing survives next to len-1 literal columns
       throw Error(CHDB_ERR_INVALID_ARGUMENT, "Invalid argument error: all columns in a record batch must have the same length");
-    out->num_rows = all_const ? 1 : n;
-    if (compact && !all_const) out->num_rows = 0;   // n == 0
-    return out;
+    out->num_rows = P.all_const ? 1 : n;
+    if (compact && !P.all_const) out->num_rows = 0;   // n == 0
   }
+}
 
-  hc.lap(0);
-  // ---- one launch of the stream kernel (preceded by the kernel that zeroes its workspace) ----
-  const int64_t num_tiles = (n + kTileRows - 1) / kTileRows;
-  if (num_tiles > INT32_MAX) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "batch too large");
-  const int nq = 1 + n_utf8;
-  // zeroed region: counts[n_counts] | error word | done | pad || look-back descriptors || bit-packed outputs
-  const size_t ws_counts = round_up((size_t)(n_counts + 2) * 8, 128);
-  const size_t ws_desc = compact ? round_up((size_t)nq * (size_t)num_tiles * 8, 128) : 0;
-  size_t ws_total = ws_counts + ws_desc;
-  for (auto& z : zero_reqs) { z.at = ws_total; ws_total += round_up(z.bytes, 128); }
-  auto res = std::make_shared<RunResult>();
-  res->core = core;
-  res->n_counts = n_counts;
-  res->workspace = dev_alloc(core, ws_total);
-  if ((size_t)(n_counts + 1) * 8 > CtxCore::kPinnedBlock) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "too many counted outputs");
-  res->host = (uint64_t*)core->pinned_get();
-  res->done = core->event_get();
-  uint8_t* ws = (uint8_t*)res->workspace->ptr;
-  for (auto& z : zero_reqs) {
-    DeviceColumn& dc = out->cols[z.col];
-    OutDesc& od = kp.out[z.ko];
+// Bytes of the zeroed per-batch workspace: counts | error word (| done, tickets) || look-back descriptors || bit-packed outputs
+static size_t workspace_layout(Prepared& P, size_t* ws_counts_out, size_t* ws_desc_out) {
+  const int64_t num_tiles = (P.n + kTileRows - 1) / kTileRows;
+  const int nq = 1 + P.n_utf8;
+  const size_t ws_counts = round_up((size_t)(P.n_counts + 2) * 8, 128);
+  const size_t ws_desc = P.compact ? round_up((size_t)desc_groups(nq) * (size_t)num_tiles * 8, 128) : 0;
+  size_t total = ws_counts + ws_desc;
+  for (auto& z : P.zero_reqs) { z.at = total; total += round_up(z.bytes, 128); }
+  *ws_counts_out = ws_counts;
+  *ws_desc_out = ws_desc;
+  return total;
+}
+
+// Points the batch's bit-packed outputs and its header at its part of the workspace.
+static void bind_workspace(Prepared& P, const std::shared_ptr<LaunchShared>& ls, uint8_t* ws, size_t ws_counts, BatchHeader& bh,
+                           uint64_t* host_counts, int32_t first_tile) {
+  for (auto& z : P.zero_reqs) {
+    DeviceColumn& dc = P.out->cols[z.col];
+    OutDesc& od = P.out_desc[z.ko];
     if (z.validity) {
-      dc.validity_buf = res->workspace;
+      dc.validity_buf = ls->workspace;
       dc.validity = ws + z.at;
       od.validity = ws + z.at;
     } else {
-      dc.values_buf = res->workspace;
+      dc.values_buf = ls->workspace;
       dc.values = ws + z.at;
       od.values = ws + z.at;
     }
   }
-  CUDA_CHECK(launch_zero(ws, ws_total, core->stream));
-  core->launches++;
+  std::memset(&bh, 0, sizeof(bh));
+  bh.num_rows = P.n;
+  bh.counts = (uint64_t*)ws;
+  bh.error_word = (uint64_t*)ws + P.n_counts;
+  bh.desc = (uint64_t*)(ws + ws_counts);
+  bh.host_counts = host_counts;
+  bh.num_tiles = (int32_t)((P.n + kTileRows - 1) / kTileRows);
+  bh.first_tile = first_tile;
+  auto res = std::make_shared<RunResult>();
+  res->launch = ls;
+  res->host = host_counts;
+  res->n_counts = P.n_counts;
+  P.out->result = res;
+  P.out->num_rows = P.compact ? -1 : P.n;
+}
 
-  hc.lap(1);
-  kp.b.num_rows = n;
-  kp.b.counts = (uint64_t*)ws;
-  kp.b.error_word = (uint64_t*)ws + n_counts;
-  kp.b.done = (uint32_t*)((uint64_t*)ws + n_counts + 1);
-  kp.b.desc = (uint64_t*)(ws + ws_counts);
-  kp.b.host_counts = res->host;
-  kp.b.num_tiles = (int32_t)num_tiles;
-  kp.b.first_tile = 0;
-  kp.n_counts = n_counts;
-  kp.n_out = ko;
-  kp.n_utf8 = n_utf8;
-  kp.pred_begin = compact ? p.pred_begin : 0;
-  kp.pred_end = compact ? p.pred_end : 0;
+// The program part of the kernel parameters + the plan, from the first batch of a launch.
+static void fill_program_params(const Program& p, const Prepared& P, KernelParams& kp, TilePlan& tp, bool many) {
+  kp.n_in = (int)p.slot_to_col.size();
+  kp.n_out = P.ko;
+  kp.n_utf8 = P.n_utf8;
+  kp.n_counts = P.n_counts;
+  kp.pred_begin = P.compact ? p.pred_begin : 0;
+  kp.pred_end = P.compact ? p.pred_end : 0;
+  std::memcpy(kp.in, P.in_desc, sizeof(kp.in));
+  std::memcpy(kp.out, P.out_desc, sizeof(kp.out));
   std::memcpy(kp.instrs, p.instrs.data(), p.instrs.size() * sizeof(Instr));
   std::memcpy(kp.strpool, p.strpool.data(), p.strpool.size());
   // bit-packed outputs assembled in shared memory: Boolean values and validity bitmaps
   kp.n_bits = 0;
-  for (int k = 0; k < ko; k++) kp.n_bits += (kp.out[k].type == T_BOOL ? 1 : 0) + (kp.out[k].validity != nullptr ? 1 : 0);
-  kp.long_strings = avg_utf8 > 16 ? 1 : 0;
+  for (int k = 0; k < P.ko; k++) kp.n_bits += (kp.out[k].type == T_BOOL ? 1 : 0) + (kp.out[k].validity != nullptr ? 1 : 0);
+  kp.long_strings = P.avg_utf8 > 16 ? 1 : 0;
   int64_t slot_avg[kMaxInCols];
   for (size_t s = 0; s < p.slot_to_col.size(); s++) {
-    const DeviceColumn& c = in->cols[p.slot_to_col[s]];
-    slot_avg[s] = c.meta.type == T_UTF8 && c.value_bytes >= 0 ? (c.value_bytes + n - 1) / n : -1;
-    // TMA bulk copies move 16-byte units
-    if ((((uintptr_t)c.values | (uintptr_t)c.validity | (uintptr_t)c.offsets) & 15u) != 0)
-      throw Error(CHDB_ERR_INVALID_ARGUMENT, "device buffers must be 16-byte aligned");
+    const DeviceColumn& c = P.in->cols[p.slot_to_col[s]];
+    const int64_t vb = c.meta.type == T_UTF8 ? utf8_value_bytes(c, P.n) : -1;
+    slot_avg[s] = vb >= 0 ? (vb + P.n - 1) / P.n : -1;
   }
   // which buffers the kernel touches
-  TilePlan tp;
   std::memset(&tp, 0, sizeof(tp));
   auto mark_instrs = [&](int begin, int end) {
     for (int i = begin; i < end; i++) {
@@ -811,42 +905,169 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
     }
   };
   mark_instrs(kp.pred_begin, kp.pred_end);
-  for (int k = 0; k < ko; k++) {
+  for (int k = 0; k < P.ko; k++) {
     const OutDesc& od = kp.out[k];
     if (od.kind == OUT_EXPR) mark_instrs(od.begin, od.end);
     else tp.use[od.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
   }
-  const int ctas_per_sm = plan_tile(kp, tp, slot_avg, false);
+  plan_tile(kp, tp, slot_avg, many);
+}
 
-  // Long scans run the same device code specialised for this program by NVRTC (jit.cpp); short
-  // batches, or boxes without NVRTC, run the bytecode interpreter kernels.
-  cudaError_t le = cudaSuccess;
+// Zero kernel + stream kernel.  Long scans run the same device code specialised for this program by NVRTC
+// (jit.cpp); short ones, or boxes without NVRTC, run the bytecode interpreter kernels.
+static void launch_set(const Core& core, const Program& p, const KernelParams& kp, const TilePlan& tp, void* ws, size_t ws_bytes,
+                       int64_t rows, const std::shared_ptr<LaunchShared>& ls) {
+  CUDA_CHECK(launch_zero(ws, ws_bytes, core->stream));
+  core->launches++;
   const JitKernel* jk = nullptr;
   const JitMode jm = jit_mode();
-  if (jm == JitMode::Always || (jm == JitMode::Auto && n >= kJitAutoRows)) {
+  if (jm == JitMode::Always || (jm == JitMode::Auto && rows >= kJitAutoRows)) {
     std::string why;
-    jk = jit_get(kp, p.has64, std::min(ctas_per_sm, 8), &why);
+    jk = jit_get(kp, p.has64, (int)tp.ctas_per_sm, &why);
   }
-  le = jk ? jit_launch_stream(jk, kp, tp, (unsigned)num_tiles, core->stream)
-          : launch_stream(kp, tp, p.has64, (unsigned)num_tiles, core->stream);
+  const cudaError_t le = jk ? jit_launch_stream(jk, kp, tp, core->sm_count, core->stream)
+                            : launch_stream(kp, tp, p.has64, core->sm_count, core->stream);
   core->launches++;
   if (jk) core->jit_launches++;
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
-  hc.lap(2);
-  CUDA_CHECK(cudaEventRecord(res->done, core->stream));   // the counts arrive in res->host with the kernel's last CTA
-  out->result = res;
-  out->num_rows = compact ? -1 : n;
-  if (all_const) {
+  CUDA_CHECK(cudaEventRecord(ls->done, core->stream));   // the counts arrive in pinned memory with the kernel's last CTA
+}
+
+static void after_launch(Prepared& P) {
+  chdb_device_batch* out = P.out.get();
+  if (P.all_const) {
     out->num_rows = 1;   // record_projection.rs:73 over len-1 arrays, whatever the filter kept (the launch only raises the predicate's errors)
-  } else if (any_const && compact) {
+  } else if (P.any_const && P.compact) {
     // literal columns are len 1: RecordBatch::try_new accepts them only next to exactly one surviving row
-    check_run_error(out.get());
-    resolve(out.get());
+    check_run_error(out);
+    resolve(out);
     if (out->num_rows != 1)
       throw Error(CHDB_ERR_INVALID_ARGUMENT, "Invalid argument error: all columns in a record batch must have the same length");
   }
-  hc.lap(3);
-  return out;
+}
+
+static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in_orig) {
+  const Core& core = ctx->core;
+  CUDA_CHECK(cudaSetDevice(core->device));
+  Prepared P;
+  prepare(ctx, p, in_orig, nullptr, P);
+  if (!P.launch) return std::move(P.out);
+
+  size_t ws_counts, ws_desc;
+  const size_t ws_total = workspace_layout(P, &ws_counts, &ws_desc);
+  auto ls = std::make_shared<LaunchShared>();
+  ls->core = core;
+  ls->workspace = dev_alloc(core, ws_total);
+  ls->host = core->host_get((size_t)(P.n_counts + 1) * 8, &ls->host_cls);
+  ls->done = core->event_get();
+  uint8_t* ws = (uint8_t*)ls->workspace->ptr;
+  KernelParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  bind_workspace(P, ls, ws, ws_counts, kp.b, (uint64_t*)ls->host, 0);
+  kp.done = (uint32_t*)((uint64_t*)ws + P.n_counts + 1);
+  kp.tickets = kp.done + 1;
+  kp.total_tiles = kp.b.num_tiles;
+  TilePlan tp;
+  fill_program_params(p, P, kp, tp, false);
+  launch_set(core, p, kp, tp, ws, ws_total, P.n, ls);
+  after_launch(P);
+  return std::move(P.out);
+}
+
+// One launch set over many batches of one schema (the reference's native 10 000-row records,
+// physical_planner.rs:323): outputs stay one batch per input, so the record_id <-> rec_<id>.parquet mapping
+// (materialize_files_task.rs:119) is unchanged.  Batches whose validity layout differs from the first one's, and
+// batches that need no kernel, are run one by one.
+static void execute_many(chdb_ctx* ctx, const Program& p, const chdb_device_batch* const* ins, int32_t count, chdb_device_batch** outs) {
+  const Core& core = ctx->core;
+  CUDA_CHECK(cudaSetDevice(core->device));
+  std::vector<std::unique_ptr<chdb_device_batch>> done((size_t)count);
+  // one slab for every batch's output buffers
+  size_t cap = 0;
+  for (int32_t i = 0; i < count; i++) {
+    if (!ins[i]) throw Error(CHDB_ERR_INVALID_ARGUMENT, "null batch");
+    check_schema(p, ins[i]);
+    if (ins[i]->num_rows < 0) resolve(const_cast<chdb_device_batch*>(ins[i]));
+    for (auto& c : ins[i]->cols)
+      if (c.meta.type == T_UTF8) utf8_value_bytes(c, ins[i]->num_rows);
+    cap += output_capacity(p, ins[i]);
+  }
+  Slab slab;
+  slab.buf = dev_alloc(core, cap);
+  std::vector<Prepared> preps((size_t)count);
+  std::vector<int32_t> group;
+  uint64_t shape = 0;
+  int64_t total_rows = 0;
+  for (int32_t i = 0; i < count; i++) {
+    Prepared& P = preps[(size_t)i];
+    prepare(ctx, p, ins[i], &slab, P);
+    if (!P.launch) { done[(size_t)i] = std::move(P.out); continue; }
+    if (group.empty()) shape = P.shape;
+    if (P.shape != shape || P.any_const) {   // another validity layout (or literal columns): not part of the shared launch
+      done[(size_t)i] = execute(ctx, p, ins[i]);
+      continue;
+    }
+    group.push_back(i);
+    total_rows += P.n;
+  }
+  if (!group.empty()) {
+    const int nb = (int)group.size();
+    const Prepared& P0 = preps[(size_t)group[0]];
+    const int n_in = (int)p.slot_to_col.size(), n_out = P0.ko, per = P0.n_counts + 1;
+    const size_t stride = sizeof(BatchHeader) + (size_t)n_in * sizeof(ColumnDesc) + (size_t)n_out * sizeof(OutDesc);
+    // workspace: done, tickets | per batch: counts, descriptors, bit-packed outputs
+    std::vector<size_t> ws_at((size_t)nb), ws_counts((size_t)nb);
+    size_t ws_total = 128;
+    int64_t tiles = 0;
+    for (int g = 0; g < nb; g++) {
+      Prepared& P = preps[(size_t)group[(size_t)g]];
+      size_t wd;
+      ws_at[(size_t)g] = ws_total;
+      ws_total += workspace_layout(P, &ws_counts[(size_t)g], &wd);
+      tiles += (P.n + kTileRows - 1) / kTileRows;
+    }
+    if (tiles > INT32_MAX) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "too many tiles in one launch");
+    auto ls = std::make_shared<LaunchShared>();
+    ls->core = core;
+    ls->workspace = dev_alloc(core, ws_total);
+    const size_t rec_bytes = round_up((size_t)nb * stride, 16), tab_bytes = round_up((size_t)tiles * 4, 16);
+    const size_t host_counts_bytes = round_up((size_t)nb * (size_t)per * 8, 16);
+    ls->host = core->host_get(host_counts_bytes + rec_bytes + tab_bytes, &ls->host_cls);
+    ls->params = dev_alloc(core, rec_bytes + tab_bytes);
+    ls->done = core->event_get();
+    uint8_t* ws = (uint8_t*)ls->workspace->ptr;
+    uint8_t* stage = (uint8_t*)ls->host + host_counts_bytes;   // pinned staging of the records and the tile table
+    int32_t* tab = (int32_t*)(stage + rec_bytes);
+    int32_t first_tile = 0;
+    for (int g = 0; g < nb; g++) {
+      Prepared& P = preps[(size_t)group[(size_t)g]];
+      uint8_t* rec = stage + (size_t)g * stride;
+      BatchHeader bh;
+      bind_workspace(P, ls, ws + ws_at[(size_t)g], ws_counts[(size_t)g], bh, (uint64_t*)ls->host + (size_t)g * (size_t)per, first_tile);
+      std::memcpy(rec, &bh, sizeof(bh));
+      std::memcpy(rec + sizeof(bh), P.in_desc, (size_t)n_in * sizeof(ColumnDesc));
+      std::memcpy(rec + sizeof(bh) + (size_t)n_in * sizeof(ColumnDesc), P.out_desc, (size_t)n_out * sizeof(OutDesc));
+      for (int32_t t = 0; t < bh.num_tiles; t++) tab[first_tile + t] = g;
+      first_tile += bh.num_tiles;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(ls->params->ptr, stage, rec_bytes + tab_bytes, cudaMemcpyHostToDevice, core->stream));
+    KernelParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    std::memcpy(&kp.b, stage, sizeof(BatchHeader));   // (batch 0's; the kernel reads every batch's own from its record)
+    kp.done = (uint32_t*)ws;
+    kp.tickets = kp.done + 1;
+    kp.total_tiles = (int32_t)tiles;
+    kp.many = (const uint8_t*)ls->params->ptr;
+    kp.many_tile_batch = (const int32_t*)((const uint8_t*)ls->params->ptr + rec_bytes);
+    kp.many_batches = nb;
+    kp.many_stride = (int32_t)stride;
+    TilePlan tp;
+    Prepared& F = preps[(size_t)group[0]];
+    fill_program_params(p, F, kp, tp, true);
+    launch_set(core, p, kp, tp, ws, ws_total, total_rows, ls);
+    for (int g = 0; g < nb; g++) done[(size_t)group[(size_t)g]] = std::move(preps[(size_t)group[(size_t)g]].out);
+  }
+  for (int32_t i = 0; i < count; i++) outs[i] = done[(size_t)i].release();
 }
 
 // Kernel parameter block with the *shape* execute() would produce for a batch whose nullable
@@ -961,7 +1182,7 @@ size_t chdb_program_jit_source(const chdb_program* prog, char* buf, size_t cap) 
   if (!prog) return 0;
   KernelParams kp;
   shape_params(*prog->p, kp);
-  std::string s = jit_prologue(kp, prog->p->has64, 5);
+  std::string s = jit_prologue(kp, prog->p->has64, 2);
   if (buf && cap) {
     size_t n = std::min(cap - 1, s.size());
     std::memcpy(buf, s.data(), n);
@@ -977,6 +1198,9 @@ int32_t chdb_program_jit_check(const chdb_program* prog, int64_t* cubin_bytes, c
     std::string l;
     std::vector<char> cubin = jit_compile_offline(kp, prog->p->has64, &l);
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    if (const char* dump = std::getenv("CHDB_JIT_DUMP")) {   // for cuobjdump -sass (profiles/)
+      if (FILE* f = std::fopen(dump, "wb")) { std::fwrite(cubin.data(), 1, cubin.size(), f); std::fclose(f); }
+    }
     if (log && cap) std::snprintf(log, cap, "%s", l.c_str());
   });
 }
@@ -1050,12 +1274,8 @@ int32_t chdb_device_batch_wrap(chdb_ctx* ctx, const struct ArrowSchema* schema, 
       dc.null_count = dc.validity ? -2 : 0;
       if (dc.meta.type == T_UTF8) {
         if (!dc.offsets) throw Error(CHDB_ERR_INVALID_ARGUMENT, "Utf8 column without offsets");
-        int32_t ends[2] = {0, 0};
-        CUDA_CHECK(cudaSetDevice(ctx->core->device));
-        CUDA_CHECK(cudaMemcpy(&ends[0], dc.offsets, 4, cudaMemcpyDeviceToHost));
-        CUDA_CHECK(cudaMemcpy(&ends[1], dc.offsets + num_rows, 4, cudaMemcpyDeviceToHost));
-        dc.first_offset = ends[0];
-        dc.value_bytes = ends[1] - ends[0];
+        dc.first_offset = -3;   // learnt from the offsets on first use (utf8_value_bytes): wrapping never touches the device
+        dc.value_bytes = -3;
       }
       b->cols.push_back(std::move(dc));
     }
@@ -1070,6 +1290,26 @@ int32_t chdb_run_device(chdb_ctx* ctx, const chdb_program* prog, const chdb_devi
     *out = nullptr;
     *out = execute(ctx, *prog->p, in).release();
   });
+}
+
+int32_t chdb_run_device_many(chdb_ctx* ctx, const chdb_program* prog, const chdb_device_batch* const* in, int32_t count,
+                             chdb_device_batch** out, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!ctx || !prog || (count > 0 && (!in || !out)) || count < 0) throw Error(CHDB_ERR_INVALID_ARGUMENT, "null argument");
+    for (int32_t i = 0; i < count; i++) out[i] = nullptr;
+    if (count == 0) return;
+    execute_many(ctx, *prog->p, in, count, out);
+  });
+}
+
+int32_t chdb_device_batch_ready(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st) {
+  (void)ctx;
+  int32_t ready = -1;
+  guarded(st, [&] {
+    if (!b) throw Error(CHDB_ERR_INVALID_ARGUMENT, "batch is null");
+    ready = (!b->result || b->result->launch->ready()) ? 1 : 0;
+  });
+  return ready;
 }
 
 int32_t chdb_device_batch_status(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st) {
@@ -1106,7 +1346,8 @@ int32_t chdb_device_batch_column(chdb_ctx* ctx, const chdb_device_batch* b, int3
     if (offsets) *offsets = c.meta.type == T_UTF8 ? c.offsets : nullptr;
     if (offsets_bytes) *offsets_bytes = c.meta.type == T_UTF8 ? (n + 1) * 4 : 0;
     if (c.meta.type == T_UTF8) {
-      if (c.value_bytes < 0 || c.first_offset < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "column buffers of a sliced Utf8 view");
+      CUDA_CHECK(cudaSetDevice(b->core->device));
+      if (utf8_value_bytes(c, n) < 0 || c.first_offset < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "column buffers of a sliced Utf8 view");
       if (values) *values = (const uint8_t*)c.values + c.first_offset;
       if (values_bytes) *values_bytes = c.value_bytes;
     } else {
@@ -1125,7 +1366,7 @@ int64_t chdb_device_batch_nbytes(chdb_ctx* ctx, const chdb_device_batch* b, chdb
     const int64_t n = b->num_rows;
     for (auto& c : b->cols) {
       if (c.validity) t += (int64_t)bitmap_bytes(n);
-      if (c.meta.type == T_UTF8) t += (n + 1) * 4 + std::max<int64_t>(c.value_bytes, 0);
+      if (c.meta.type == T_UTF8) t += (n + 1) * 4 + std::max<int64_t>(utf8_value_bytes(c, n), 0);
       else if (c.meta.type == T_BOOL) t += (int64_t)bitmap_bytes(n);
       else t += n * c.meta.width;
     }
@@ -1151,8 +1392,27 @@ int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_b
     check_run_error(src);
     resolve(const_cast<chdb_device_batch*>(src));
     const Core& dc = dst_ctx->core;
-    const int sdev = src->core->device;
+    const Core& sc = src->core;
+    const int sdev = sc->device;
     CUDA_CHECK(cudaSetDevice(dc->device));
+    if (sdev != dc->device) {   // direct NVLink path (without peer access the copy is staged through the host)
+      int can = 0;
+      CUDA_CHECK(cudaDeviceCanAccessPeer(&can, dc->device, sdev));
+      if (can) {
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(sdev, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(pe);
+        cudaGetLastError();
+      }
+    }
+    // the copies read what the source ctx's stream produced: order them behind it
+    {
+      CUDA_CHECK(cudaSetDevice(sdev));
+      cudaEvent_t ev = sc->event_get();
+      CUDA_CHECK(cudaEventRecord(ev, sc->stream));
+      CUDA_CHECK(cudaSetDevice(dc->device));
+      CUDA_CHECK(cudaStreamWaitEvent(dc->stream, ev, 0));
+      sc->event_put(ev);
+    }
     const int64_t n = src->num_rows;
     std::unique_ptr<chdb_device_batch> b(new chdb_device_batch);
     b->core = dc;
@@ -1173,7 +1433,7 @@ int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_b
         o.null_count = 0;
       }
       if (c.meta.type == T_UTF8) {
-        if (c.value_bytes < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "peer copy of a sliced Utf8 view");
+        if (utf8_value_bytes(c, n) < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "peer copy of a sliced Utf8 view");
         o.offsets_buf = copy(c.offsets, (size_t)(n + 1) * 4);
         o.offsets = (const int32_t*)o.offsets_buf->ptr;
         const size_t lead = (size_t)(c.first_offset & 15);
@@ -1189,6 +1449,16 @@ int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_b
         o.values = o.values_buf->ptr;
       }
       b->cols.push_back(std::move(o));
+    }
+    // A released source block goes back to the source ctx's cache and may be handed to that ctx's next launch:
+    // make the source stream wait until the copies have read it.
+    {
+      cudaEvent_t ev = dc->event_get();
+      CUDA_CHECK(cudaEventRecord(ev, dc->stream));
+      CUDA_CHECK(cudaSetDevice(sdev));
+      CUDA_CHECK(cudaStreamWaitEvent(sc->stream, ev, 0));
+      CUDA_CHECK(cudaSetDevice(dc->device));
+      dc->event_put(ev);
     }
     *out = b.release();
   });
@@ -1215,6 +1485,70 @@ int32_t chdb_project_record(chdb_ctx* ctx, const chdb_program* prog, const struc
                             chdb_status* st) {
   return chdb_filter_record(ctx, prog, in, in_schema, out, out_schema, st);
 }
+// ---- the same without parking the calling thread (filter_task.rs:86-125 runs inside a tokio task) ----
+int32_t chdb_filter_record_async(chdb_ctx* ctx, const chdb_program* prog, const struct ArrowArray* in,
+                                 const struct ArrowSchema* in_schema, chdb_pending** out, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!ctx || !prog || !in || !in_schema || !out) throw Error(CHDB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    std::unique_ptr<chdb_pending> pd(new chdb_pending);
+    pd->core = ctx->core;
+    pd->dev_in = upload_batch(ctx->core, in, in_schema);          // H2D copies enqueued; `in` stays borrowed until ready
+    pd->dev_out = execute(ctx, *prog->p, pd->dev_in.get());       // kernels enqueued
+    *out = pd.release();
+  });
+}
+int32_t chdb_project_record_async(chdb_ctx* ctx, const chdb_program* prog, const struct ArrowArray* in,
+                                  const struct ArrowSchema* in_schema, chdb_pending** out, chdb_status* st) {
+  return chdb_filter_record_async(ctx, prog, in, in_schema, out, st);
+}
+
+// 1: the result can be taken with chdb_pending_result; 0: not yet (never blocks); negative codes: see *st.
+int32_t chdb_poll(chdb_pending* pd, chdb_status* st) {
+  int32_t state = -1;
+  const int32_t rc = guarded(st, [&] {
+    if (!pd) throw Error(CHDB_ERR_INVALID_ARGUMENT, "pending is null");
+    CUDA_CHECK(cudaSetDevice(pd->core->device));
+    if (pd->stage == 0) {   // kernels running
+      if (pd->dev_out->result && !pd->dev_out->result->launch->ready()) { state = 0; return; }
+      if (!pd->dev_out->result) {   // nothing was launched (shared pass-through columns): wait for the uploads only
+        if (!pd->copied) { pd->copied = pd->core->event_get(); CUDA_CHECK(cudaEventRecord(pd->copied, pd->core->stream)); }
+      }
+      download_begin(pd->dev_out.get(), pd->dl);   // counts are known: sizes the host buffers, enqueues the D2H copies
+      if (pd->copied) pd->core->event_put(pd->copied);
+      pd->copied = pd->core->event_get();
+      CUDA_CHECK(cudaEventRecord(pd->copied, pd->core->stream));
+      pd->stage = 1;
+    }
+    if (pd->stage == 1) {
+      const cudaError_t e = cudaEventQuery(pd->copied);
+      if (e == cudaErrorNotReady) { state = 0; return; }
+      CUDA_CHECK(e);
+      pd->stage = 2;
+    }
+    state = 1;
+  });
+  return rc == 0 ? state : -rc;
+}
+int32_t chdb_pending_result(chdb_pending* pd, struct ArrowArray* out, struct ArrowSchema* out_schema, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!pd || !out || !out_schema) throw Error(CHDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (pd->stage == 3) throw Error(CHDB_ERR_INVALID_ARGUMENT, "result already taken");
+    CUDA_CHECK(cudaSetDevice(pd->core->device));
+    if (pd->stage == 0) download_begin(pd->dev_out.get(), pd->dl);   // (blocking use: waits for the launch)
+    if (pd->stage < 2) CUDA_CHECK(cudaStreamSynchronize(pd->core->stream));
+    download_end(pd->dev_out.get(), pd->dl, out, out_schema);
+    pd->stage = 3;
+  });
+}
+void chdb_pending_release(chdb_pending* pd) {
+  if (!pd) return;
+  cudaSetDevice(pd->core->device);
+  if (pd->stage < 2) cudaStreamSynchronize(pd->core->stream);   // copies into / out of caller and pool memory must not outlive this
+  if (pd->copied) pd->core->event_put(pd->copied);
+  delete pd;
+}
+
 int32_t chdb_filter_record_expr(chdb_ctx* ctx, const struct ArrowArray* in, const struct ArrowSchema* in_schema,
                                 const char* table_aliases_json, const char* expr_json, struct ArrowArray* out,
                                 struct ArrowSchema* out_schema, chdb_status* st) {

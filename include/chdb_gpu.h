@@ -167,6 +167,19 @@ int32_t chdb_filter_record(chdb_ctx* ctx, const chdb_program* prog, const struct
 int32_t chdb_project_record(chdb_ctx* ctx, const chdb_program* prog, const struct ArrowArray* in,
                             const struct ArrowSchema* in_schema, struct ArrowArray* out,
                             struct ArrowSchema* out_schema, chdb_status* st);
+/* Non-blocking forms for callers that must not park their thread (the reference calls filter_record inline on a
+ * tokio worker, filter_task.rs:86-125): *_async enqueues upload + kernels and returns at once; `in` stays
+ * borrowed until chdb_poll() has returned 1.  chdb_poll never blocks: 0 = not ready, 1 = ready, < 0 = -chdb_code
+ * (see *st).  chdb_pending_result hands the output over (it waits if called early); release the handle after. */
+typedef struct chdb_pending chdb_pending;
+int32_t chdb_filter_record_async(chdb_ctx* ctx, const chdb_program* prog, const struct ArrowArray* in,
+                                 const struct ArrowSchema* in_schema, chdb_pending** out, chdb_status* st);
+int32_t chdb_project_record_async(chdb_ctx* ctx, const chdb_program* prog, const struct ArrowArray* in,
+                                  const struct ArrowSchema* in_schema, chdb_pending** out, chdb_status* st);
+int32_t chdb_poll(chdb_pending* pending, chdb_status* st);
+int32_t chdb_pending_result(chdb_pending* pending, struct ArrowArray* out, struct ArrowSchema* out_schema,
+                            chdb_status* st);
+void chdb_pending_release(chdb_pending* pending);
 /* One-shot forms taking the expression each call (exactly the reference signatures). */
 int32_t chdb_filter_record_expr(chdb_ctx* ctx, const struct ArrowArray* in, const struct ArrowSchema* in_schema,
                                 const char* table_aliases_json, const char* expr_json,
@@ -195,6 +208,16 @@ int32_t chdb_device_batch_wrap(chdb_ctx* ctx, const struct ArrowSchema* schema, 
  * (filter, project or fused). */
 int32_t chdb_run_device(chdb_ctx* ctx, const chdb_program* prog, const chdb_device_batch* in,
                         chdb_device_batch** out, chdb_status* st);
+/* The same over `count` batches of one schema in ONE launch set: the reference's native records are at most
+ * 10 000 rows (src/planner/physical_planner.rs:323, read_files_task.rs:249-252), far too small to fill a GPU one
+ * at a time.  out[i] is the result of in[i] -- one output batch per record, so the record_id <-> rec_<id>.parquet
+ * mapping of materialize_files_task.rs:119 is unchanged.  Errors of the data (overflow, divide by zero) stay
+ * per batch (chdb_device_batch_status). */
+int32_t chdb_run_device_many(chdb_ctx* ctx, const chdb_program* prog, const chdb_device_batch* const* in,
+                             int32_t count, chdb_device_batch** out, chdb_status* st);
+/* 1 if the run that produces `b` has finished (row count, status and buffers can be read without waiting),
+ * 0 if not; never blocks (cudaEventQuery). */
+int32_t chdb_device_batch_ready(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
 /* Checks the device error word of a finished run (ArithmeticOverflow / DivideByZero). */
 int32_t chdb_device_batch_status(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
 int64_t chdb_device_batch_num_rows(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
@@ -209,8 +232,9 @@ int32_t chdb_device_batch_column(chdb_ctx* ctx, const chdb_device_batch* b, int3
 int64_t chdb_device_batch_nbytes(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
 int32_t chdb_download(chdb_ctx* ctx, const chdb_device_batch* b, struct ArrowArray* out,
                       struct ArrowSchema* out_schema, chdb_status* st);
-/* Copy a finished batch's buffers to another ctx's GPU (cudaMemcpyPeerAsync over NVLink):
- * the materialize-side gather of per-GPU results. */
+/* Copy a finished batch's buffers to another ctx's GPU (cudaMemcpyPeerAsync over NVLink; peer access is
+ * enabled on first use): the materialize-side gather of per-GPU results.  Asynchronous on the destination
+ * ctx's stream, ordered after the source ctx's stream; the source may be released right after the call. */
 int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_batch* src,
                        chdb_device_batch** out, chdb_status* st);
 void chdb_device_batch_release(chdb_device_batch* b);
