@@ -594,7 +594,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         del keep
         dtg_ms, (gathered,) = multigpu.reduce_step(dtg * 1e3, [gathered], device)
         line["gather"] = {"value": all_rows * args.gather_steps / (dtg_ms / 1e3), "unit": UNIT, "steps": args.gather_steps,
-                          "to_rank": 0, "ingest_gbs_rank0": gathered / (dtg_ms / 1e3) / 1e9 / max(args.gather_steps, 1) * args.gather_steps,
+                          "to_rank": 0, "ingest_gbs_rank0": gathered * args.gather_steps / (dtg_ms / 1e3) / 1e9,
                           "transport": multigpu.GATHER_TRANSPORT,
                           "note": "one pass of filter + variable-size gather of every result buffer to rank 0; the reference's "
                                   "per-record result files allow per-GPU materialize instead, which is what `value` measures"}
@@ -602,7 +602,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     # ---- e2e: host batches (pinned) -> chdb_filter_record -> host batches, copies inside the timed region ----
     if not args.no_e2e:
         import concurrent.futures as cf
-        e2e_records = min(len(tensors), max(8, 100_000_000 // args.batch_rows // 4 if many else len(tensors)))
+        e2e_records = min(len(tensors), 2000) if many else len(tensors)
         host = [to_host_batch(cfg, t, pin=True) for t in tensors[:e2e_records]]
         e2e_rows = sum(rb.num_rows for rb, _ in host)
         n_inst = max(1, args.e2e_instances)

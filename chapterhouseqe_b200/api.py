@@ -114,7 +114,14 @@ def load_library():
         ctypes.POINTER(i64), stp)
     sig("chdb_download", i32, vp, vp, vp, vp, stp)
     sig("chdb_peer_copy", i32, vp, vp, vp, pvp, stp)
+    sig("chdb_device_batch_retain", None, vp)
     sig("chdb_device_batch_release", None, vp)
+    sig("chdb_record_pool_create", i32, vp, i64, pvp, stp)
+    sig("chdb_record_pool_destroy", None, vp)
+    sig("chdb_record_pool_add", i32, vp, ctypes.c_uint64, vp, i32, stp)
+    sig("chdb_record_pool_get", i32, vp, ctypes.c_uint64, pvp, stp)
+    sig("chdb_record_pool_complete", i32, vp, ctypes.c_uint64, stp)
+    sig("chdb_record_pool_stats", None, vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64))
     _LIB = L
     return L
 
@@ -130,8 +137,9 @@ EXPORTED_SYMBOLS = [
     "chdb_filter_record_async", "chdb_project_record_async", "chdb_poll", "chdb_pending_result", "chdb_pending_release",
     "chdb_device_batch_status", "chdb_device_batch_num_rows",
     "chdb_device_batch_num_columns", "chdb_device_batch_column", "chdb_device_batch_nbytes", "chdb_download",
-    "chdb_peer_copy",
-    "chdb_device_batch_release",
+    "chdb_peer_copy", "chdb_device_batch_retain",
+    "chdb_device_batch_release", "chdb_record_pool_create", "chdb_record_pool_destroy", "chdb_record_pool_add",
+    "chdb_record_pool_get", "chdb_record_pool_complete", "chdb_record_pool_stats",
 ]
 
 
@@ -501,6 +509,47 @@ class DeviceBatch:
     def close(self):
         if getattr(self, "_h", None):
             load_library().chdb_device_batch_release(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class RecordPool:
+    """Device-resident RecordPool of a GPU-aware exchange (exchange_operator.rs:566-777): records by reference,
+    dropped after the last consumer operator completes them, spilled to pinned host memory beyond the budget."""
+
+    def __init__(self, ctx: Context | None = None, budget_bytes: int = 0):
+        L = load_library()
+        self.ctx = ctx or default_context()
+        h, st = ctypes.c_void_p(), _Status()
+        _check(L.chdb_record_pool_create(self.ctx._h, budget_bytes, ctypes.byref(h), ctypes.byref(st)), st)
+        self._h = h
+
+    def add(self, record_id: int, batch: DeviceBatch, consumers: int = 1):
+        st = _Status()
+        _check(load_library().chdb_record_pool_add(self._h, record_id, batch._h, consumers, ctypes.byref(st)), st)
+
+    def get(self, record_id: int) -> DeviceBatch:
+        h, st = ctypes.c_void_p(), _Status()
+        _check(load_library().chdb_record_pool_get(self._h, record_id, ctypes.byref(h), ctypes.byref(st)), st)
+        return DeviceBatch(h, self.ctx)
+
+    def complete(self, record_id: int):
+        st = _Status()
+        _check(load_library().chdb_record_pool_complete(self._h, record_id, ctypes.byref(st)), st)
+
+    def stats(self) -> dict:
+        vals = [ctypes.c_int64() for _ in range(4)]
+        load_library().chdb_record_pool_stats(self._h, *[ctypes.byref(v) for v in vals])
+        return dict(zip(("records", "device_bytes", "spilled_records", "spilled_bytes"), [v.value for v in vals]))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().chdb_record_pool_destroy(self._h)
             self._h = None
 
     def __del__(self):

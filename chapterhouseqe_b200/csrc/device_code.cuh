@@ -798,44 +798,51 @@ __device__ __forceinline__ uint64_t load_descriptor(const uint64_t* p) {
   return v;
 }
 // Exclusive prefix of chunk `chunk`, by one full warp; the chunk's own aggregate is already public.
-constexpr int kLookBackPerLane = 8;   // 256 predecessors per hop, all loads of a hop in flight together
+// A hop reads kLookBackRows rows of 32 consecutive descriptors (lane l of row j: predecessor j * 32 + l), so one
+// load instruction touches 256 contiguous bytes: every resident CTA reads the same few hundred descriptors each
+// round, and it is the number of sectors requested from the two or three L2 slices holding them that bounds the
+// look-back (lane-major indexing -- 32 sectors per instruction -- took 3-5x longer under load).
+constexpr int kLookBackRows = 10;   // 320 predecessors per hop (a whole round of resident CTAs), all loads in flight together
 __device__ __forceinline__ uint64_t lookback(uint64_t* d, uint32_t chunk, uint64_t agg, int lane) {
   if (chunk == 0) return 0;
-  uint64_t excl = 0;
+  uint64_t part = 0;   // this lane's share of the sum of everything nearer than the nearest known prefix
   int64_t base = (int64_t)chunk - 1;
-  while (true) {
-    uint64_t v[kLookBackPerLane];
+  bool done = false;
+  while (!done) {
+    uint64_t v[kLookBackRows];
 #pragma unroll
-    for (int j = 0; j < kLookBackPerLane; j++) {
-      const int64_t idx = base - (lane * kLookBackPerLane + j);
+    for (int j = 0; j < kLookBackRows; j++) {
+      const int64_t idx = base - (j * 32 + lane);
       v[j] = 2ull << 62;   // chunks "before 0" contribute an inclusive prefix of 0
       if (idx >= 0) v[j] = load_descriptor(d + idx);
     }
-    uint64_t part = 0;
-    bool found = false;
 #pragma unroll
-    for (int j = 0; j < kLookBackPerLane; j++) {
-      if (!found) {
-        const int64_t idx = base - (lane * kLookBackPerLane + j);
+    for (int j = 0; j < kLookBackRows; j++) {
+      if (!done) {
+        const int64_t idx = base - (j * 32 + lane);
         uint32_t spins = 0;
-        while ((v[j] >> 62) == 0) {
-          __nanosleep(40);
-          v[j] = load_descriptor(d + idx);
-          if (++spins > (1u << 22)) wait_timed_out("look-back", chunk, (uint32_t)idx);
+        while (true) {   // every descriptor of the row must at least carry its aggregate
+          const bool missing = (v[j] >> 62) == 0;
+          if (!__any_sync(FULL, missing)) break;
+          if (missing) {
+            __nanosleep(40);
+            v[j] = load_descriptor(d + idx);
+            if (++spins > (1u << 22)) wait_timed_out("look-back", chunk, (uint32_t)idx);
+          }
         }
-        part += v[j] & kValueMask;
-        found = (v[j] >> 62) == 2;
+        const uint32_t pm = __ballot_sync(FULL, (v[j] >> 62) == 2);
+        if (pm) {
+          const int first = __ffs(pm) - 1;  // lane holding the nearest predecessor that already knows its prefix
+          if (lane <= first) part += v[j] & kValueMask;
+          done = true;
+        } else {
+          part += v[j] & kValueMask;
+        }
       }
     }
-    const uint32_t pm = __ballot_sync(FULL, found);
-    if (pm) {
-      const int first = __ffs(pm) - 1;  // lane holding the nearest predecessor that already knows its prefix
-      excl += warp_sum64(lane <= first ? part : 0);
-      break;
-    }
-    excl += warp_sum64(part);
-    base -= 32 * kLookBackPerLane;
+    base -= 32 * kLookBackRows;
   }
+  const uint64_t excl = warp_sum64(part);
   if (lane == 0) publish_descriptor(d + chunk, kFlagPrefix, excl + agg);
   return excl;
 }
@@ -865,6 +872,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+// A probe that never suspends the warp (try_wait may: it blocks up to a hardware time limit before reporting failure).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
       "selp.u32 %0, 1, 0, P1;\n"
       "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
@@ -899,25 +917,78 @@ struct TileShared {
 };
 
 // ------------------------------------------------------------------------------------------
-// Loading a tile: the producer warp, lane s for input slot s.  The tile's slice of every staged buffer goes
-// into the ring stage with a TMA bulk copy (completion is counted in bytes on the stage's `full` mbarrier)
-// and the column's biased pointer into the stage's column table; buffers that are used but not staged get a
-// bulk L2 prefetch.  Utf8 value bytes start at offsets[row0]: those copies are issued in a second step (the
-// two bounds are a global load away), after the fixed-size ones are already in flight.
-// `in`: the batch's input columns (kernel parameters, or with MANY the batch's record in global memory).
+// Loading a tile: the producer warp, lane s for input slot s, in two steps.
+//   prepare(): everything that does not need a free ring stage -- the tile's place in its batch, the lane's
+//              column descriptor and, for Utf8 values, the two offsets that bound the tile's value bytes (a global
+//              load away).  Runs one tile ahead, while the producer waits for a stage.
+//   issue():   once a stage is free: the tile's slice of every staged buffer goes into the stage with a TMA bulk
+//              copy (completion is counted in bytes on the stage's `full` mbarrier) and the column's biased
+//              pointer into the stage's column table; buffers that are used but not staged get a bulk L2 prefetch.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan& TP, const ColumnDesc* in, ColumnDesc* cols,
-                                          uint8_t* stage, uint32_t full, int64_t row0, uint32_t tile_rows, int lane) {
+struct TileLoad {
+  int64_t tile, row0;
+  int32_t rows, batch;
+  ColumnDesc c;             // this lane's input column
+  uint32_t o0, o1;          // Utf8: offsets[row0], offsets[row0 + rows]
+  uint4 many0, many1;       // MANY: this lane's 16-byte units of the batch's header + output descriptors
+};
+
+template <bool MANY>
+__device__ __forceinline__ void prepare_tile(const KernelParams& P, const TilePlan& TP, uint32_t ticket, int lane, TileLoad& T) {
+  T.tile = ticket;
+  T.batch = 0;
+  int64_t num_rows = P.b.num_rows;
+  const ColumnDesc* in = P.in;
+  T.many0 = make_uint4(0, 0, 0, 0);
+  T.many1 = make_uint4(0, 0, 0, 0);
+  if (MANY) {
+    T.batch = P.many_tile_batch[ticket];
+    const uint8_t* rec = P.many + (size_t)T.batch * (size_t)P.many_stride;
+    const BatchHeader* gh = (const BatchHeader*)rec;
+    T.tile = (int64_t)ticket - gh->first_tile;
+    num_rows = gh->num_rows;
+    in = (const ColumnDesc*)(rec + sizeof(BatchHeader));
+    const uint4* s16 = (const uint4*)rec;
+    const int n_in16 = CHDB_N_IN * 2, n_hdr16 = (int)(sizeof(BatchHeader) / 16), n16 = n_hdr16 + CHDB_N_OUT * 2;
+    if (lane < n16) T.many0 = s16[lane < n_hdr16 ? lane : lane + n_in16];
+    if (lane + 32 < n16) T.many1 = s16[lane + 32 + n_in16];
+  }
+  T.row0 = T.tile * kTileRows;
+  T.rows = (int32_t)(T.row0 + kTileRows < num_rows ? kTileRows : num_rows - T.row0);
+  T.c.values = nullptr; T.c.validity = nullptr; T.c.offsets = nullptr; T.c.type = 0; T.c.width = 0;
+  T.o0 = 0;
+  T.o1 = 0;
+  if (lane < CHDB_N_IN) {
+    T.c = in[lane];
+    if (T.c.type == T_UTF8 && (TP.use[lane] & USE_VALUES)) {
+      T.o0 = (uint32_t)T.c.offsets[T.row0];
+      T.o1 = (uint32_t)T.c.offsets[T.row0 + T.rows];
+    }
+  }
+}
+
+template <bool MANY>
+__device__ __forceinline__ void issue_tile(const KernelParams& P, const TilePlan& TP, const TileLoad& T, StageCtx* sc, uint8_t* stage,
+                                           uint32_t full, int lane) {
+  ColumnDesc* cols = (ColumnDesc*)(sc + 1);
+  if (MANY) {   // the batch's header and output descriptors travel with the stage
+    uint4* dh = (uint4*)(cols + CHDB_N_IN);
+    const int n16 = (int)(sizeof(BatchHeader) / 16) + CHDB_N_OUT * 2;
+    if (lane < n16) dh[lane] = T.many0;
+    if (lane + 32 < n16) dh[lane + 32] = T.many1;
+  }
+  if (lane == 0) { sc->tile = T.tile; sc->row0 = T.row0; sc->rows = T.rows; sc->batch = T.batch; }
+  const int64_t row0 = T.row0;
+  const uint32_t tile_rows = (uint32_t)T.rows;
   const uint32_t ss = smem_u32(stage);
   const uint32_t bits_bytes = (((tile_rows + 7u) >> 3) + 15u) & ~15u;
   uint32_t nb[3] = {0, 0, 0}, so[3] = {0, 0, 0}, pf[3] = {0, 0, 0};   // 0: validity, 1: offsets, 2: values
   const uint8_t* src[3] = {nullptr, nullptr, nullptr};
-  bool utf8_values = false;
-  uint32_t cap = 0, vso = 0;
-  ColumnDesc c;
-  c.values = nullptr; c.validity = nullptr; c.offsets = nullptr; c.type = 0; c.width = 0;
+  uint32_t vbytes = 0;
+  const uint8_t* vsrc = nullptr;
+  uint32_t vso = 0;
   if (lane < CHDB_N_IN) {
-    c = in[lane];
+    const ColumnDesc& c = T.c;
     const StageSlot sl = TP.slot[lane];
     const uint32_t use = TP.use[lane];
     ColumnDesc t = c;   // this tile's view
@@ -933,7 +1004,14 @@ __device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan&
         if (sl.offsets != kNotStaged) { nb[1] = bytes; so[1] = sl.offsets; t.offsets = (const int32_t*)(stage + sl.offsets) - row0; }
         else pf[1] = bytes;
       }
-      if (use & USE_VALUES) { utf8_values = true; cap = sl.values != kNotStaged ? sl.values_cap : 0u; vso = sl.values; }
+      if (use & USE_VALUES) {   // value bytes start at offsets[row0] (16-byte units around them)
+        const uint32_t cap = sl.values != kNotStaged ? sl.values_cap : 0u;
+        const uint32_t lo = T.o0 & ~15u, len = (T.o1 - lo + 15u) & ~15u;
+        vsrc = (const uint8_t*)c.values + lo;
+        vso = sl.values;
+        if (cap != 0 && len <= cap) { vbytes = len; t.values = stage + vso - lo; }
+        else if (len) tma_prefetch_l2(vsrc, len);
+      }
     } else if (use & USE_VALUES) {
       const uint32_t w = c.width;
       const uint32_t bytes = w ? (tile_rows * w + 15u) & ~15u : bits_bytes;
@@ -944,29 +1022,15 @@ __device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan&
     }
     cols[lane] = t;
   }
-  // Utf8 bounds: in flight while the fixed-size copies are issued
-  uint32_t o0 = 0, o1 = 0;
-  if (utf8_values) { o0 = (uint32_t)c.offsets[row0]; o1 = (uint32_t)c.offsets[row0 + tile_rows]; }
-  const uint32_t tx = __reduce_add_sync(FULL, nb[0] + nb[1] + nb[2]);
-  if (lane == 0) mbar_expect_tx(full, tx);
+  const uint32_t tx = __reduce_add_sync(FULL, nb[0] + nb[1] + nb[2] + vbytes);
+  __syncwarp();   // the stage's tables are complete before the arrival that publishes them
+  if (lane == 0) mbar_arrive_expect_tx(full, tx);
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     if (nb[i]) tma_load(ss + so[i], src[i], nb[i], full);
     if (pf[i]) tma_prefetch_l2(src[i], pf[i]);
   }
-  uint32_t vbytes = 0;
-  const uint8_t* vsrc = nullptr;
-  if (utf8_values) {
-    const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
-    vsrc = (const uint8_t*)c.values + lo;
-    if (cap != 0 && len <= cap) { vbytes = len; cols[lane].values = stage + vso - lo; }
-    else if (len) tma_prefetch_l2(vsrc, len);
-  }
-  const uint32_t tx2 = __reduce_add_sync(FULL, vbytes);
-  __syncwarp();   // the stage's tables are complete before the arrival that publishes them
-  if (lane == 0) mbar_arrive_expect_tx(full, tx2);
-  __syncwarp();
   if (vbytes) tma_load(ss + vso, vsrc, vbytes, full);
 }
 // ------------------------------------------------------------------------------------------
@@ -1316,12 +1380,26 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, const OutDesc*
 // travel with its ring stage.
 // Every input byte is read from HBM once and every output byte written once.
 // ------------------------------------------------------------------------------------------
+// Pipeline waits.  try_wait itself suspends the warp for a hardware-chosen time; roles that wait long (producer, scan)
+// back off a little more so that their polling does not take issue slots from the compute warps.
+#ifndef CHDB_COMPUTE_SLEEP
+#define CHDB_COMPUTE_SLEEP 0
+#endif
+#ifndef CHDB_IDLE_SLEEP
+#define CHDB_IDLE_SLEEP 20
+#endif
+#ifndef CHDB_SCAN_SLEEP
+#define CHDB_SCAN_SLEEP 20
+#endif
+#ifndef CHDB_PRODUCER_SLEEP
+#define CHDB_PRODUCER_SLEEP 40
+#endif
 template <int SLEEP>
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(SLEEP);
-    if (++spins > (1u << 22)) wait_timed_out("mbarrier wait", bar, parity);
+    if (SLEEP > 0) __nanosleep(SLEEP);
+    if (++spins > (1u << 24)) wait_timed_out("mbarrier wait", bar, parity);
   }
 }
 
@@ -1336,11 +1414,19 @@ __device__ __forceinline__ uint64_t warp_excl_scan64(uint64_t v, int lane, uint6
   return x - v;
 }
 
+// CHDB_TRACE: events 0 stage free, 1 loads issued (producer); 2 tile landed, 3 A done, 4 prefix there, 5 B done
+// (compute warp 0); 6 slices counted, 7 look-back done (scan warp).
+__device__ __forceinline__ void trace_event(const KernelParams& P, int it, int ev, int lane) {
+  if (P.trace != nullptr && lane == 0 && it < kTraceIters)
+    P.trace[((size_t)blockIdx.x * kTraceIters + (size_t)it) * 8 + ev] = (uint64_t)clock64();
+}
+
 template <typename V, bool MANY>
 __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePlan& TP) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kMaxStages + 4];   // full[stage], empty[stage], counted[2], prefix[2]
+  __shared__ __align__(8) uint64_t s_bars[4 * kMaxStages];   // full, empty, counted, prefix: one of each per ring stage
   __shared__ uint64_t s_tot[kMaxQuantities];
+  __shared__ uint32_t s_arrived[kMaxStages];   // compute warps that have counted their slice of the stage's tile
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = (int)TP.stages;
@@ -1355,15 +1441,20 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
   const uint32_t bar0 = smem_u32(s_bars);
 #define CHDB_FULL(st) (bar0 + 8u * (uint32_t)(st))
 #define CHDB_EMPTY(st) (bar0 + 8u * (uint32_t)(kMaxStages + (st)))
-#define CHDB_COUNTED(b) (bar0 + 8u * (uint32_t)(2 * kMaxStages + (b)))
-#define CHDB_PREFIX(b) (bar0 + 8u * (uint32_t)(2 * kMaxStages + 2 + (b)))
+#define CHDB_COUNTED(st) (bar0 + 8u * (uint32_t)(2 * kMaxStages + (st)))
+#define CHDB_PREFIX(st) (bar0 + 8u * (uint32_t)(3 * kMaxStages + (st)))
 #define CHDB_SCTX(st) ((StageCtx*)(smem + TP.sctx_off + (uint32_t)(st) * TP.sctx_stride))
 #define CHDB_COLS(st) ((ColumnDesc*)(CHDB_SCTX(st) + 1))
 #define CHDB_HDR(st) ((BatchHeader*)(CHDB_COLS(st) + CHDB_N_IN))
 #define CHDB_OUTS(st) ((OutDesc*)(CHDB_HDR(st) + 1))
   if (tid == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(CHDB_FULL(s), 1); mbar_init(CHDB_EMPTY(s), kComputeWarps); }
-    for (int b = 0; b < 2; b++) { mbar_init(CHDB_COUNTED(b), kComputeWarps); mbar_init(CHDB_PREFIX(b), 1); }
+    for (int s = 0; s < S; s++) {
+      s_arrived[s] = 0;
+      mbar_init(CHDB_FULL(s), 1);
+      mbar_init(CHDB_EMPTY(s), kComputeWarps);
+      mbar_init(CHDB_COUNTED(s), kComputeWarps);
+      mbar_init(CHDB_PREFIX(s), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -1387,11 +1478,13 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
     uint32_t ticket = 0;
     if (lane == 0) ticket = atomicAdd(P.tickets, 1u);
     ticket = __shfl_sync(FULL, ticket, 0);
+    TileLoad T;
+    if (ticket < (uint32_t)P.total_tiles) prepare_tile<MANY>(P, TP, ticket, lane, T);
     int it = 0;
     for (;; it++) {
       const int st = it % S;
       if (it >= S) {
-        mbar_wait_sleep<200>(CHDB_EMPTY(st), (uint32_t)((it / S) - 1) & 1u);
+        mbar_wait_sleep<CHDB_PRODUCER_SLEEP>(CHDB_EMPTY(st), (uint32_t)((it / S) - 1) & 1u);
         if (MANY) {   // the finished tile's NULL counts go to its batch before the stage changes hands
           if (lane < CHDB_N_OUT) {
             const uint32_t v = s_nulls[st * kMaxOutCols + lane];
@@ -1403,52 +1496,37 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
           __syncwarp();
         }
       }
+      trace_event(P, it, 0, lane);
       StageCtx* sc = CHDB_SCTX(st);
       if (ticket >= (uint32_t)P.total_tiles) {
         if (lane == 0) { sc->tile = -1; mbar_arrive(CHDB_FULL(st)); }
         break;
       }
-      int64_t tile = ticket, num_rows = P.b.num_rows;
-      int32_t batch = 0;
-      const ColumnDesc* in = P.in;
-      if (MANY) {
-        batch = P.many_tile_batch[ticket];
-        const uint8_t* rec = P.many + (size_t)batch * (size_t)P.many_stride;
-        const BatchHeader* gh = (const BatchHeader*)rec;
-        tile = (int64_t)ticket - gh->first_tile;
-        num_rows = gh->num_rows;
-        in = (const ColumnDesc*)(rec + sizeof(BatchHeader));
-        // the batch's header and output descriptors travel with the stage
-        const uint4* s16 = (const uint4*)rec;
-        uint4* dh = (uint4*)CHDB_HDR(st);
-        const int n_in16 = CHDB_N_IN * 2, n_hdr16 = (int)(sizeof(BatchHeader) / 16), n_out16 = CHDB_N_OUT * 2;
-        for (int i = lane; i < n_hdr16 + n_out16; i += 32) dh[i] = s16[i < n_hdr16 ? i : i + n_in16];
-      }
-      const int64_t row0 = tile * kTileRows;
-      const int32_t rows = (int32_t)(row0 + kTileRows < num_rows ? kTileRows : num_rows - row0);
-      if (lane == 0) { sc->tile = tile; sc->row0 = row0; sc->rows = rows; sc->batch = batch; }
       uint32_t next = 0;
       if (lane == 0) next = atomicAdd(P.tickets, 1u);   // in flight while this tile's copies are issued
-      load_tile(P, TP, in, CHDB_COLS(st), smem + (size_t)st * TP.stage_bytes, CHDB_FULL(st), row0, (uint32_t)rows, lane);
+      issue_tile<MANY>(P, TP, T, sc, smem + (size_t)st * TP.stage_bytes, CHDB_FULL(st), lane);
+      trace_event(P, it, 1, lane);
       ticket = __shfl_sync(FULL, next, 0);
+      // the next tile's descriptors and Utf8 bounds: on their way while this warp waits for a free stage
+      if (ticket < (uint32_t)P.total_tiles) prepare_tile<MANY>(P, TP, ticket, lane, T);
     }
     if (MANY) {   // the tiles still in the ring when the tickets ran out
       for (int j = it - S + 1 > 0 ? it - S + 1 : 0; j < it; j++) {
         const int st = j % S;
-        mbar_wait_sleep<200>(CHDB_EMPTY(st), (uint32_t)(j / S) & 1u);
+        mbar_wait_sleep<CHDB_PRODUCER_SLEEP>(CHDB_EMPTY(st), (uint32_t)(j / S) & 1u);
         if (lane < CHDB_N_OUT) {
           const uint32_t v = s_nulls[st * kMaxOutCols + lane];
           if (v) atomicAdd((unsigned long long*)(CHDB_HDR(st)->counts + P.out[lane].count_index), (unsigned long long)v);
         }
       }
     }
-  } else if (warp == kScanWarp) {
+  } else if (warp >= kScanWarp) {
     // ================= scan: slice counts -> batch-wide exclusive prefixes =================
     if (has_pred) {
       const int ng = desc_groups(nq);
       for (int it = 0;; it++) {
-        const int st = it % S, b = it & 1;
-        mbar_wait_sleep<100>(CHDB_FULL(st), (uint32_t)(it / S) & 1u);
+        const int st = it % S;
+        mbar_wait_sleep<CHDB_SCAN_SLEEP>(CHDB_FULL(st), (uint32_t)(it / S) & 1u);
         const StageCtx* sc = CHDB_SCTX(st);
         const int64_t tile = sc->tile;
         if (tile < 0) break;
@@ -1456,9 +1534,13 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
         const int32_t num_tiles = bh->num_tiles;
         uint64_t* const desc0 = bh->desc;
         const bool last_tile = tile == (int64_t)num_tiles - 1;
-        mbar_wait_sleep<100>(CHDB_COUNTED(b), (uint32_t)(it >> 1) & 1u);
-        const uint32_t* cnt = s_cnt + b * nq * kTileSlices;
-        uint64_t* pre = s_pre + b * nq * kTileSlices;
+        mbar_wait_sleep<CHDB_SCAN_SLEEP>(CHDB_COUNTED(st), (uint32_t)(it / S) & 1u);
+        // (every scan warp observes every phase of the barriers -- a parity wait is only sound then -- and takes every
+        // kScanWarps-th tile: one look-back is an L2 round trip or two, several are in flight per CTA)
+        if (it % kScanWarps != warp - kScanWarp) continue;
+        trace_event(P, it, 6, lane);
+        const uint32_t* cnt = s_cnt + st * nq * kTileSlices;
+        uint64_t* pre = s_pre + st * nq * kTileSlices;
         for (int g = 0; g < ng; g++) {
           const int q0 = 2 * g, q1 = 2 * g + 1;
           uint64_t c = 0;
@@ -1468,8 +1550,7 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
           }
           uint64_t agg;
           const uint64_t before = warp_excl_scan64(c, lane, agg);
-          uint64_t* desc = desc0 + (size_t)g * (size_t)num_tiles;
-          if (lane == 0) publish_descriptor(desc + tile, tile == 0 ? kFlagPrefix : kFlagAgg, agg);
+          uint64_t* desc = desc0 + (size_t)g * (size_t)num_tiles;   // (the tile's aggregate is already public)
           const uint64_t excl = lookback(desc, (uint32_t)tile, agg, lane);
           const uint64_t mine = excl + before;
           if (lane < kTileSlices) {
@@ -1493,76 +1574,123 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
           }
           __syncwarp();
         }
-        if (lane == 0) mbar_arrive(CHDB_PREFIX(b));
+        trace_event(P, it, 7, lane);
+        if (lane == 0) mbar_arrive(CHDB_PREFIX(st));
       }
     }
   } else {
     // ================= compute =================
+    // Event driven: A(a) as soon as tile a has landed (so its aggregate is public as early as possible: other
+    // CTAs' look-backs wait for it), B(b) once tile b's prefix is there; A runs at most `stages` tiles ahead of B
+    // (the ring), and with nothing to store it waits for the next tile.
     TileShared sh;
     sh.pool = (const uint8_t*)P.strpool;
     sh.pext4 = pext4;
     sh.nulls = s_nulls;
     uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
-    uint32_t sel_prev = 0, rank_prev = 0;
-    for (int it = 0;; it++) {
-      const int st = it % S;
-      mbar_wait_sleep<32>(CHDB_FULL(st), (uint32_t)(it / S) & 1u);
-      const StageCtx* sc = CHDB_SCTX(st);
-      const int64_t tile = sc->tile;
-      uint32_t sel4 = 0, rank = 0;
-      if (tile >= 0 && has_pred) {
-        // ---- A(it): predicate -> selection bits, ranks, slice counts ----
-        const ColumnDesc* cols = CHDB_COLS(st);
-        uint64_t* const errw = MANY ? CHDB_HDR(st)->error_word : P.b.error_word;
-        const int32_t rows = sc->rows;
-        const int64_t qb[1] = {sc->row0 + warp * kWarpRows + lane * 4};
-        const int left = rows - (warp * kWarpRows + lane * 4);
-        const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
-        V acc[4];
-        uint32_t accm, accv;
+    uint8_t* const s_sel = smem + TP.sel_off;   // [stage][warp][lane]: the lane's 4 selection bits between A and B
+    int a = 0, b = 0;       // next iteration to evaluate / to store
+    bool more = true;       // the ticket counter has not run out
+    while (true) {
+      // Neither wait blocks: while tile b's prefix is still on its way the next tile may land, and its aggregate
+      // must become public at once (every later tile's look-back needs it).
+      if (more && a - b < S && mbar_test_wait(CHDB_FULL(a % S), (uint32_t)(a / S) & 1u)) {
+        const int st = a % S;
+        {
+          if (warp == 0) trace_event(P, a, 2, lane);
+          const StageCtx* sc = CHDB_SCTX(st);
+          const int64_t tile = sc->tile;
+          if (tile < 0) { more = false; continue; }
+          if (has_pred) {
+            // ---- A(a): predicate -> selection bits, ranks, slice counts ----
+            const ColumnDesc* cols = CHDB_COLS(st);
+            uint64_t* const errw = MANY ? CHDB_HDR(st)->error_word : P.b.error_word;
+            const int32_t rows = sc->rows;
+            const int64_t qb[1] = {sc->row0 + warp * kWarpRows + lane * 4};
+            const int left = rows - (warp * kWarpRows + lane * 4);
+            const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
+            V acc[4];
+            uint32_t accm, accv;
 #ifdef CHDB_JIT
-        run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, errw, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
+            run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, errw, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
 #else
-        run_program<V, 1>(P, errw, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
+            run_program<V, 1>(P, errw, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
 #endif
-        sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
-        uint32_t wrows;
-        rank = warp_excl_scan((uint32_t)__popc(sel4), lane, wrows);
-        uint32_t* cnt = s_cnt + (it & 1) * nq * kTileSlices;
-        if (lane == 0) cnt[warp] = wrows;
-        // selected value bytes per Utf8 output
-        CHDB_STATIC_UNROLL
-        for (int k = 0; k < CHDB_N_OUT; k++) {
-          const uint64_t meta = CHDB_OUT_META(P, k);
-          const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
-          if (o_utf8 == 0xFFu) continue;   // uniform branch
-          const int32_t* off = cols[o_slot].offsets;
-          uint32_t bytes = 0;
-          if (sel4) {
-            const int4 a = *(const int4*)(off + qb[0]);
-            const int a4 = off[qb[0] + 4];
-            if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
-            if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
-            if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
-            if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
+            const uint32_t sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
+            const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel4));
+            s_sel[(st * kComputeWarps + warp) * 32 + lane] = (uint8_t)sel4;
+            uint32_t* cnt = s_cnt + st * nq * kTileSlices;
+            if (lane == 0) cnt[warp] = wrows;
+            // selected value bytes per Utf8 output
+            CHDB_STATIC_UNROLL
+            for (int k = 0; k < CHDB_N_OUT; k++) {
+              const uint64_t meta = CHDB_OUT_META(P, k);
+              const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+              if (o_utf8 == 0xFFu) continue;   // uniform branch
+              const int32_t* off = cols[o_slot].offsets;
+              uint32_t bytes = 0;
+              if (sel4) {
+                const int4 o4 = *(const int4*)(off + qb[0]);
+                const int o5 = off[qb[0] + 4];
+                if (sel4 & 1u) bytes += (uint32_t)(o4.y - o4.x);
+                if (sel4 & 2u) bytes += (uint32_t)(o4.z - o4.y);
+                if (sel4 & 4u) bytes += (uint32_t)(o4.w - o4.z);
+                if (sel4 & 8u) bytes += (uint32_t)(o5 - o4.w);
+              }
+              const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+              if (lane == 0) cnt[(1 + o_utf8) * kTileSlices + warp] = wbytes;
+            }
+            // The last warp to finish A publishes the tile's aggregate right away (the scan warp may still be busy
+            // with an earlier tile's look-back; neighbours' look-backs must not wait for it).
+            __syncwarp();
+            uint32_t arrived = 0;
+            if (lane == 0) {
+              __threadfence_block();
+              arrived = atomicAdd(&s_arrived[st], 1u);
+            }
+            arrived = __shfl_sync(FULL, arrived, 0);
+            if (arrived == kComputeWarps - 1) {
+              __threadfence_block();
+              const BatchHeader* bh = MANY ? CHDB_HDR(st) : &P.b;
+              const int ng = desc_groups(nq);
+              for (int g = lane; g < ng; g += 32) {
+                uint64_t agg = 0;
+#pragma unroll
+                for (int w = 0; w < kTileSlices; w++) {
+                  agg += cnt[(2 * g) * kTileSlices + w];
+                  if (2 * g + 1 < nq) agg += (uint64_t)cnt[(2 * g + 1) * kTileSlices + w] << 31;
+                }
+                publish_descriptor(bh->desc + (size_t)g * (size_t)bh->num_tiles + tile, tile == 0 ? kFlagPrefix : kFlagAgg, agg);
+              }
+              if (lane == 0) s_arrived[st] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(CHDB_COUNTED(st));
+            if (warp == 0) trace_event(P, a, 3, lane);
           }
-          const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
-          if (lane == 0) cnt[(1 + o_utf8) * kTileSlices + warp] = wbytes;
+          a++;
+          continue;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(CHDB_COUNTED(it & 1));
       }
-      // ---- B: the selected rows of the tile one iteration back (this iteration's tile without a predicate) ----
-      const int bit = has_pred ? it - 1 : it;
-      if (bit >= 0 && (has_pred || tile >= 0)) {
-        const int pst = bit % S, pb = bit & 1;
+      if (b == a) {
+        if (!more) break;
+        __nanosleep(CHDB_IDLE_SLEEP);
+        continue;
+      }
+      if (has_pred && !mbar_test_wait(CHDB_PREFIX(b % S), (uint32_t)(b / S) & 1u)) {
+        __nanosleep(CHDB_IDLE_SLEEP);
+        continue;
+      }
+      {
+        // ---- B(b): the selected rows of tile b, to their final positions ----
+        const int pst = b % S;
         const StageCtx* psc = CHDB_SCTX(pst);
         const ColumnDesc* cols = CHDB_COLS(pst);
         const OutDesc* outs = MANY ? CHDB_OUTS(pst) : P.out;
         uint64_t* const errw = MANY ? CHDB_HDR(pst)->error_word : P.b.error_word;
         const int32_t rows = psc->rows;
         const int64_t row0 = psc->row0;
-        if (has_pred) mbar_wait_sleep<32>(CHDB_PREFIX(pb), (uint32_t)(bit >> 1) & 1u);
+        if (warp == 0) trace_event(P, b, 4, lane);
         if (warp * kWarpRows < rows) {   // (tail tile: this warp's slice may not exist)
           LaneCtx L;
           L.lane = lane;
@@ -1572,10 +1700,9 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
           const int left = rows - (warp * kWarpRows + lane * 4);
           L.inrange = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
           if (has_pred) {
-            L.sel = sel_prev;
-            L.rank = rank_prev;
-            L.prefix = s_pre + pb * nq * kTileSlices;
-            L.count = s_cnt[pb * nq * kTileSlices + warp];
+            L.sel = s_sel[(pst * kComputeWarps + warp) * 32 + lane];
+            L.rank = warp_excl_scan((uint32_t)__popc(L.sel), lane, L.count);
+            L.prefix = s_pre + pst * nq * kTileSlices;
             L.obase = L.prefix[warp];
           } else {
             L.sel = L.inrange;
@@ -1609,10 +1736,9 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(CHDB_EMPTY(pst));
+        if (warp == 0) trace_event(P, b, 5, lane);
+        b++;
       }
-      if (tile < 0) break;
-      sel_prev = sel4;
-      rank_prev = rank;
     }
   }
 

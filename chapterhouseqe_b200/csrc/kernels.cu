@@ -42,7 +42,7 @@ void plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bo
     if (c.type == T_UTF8) {
       if (use & USE_OFFSETS) bufs.push_back({s, 1, (size_t)(kTileRows + 4) * 4});
       const int64_t avg = avg_utf8 ? avg_utf8[s] : -1;
-      if ((use & USE_VALUES) && avg >= 0 && avg <= 32) bufs.push_back({s, 2, up16((size_t)kTileRows * (size_t)avg * 17 / 16 + 64)});
+      if ((use & USE_VALUES) && avg >= 0 && avg <= 32) bufs.push_back({s, 2, up16((size_t)kTileRows * (size_t)avg + std::max<size_t>((size_t)kTileRows * (size_t)avg / 32, 128) + 32)});
     } else if (use & USE_VALUES) {
       bufs.push_back({s, 2, c.width ? (size_t)kTileRows * c.width : (size_t)kTileRows / 8});
     }
@@ -66,8 +66,9 @@ void plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bo
     // the tables behind the ring (their size depends on the ring depth only through the per-stage ones)
     auto fixed_for = [&](int st) {
       size_t t = 0;
-      t += up16((size_t)2 * nq * kTileSlices * 4);
-      t += up16((size_t)2 * nq * kTileSlices * 8);
+      t += up16((size_t)st * nq * kTileSlices * 4);
+      t += up16((size_t)st * nq * kTileSlices * 8);
+      t += up16(has_pred ? (size_t)st * kComputeWarps * 32 : 0);
       t += up16((size_t)(many ? st : 1) * kMaxOutCols * 4);
       t += up16((size_t)kComputeWarps * kp.n_bits * kBitWords * 4);
       t += up16(kp.long_strings ? (size_t)kComputeWarps * 2 * (kWarpRows + 4) * 4 : 0);
@@ -101,8 +102,9 @@ void plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bo
   auto table = [&](size_t bytes) { const size_t here = at; at += up16(bytes); return (uint32_t)here; };
   tp.sctx_off = table((size_t)stages * sctx_stride);
   tp.sctx_stride = (uint32_t)sctx_stride;
-  tp.cnt_off = table((size_t)2 * nq * kTileSlices * 4);
-  tp.pre_off = table((size_t)2 * nq * kTileSlices * 8);
+  tp.cnt_off = table((size_t)stages * nq * kTileSlices * 4);
+  tp.pre_off = table((size_t)stages * nq * kTileSlices * 8);
+  tp.sel_off = table(has_pred ? (size_t)stages * kComputeWarps * 32 : 0);
   tp.nulls_off = table((size_t)(many ? stages : 1) * kMaxOutCols * 4);
   tp.bits_off = table((size_t)kComputeWarps * kp.n_bits * kBitWords * 4);
   tp.ltab_off = table(kp.long_strings ? (size_t)kComputeWarps * 2 * (kWarpRows + 4) * 4 : 0);
@@ -110,6 +112,18 @@ void plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bo
   tp.dyn_smem = (uint32_t)at;
   (void)fixed;
   tp.ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)want, kSmemPerSm / (at + kStaticSmem + 1024)));
+  if (const char* e = std::getenv("CHDB_PLAN_VERBOSE")) {
+    if (*e == '1') {
+      int staged = 0, unstaged = 0;
+      for (int s = 0; s < kp.n_in; s++) {
+        const StageSlot& sl = tp.slot[s];
+        staged += (sl.values != kNotStaged) + (sl.validity != kNotStaged) + (sl.offsets != kNotStaged);
+        unstaged += ((tp.use[s] & USE_VALUES) && sl.values == kNotStaged) + ((tp.use[s] & USE_OFFSETS) && kp.in[s].type == T_UTF8 && sl.offsets == kNotStaged);
+      }
+      std::fprintf(stderr, "[chdb plan] stages %u x %u B, tables %zu B, dyn smem %u B, %u CTAs/SM, %d staged buffers, %d read from global\n",
+                   tp.stages, tp.stage_bytes, at - (size_t)stages * tp.stage_bytes, tp.dyn_smem, tp.ctas_per_sm, staged, unstaged);
+    }
+  }
 }
 
 namespace {
@@ -131,6 +145,10 @@ cudaError_t grant_smem(const void* kern) {
   e = cudaFuncGetAttributes(&fa, kern);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerCtaMax - fa.sharedSizeBytes));
+  if (e != cudaSuccess) return e;
+  // The plan counts on the whole 228 KB of the SM being shared memory (two CTAs of ~114 KB each): without this the
+  // driver may pick a smaller carve-out, one CTA per SM becomes resident and the launch takes twice as long.
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   ok = true;
   return cudaSuccess;

@@ -13,7 +13,7 @@ namespace chdb {
 // ticket counter.  A tile is kTileSlices slices of 128 rows; a slice is the unit one compute warp works on
 // (4 consecutive rows per lane, so every column access is a 128-bit load); compute warp w owns slice w of
 // every tile of its CTA.  Besides the compute warps a CTA has one producer warp (tickets, TMA bulk loads
-// into a ring of shared-memory stages) and one scan warp (decoupled look-back).
+// into a ring of shared-memory stages) and kScanWarps scan warps (decoupled look-back).
 #ifndef CHDB_COMPUTE_WARPS
 #define CHDB_COMPUTE_WARPS 8
 #endif
@@ -21,9 +21,14 @@ constexpr int kComputeWarps = CHDB_COMPUTE_WARPS;
 constexpr int kTileSlices = kComputeWarps;
 constexpr int kWarpRows = 128;                        // rows of one slice
 constexpr int kTileRows = kTileSlices * kWarpRows;    // 1024 rows per tile
-constexpr int kProducerWarp = kComputeWarps, kScanWarp = kComputeWarps + 1;
-constexpr int kThreads = (kComputeWarps + 2) * 32;
+#ifndef CHDB_SCAN_WARPS
+#define CHDB_SCAN_WARPS 2
+#endif
+constexpr int kScanWarps = CHDB_SCAN_WARPS;           // look-backs of consecutive tiles run concurrently, one per scan warp
+constexpr int kProducerWarp = kComputeWarps, kScanWarp = kComputeWarps + 1;   // scan warps: kScanWarp .. kScanWarp + kScanWarps - 1
+constexpr int kThreads = (kComputeWarps + 1 + kScanWarps) * 32;
 constexpr int kMaxStages = 8;
+constexpr int kTraceIters = 32;
 constexpr int kMaxQuantities = 1 + kMaxOutCols;       // scanned quantities: rows + bytes per Utf8 output
 constexpr int kBitWords = kWarpRows / 32 + 2;         // words of one slice's bit-packed output stage
 constexpr uint32_t kNotStaged = 0xFFFFFFFFu;
@@ -95,8 +100,9 @@ struct TilePlan {
   uint32_t stages;               // ring depth
   uint32_t stage_bytes;          // staged buffers of one stage (multiple of 128)
   uint32_t sctx_off, sctx_stride;  // StageCtx [+ cols + header + outs] per stage
-  uint32_t cnt_off;              // uint32[2][quantity][kTileSlices]: per-slice counts (two tiles in flight)
-  uint32_t pre_off;              // uint64[2][quantity][kTileSlices]: per-slice exclusive prefixes (batch-wide)
+  uint32_t cnt_off;              // uint32[stage][quantity][kTileSlices]: per-slice counts
+  uint32_t pre_off;              // uint64[stage][quantity][kTileSlices]: per-slice exclusive prefixes (batch-wide)
+  uint32_t sel_off;              // uint8[stage][compute warp][lane]: the lanes' selection bits between A and B
   uint32_t nulls_off;            // uint32[stages][kMaxOutCols]: NULLs written per output (per stage with MANY)
   uint32_t bits_off;             // uint32[compute warp][n_bits][kBitWords]: per-warp bit stages
   uint32_t ltab_off;             // long strings: per-warp row tables
@@ -121,6 +127,7 @@ struct KernelParams {
   int32_t n_counts;              // entries of counts[] before the error word
   // MANY (one launch over several batches of one schema and shape): packed per-batch records in global memory
   int32_t many_batches, many_stride;
+  uint64_t* trace;               // debugging aid (CHDB_TRACE): [cta][kTraceIters][8] clock64() stamps of the pipeline, or nullptr
   const uint8_t* many;           // nullptr: single batch (everything is in this block)
   const int32_t* many_tile_batch;  // [total_tiles] batch index of every ticket
   ColumnDesc in[kMaxInCols];

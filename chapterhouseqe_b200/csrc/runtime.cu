@@ -234,6 +234,7 @@ struct chdb_program {
 };
 
 struct chdb_device_batch {
+  std::atomic<int> refs{1};          // chdb_device_batch_retain / _release
   chdb::Core core;
   int64_t num_rows = 0;              // -1: result->host[0]
   std::vector<chdb::DeviceColumn> cols;
@@ -915,8 +916,21 @@ static void fill_program_params(const Program& p, const Prepared& P, KernelParam
 
 // Zero kernel + stream kernel.  Long scans run the same device code specialised for this program by NVRTC
 // (jit.cpp); short ones, or boxes without NVRTC, run the bytecode interpreter kernels.
-static void launch_set(const Core& core, const Program& p, const KernelParams& kp, const TilePlan& tp, void* ws, size_t ws_bytes,
+static void launch_set(const Core& core, const Program& p, const KernelParams& kp_in, const TilePlan& tp, void* ws, size_t ws_bytes,
                        int64_t rows, const std::shared_ptr<LaunchShared>& ls) {
+  KernelParams kp_traced;
+  const KernelParams* kpp = &kp_in;
+  Buf trace_buf;
+  const char* trace_path = std::getenv("CHDB_TRACE");   // debugging aid: per-CTA pipeline time stamps of this launch -> file
+  const size_t trace_bytes = (size_t)core->sm_count * 4 * kTraceIters * 8 * 8;
+  if (trace_path && *trace_path) {
+    trace_buf = dev_alloc(core, trace_bytes);
+    CUDA_CHECK(cudaMemsetAsync(trace_buf->ptr, 0, trace_bytes, core->stream));
+    kp_traced = kp_in;
+    kp_traced.trace = (uint64_t*)trace_buf->ptr;
+    kpp = &kp_traced;
+  }
+  const KernelParams& kp = *kpp;
   CUDA_CHECK(launch_zero(ws, ws_bytes, core->stream));
   core->launches++;
   const JitKernel* jk = nullptr;
@@ -931,6 +945,12 @@ static void launch_set(const Core& core, const Program& p, const KernelParams& k
   if (jk) core->jit_launches++;
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
   CUDA_CHECK(cudaEventRecord(ls->done, core->stream));   // the counts arrive in pinned memory with the kernel's last CTA
+  if (trace_buf) {
+    std::vector<uint64_t> h(trace_bytes / 8);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), trace_buf->ptr, trace_bytes, cudaMemcpyDeviceToHost, core->stream));
+    CUDA_CHECK(cudaStreamSynchronize(core->stream));
+    if (FILE* f = std::fopen(trace_path, "wb")) { std::fwrite(h.data(), 8, h.size(), f); std::fclose(f); }
+  }
 }
 
 static void after_launch(Prepared& P) {
@@ -1382,7 +1402,161 @@ int32_t chdb_download(chdb_ctx* ctx, const chdb_device_batch* b, struct ArrowArr
     download_batch(const_cast<chdb_device_batch*>(b), out, out_schema);
   });
 }
-void chdb_device_batch_release(chdb_device_batch* b) { delete b; }
+void chdb_device_batch_retain(chdb_device_batch* b) {
+  if (b) b->refs.fetch_add(1, std::memory_order_relaxed);
+}
+void chdb_device_batch_release(chdb_device_batch* b) {
+  if (b && b->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) delete b;
+}
+
+// ---- device-resident record pool ---------------------------------------------------------------
+// What a GPU-aware exchange keeps instead of `RecordPool.records: HashMap<u64, Arc<RecordBatch>>`
+// (exchange_operator.rs:566-777): records stay in HBM between read_files, filter and materialize, are handed out
+// by reference, dropped once every consumer operator has completed them (:727-733), and -- the memory management
+// the reference lists as a TODO (DEV_NOTES.md:133-140) -- spilled to pinned host memory, least recently used
+// first, when the pool holds more than its byte budget; a spilled record is uploaded again when it is asked for.
+struct chdb_record_pool {
+  struct Entry {
+    chdb_device_batch* dev = nullptr;          // resident copy (the pool's own reference), or nullptr when spilled
+    struct ArrowArray host_array;              // spilled copy (release != nullptr when present)
+    struct ArrowSchema host_schema;
+    int32_t consumers = 1;
+    int64_t held = 0;                          // device bytes this record keeps alive
+    uint64_t tick = 0;                         // last add / get
+  };
+  chdb_ctx* ctx = nullptr;
+  int64_t budget = 0;
+  std::mutex mu;
+  std::map<uint64_t, Entry> records;
+  std::map<const DevBuf*, int> bufs;           // device blocks held by resident records (shared blocks count once)
+  int64_t device_bytes = 0, spilled_bytes = 0, spilled_records = 0;
+  uint64_t clock = 0;
+};
+
+namespace chdb {
+static void pool_account(chdb_record_pool* p, const chdb_device_batch* b, int sign, int64_t* held) {
+  int64_t delta = 0;
+  auto touch = [&](const Buf& buf) {
+    if (!buf) return;
+    int& n = p->bufs[buf.get()];
+    if (sign > 0) { if (n++ == 0) delta += (int64_t)buf->bytes; }
+    else if (--n == 0) { delta += (int64_t)buf->bytes; p->bufs.erase(buf.get()); }
+  };
+  for (auto& c : b->cols) { touch(c.values_buf); touch(c.validity_buf); touch(c.offsets_buf); }
+  p->device_bytes += sign * delta;
+  if (held) *held = delta;
+}
+static void pool_drop_host(chdb_record_pool::Entry& e) {
+  if (e.host_array.release) e.host_array.release(&e.host_array);
+  if (e.host_schema.release) e.host_schema.release(&e.host_schema);
+  e.host_array.release = nullptr;
+  e.host_schema.release = nullptr;
+}
+// Spills least-recently-used records nobody else references until the pool is within budget (or nothing is left to spill).
+static void pool_enforce_budget(chdb_record_pool* p, uint64_t keep_id) {
+  while (p->budget > 0 && p->device_bytes > p->budget) {
+    chdb_record_pool::Entry* victim = nullptr;
+    for (auto& kv : p->records) {
+      chdb_record_pool::Entry& e = kv.second;
+      if (!e.dev || kv.first == keep_id || e.dev->refs.load() > 1) continue;   // in use by a consumer: stays
+      if (!victim || e.tick < victim->tick) victim = &e;
+    }
+    if (!victim) return;
+    download_batch(victim->dev, &victim->host_array, &victim->host_schema);
+    int64_t freed = 0;
+    pool_account(p, victim->dev, -1, &freed);
+    p->spilled_bytes += freed;
+    p->spilled_records++;
+    chdb_device_batch_release(victim->dev);
+    victim->dev = nullptr;
+  }
+}
+}  // namespace chdb
+
+int32_t chdb_record_pool_create(chdb_ctx* ctx, int64_t budget_bytes, chdb_record_pool** out, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!ctx || !out) throw Error(CHDB_ERR_INVALID_ARGUMENT, "ctx / out is null");
+    auto* p = new chdb_record_pool;
+    p->ctx = ctx;
+    p->budget = budget_bytes;
+    *out = p;
+  });
+}
+void chdb_record_pool_destroy(chdb_record_pool* pool) {
+  if (!pool) return;
+  for (auto& kv : pool->records) {
+    if (kv.second.dev) chdb_device_batch_release(kv.second.dev);
+    pool_drop_host(kv.second);
+  }
+  delete pool;
+}
+int32_t chdb_record_pool_add(chdb_record_pool* pool, uint64_t record_id, chdb_device_batch* batch, int32_t consumers, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!pool || !batch) throw Error(CHDB_ERR_INVALID_ARGUMENT, "pool / batch is null");
+    if (batch->core->device != pool->ctx->core->device) throw Error(CHDB_ERR_INVALID_ARGUMENT, "batch lives on another device than the pool");
+    std::lock_guard<std::mutex> g(pool->mu);
+    if (pool->records.count(record_id)) throw Error(CHDB_ERR_INVALID_ARGUMENT, "record id already in the pool");
+    chdb_record_pool::Entry& e = pool->records[record_id];
+    std::memset(&e.host_array, 0, sizeof(e.host_array));
+    std::memset(&e.host_schema, 0, sizeof(e.host_schema));
+    chdb_device_batch_retain(batch);
+    e.dev = batch;
+    e.consumers = std::max(consumers, 1);
+    e.tick = ++pool->clock;
+    pool_account(pool, batch, +1, &e.held);
+    pool_enforce_budget(pool, record_id);
+  });
+}
+int32_t chdb_record_pool_get(chdb_record_pool* pool, uint64_t record_id, chdb_device_batch** out, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!pool || !out) throw Error(CHDB_ERR_INVALID_ARGUMENT, "pool / out is null");
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(pool->mu);
+    auto it = pool->records.find(record_id);
+    if (it == pool->records.end()) throw Error(CHDB_ERR_INVALID_ARGUMENT, "record id not in the pool");
+    chdb_record_pool::Entry& e = it->second;
+    e.tick = ++pool->clock;
+    if (!e.dev) {   // spilled: bring it back
+      CUDA_CHECK(cudaSetDevice(pool->ctx->core->device));
+      auto b = upload_batch(pool->ctx->core, &e.host_array, &e.host_schema);
+      CUDA_CHECK(cudaStreamSynchronize(pool->ctx->core->stream));   // the host copy is released next
+      pool_drop_host(e);
+      e.dev = b.release();
+      pool_account(pool, e.dev, +1, &e.held);
+      pool->spilled_records--;
+      pool_enforce_budget(pool, record_id);
+    }
+    chdb_device_batch_retain(e.dev);
+    *out = e.dev;
+  });
+}
+int32_t chdb_record_pool_complete(chdb_record_pool* pool, uint64_t record_id, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!pool) throw Error(CHDB_ERR_INVALID_ARGUMENT, "pool is null");
+    std::lock_guard<std::mutex> g(pool->mu);
+    auto it = pool->records.find(record_id);
+    if (it == pool->records.end()) throw Error(CHDB_ERR_INVALID_ARGUMENT, "record id not in the pool");
+    chdb_record_pool::Entry& e = it->second;
+    if (--e.consumers > 0) return;
+    if (e.dev) {
+      pool_account(pool, e.dev, -1, nullptr);
+      chdb_device_batch_release(e.dev);
+    } else {
+      pool->spilled_records--;
+    }
+    pool_drop_host(e);
+    pool->records.erase(it);
+  });
+}
+void chdb_record_pool_stats(chdb_record_pool* pool, int64_t* records, int64_t* device_bytes, int64_t* spilled_records,
+                            int64_t* spilled_bytes) {
+  if (!pool) return;
+  std::lock_guard<std::mutex> g(pool->mu);
+  if (records) *records = (int64_t)pool->records.size();
+  if (device_bytes) *device_bytes = pool->device_bytes;
+  if (spilled_records) *spilled_records = pool->spilled_records;
+  if (spilled_bytes) *spilled_bytes = pool->spilled_bytes;
+}
 
 int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_batch* src, chdb_device_batch** out,
                        chdb_status* st) {

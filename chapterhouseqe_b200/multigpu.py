@@ -35,35 +35,82 @@ def reduce_step(elapsed_ms: float, sums: Sequence[float], device=None):
     return float(t.item()), [float(x) for x in s.tolist()]
 
 
-def gather_buffers(buffers: Sequence, dst: int = 0):
-    """Variable-size gather of byte buffers (1-D uint8 tensors, one list per rank) onto rank `dst`:
-    sizes travel in one all_gather, payloads as point-to-point send/recv (NVLink peer copies under
-    NCCL).  Returns on dst a list (per source rank) of lists of tensors; elsewhere None."""
+GATHER_TRANSPORT = ("one ncclGroupStart/End per step (torch.distributed.batch_isend_irecv): every result buffer of every "
+                    "rank is one grouped NCCL send/recv over NVLink, received into one slab per source rank")
+
+
+def gather_buffers(buffers: Sequence, dst: int = 0, packed: bool | None = None):
+    """Variable-size gather of byte buffers (1-D uint8 tensors, one list per rank) onto rank `dst`.
+
+    Sizes travel in one all_gather; the payloads as ONE group of point-to-point operations
+    (ncclGroupStart/End through batch_isend_irecv), so NCCL runs them concurrently on all its channels instead
+    of serialising one kernel per buffer; the receiver lands every source rank's buffers in one slab (one
+    allocation per source, 256-byte aligned pieces).  packed=True first concatenates a rank's buffers on the
+    sender (one extra HBM pass, one message per rank).  Returns on dst a list (per source rank) of lists of
+    tensors; elsewhere None."""
+    import os
+
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
+    if packed is None:
+        packed = os.environ.get("CHDB_GATHER_PACKED", "0") == "1"
     dev = buffers[0].device if buffers else torch.device("cpu")
     sizes = torch.tensor([int(b.numel()) for b in buffers], dtype=torch.int64, device=dev)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
+    up = lambda n: (n + 255) // 256 * 256  # noqa: E731
+    ops, out = [], None
     if rank == dst:
-        out, reqs = [], []
+        out = []
         for src in range(world):
             if src == dst:
                 out.append(list(buffers))
                 continue
-            bufs = [torch.empty(int(n), dtype=torch.uint8, device=dev) for n in all_sizes[src].tolist()]
-            for b in bufs:
-                if b.numel():
-                    reqs.append(dist.irecv(b, src=src))
-            out.append(bufs)
-        for r in reqs:
+            ns = [int(n) for n in all_sizes[src].tolist()]
+            if packed:
+                slab = torch.empty(sum(ns), dtype=torch.uint8, device=dev)
+                views, at = [], 0
+                for n in ns:
+                    views.append(slab[at:at + n])
+                    at += n
+                if slab.numel():
+                    ops.append(dist.P2POp(dist.irecv, slab, src))
+            else:
+                slab = torch.empty(sum(up(n) for n in ns), dtype=torch.uint8, device=dev)
+                views, at = [], 0
+                for n in ns:
+                    v = slab[at:at + n]
+                    views.append(v)
+                    at += up(n)
+                    if n:
+                        ops.append(dist.P2POp(dist.irecv, v, src))
+            out.append(views)
+    elif packed:
+        nonempty = [b for b in buffers if b.numel()]
+        if nonempty:
+            ops.append(dist.P2POp(dist.isend, torch.cat(nonempty), dst))
+    else:
+        ops = [dist.P2POp(dist.isend, b, dst) for b in buffers if b.numel()]
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
             r.wait()
-        return out
-    reqs = [dist.isend(b, dst=dst) for b in buffers if b.numel()]
-    for r in reqs:
-        r.wait()
-    return None
+    return out
+
+
+def gather_batches(batches: Sequence, dst: int = 0):
+    """The materialize-side gather: every buffer of every result DeviceBatch of every rank onto rank `dst`."""
+    bufs = [t for b in batches for t in device_batch_buffers(b)]
+    return gather_buffers(bufs, dst=dst)
+
+
+def gathered_bytes(got) -> int:
+    """Bytes rank `dst` received from the other ranks (its own buffers are not counted)."""
+    import torch.distributed as dist
+    if got is None:
+        return 0
+    rank = dist.get_rank()
+    return sum(int(t.numel()) for src, bufs in enumerate(got) if src != rank for t in bufs)
 
 
 class _CudaView:

@@ -237,7 +237,30 @@ int32_t chdb_download(chdb_ctx* ctx, const chdb_device_batch* b, struct ArrowArr
  * ctx's stream, ordered after the source ctx's stream; the source may be released right after the call. */
 int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_batch* src,
                        chdb_device_batch** out, chdb_status* st);
+/* Batch handles are reference counted: a new handle starts at 1, _retain adds a reference, _release drops one
+ * (the buffers go back to the ctx's block cache with the last one). */
+void chdb_device_batch_retain(chdb_device_batch* b);
 void chdb_device_batch_release(chdb_device_batch* b);
+
+/* ---- device-resident record pool: the GPU-aware exchange's RecordPool ----
+ * The reference's exchange keeps `records: HashMap<u64, Arc<RecordBatch>>` with a per-consumer-operator queue
+ * and drops a record once every consumer operator has completed it (exchange_operator.rs:566-777, :727-733);
+ * memory management of that pool is a listed TODO (DEV_NOTES.md:133-140).  This is that pool for device batches:
+ * records are held by reference, handed out by reference, and -- beyond `budget_bytes` of HBM held -- spilled to
+ * pinned host memory, least recently used first (records a consumer currently holds are never spilled); a spilled
+ * record is uploaded again by _get.  budget_bytes <= 0: no limit.  Thread-safe. */
+typedef struct chdb_record_pool chdb_record_pool;
+int32_t chdb_record_pool_create(chdb_ctx* ctx, int64_t budget_bytes, chdb_record_pool** out, chdb_status* st);
+void chdb_record_pool_destroy(chdb_record_pool* pool);
+/* add_record (exchange_operator.rs:596-619): the pool takes its own reference; `consumers` = consumer operators. */
+int32_t chdb_record_pool_add(chdb_record_pool* pool, uint64_t record_id, chdb_device_batch* batch, int32_t consumers,
+                             chdb_status* st);
+/* get_next_record (:621-667): a new reference to the record's device batch (caller releases it). */
+int32_t chdb_record_pool_get(chdb_record_pool* pool, uint64_t record_id, chdb_device_batch** out, chdb_status* st);
+/* operator completed the record (:727-733): the record is dropped after the last consumer. */
+int32_t chdb_record_pool_complete(chdb_record_pool* pool, uint64_t record_id, chdb_status* st);
+void chdb_record_pool_stats(chdb_record_pool* pool, int64_t* records, int64_t* device_bytes, int64_t* spilled_records,
+                            int64_t* spilled_bytes);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,8 @@
-//! Raw bindings of include/chdb_gpu.h (only what the filter / materialize tasks need).
+//! Raw bindings of include/chdb_gpu.h -- every function the header declares, in header order.
+//! SOURCE ONLY (no Rust toolchain in the build image); tests/test_library_cpu.py checks that the
+//! names declared here are exported by libchdb_gpu.so with the header's signatures.
 use arrow::ffi::{FFI_ArrowArray, FFI_ArrowSchema};
-use std::os::raw::c_char;
+use std::os::raw::{c_char, c_void};
 
 #[repr(C)]
 pub struct ChdbStatus {
@@ -8,19 +10,37 @@ pub struct ChdbStatus {
     pub message: [c_char; 508],
 }
 
-#[repr(C)]
-pub struct ChdbCtx {
-    _private: [u8; 0],
+macro_rules! opaque {
+    ($name:ident) => {
+        #[repr(C)]
+        pub struct $name {
+            _private: [u8; 0],
+        }
+    };
 }
-#[repr(C)]
-pub struct ChdbProgram {
-    _private: [u8; 0],
-}
+opaque!(ChdbCtx);
+opaque!(ChdbProgram);
+opaque!(ChdbDeviceBatch);
+opaque!(ChdbPending);
+opaque!(ChdbRecordPool);
 
 extern "C" {
+    // ---- status ----
     pub fn chdb_code_name(code: i32) -> *const c_char;
+    pub fn chdb_version() -> *const c_char;
+    pub fn chdb_compiled_arch() -> *const c_char;
+
+    // ---- context: one per operator instance (one GPU, one stream) ----
     pub fn chdb_ctx_create(device: i32, out: *mut *mut ChdbCtx, st: *mut ChdbStatus) -> i32;
     pub fn chdb_ctx_destroy(ctx: *mut ChdbCtx);
+    pub fn chdb_ctx_stream(ctx: *mut ChdbCtx) -> *mut c_void;
+    pub fn chdb_ctx_device(ctx: *mut ChdbCtx) -> i32;
+    pub fn chdb_ctx_synchronize(ctx: *mut ChdbCtx, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_ctx_launch_count(ctx: *mut ChdbCtx) -> i64;
+    pub fn chdb_ctx_jit_launch_count(ctx: *mut ChdbCtx) -> i64;
+    pub fn chdb_jit_available(why: *mut c_char, cap: usize) -> i32;
+
+    // ---- programs ----
     pub fn chdb_program_compile_filter(
         expr_json: *const c_char,
         in_schema: *const FFI_ArrowSchema,
@@ -35,7 +55,27 @@ extern "C" {
         out: *mut *mut ChdbProgram,
         st: *mut ChdbStatus,
     ) -> i32;
+    pub fn chdb_program_compile_filter_project(
+        expr_json: *const c_char,
+        select_items_json: *const c_char,
+        in_schema: *const FFI_ArrowSchema,
+        table_aliases_json: *const c_char,
+        out: *mut *mut ChdbProgram,
+        st: *mut ChdbStatus,
+    ) -> i32;
     pub fn chdb_program_release(prog: *mut ChdbProgram);
+    pub fn chdb_program_disassemble(prog: *const ChdbProgram, buf: *mut c_char, cap: usize) -> usize;
+    pub fn chdb_program_num_instructions(prog: *const ChdbProgram) -> i32;
+    pub fn chdb_program_jit_source(prog: *const ChdbProgram, buf: *mut c_char, cap: usize) -> usize;
+    pub fn chdb_program_jit_check(
+        prog: *const ChdbProgram,
+        cubin_bytes: *mut i64,
+        log: *mut c_char,
+        cap: usize,
+        st: *mut ChdbStatus,
+    ) -> i32;
+
+    // ---- host batches: the reference's contract ----
     pub fn chdb_filter_record(
         ctx: *mut ChdbCtx,
         prog: *const ChdbProgram,
@@ -54,4 +94,151 @@ extern "C" {
         out_schema: *mut FFI_ArrowSchema,
         st: *mut ChdbStatus,
     ) -> i32;
+    pub fn chdb_filter_record_async(
+        ctx: *mut ChdbCtx,
+        prog: *const ChdbProgram,
+        input: *const FFI_ArrowArray,
+        in_schema: *const FFI_ArrowSchema,
+        out: *mut *mut ChdbPending,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_project_record_async(
+        ctx: *mut ChdbCtx,
+        prog: *const ChdbProgram,
+        input: *const FFI_ArrowArray,
+        in_schema: *const FFI_ArrowSchema,
+        out: *mut *mut ChdbPending,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_poll(pending: *mut ChdbPending, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_pending_result(
+        pending: *mut ChdbPending,
+        out: *mut FFI_ArrowArray,
+        out_schema: *mut FFI_ArrowSchema,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_pending_release(pending: *mut ChdbPending);
+    pub fn chdb_filter_record_expr(
+        ctx: *mut ChdbCtx,
+        input: *const FFI_ArrowArray,
+        in_schema: *const FFI_ArrowSchema,
+        table_aliases_json: *const c_char,
+        expr_json: *const c_char,
+        out: *mut FFI_ArrowArray,
+        out_schema: *mut FFI_ArrowSchema,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_project_record_items(
+        ctx: *mut ChdbCtx,
+        select_items_json: *const c_char,
+        input: *const FFI_ArrowArray,
+        in_schema: *const FFI_ArrowSchema,
+        table_aliases_json: *const c_char,
+        out: *mut FFI_ArrowArray,
+        out_schema: *mut FFI_ArrowSchema,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_compute_value(
+        ctx: *mut ChdbCtx,
+        input: *const FFI_ArrowArray,
+        in_schema: *const FFI_ArrowSchema,
+        table_aliases_json: *const c_char,
+        expr_json: *const c_char,
+        out: *mut FFI_ArrowArray,
+        out_schema: *mut FFI_ArrowSchema,
+        is_scalar: *mut i32,
+        st: *mut ChdbStatus,
+    ) -> i32;
+
+    // ---- device-resident batches ----
+    pub fn chdb_upload(
+        ctx: *mut ChdbCtx,
+        input: *const FFI_ArrowArray,
+        in_schema: *const FFI_ArrowSchema,
+        out: *mut *mut ChdbDeviceBatch,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_device_batch_wrap(
+        ctx: *mut ChdbCtx,
+        schema: *const FFI_ArrowSchema,
+        num_rows: i64,
+        values: *const *const c_void,
+        validity: *const *const c_void,
+        offsets: *const *const c_void,
+        out: *mut *mut ChdbDeviceBatch,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_run_device(
+        ctx: *mut ChdbCtx,
+        prog: *const ChdbProgram,
+        input: *const ChdbDeviceBatch,
+        out: *mut *mut ChdbDeviceBatch,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_run_device_many(
+        ctx: *mut ChdbCtx,
+        prog: *const ChdbProgram,
+        input: *const *const ChdbDeviceBatch,
+        count: i32,
+        out: *mut *mut ChdbDeviceBatch,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_device_batch_ready(ctx: *mut ChdbCtx, b: *const ChdbDeviceBatch, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_device_batch_status(ctx: *mut ChdbCtx, b: *const ChdbDeviceBatch, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_device_batch_num_rows(ctx: *mut ChdbCtx, b: *const ChdbDeviceBatch, st: *mut ChdbStatus) -> i64;
+    pub fn chdb_device_batch_num_columns(b: *const ChdbDeviceBatch) -> i32;
+    pub fn chdb_device_batch_column(
+        ctx: *mut ChdbCtx,
+        b: *const ChdbDeviceBatch,
+        col: i32,
+        values: *mut *const c_void,
+        values_bytes: *mut i64,
+        validity: *mut *const c_void,
+        validity_bytes: *mut i64,
+        offsets: *mut *const c_void,
+        offsets_bytes: *mut i64,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_device_batch_nbytes(ctx: *mut ChdbCtx, b: *const ChdbDeviceBatch, st: *mut ChdbStatus) -> i64;
+    pub fn chdb_download(
+        ctx: *mut ChdbCtx,
+        b: *const ChdbDeviceBatch,
+        out: *mut FFI_ArrowArray,
+        out_schema: *mut FFI_ArrowSchema,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_peer_copy(
+        dst_ctx: *mut ChdbCtx,
+        src_ctx: *mut ChdbCtx,
+        src: *const ChdbDeviceBatch,
+        out: *mut *mut ChdbDeviceBatch,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_device_batch_retain(b: *mut ChdbDeviceBatch);
+    pub fn chdb_device_batch_release(b: *mut ChdbDeviceBatch);
+
+    // ---- device-resident record pool (what a GPU-aware exchange keeps instead of Arc<RecordBatch>) ----
+    pub fn chdb_record_pool_create(ctx: *mut ChdbCtx, budget_bytes: i64, out: *mut *mut ChdbRecordPool, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_record_pool_destroy(pool: *mut ChdbRecordPool);
+    pub fn chdb_record_pool_add(
+        pool: *mut ChdbRecordPool,
+        record_id: u64,
+        batch: *mut ChdbDeviceBatch,
+        consumers: i32,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_record_pool_get(
+        pool: *mut ChdbRecordPool,
+        record_id: u64,
+        out: *mut *mut ChdbDeviceBatch,
+        st: *mut ChdbStatus,
+    ) -> i32;
+    pub fn chdb_record_pool_complete(pool: *mut ChdbRecordPool, record_id: u64, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_record_pool_stats(
+        pool: *mut ChdbRecordPool,
+        records: *mut i64,
+        device_bytes: *mut i64,
+        spilled_records: *mut i64,
+        spilled_bytes: *mut i64,
+    );
 }
