@@ -1,15 +1,22 @@
-// Filter / projection / compaction on sm_100a: one fused single-pass kernel per batch (or per group of batches).
+// Filter / projection / compaction on sm_100a: one fused single-pass kernel per batch.
 //
-// Persistent CTAs stream the batch through a ring of shared-memory stages: a producer warp brings each
-// 1024-row tile's slice of every column the program touches in with TMA bulk copies; compute warps
-// evaluate the predicate bytecode on their slices (accumulator in registers, 128-bit shared-memory loads;
-// compute_value.rs), keep the selection bits in registers and post the slice counts; a scan warp publishes the
-// tile's aggregate and obtains the tile's batch-wide exclusive prefix by decoupled look-back over its
-// predecessors' descriptors -- one tile period before the compute warps need it; the compute warps then write
-// the selected rows of their slices straight to their final positions (neighbouring lanes hit neighbouring
-// addresses); validity / Boolean bits are assembled per warp in shared memory and written as words; Utf8
-// offsets restart at 0; projection expressions are evaluated under the selection mask, so checked-integer
-// errors are raised for surviving rows only (filter_record.rs:37, record_projection.rs).
+// A CTA owns one tile of 1024 rows.  Warp 0 brings the tile's slice of every column the program touches
+// into shared memory with TMA bulk copies; every warp then evaluates the predicate bytecode on its
+// slices (accumulator in registers, 128-bit shared-memory loads; compute_value.rs), keeps the
+// selection bits in registers and posts the slice counts; one warp per scanned quantity (selected
+// rows, selected value bytes per Utf8 output) publishes the tile's aggregate and obtains the tile's
+// batch-wide exclusive prefix by decoupled look-back over its predecessors' descriptors; finally every
+// warp writes the selected rows of its slices straight to their final positions (neighbouring lanes
+// hit neighbouring addresses); validity / Boolean bits are assembled per warp in shared memory and
+// written as words; Utf8 offsets restart at 0; projection expressions are evaluated under the
+// selection mask, so checked-integer errors are raised for surviving rows only
+// (filter_record.rs:37, record_projection.rs).
+//
+// Every input byte is read from HBM once and every output byte written once.  Latency (the tile's
+// loads, the look-back's L2 round trips) is hidden the way GPUs hide latency: by 5-6 other tiles
+// resident on the same SM, each in a different phase.  (Round 1 ran one persistent CTA per SM, first
+// with a per-tile look-back on its critical path -- 29 % of HBM peak -- then as three kernels with a
+// second read of the predicate columns -- 45 %.)
 //
 // Accumulator convention: for 8/16/32-bit integers and Float32 only the low 32 bits of the
 // container are meaningful (integers sign-/zero-extended to 32 bits); 64-bit types use all of it.
@@ -66,14 +73,14 @@ template <> struct Cont<uint64_t> { static constexpr bool k64 = true; };
 // ------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void report_error(uint64_t* errw, uint32_t order, int64_t row, uint32_t code) {
+__device__ __noinline__ void report_error(const KernelParams& P, uint32_t order, int64_t row, uint32_t code) {
   unsigned long long packed = ((unsigned long long)order << 56) | (((unsigned long long)row & 0xFFFFFFFFFFFFull) << 8) | code;
-  atomicMax((unsigned long long*)errw, ~packed);
+  atomicMax((unsigned long long*)P.b.error_word, ~packed);
 }
 
 // bad / divz: per-thread row masks of failing rows (already restricted to evaluated rows)
 template <int QPT>
-__device__ __forceinline__ void report_rows(uint64_t* errw, const Instr& in, uint32_t ovf, uint32_t divz,
+__device__ __forceinline__ void report_rows(const KernelParams& P, const Instr& in, uint32_t ovf, uint32_t divz,
                                             const int64_t (&qbase)[QPT]) {
   const uint32_t any = ovf | divz;
   if (any) {
@@ -82,7 +89,7 @@ __device__ __forceinline__ void report_rows(uint64_t* errw, const Instr& in, uin
 #pragma unroll
     for (int q = 1; q < QPT; q++)
       if ((j >> 2) == q) row = qbase[q];   // static indexing keeps qbase in registers
-    report_error(errw, in.order, row + (j & 3), ((divz >> j) & 1u) ? kErrDivideByZero : kErrArithmeticOverflow);
+    report_error(P, in.order, row + (j & 3), ((divz >> j) & 1u) ? kErrDivideByZero : kErrArithmeticOverflow);
   }
 }
 
@@ -329,7 +336,7 @@ __device__ __noinline__ Slow32 slow_narrow(uint32_t op, int32_t x32, int32_t y32
 // IMM: the operand is the instruction's immediate (uniform); SWAP: operand is the LEFT side.
 // Rows that are null or filtered out may hold anything afterwards: arrow leaves them unobservable.
 template <bool IMM, bool SWAP, typename V, int QPT>
-__device__ __forceinline__ void arith(uint64_t* errw, const Instr& in, V (&a)[4 * QPT], uint32_t& av, const V (&b)[4 * QPT],
+__device__ __forceinline__ void arith(const KernelParams& P, const Instr& in, V (&a)[4 * QPT], uint32_t& av, const V (&b)[4 * QPT],
                                       uint32_t bv, uint32_t active, const int64_t (&qbase)[QPT]) {
   constexpr int R = 4 * QPT;
   const uint8_t op = in.op, t = in.type;
@@ -472,7 +479,7 @@ __device__ __forceinline__ void arith(uint64_t* errw, const Instr& in, V (&a)[4 
 #undef CHDB_B
 #undef CHDB_X
 #undef CHDB_Y
-  report_rows<QPT>(errw, in, ovf & m, divz & m, qbase);
+  report_rows<QPT>(P, in, ovf & m, divz & m, qbase);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -637,7 +644,7 @@ __device__ __forceinline__ void fetch_operand(const KernelParams& P, const Colum
 // Executes one instruction on the accumulator.  `in` is a run-time value in the generic kernel and
 // a compile-time constant under CHDB_JIT (everything below then folds to the one handler).
 template <typename V, int QI>
-__device__ __forceinline__ void exec_instr(const KernelParams& P, uint64_t* errw, const ColumnDesc* cols, const Instr in, const int64_t (&qbase)[QI], uint32_t inrange,
+__device__ __forceinline__ void exec_instr(const KernelParams& P, const ColumnDesc* cols, const Instr in, const int64_t (&qbase)[QI], uint32_t inrange,
                                            uint32_t active, const uint8_t* s_pool, Spill<V, QI>& stk, V (&acc)[4 * QI],
                                            uint32_t& accm, uint32_t& accv) {
   constexpr int R = 4 * QI;
@@ -656,14 +663,14 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, uint64_t* errw
     case OP_CAST: cast_vals<V, R>(acc, in.from_type, in.type); break;
     case OP_ADD: case OP_MUL: case OP_DIV: case OP_REM: case OP_SUB:
       if (imm) {
-        if (in.flags & OPF_SWAP) arith<true, true, V, QI>(errw, in, acc, accv, acc, FULL, active, qbase);
-        else arith<true, false, V, QI>(errw, in, acc, accv, acc, FULL, active, qbase);
+        if (in.flags & OPF_SWAP) arith<true, true, V, QI>(P, in, acc, accv, acc, FULL, active, qbase);
+        else arith<true, false, V, QI>(P, in, acc, accv, acc, FULL, active, qbase);
       } else {
         V b[R];
         uint32_t bm, bv;
         fetch_operand<V, QI>(P, cols, in, qbase, inrange, stk, b, bm, bv);
-        if (in.flags & OPF_SWAP) arith<false, true, V, QI>(errw, in, acc, accv, b, bv, active, qbase);
-        else arith<false, false, V, QI>(errw, in, acc, accv, b, bv, active, qbase);
+        if (in.flags & OPF_SWAP) arith<false, true, V, QI>(P, in, acc, accv, b, bv, active, qbase);
+        else arith<false, false, V, QI>(P, in, acc, accv, b, bv, active, qbase);
       }
       break;
     case OP_CMP:
@@ -714,20 +721,20 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, uint64_t* errw
 
 #ifdef CHDB_JIT
 template <typename V, int QI, int PC, int END>
-__device__ __forceinline__ void run_range(const KernelParams& P, uint64_t* errw, const ColumnDesc* cols, const int64_t (&qbase)[QI], uint32_t inrange, uint32_t active,
+__device__ __forceinline__ void run_range(const KernelParams& P, const ColumnDesc* cols, const int64_t (&qbase)[QI], uint32_t inrange, uint32_t active,
                                           const uint8_t* s_pool, Spill<V, QI>& stk, V (&acc)[4 * QI], uint32_t& accm,
                                           uint32_t& accv) {
   if constexpr (PC < END) {
     constexpr Instr in = chdb_jit::kInstrs[PC];
-    exec_instr<V, QI>(P, errw, cols, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
-    run_range<V, QI, PC + 1, END>(P, errw, cols, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    exec_instr<V, QI>(P, cols, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    run_range<V, QI, PC + 1, END>(P, cols, qbase, inrange, active, s_pool, stk, acc, accm, accv);
   }
 }
 #endif
 
 // BEGIN/END >= 0: instruction range known at compile time (CHDB_JIT); otherwise [begin, end).
 template <typename V, int QI, int BEGIN = -1, int END = -1>
-__device__ __forceinline__ void run_program(const KernelParams& P, uint64_t* errw, const ColumnDesc* cols, int begin, int end, const int64_t (&qbase)[QI], uint32_t inrange,
+__device__ __forceinline__ void run_program(const KernelParams& P, const ColumnDesc* cols, int begin, int end, const int64_t (&qbase)[QI], uint32_t inrange,
                                             uint32_t active, const uint8_t* s_pool, V (&acc)[4 * QI], uint32_t& accm,
                                             uint32_t& accv) {
   constexpr int R = 4 * QI;
@@ -738,7 +745,7 @@ __device__ __forceinline__ void run_program(const KernelParams& P, uint64_t* err
   accv = FULL;
 #ifdef CHDB_JIT
   if constexpr (BEGIN >= 0) {
-    run_range<V, QI, BEGIN, END>(P, errw, cols, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    run_range<V, QI, BEGIN, END>(P, cols, qbase, inrange, active, s_pool, stk, acc, accm, accv);
     return;
   }
 #endif
@@ -750,7 +757,7 @@ __device__ __forceinline__ void run_program(const KernelParams& P, uint64_t* err
     in.op = (uint8_t)w.x; in.type = (uint8_t)(w.x >> 8); in.src = (uint8_t)(w.x >> 16); in.flags = (uint8_t)(w.x >> 24);
     in.slot = (uint8_t)w.y; in.from_type = (uint8_t)(w.y >> 8); in.aux = (uint8_t)(w.y >> 16); in.order = (uint8_t)(w.y >> 24);
     in.imm = P.instrs[pc].imm;
-    exec_instr<V, QI>(P, errw, cols, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
+    exec_instr<V, QI>(P, cols, in, qbase, inrange, active, s_pool, stk, acc, accm, accv);
   }
 }
 
@@ -799,10 +806,10 @@ __device__ __forceinline__ uint64_t load_descriptor(const uint64_t* p) {
 }
 // Exclusive prefix of chunk `chunk`, by one full warp; the chunk's own aggregate is already public.
 // A hop reads kLookBackRows rows of 32 consecutive descriptors (lane l of row j: predecessor j * 32 + l), so one
-// load instruction touches 256 contiguous bytes: every resident CTA reads the same few hundred descriptors each
-// round, and it is the number of sectors requested from the two or three L2 slices holding them that bounds the
-// look-back (lane-major indexing -- 32 sectors per instruction -- took 3-5x longer under load).
-constexpr int kLookBackRows = 10;   // 320 predecessors per hop (a whole round of resident CTAs), all loads in flight together
+// load instruction touches 256 contiguous bytes.  Every resident CTA reads the same few hundred descriptors at
+// about the same time: what bounds a look-back under load is the number of sectors requested from the two or three
+// L2 slices holding them (lane-major indexing -- 32 sectors per instruction -- measured 3-5x slower).
+constexpr int kLookBackRows = 6;   // 192 predecessors per hop, all loads of a hop in flight together
 __device__ __forceinline__ uint64_t lookback(uint64_t* d, uint32_t chunk, uint64_t agg, int lane) {
   if (chunk == 0) return 0;
   uint64_t part = 0;   // this lane's share of the sum of everything nearer than the nearest known prefix
@@ -863,9 +870,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -876,22 +880,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
 }
-// A probe that never suspends the warp (try_wait may: it blocks up to a hardware time limit before reporting failure).
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, P1;\n"
-      "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  return done != 0;
-}
-// (try_wait suspends the warp in hardware for a while before it reports failure: the loop is not a busy poll)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) wait_timed_out("mbarrier wait", bar, parity);
+    __nanosleep(64);
+    if (++spins > (1u << 22)) wait_timed_out("mbarrier wait", bar, parity);
   }
 }
 // global -> shared bulk copy (TMA, 1-D); dst, src and bytes are multiples of 16
@@ -913,82 +906,28 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 struct TileShared {
   const uint8_t* pool;      // string literals (kernel parameter space)
   const uint8_t* pext4;     // [sel4 << 4 | bits4] -> the selected bits, packed
-  uint32_t* nulls;          // [n_out] NULLs written (this CTA, or with MANY this tile)
+  uint32_t* nulls;          // [n_out] NULLs written by this CTA
 };
 
 // ------------------------------------------------------------------------------------------
-// Loading a tile: the producer warp, lane s for input slot s, in two steps.
-//   prepare(): everything that does not need a free ring stage -- the tile's place in its batch, the lane's
-//              column descriptor and, for Utf8 values, the two offsets that bound the tile's value bytes (a global
-//              load away).  Runs one tile ahead, while the producer waits for a stage.
-//   issue():   once a stage is free: the tile's slice of every staged buffer goes into the stage with a TMA bulk
-//              copy (completion is counted in bytes on the stage's `full` mbarrier) and the column's biased
-//              pointer into the stage's column table; buffers that are used but not staged get a bulk L2 prefetch.
+// Loading the tile: warp 0, lane s for input slot s.  The tile's slice of every staged buffer goes into
+// the stage with a TMA bulk copy (completion is counted in bytes on the `full` mbarrier) and the
+// column's biased pointer into the tile's column table; buffers that are used but not staged get a
+// bulk L2 prefetch.  Utf8 value bytes start at offsets[row0]: those copies are issued in a second
+// step (the two bounds are a global load away), after the fixed-size ones are already in flight.
 // ------------------------------------------------------------------------------------------
-struct TileLoad {
-  int64_t tile, row0;
-  int32_t rows, batch;
-  ColumnDesc c;             // this lane's input column
-  uint32_t o0, o1;          // Utf8: offsets[row0], offsets[row0 + rows]
-  uint4 many0, many1;       // MANY: this lane's 16-byte units of the batch's header + output descriptors
-};
-
-template <bool MANY>
-__device__ __forceinline__ void prepare_tile(const KernelParams& P, const TilePlan& TP, uint32_t ticket, int lane, TileLoad& T) {
-  T.tile = ticket;
-  T.batch = 0;
-  int64_t num_rows = P.b.num_rows;
-  const ColumnDesc* in = P.in;
-  T.many0 = make_uint4(0, 0, 0, 0);
-  T.many1 = make_uint4(0, 0, 0, 0);
-  if (MANY) {
-    T.batch = P.many_tile_batch[ticket];
-    const uint8_t* rec = P.many + (size_t)T.batch * (size_t)P.many_stride;
-    const BatchHeader* gh = (const BatchHeader*)rec;
-    T.tile = (int64_t)ticket - gh->first_tile;
-    num_rows = gh->num_rows;
-    in = (const ColumnDesc*)(rec + sizeof(BatchHeader));
-    const uint4* s16 = (const uint4*)rec;
-    const int n_in16 = CHDB_N_IN * 2, n_hdr16 = (int)(sizeof(BatchHeader) / 16), n16 = n_hdr16 + CHDB_N_OUT * 2;
-    if (lane < n16) T.many0 = s16[lane < n_hdr16 ? lane : lane + n_in16];
-    if (lane + 32 < n16) T.many1 = s16[lane + 32 + n_in16];
-  }
-  T.row0 = T.tile * kTileRows;
-  T.rows = (int32_t)(T.row0 + kTileRows < num_rows ? kTileRows : num_rows - T.row0);
-  T.c.values = nullptr; T.c.validity = nullptr; T.c.offsets = nullptr; T.c.type = 0; T.c.width = 0;
-  T.o0 = 0;
-  T.o1 = 0;
-  if (lane < CHDB_N_IN) {
-    T.c = in[lane];
-    if (T.c.type == T_UTF8 && (TP.use[lane] & USE_VALUES)) {
-      T.o0 = (uint32_t)T.c.offsets[T.row0];
-      T.o1 = (uint32_t)T.c.offsets[T.row0 + T.rows];
-    }
-  }
-}
-
-template <bool MANY>
-__device__ __forceinline__ void issue_tile(const KernelParams& P, const TilePlan& TP, const TileLoad& T, StageCtx* sc, uint8_t* stage,
-                                           uint32_t full, int lane) {
-  ColumnDesc* cols = (ColumnDesc*)(sc + 1);
-  if (MANY) {   // the batch's header and output descriptors travel with the stage
-    uint4* dh = (uint4*)(cols + CHDB_N_IN);
-    const int n16 = (int)(sizeof(BatchHeader) / 16) + CHDB_N_OUT * 2;
-    if (lane < n16) dh[lane] = T.many0;
-    if (lane + 32 < n16) dh[lane + 32] = T.many1;
-  }
-  if (lane == 0) { sc->tile = T.tile; sc->row0 = T.row0; sc->rows = T.rows; sc->batch = T.batch; }
-  const int64_t row0 = T.row0;
-  const uint32_t tile_rows = (uint32_t)T.rows;
+__device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan& TP, ColumnDesc* cols, uint8_t* stage, uint32_t full,
+                                          uint32_t full_values, int64_t row0, uint32_t tile_rows, int lane) {
   const uint32_t ss = smem_u32(stage);
   const uint32_t bits_bytes = (((tile_rows + 7u) >> 3) + 15u) & ~15u;
   uint32_t nb[3] = {0, 0, 0}, so[3] = {0, 0, 0}, pf[3] = {0, 0, 0};   // 0: validity, 1: offsets, 2: values
   const uint8_t* src[3] = {nullptr, nullptr, nullptr};
-  uint32_t vbytes = 0;
-  const uint8_t* vsrc = nullptr;
-  uint32_t vso = 0;
+  bool utf8_values = false;
+  uint32_t cap = 0, vso = 0;
+  ColumnDesc c;
+  c.values = nullptr; c.validity = nullptr; c.offsets = nullptr; c.type = 0; c.width = 0;
   if (lane < CHDB_N_IN) {
-    const ColumnDesc& c = T.c;
+    c = P.in[lane];
     const StageSlot sl = TP.slot[lane];
     const uint32_t use = TP.use[lane];
     ColumnDesc t = c;   // this tile's view
@@ -1004,14 +943,7 @@ __device__ __forceinline__ void issue_tile(const KernelParams& P, const TilePlan
         if (sl.offsets != kNotStaged) { nb[1] = bytes; so[1] = sl.offsets; t.offsets = (const int32_t*)(stage + sl.offsets) - row0; }
         else pf[1] = bytes;
       }
-      if (use & USE_VALUES) {   // value bytes start at offsets[row0] (16-byte units around them)
-        const uint32_t cap = sl.values != kNotStaged ? sl.values_cap : 0u;
-        const uint32_t lo = T.o0 & ~15u, len = (T.o1 - lo + 15u) & ~15u;
-        vsrc = (const uint8_t*)c.values + lo;
-        vso = sl.values;
-        if (cap != 0 && len <= cap) { vbytes = len; t.values = stage + vso - lo; }
-        else if (len) tma_prefetch_l2(vsrc, len);
-      }
+      if (use & USE_VALUES) { utf8_values = true; cap = sl.values != kNotStaged ? sl.values_cap : 0u; vso = sl.values; }
     } else if (use & USE_VALUES) {
       const uint32_t w = c.width;
       const uint32_t bytes = w ? (tile_rows * w + 15u) & ~15u : bits_bytes;
@@ -1022,8 +954,11 @@ __device__ __forceinline__ void issue_tile(const KernelParams& P, const TilePlan
     }
     cols[lane] = t;
   }
-  const uint32_t tx = __reduce_add_sync(FULL, nb[0] + nb[1] + nb[2] + vbytes);
-  __syncwarp();   // the stage's tables are complete before the arrival that publishes them
+  // Utf8 bounds: in flight while the fixed-size copies are issued
+  uint32_t o0 = 0, o1 = 0;
+  if (utf8_values) { o0 = (uint32_t)c.offsets[row0]; o1 = (uint32_t)c.offsets[row0 + tile_rows]; }
+  const uint32_t tx = __reduce_add_sync(FULL, nb[0] + nb[1] + nb[2]);
+  __syncwarp();   // the column table (but for the Utf8 value pointers) is complete before the arrival that publishes it
   if (lane == 0) mbar_arrive_expect_tx(full, tx);
   __syncwarp();
 #pragma unroll
@@ -1031,7 +966,21 @@ __device__ __forceinline__ void issue_tile(const KernelParams& P, const TilePlan
     if (nb[i]) tma_load(ss + so[i], src[i], nb[i], full);
     if (pf[i]) tma_prefetch_l2(src[i], pf[i]);
   }
-  if (vbytes) tma_load(ss + vso, vsrc, vbytes, full);
+  uint32_t vbytes = 0;
+  const uint8_t* vsrc = nullptr;
+  if (utf8_values) {
+    const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
+    vsrc = (const uint8_t*)c.values + lo;
+    if (cap != 0 && len <= cap) { vbytes = len; cols[lane].values = stage + vso - lo; }
+    else if (len) tma_prefetch_l2(vsrc, len);
+  }
+  // The Utf8 value bytes (their bounds were a global load away) complete a second barrier: the predicate does not
+  // wait for them, only the stores do (and a predicate that compares strings).
+  const uint32_t tx2 = __reduce_add_sync(FULL, vbytes);
+  __syncwarp();
+  if (lane == 0) mbar_arrive_expect_tx(full_values, tx2);
+  __syncwarp();
+  if (vbytes) tma_load(ss + vso, vsrc, vbytes, full_values);
 }
 // ------------------------------------------------------------------------------------------
 // gather: writing the selected rows
@@ -1210,13 +1159,13 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const ColumnD
 // Writes output column k for this lane's rows.  BEGIN/END: the expression's instruction range when known at
 // compile time.  kb: running index of the bit-packed outputs (Boolean values, validity bitmaps) in the bit stage.
 template <typename V, int BEGIN = -1, int END = -1>
-__device__ __forceinline__ void store_output(const KernelParams& P, const OutDesc* outs, uint64_t* errw, const ColumnDesc* cols, const int k, const uint64_t meta,
+__device__ __forceinline__ void store_output(const KernelParams& P, const ColumnDesc* cols, const int k, const uint64_t meta,
                                              const LaneCtx& L, const OutRegs& R, const TileShared& sh, uint32_t* bitstage,
                                              uint32_t* ltab, int& kb) {
   const uint32_t o_kind = (uint32_t)meta & 0xFFu, o_type = (uint32_t)(meta >> 8) & 0xFFu, o_width = (uint32_t)(meta >> 16) & 0xFFu;
   const uint32_t o_slot = (uint32_t)(meta >> 24) & 0xFFu, o_begin = (uint32_t)(meta >> 32) & 0xFFu, o_end = (uint32_t)(meta >> 40) & 0xFFu;
   const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu;
-  uint8_t* const o_values = (uint8_t*)outs[k].values;
+  uint8_t* const o_values = (uint8_t*)P.out[k].values;
   const bool o_has_validity = CHDB_OUT_HAS_VALIDITY(P, k);
   const uint32_t sel = L.sel;
   const int lane = L.lane;
@@ -1229,7 +1178,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const OutDes
       const int64_t qb[1] = {L.row_base};
       V a4[4];
       // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
-      run_program<V, 1, BEGIN, END>(P, errw, cols, (int)o_begin, (int)o_end, qb, L.inrange, sel, sh.pool, a4, accm, vbits);
+      run_program<V, 1, BEGIN, END>(P, cols, (int)o_begin, (int)o_end, qb, L.inrange, sel, sh.pool, a4, accm, vbits);
       if (o_type == T_BOOL) {}
       else if (o_width == 4) store_sel<uint32_t>((uint32_t*)o_values + o, sel, (uint32_t)a4[0], (uint32_t)a4[1], (uint32_t)a4[2], (uint32_t)a4[3]);
       else if (o_width == 8) store_sel<uint64_t>((uint64_t*)o_values + o, sel, (uint64_t)a4[0], (uint64_t)a4[1], (uint64_t)a4[2], (uint64_t)a4[3]);
@@ -1246,7 +1195,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const OutDes
       // offsets: running sum of the selected lengths, restarted at 0 for the output
       const uint8_t* sv = (const uint8_t*)c.values;
       const uint64_t byte_base = L.prefix[(1 + o_utf8) * kTileSlices + L.slice];   // output byte offset of this slice's first value
-      int32_t* const o_off = outs[k].offsets;
+      int32_t* const o_off = P.out[k].offsets;
       const int32_t o5[5] = {(int32_t)R.x.x, (int32_t)R.x.y, (int32_t)R.x.z, (int32_t)R.x.w, (int32_t)R.z};
       uint32_t len[4];
 #pragma unroll
@@ -1315,12 +1264,12 @@ __device__ __forceinline__ void load_outputs_range(const KernelParams& P, const 
   }
 }
 template <typename V, int K, int N>
-__device__ __forceinline__ void store_outputs_range(const KernelParams& P, const OutDesc* outs, uint64_t* errw, const ColumnDesc* cols, const LaneCtx& L, const OutRegs (&R)[N > 0 ? N : 1],
+__device__ __forceinline__ void store_outputs_range(const KernelParams& P, const ColumnDesc* cols, const LaneCtx& L, const OutRegs (&R)[N > 0 ? N : 1],
                                                     const TileShared& sh, uint32_t* bitstage, uint32_t* ltab, int& kb) {
   if constexpr (K < N) {
     constexpr uint64_t meta = chdb_jit::kOutMeta[K];
-    store_output<V, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, outs, errw, cols, K, meta, L, R[K], sh, bitstage, ltab, kb);
-    store_outputs_range<V, K + 1, N>(P, outs, errw, cols, L, R, sh, bitstage, ltab, kb);
+    store_output<V, (int)((meta >> 32) & 0xFFu), (int)((meta >> 40) & 0xFFu)>(P, cols, K, meta, L, R[K], sh, bitstage, ltab, kb);
+    store_outputs_range<V, K + 1, N>(P, cols, L, R, sh, bitstage, ltab, kb);
   }
 }
 #endif
@@ -1328,7 +1277,7 @@ __device__ __forceinline__ void store_outputs_range(const KernelParams& P, const
 // The warp's bit stage -> global bitmaps.  Stage bit (obase & 31) + r belongs to output row obase + r;
 // whole words are stored, the (at most two) words shared with neighbouring slices are merged with
 // atomicOr (the bitmaps are zero-initialised).  The stage is left zeroed for the warp's next slice.
-__device__ __forceinline__ void flush_bits(const KernelParams& P, const OutDesc* outs, uint32_t* bitstage, uint64_t obase, uint32_t count, int lane) {
+__device__ __forceinline__ void flush_bits(const KernelParams& P, uint32_t* bitstage, uint64_t obase, uint32_t count, int lane) {
   const uint32_t o = (uint32_t)obase & 31u, end = o + count;
   const uint32_t nwords = (end + 31u) >> 5;
   const uint64_t g0 = obase >> 5;
@@ -1337,12 +1286,12 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, const OutDesc*
   for (int k = 0; k < CHDB_N_OUT; k++) {
     const uint64_t meta = CHDB_OUT_META(P, k);
     const bool is_bool = ((uint32_t)(meta >> 8) & 0xFFu) == T_BOOL;
-    uint8_t* const validity = outs[k].validity;
+    uint8_t* const validity = P.out[k].validity;
 #pragma unroll
     for (int which = 0; which < 2; which++) {   // 0: Boolean values, 1: validity
       if (which == 0 ? !is_bool : !CHDB_OUT_HAS_VALIDITY(P, k)) continue;
       uint32_t* sb = bitstage + kb * kBitWords;
-      uint32_t* g = (uint32_t*)(which == 0 ? (uint8_t*)outs[k].values : validity);
+      uint32_t* g = (uint32_t*)(which == 0 ? (uint8_t*)P.out[k].values : validity);
       if (lane < kBitWords) {
         const uint32_t w = (uint32_t)lane;
         uint32_t word = sb[w];
@@ -1363,98 +1312,66 @@ __device__ __forceinline__ void flush_bits(const KernelParams& P, const OutDesc*
 
 
 // ------------------------------------------------------------------------------------------
-// The stream kernel: persistent CTAs (TP.ctas_per_sm per SM), each a software pipeline over the tiles it
-// draws from a ticket counter (tickets, not a static assignment: only running CTAs hold tiles, so a look-back
-// never waits for a CTA that is not resident).
-//   producer warp : ticket -> the tile's slice of every column the program touches into the next free ring
-//                   stage (TMA bulk copies, `full` mbarrier); runs up to `stages - 2` tiles ahead;
-//   compute warps : warp w owns slice w of every tile.  Iteration i: A(i) -- evaluate the predicate on the slice,
-//                   selection bits and ranks stay in registers, slice counts go to shared memory -- then B(i-1) --
-//                   write the selected rows of tile i-1 to their final positions.  The prefix B(i-1) needs was
-//                   requested one whole tile period earlier, so the look-back's L2 round trips are off the
-//                   critical path (round 1: 29 % of HBM peak with the look-back on it, 45 % as three kernels);
-//   scan warp     : per tile, once all slices are counted: tile aggregate -> descriptor, decoupled look-back over
-//                   the predecessors' descriptors, per-slice exclusive prefixes -> shared memory.
-// Without a predicate (plain projection) every row is kept: no scan, B(i) follows the load directly.
-// MANY: one launch over several batches of one schema: a tile's batch-dependent parameters (buffers, counts)
-// travel with its ring stage.
-// Every input byte is read from HBM once and every output byte written once.
+// The stream kernel: one CTA per tile of kTileRows rows.
+//   1. warp 0 brings the tile's slice of every column the program touches into shared memory (TMA);
+//   2. every warp evaluates the predicate on its slices: selection bits and ranks stay in registers, the
+//      slice counts (selected rows; selected value bytes per Utf8 output) go to shared memory;
+//   3. warp q turns quantity q's slice counts into batch-wide exclusive prefixes: it publishes the tile's
+//      aggregate and walks back over its predecessors' descriptors (decoupled look-back) -- the other
+//      resident CTAs of the SM keep the memory system busy meanwhile;
+//   4. every warp writes the selected rows of its slices to their final positions.
+// Without a predicate steps 2-3 fall away (every row is kept, output row = input row).
+// MANY: one launch over several batches of one schema: the CTA first fetches its batch's record.
 // ------------------------------------------------------------------------------------------
-// Pipeline waits.  try_wait itself suspends the warp for a hardware-chosen time; roles that wait long (producer, scan)
-// back off a little more so that their polling does not take issue slots from the compute warps.
-#ifndef CHDB_COMPUTE_SLEEP
-#define CHDB_COMPUTE_SLEEP 0
-#endif
-#ifndef CHDB_IDLE_SLEEP
-#define CHDB_IDLE_SLEEP 20
-#endif
-#ifndef CHDB_SCAN_SLEEP
-#define CHDB_SCAN_SLEEP 20
-#endif
-#ifndef CHDB_PRODUCER_SLEEP
-#define CHDB_PRODUCER_SLEEP 40
-#endif
-template <int SLEEP>
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (SLEEP > 0) __nanosleep(SLEEP);
-    if (++spins > (1u << 24)) wait_timed_out("mbarrier wait", bar, parity);
-  }
-}
-
-__device__ __forceinline__ uint64_t warp_excl_scan64(uint64_t v, int lane, uint64_t& total) {
-  uint64_t x = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint64_t y = __shfl_up_sync(FULL, x, d);
-    if (lane >= d) x += y;
-  }
-  total = __shfl_sync(FULL, x, 31);
-  return x - v;
-}
-
-// CHDB_TRACE: events 0 stage free, 1 loads issued (producer); 2 tile landed, 3 A done, 4 prefix there, 5 B done
-// (compute warp 0); 6 slices counted, 7 look-back done (scan warp).
-__device__ __forceinline__ void trace_event(const KernelParams& P, int it, int ev, int lane) {
-  if (P.trace != nullptr && lane == 0 && it < kTraceIters)
-    P.trace[((size_t)blockIdx.x * kTraceIters + (size_t)it) * 8 + ev] = (uint64_t)clock64();
+// CHDB_TRACE: per tile, clock64() at: 0 CTA ready to load, 1 tile landed, 2 predicate done, 3 look-back done (warp 0),
+// 4 Utf8 values landed, 5 rows stored, 6 CTA done; slot 7: the SM the CTA ran on.
+__device__ __forceinline__ void trace_event(const KernelParams& P, int ev) {
+  if (P.trace != nullptr && blockIdx.x < 8192) P.trace[(size_t)blockIdx.x * 8 + ev] = (uint64_t)clock64();
 }
 
 template <typename V, bool MANY>
-__device__ __forceinline__ void stream_body(const KernelParams& P, const TilePlan& TP) {
+__device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePlan& TP) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_bars[4 * kMaxStages];   // full, empty, counted, prefix: one of each per ring stage
-  __shared__ uint64_t s_tot[kMaxQuantities];
-  __shared__ uint32_t s_arrived[kMaxStages];   // compute warps that have counted their slice of the stage's tile
+  __shared__ __align__(8) uint64_t s_full, s_full_values;
+  __shared__ uint32_t s_nulls[kMaxOutCols];
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int S = (int)TP.stages;
+  int64_t tile = blockIdx.x;
+  if (MANY) {
+    // this tile's parameter block: the program part from the launch parameters, the batch part from its record
+    KernelParams* mine = (KernelParams*)(smem + TP.params_off);
+    const int32_t k = PP.many_tile_batch[blockIdx.x];   // (one entry per tile: the batch it belongs to)
+    const uint8_t* rec = PP.many + (size_t)k * (size_t)PP.many_stride;
+    uint32_t* d32 = (uint32_t*)mine;
+    const uint32_t* s32 = (const uint32_t*)&PP;
+    for (int i = tid; i < (int)(sizeof(KernelParams) / 4); i += kThreads) d32[i] = s32[i];
+    __syncthreads();
+    const int n_in = PP.n_in, n_out = PP.n_out;
+    const uint32_t* r32 = (const uint32_t*)rec;
+    uint32_t* hb = (uint32_t*)&mine->b;
+    for (int i = tid; i < (int)(sizeof(BatchHeader) / 4); i += kThreads) hb[i] = r32[i];
+    uint32_t* hi = (uint32_t*)mine->in;
+    for (int i = tid; i < n_in * 8; i += kThreads) hi[i] = r32[sizeof(BatchHeader) / 4 + i];
+    uint32_t* ho = (uint32_t*)mine->out;
+    for (int i = tid; i < n_out * 8; i += kThreads) ho[i] = r32[sizeof(BatchHeader) / 4 + n_in * 8 + i];
+    __syncthreads();
+    tile -= mine->b.first_tile;
+  }
+  const KernelParams& P = MANY ? *(const KernelParams*)(smem + TP.params_off) : PP;
   const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
   const int nq = 1 + CHDB_N_UTF8;
+  uint8_t* const stage = smem;
+  ColumnDesc* const cols = (ColumnDesc*)(smem + TP.cols_off);
   uint32_t* const s_cnt = (uint32_t*)(smem + TP.cnt_off);
   uint64_t* const s_pre = (uint64_t*)(smem + TP.pre_off);
-  uint32_t* const s_nulls = (uint32_t*)(smem + TP.nulls_off);
+  uint64_t* const s_tot = (uint64_t*)(smem + TP.tot_off);
   uint32_t* const bitstages = (uint32_t*)(smem + TP.bits_off);
   uint32_t* const ltab = (uint32_t*)(smem + TP.ltab_off);
   uint8_t* const pext4 = smem + TP.pext_off;
-  const uint32_t bar0 = smem_u32(s_bars);
-#define CHDB_FULL(st) (bar0 + 8u * (uint32_t)(st))
-#define CHDB_EMPTY(st) (bar0 + 8u * (uint32_t)(kMaxStages + (st)))
-#define CHDB_COUNTED(st) (bar0 + 8u * (uint32_t)(2 * kMaxStages + (st)))
-#define CHDB_PREFIX(st) (bar0 + 8u * (uint32_t)(3 * kMaxStages + (st)))
-#define CHDB_SCTX(st) ((StageCtx*)(smem + TP.sctx_off + (uint32_t)(st) * TP.sctx_stride))
-#define CHDB_COLS(st) ((ColumnDesc*)(CHDB_SCTX(st) + 1))
-#define CHDB_HDR(st) ((BatchHeader*)(CHDB_COLS(st) + CHDB_N_IN))
-#define CHDB_OUTS(st) ((OutDesc*)(CHDB_HDR(st) + 1))
+  const uint32_t full = smem_u32(&s_full), full_values = smem_u32(&s_full_values);
   if (tid == 0) {
-    for (int s = 0; s < S; s++) {
-      s_arrived[s] = 0;
-      mbar_init(CHDB_FULL(s), 1);
-      mbar_init(CHDB_EMPTY(s), kComputeWarps);
-      mbar_init(CHDB_COUNTED(s), kComputeWarps);
-      mbar_init(CHDB_PREFIX(s), 1);
-    }
+    mbar_init(full, 1);
+    mbar_init(full_values, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -1466,318 +1383,176 @@ __device__ __forceinline__ void stream_body(const KernelParams& P, const TilePla
         if ((s >> j) & 1u) { out |= ((v >> j) & 1u) << n; n++; }
       pext4[i] = (uint8_t)out;
     }
-    for (int i = tid; i < kComputeWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
+    for (int i = tid; i < kWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
   }
-  for (int i = tid; i < (MANY ? S : 1) * kMaxOutCols; i += kThreads) s_nulls[i] = 0;
+  if (tid < kMaxOutCols) s_nulls[tid] = 0;
+  const int64_t row0 = tile * kTileRows;
+  const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.b.num_rows ? kTileRows : P.b.num_rows - row0);
+  const bool last_tile = tile == (int64_t)P.b.num_tiles - 1;
   __syncthreads();
   grid_launch_dependents();
   grid_dependency_wait();     // the zeroed workspace; inputs an earlier kernel on this stream may still be writing
+  if (tid == 0) {
+    trace_event(P, 0);
+    if (P.trace != nullptr && blockIdx.x < 8192) { uint32_t smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); P.trace[(size_t)blockIdx.x * 8 + 7] = smid; }
+  }
+  if (warp == 0) load_tile(P, TP, cols, stage, full, full_values, row0, (uint32_t)tile_rows, lane);
+  mbar_wait(full, 0);
+  if (TP.pred_reads_utf8) mbar_wait(full_values, 0);
+  if (tid == 0) trace_event(P, 1);
 
-  if (warp == kProducerWarp) {
-    // ================= producer: tickets and TMA loads =================
-    uint32_t ticket = 0;
-    if (lane == 0) ticket = atomicAdd(P.tickets, 1u);
-    ticket = __shfl_sync(FULL, ticket, 0);
-    TileLoad T;
-    if (ticket < (uint32_t)P.total_tiles) prepare_tile<MANY>(P, TP, ticket, lane, T);
-    int it = 0;
-    for (;; it++) {
-      const int st = it % S;
-      if (it >= S) {
-        mbar_wait_sleep<CHDB_PRODUCER_SLEEP>(CHDB_EMPTY(st), (uint32_t)((it / S) - 1) & 1u);
-        if (MANY) {   // the finished tile's NULL counts go to its batch before the stage changes hands
-          if (lane < CHDB_N_OUT) {
-            const uint32_t v = s_nulls[st * kMaxOutCols + lane];
-            if (v) {
-              atomicAdd((unsigned long long*)(CHDB_HDR(st)->counts + P.out[lane].count_index), (unsigned long long)v);
-              s_nulls[st * kMaxOutCols + lane] = 0;
-            }
-          }
-          __syncwarp();
-        }
-      }
-      trace_event(P, it, 0, lane);
-      StageCtx* sc = CHDB_SCTX(st);
-      if (ticket >= (uint32_t)P.total_tiles) {
-        if (lane == 0) { sc->tile = -1; mbar_arrive(CHDB_FULL(st)); }
-        break;
-      }
-      uint32_t next = 0;
-      if (lane == 0) next = atomicAdd(P.tickets, 1u);   // in flight while this tile's copies are issued
-      issue_tile<MANY>(P, TP, T, sc, smem + (size_t)st * TP.stage_bytes, CHDB_FULL(st), lane);
-      trace_event(P, it, 1, lane);
-      ticket = __shfl_sync(FULL, next, 0);
-      // the next tile's descriptors and Utf8 bounds: on their way while this warp waits for a free stage
-      if (ticket < (uint32_t)P.total_tiles) prepare_tile<MANY>(P, TP, ticket, lane, T);
-    }
-    if (MANY) {   // the tiles still in the ring when the tickets ran out
-      for (int j = it - S + 1 > 0 ? it - S + 1 : 0; j < it; j++) {
-        const int st = j % S;
-        mbar_wait_sleep<CHDB_PRODUCER_SLEEP>(CHDB_EMPTY(st), (uint32_t)(j / S) & 1u);
-        if (lane < CHDB_N_OUT) {
-          const uint32_t v = s_nulls[st * kMaxOutCols + lane];
-          if (v) atomicAdd((unsigned long long*)(CHDB_HDR(st)->counts + P.out[lane].count_index), (unsigned long long)v);
-        }
-      }
-    }
-  } else if (warp >= kScanWarp) {
-    // ================= scan: slice counts -> batch-wide exclusive prefixes =================
-    if (has_pred) {
-      const int ng = desc_groups(nq);
-      for (int it = 0;; it++) {
-        const int st = it % S;
-        mbar_wait_sleep<CHDB_SCAN_SLEEP>(CHDB_FULL(st), (uint32_t)(it / S) & 1u);
-        const StageCtx* sc = CHDB_SCTX(st);
-        const int64_t tile = sc->tile;
-        if (tile < 0) break;
-        const BatchHeader* bh = MANY ? CHDB_HDR(st) : &P.b;
-        const int32_t num_tiles = bh->num_tiles;
-        uint64_t* const desc0 = bh->desc;
-        const bool last_tile = tile == (int64_t)num_tiles - 1;
-        mbar_wait_sleep<CHDB_SCAN_SLEEP>(CHDB_COUNTED(st), (uint32_t)(it / S) & 1u);
-        // (every scan warp observes every phase of the barriers -- a parity wait is only sound then -- and takes every
-        // kScanWarps-th tile: one look-back is an L2 round trip or two, several are in flight per CTA)
-        if (it % kScanWarps != warp - kScanWarp) continue;
-        trace_event(P, it, 6, lane);
-        const uint32_t* cnt = s_cnt + st * nq * kTileSlices;
-        uint64_t* pre = s_pre + st * nq * kTileSlices;
-        for (int g = 0; g < ng; g++) {
-          const int q0 = 2 * g, q1 = 2 * g + 1;
-          uint64_t c = 0;
-          if (lane < kTileSlices) {
-            c = cnt[q0 * kTileSlices + lane];
-            if (q1 < nq) c |= (uint64_t)cnt[q1 * kTileSlices + lane] << 31;
-          }
-          uint64_t agg;
-          const uint64_t before = warp_excl_scan64(c, lane, agg);
-          uint64_t* desc = desc0 + (size_t)g * (size_t)num_tiles;   // (the tile's aggregate is already public)
-          const uint64_t excl = lookback(desc, (uint32_t)tile, agg, lane);
-          const uint64_t mine = excl + before;
-          if (lane < kTileSlices) {
-            pre[q0 * kTileSlices + lane] = mine & 0x7FFFFFFFull;
-            if (q1 < nq) pre[q1 * kTileSlices + lane] = (mine >> 31) & 0x7FFFFFFFull;
-          }
-          if (last_tile && lane == 0) {
-            const uint64_t tot = excl + agg;
-            s_tot[q0] = tot & 0x7FFFFFFFull;
-            if (q1 < nq) s_tot[q1] = (tot >> 31) & 0x7FFFFFFFull;
-          }
-        }
-        __syncwarp();
-        if (last_tile) {
-          // batch totals, and the closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
-          const OutDesc* outs = MANY ? CHDB_OUTS(st) : P.out;
-          if (lane < nq) bh->counts[lane] = s_tot[lane];
-          if (lane < CHDB_N_OUT) {
-            const OutDesc& o = outs[lane];
-            if (o.utf8_index != 0xFFu) o.offsets[s_tot[0]] = (int32_t)s_tot[1 + o.utf8_index];
-          }
-          __syncwarp();
-        }
-        trace_event(P, it, 7, lane);
-        if (lane == 0) mbar_arrive(CHDB_PREFIX(st));
-      }
-    }
-  } else {
-    // ================= compute =================
-    // Event driven: A(a) as soon as tile a has landed (so its aggregate is public as early as possible: other
-    // CTAs' look-backs wait for it), B(b) once tile b's prefix is there; A runs at most `stages` tiles ahead of B
-    // (the ring), and with nothing to store it waits for the next tile.
-    TileShared sh;
-    sh.pool = (const uint8_t*)P.strpool;
-    sh.pext4 = pext4;
-    sh.nulls = s_nulls;
-    uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
-    uint8_t* const s_sel = smem + TP.sel_off;   // [stage][warp][lane]: the lane's 4 selection bits between A and B
-    int a = 0, b = 0;       // next iteration to evaluate / to store
-    bool more = true;       // the ticket counter has not run out
-    while (true) {
-      // Neither wait blocks: while tile b's prefix is still on its way the next tile may land, and its aggregate
-      // must become public at once (every later tile's look-back needs it).
-      if (more && a - b < S && mbar_test_wait(CHDB_FULL(a % S), (uint32_t)(a / S) & 1u)) {
-        const int st = a % S;
-        {
-          if (warp == 0) trace_event(P, a, 2, lane);
-          const StageCtx* sc = CHDB_SCTX(st);
-          const int64_t tile = sc->tile;
-          if (tile < 0) { more = false; continue; }
-          if (has_pred) {
-            // ---- A(a): predicate -> selection bits, ranks, slice counts ----
-            const ColumnDesc* cols = CHDB_COLS(st);
-            uint64_t* const errw = MANY ? CHDB_HDR(st)->error_word : P.b.error_word;
-            const int32_t rows = sc->rows;
-            const int64_t qb[1] = {sc->row0 + warp * kWarpRows + lane * 4};
-            const int left = rows - (warp * kWarpRows + lane * 4);
-            const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
-            V acc[4];
-            uint32_t accm, accv;
-#ifdef CHDB_JIT
-            run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, errw, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
-#else
-            run_program<V, 1>(P, errw, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
-#endif
-            const uint32_t sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
-            const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel4));
-            s_sel[(st * kComputeWarps + warp) * 32 + lane] = (uint8_t)sel4;
-            uint32_t* cnt = s_cnt + st * nq * kTileSlices;
-            if (lane == 0) cnt[warp] = wrows;
-            // selected value bytes per Utf8 output
-            CHDB_STATIC_UNROLL
-            for (int k = 0; k < CHDB_N_OUT; k++) {
-              const uint64_t meta = CHDB_OUT_META(P, k);
-              const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
-              if (o_utf8 == 0xFFu) continue;   // uniform branch
-              const int32_t* off = cols[o_slot].offsets;
-              uint32_t bytes = 0;
-              if (sel4) {
-                const int4 o4 = *(const int4*)(off + qb[0]);
-                const int o5 = off[qb[0] + 4];
-                if (sel4 & 1u) bytes += (uint32_t)(o4.y - o4.x);
-                if (sel4 & 2u) bytes += (uint32_t)(o4.z - o4.y);
-                if (sel4 & 4u) bytes += (uint32_t)(o4.w - o4.z);
-                if (sel4 & 8u) bytes += (uint32_t)(o5 - o4.w);
-              }
-              const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
-              if (lane == 0) cnt[(1 + o_utf8) * kTileSlices + warp] = wbytes;
-            }
-            // The last warp to finish A publishes the tile's aggregate right away (the scan warp may still be busy
-            // with an earlier tile's look-back; neighbours' look-backs must not wait for it).
-            __syncwarp();
-            uint32_t arrived = 0;
-            if (lane == 0) {
-              __threadfence_block();
-              arrived = atomicAdd(&s_arrived[st], 1u);
-            }
-            arrived = __shfl_sync(FULL, arrived, 0);
-            if (arrived == kComputeWarps - 1) {
-              __threadfence_block();
-              const BatchHeader* bh = MANY ? CHDB_HDR(st) : &P.b;
-              const int ng = desc_groups(nq);
-              for (int g = lane; g < ng; g += 32) {
-                uint64_t agg = 0;
+  TileShared sh;
+  sh.pool = (const uint8_t*)P.strpool;
+  sh.pext4 = pext4;
+  sh.nulls = s_nulls;
+
+  // ---- 2. predicate -> selection bits, ranks, slice counts ----
+  uint32_t sels = 0;        // 4 selection bits per slice of this warp
+  uint32_t ranks[kSpw];     // slice-local rank of the lane's first selected row
 #pragma unroll
-                for (int w = 0; w < kTileSlices; w++) {
-                  agg += cnt[(2 * g) * kTileSlices + w];
-                  if (2 * g + 1 < nq) agg += (uint64_t)cnt[(2 * g + 1) * kTileSlices + w] << 31;
-                }
-                publish_descriptor(bh->desc + (size_t)g * (size_t)bh->num_tiles + tile, tile == 0 ? kFlagPrefix : kFlagAgg, agg);
-              }
-              if (lane == 0) s_arrived[st] = 0;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(CHDB_COUNTED(st));
-            if (warp == 0) trace_event(P, a, 3, lane);
-          }
-          a++;
-          continue;
-        }
-      }
-      if (b == a) {
-        if (!more) break;
-        __nanosleep(CHDB_IDLE_SLEEP);
-        continue;
-      }
-      if (has_pred && !mbar_test_wait(CHDB_PREFIX(b % S), (uint32_t)(b / S) & 1u)) {
-        __nanosleep(CHDB_IDLE_SLEEP);
-        continue;
-      }
-      {
-        // ---- B(b): the selected rows of tile b, to their final positions ----
-        const int pst = b % S;
-        const StageCtx* psc = CHDB_SCTX(pst);
-        const ColumnDesc* cols = CHDB_COLS(pst);
-        const OutDesc* outs = MANY ? CHDB_OUTS(pst) : P.out;
-        uint64_t* const errw = MANY ? CHDB_HDR(pst)->error_word : P.b.error_word;
-        const int32_t rows = psc->rows;
-        const int64_t row0 = psc->row0;
-        if (warp == 0) trace_event(P, b, 4, lane);
-        if (warp * kWarpRows < rows) {   // (tail tile: this warp's slice may not exist)
-          LaneCtx L;
-          L.lane = lane;
-          L.slice = warp;
-          L.wid = warp;
-          L.row_base = row0 + warp * kWarpRows + lane * 4;
-          const int left = rows - (warp * kWarpRows + lane * 4);
-          L.inrange = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
-          if (has_pred) {
-            L.sel = s_sel[(pst * kComputeWarps + warp) * 32 + lane];
-            L.rank = warp_excl_scan((uint32_t)__popc(L.sel), lane, L.count);
-            L.prefix = s_pre + pst * nq * kTileSlices;
-            L.obase = L.prefix[warp];
-          } else {
-            L.sel = L.inrange;
-            L.rank = (uint32_t)lane * 4u;
-            L.prefix = nullptr;
-            const int here = rows - warp * kWarpRows;
-            L.count = (uint32_t)(here < kWarpRows ? here : kWarpRows);
-            L.obase = (uint64_t)(row0 + warp * kWarpRows);
-          }
-          sh.nulls = s_nulls + (MANY ? pst * kMaxOutCols : 0);
-          int kb = 0;
+  for (int j = 0; j < kSpw; j++) {
+    const int slice = warp * kSpw + j;
+    const int64_t qb[1] = {row0 + slice * kWarpRows + lane * 4};
+    const int left = tile_rows - (slice * kWarpRows + lane * 4);
+    const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
+    uint32_t sel4 = in4;
+    if (has_pred) {
+      V acc[4];
+      uint32_t accm, accv;
 #ifdef CHDB_JIT
-          {
-            OutRegs R[chdb_jit::kNumOut > 0 ? chdb_jit::kNumOut : 1];
-            load_outputs_range<0, chdb_jit::kNumOut>(P, cols, L, R);
-            store_outputs_range<V, 0, chdb_jit::kNumOut>(P, outs, errw, cols, L, R, sh, bitstage, ltab, kb);
-          }
+      run_program<V, 1, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, cols, 0, 0, qb, in4, in4, sh.pool, acc, accm, accv);
+#else
+      run_program<V, 1>(P, cols, P.pred_begin, P.pred_end, qb, in4, in4, sh.pool, acc, accm, accv);
+#endif
+      sel4 = accm & accv & in4;   // NULL predicate rows are dropped (arrow-select filter)
+    }
+    uint32_t wrows;
+    ranks[j] = warp_excl_scan((uint32_t)__popc(sel4), lane, wrows);
+    sels |= sel4 << (4 * j);
+    if (lane == 0) s_cnt[slice] = wrows;
+    if (has_pred) {
+      // selected value bytes per Utf8 output
+      CHDB_STATIC_UNROLL
+      for (int k = 0; k < CHDB_N_OUT; k++) {
+        const uint64_t meta = CHDB_OUT_META(P, k);
+        const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+        if (o_utf8 == 0xFFu) continue;   // uniform branch
+        const int32_t* off = cols[o_slot].offsets;
+        uint32_t bytes = 0;
+        if (sel4) {
+          const int4 a = *(const int4*)(off + qb[0]);
+          const int a4 = off[qb[0] + 4];
+          if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
+          if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
+          if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
+          if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
+        }
+        const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+        if (lane == 0) s_cnt[(1 + o_utf8) * kTileSlices + slice] = wbytes;
+      }
+    }
+  }
+
+  // ---- 3. slice counts -> batch-wide exclusive prefixes ----
+  if (has_pred) {
+    __syncthreads();
+    if (tid == 0) trace_event(P, 2);
+    for (int q = warp; q < nq; q += kWarps) {
+      const uint32_t c = lane < kTileSlices ? s_cnt[q * kTileSlices + lane] : 0u;
+      uint32_t agg;
+      const uint32_t before = warp_excl_scan(c, lane, agg);
+      uint64_t* desc = P.b.desc + (size_t)q * (size_t)P.b.num_tiles;
+      if (lane == 0) publish_descriptor(desc + tile, tile == 0 ? kFlagPrefix : kFlagAgg, agg);
+      const uint64_t excl = lookback(desc, (uint32_t)tile, agg, lane);
+      if (lane < kTileSlices) s_pre[q * kTileSlices + lane] = excl + before;
+      if (lane == 0) s_tot[q] = excl + agg;
+      if (q == 0 && lane == 0) trace_event(P, 3);
+    }
+    __syncthreads();
+    if (last_tile) {
+      // batch totals, and the closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
+      if (tid < nq) P.b.counts[tid] = s_tot[tid];
+      if (tid < CHDB_N_OUT) {
+        const OutDesc& o = P.out[tid];
+        if (o.utf8_index != 0xFFu) o.offsets[s_tot[0]] = (int32_t)s_tot[1 + o.utf8_index];
+      }
+    }
+  }
+
+  // ---- 4. the selected rows, to their final positions ----
+  if (!TP.pred_reads_utf8) mbar_wait(full_values, 0);
+  if (tid == 0) trace_event(P, 4);
+  uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
+#pragma unroll
+  for (int j = 0; j < kSpw; j++) {
+    const int slice = warp * kSpw + j;
+    if (slice * kWarpRows >= tile_rows) break;   // (tail tile)
+    LaneCtx L;
+    L.lane = lane;
+    L.slice = slice;
+    L.wid = warp;
+    L.row_base = row0 + slice * kWarpRows + lane * 4;
+    {
+      const int left = tile_rows - (slice * kWarpRows + lane * 4);
+      L.inrange = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
+    }
+    L.sel = (sels >> (4 * j)) & 0xFu;
+    L.rank = ranks[j];
+    L.count = s_cnt[slice];
+    if (has_pred) {
+      L.prefix = s_pre;
+      L.obase = s_pre[slice];
+    } else {
+      L.prefix = nullptr;
+      L.obase = (uint64_t)(row0 + slice * kWarpRows);
+    }
+    int kb = 0;
+#ifdef CHDB_JIT
+    {
+      OutRegs R[chdb_jit::kNumOut > 0 ? chdb_jit::kNumOut : 1];
+      load_outputs_range<0, chdb_jit::kNumOut>(P, cols, L, R);
+      store_outputs_range<V, 0, chdb_jit::kNumOut>(P, cols, L, R, sh, bitstage, ltab, kb);
+    }
 #else
 #pragma unroll 1
-          for (int k = 0; k < P.n_out; k++) {
-            OutRegs R;
-            const uint64_t meta = CHDB_OUT_META(P, k);
-            load_output(P, cols, k, meta, L, R);
-            store_output<V>(P, outs, errw, cols, k, meta, L, R, sh, bitstage, ltab, kb);
-          }
+    for (int k = 0; k < P.n_out; k++) {
+      OutRegs R;
+      const uint64_t meta = CHDB_OUT_META(P, k);
+      load_output(P, cols, k, meta, L, R);
+      store_output<V>(P, cols, k, meta, L, R, sh, bitstage, ltab, kb);
+    }
 #endif
-          if (P.n_bits > 0) {
-            __syncwarp();
-            flush_bits(P, outs, bitstage, L.obase, L.count, lane);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(CHDB_EMPTY(pst));
-        if (warp == 0) trace_event(P, b, 5, lane);
-        b++;
-      }
+    if (P.n_bits > 0) {
+      __syncwarp();
+      flush_bits(P, bitstage, L.obase, L.count, lane);
+      __syncwarp();
     }
   }
 
-  // ---- null counts (one batch: accumulated over the CTA's tiles); the last CTA to finish mirrors the counts
-  //      of every batch into pinned host memory ----
+  // ---- null counts; the last CTA to finish mirrors the counts into pinned host memory (warp 0 only: the other warps
+  //      are done once their rows are stored) ----
   __syncthreads();
-  if (!MANY && tid < CHDB_N_OUT && P.out[tid].validity != nullptr && s_nulls[tid] != 0)
-    atomicAdd((unsigned long long*)(P.b.counts + P.out[tid].count_index), (unsigned long long)s_nulls[tid]);
-  __syncthreads();
-  if (tid == 0) {
+  if (tid == 0) trace_event(P, 5);
+  if (warp != 0) return;
+  if (lane < CHDB_N_OUT && P.out[lane].validity != nullptr && s_nulls[lane] != 0)
+    atomicAdd((unsigned long long*)(P.b.counts + P.out[lane].count_index), (unsigned long long)s_nulls[lane]);
+  __syncwarp();
+  uint32_t last = 0;
+  if (lane == 0) {
     __threadfence();
-    s_last = atomicAdd(P.done, 1u) == gridDim.x - 1u ? 1u : 0u;
+    last = atomicAdd(P.b.done, 1u) == (uint32_t)P.b.num_tiles - 1u ? 1u : 0u;
   }
-  __syncthreads();
-  if (s_last) {
+  last = __shfl_sync(FULL, last, 0);
+  if (last) {
     __threadfence();
-    const int per = P.n_counts + 1;
-    if (MANY) {
-      for (int i = tid; i < P.many_batches * per; i += kThreads) {
-        const BatchHeader* gh = (const BatchHeader*)(P.many + (size_t)(i / per) * (size_t)P.many_stride);
-        gh->host_counts[i % per] = __ldcg((const unsigned long long*)gh->counts + (i % per));
-      }
-    } else {
-      for (int i = tid; i < per; i += kThreads) P.b.host_counts[i] = __ldcg((const unsigned long long*)P.b.counts + i);
-    }
+    for (int i = lane; i <= P.n_counts; i += 32) P.b.host_counts[i] = __ldcg((const unsigned long long*)P.b.counts + i);
   }
-#undef CHDB_FULL
-#undef CHDB_EMPTY
-#undef CHDB_COUNTED
-#undef CHDB_PREFIX
-#undef CHDB_SCTX
-#undef CHDB_COLS
-#undef CHDB_HDR
-#undef CHDB_OUTS
+  if (tid == 0) trace_event(P, 6);
 }
 
 }  // namespace
 
-// Zeroes the workspace of one launch (look-back descriptors, counts, error word, tickets, bit-packed outputs).
+// Zeroes the workspace of one launch (look-back descriptors, counts, error word, bit-packed outputs).
 __device__ __forceinline__ void zero_body(uint4* p, size_t n16) {
   grid_launch_dependents();
   const size_t step = (size_t)gridDim.x * blockDim.x;

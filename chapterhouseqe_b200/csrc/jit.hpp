@@ -26,7 +26,7 @@ bool jit_available(std::string* why);
 std::string jit_prologue(const KernelParams& kp, bool has64, int min_blocks);
 // Cached; returns nullptr (and the reason) when specialisation is impossible -> use the interpreter.
 const JitKernel* jit_get(const KernelParams& kp, bool has64, int min_blocks, std::string* err);
-cudaError_t jit_launch_stream(const JitKernel* k, const KernelParams& p, const TilePlan& tp, int sm_count, cudaStream_t stream);
+cudaError_t jit_launch_stream(const JitKernel* k, const KernelParams& p, const TilePlan& tp, unsigned grid, cudaStream_t stream);
 void jit_stats(int64_t* compiles, double* seconds);
 std::vector<char> jit_compile_offline(const KernelParams& kp, bool has64, std::string* log);
 

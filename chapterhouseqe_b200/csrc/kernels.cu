@@ -13,7 +13,7 @@
 #include <vector>
 
 namespace chdb {
-constexpr int kMinCtasPerSm = 2;   // register budget the interpreter kernels are compiled for
+constexpr int kMinCtasPerSm = 4;   // register budget the interpreter kernels are compiled for
 }
 #include "device_code.cuh"
 
@@ -22,16 +22,16 @@ namespace chdb {
 namespace {
 constexpr size_t kSmemPerSm = 228 * 1024;        // B200: 228 KB per SM, 1 KB of it reserved per resident CTA
 constexpr size_t kSmemPerCtaMax = 227 * 1024;
-constexpr size_t kStaticSmem = 512;              // mbarriers, s_tot, s_last + what the compiler adds
+constexpr size_t kStaticSmem = 256;              // s_full, s_nulls, s_last + what the compiler adds
 inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 inline size_t up128(size_t x) { return (x + 127) & ~(size_t)127; }
 }  // namespace
 
-// Decides what is staged and how deep the ring is.  Every buffer the kernel uses is a candidate; when the tile's
-// slice of everything would not leave room for the wanted CTAs per SM with a ring of the minimum depth, the
-// largest buffers are read from global memory instead (the producer warp then prefetches their slices into L2).
-// Utf8 value bytes are staged only when the values are short (long values are copied global -> global by whole warps).
-void plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many) {
+// Decides what is staged.  Every buffer the kernel uses is a candidate; when the tile's slice of everything
+// would leave room for fewer than kWantCtas CTAs per SM, the largest buffers are read from global memory instead
+// (the loading warp then prefetches their slices into L2).  Utf8 value bytes are staged only when the values
+// are short (long values are copied global -> global by whole warps).
+int plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many) {
   struct Buf { int slot; int kind; size_t bytes; };   // kind 0: validity, 1: offsets, 2: values
   std::vector<Buf> bufs;
   for (int s = 0; s < kp.n_in; s++) {
@@ -42,52 +42,37 @@ void plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bo
     if (c.type == T_UTF8) {
       if (use & USE_OFFSETS) bufs.push_back({s, 1, (size_t)(kTileRows + 4) * 4});
       const int64_t avg = avg_utf8 ? avg_utf8[s] : -1;
-      if ((use & USE_VALUES) && avg >= 0 && avg <= 32) bufs.push_back({s, 2, up16((size_t)kTileRows * (size_t)avg + std::max<size_t>((size_t)kTileRows * (size_t)avg / 32, 128) + 32)});
+      if ((use & USE_VALUES) && avg >= 0 && avg <= 32) bufs.push_back({s, 2, up16((size_t)kTileRows * (size_t)avg * 5 / 4 + 64)});
     } else if (use & USE_VALUES) {
       bufs.push_back({s, 2, c.width ? (size_t)kTileRows * c.width : (size_t)kTileRows / 8});
     }
   }
-  const bool has_pred = kp.pred_end > kp.pred_begin;
   const int nq = 1 + kp.n_utf8;
-  const size_t sctx_stride = up16(sizeof(StageCtx) + (size_t)std::max(kp.n_in, 1) * sizeof(ColumnDesc) +
-                                  (many ? sizeof(BatchHeader) + (size_t)std::max(kp.n_out, 1) * sizeof(OutDesc) : 0));
+  // the tables behind the stage
+  size_t tables = 0;
+  auto table = [&](size_t bytes) { const size_t at = tables; tables += up16(bytes); return at; };
+  const size_t t_cols = table((size_t)std::max(kp.n_in, 1) * sizeof(ColumnDesc));
+  const size_t t_cnt = table((size_t)nq * kTileSlices * 4);
+  const size_t t_pre = table((size_t)nq * kTileSlices * 8);
+  const size_t t_tot = table((size_t)nq * 8);
+  const size_t t_bits = table((size_t)kWarps * kp.n_bits * kBitWords * 4);
+  const size_t t_ltab = table(kp.long_strings ? (size_t)kWarps * 2 * (kWarpRows + 4) * 4 : 0);
+  const size_t t_pext = table(kp.n_bits > 0 ? 256 : 0);
+  const size_t t_params = table(many ? sizeof(KernelParams) : 0);
   auto stage_bytes = [&]() {
     size_t t = 0;
     for (auto& b : bufs) t += up16(b.bytes);
     return up128(t);
   };
-  int want = 2;   // resident CTAs per SM: two pipelines hide each other's bubbles; more cost registers
-  if (const char* e = std::getenv("CHDB_WANT_CTAS")) want = std::max(1, std::min(4, std::atoi(e)));
-  int min_stages = has_pred ? 3 : 2;   // A(i) and B(i-1) hold two stages; at least one more is being filled
-  if (const char* e = std::getenv("CHDB_MIN_STAGES")) min_stages = std::max(min_stages, std::min(kMaxStages, std::atoi(e)));
-  int stages = min_stages;
-  size_t fixed = 0;
-  while (true) {
-    // the tables behind the ring (their size depends on the ring depth only through the per-stage ones)
-    auto fixed_for = [&](int st) {
-      size_t t = 0;
-      t += up16((size_t)st * nq * kTileSlices * 4);
-      t += up16((size_t)st * nq * kTileSlices * 8);
-      t += up16(has_pred ? (size_t)st * kComputeWarps * 32 : 0);
-      t += up16((size_t)(many ? st : 1) * kMaxOutCols * 4);
-      t += up16((size_t)kComputeWarps * kp.n_bits * kBitWords * 4);
-      t += up16(kp.long_strings ? (size_t)kComputeWarps * 2 * (kWarpRows + 4) * 4 : 0);
-      t += up16(kp.n_bits > 0 ? 256 : 0);
-      return t;
-    };
-    const size_t avail = std::min(kSmemPerCtaMax, kSmemPerSm / (size_t)want - 1024) - kStaticSmem;
-    const size_t per_stage = stage_bytes() + sctx_stride;
-    int fit = kMaxStages;
-    while (fit > 0 && (size_t)fit * per_stage + fixed_for(fit) > avail) fit--;
-    if (fit >= min_stages || bufs.empty()) {
-      stages = std::max(min_stages, std::min(fit, bufs.empty() ? min_stages : kMaxStages));
-      fixed = fixed_for(stages);
-      break;
-    }
+  int want = 4;   // fewer resident tiles than this and the loads / look-backs stop overlapping
+  if (const char* e = std::getenv("CHDB_WANT_CTAS")) want = std::max(1, std::min(16, std::atoi(e)));
+  auto ctas_for = [&](size_t dyn) { return (int)std::min<size_t>(16, kSmemPerSm / (dyn + kStaticSmem + 1024)); };
+  while (!bufs.empty()) {
+    const size_t dyn = stage_bytes() + tables;
+    if (dyn + kStaticSmem <= kSmemPerCtaMax && ctas_for(dyn) >= want) break;
     auto big = std::max_element(bufs.begin(), bufs.end(), [](const Buf& a, const Buf& b) { return a.bytes < b.bytes; });
     bufs.erase(big);
   }
-  if (const char* e = std::getenv("CHDB_MAX_STAGES")) stages = std::max(min_stages, std::min(stages, std::atoi(e)));
   size_t off = 0;
   for (auto& b : bufs) {
     StageSlot& sl = tp.slot[b.slot];
@@ -96,34 +81,17 @@ void plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bo
     else { sl.values = (uint32_t)off; sl.values_cap = (uint32_t)b.bytes; }
     off += up16(b.bytes);
   }
-  tp.stages = (uint32_t)stages;
-  tp.stage_bytes = (uint32_t)stage_bytes();
-  size_t at = (size_t)stages * tp.stage_bytes;
-  auto table = [&](size_t bytes) { const size_t here = at; at += up16(bytes); return (uint32_t)here; };
-  tp.sctx_off = table((size_t)stages * sctx_stride);
-  tp.sctx_stride = (uint32_t)sctx_stride;
-  tp.cnt_off = table((size_t)stages * nq * kTileSlices * 4);
-  tp.pre_off = table((size_t)stages * nq * kTileSlices * 8);
-  tp.sel_off = table(has_pred ? (size_t)stages * kComputeWarps * 32 : 0);
-  tp.nulls_off = table((size_t)(many ? stages : 1) * kMaxOutCols * 4);
-  tp.bits_off = table((size_t)kComputeWarps * kp.n_bits * kBitWords * 4);
-  tp.ltab_off = table(kp.long_strings ? (size_t)kComputeWarps * 2 * (kWarpRows + 4) * 4 : 0);
-  tp.pext_off = table(kp.n_bits > 0 ? 256 : 0);
-  tp.dyn_smem = (uint32_t)at;
-  (void)fixed;
-  tp.ctas_per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)want, kSmemPerSm / (at + kStaticSmem + 1024)));
-  if (const char* e = std::getenv("CHDB_PLAN_VERBOSE")) {
-    if (*e == '1') {
-      int staged = 0, unstaged = 0;
-      for (int s = 0; s < kp.n_in; s++) {
-        const StageSlot& sl = tp.slot[s];
-        staged += (sl.values != kNotStaged) + (sl.validity != kNotStaged) + (sl.offsets != kNotStaged);
-        unstaged += ((tp.use[s] & USE_VALUES) && sl.values == kNotStaged) + ((tp.use[s] & USE_OFFSETS) && kp.in[s].type == T_UTF8 && sl.offsets == kNotStaged);
-      }
-      std::fprintf(stderr, "[chdb plan] stages %u x %u B, tables %zu B, dyn smem %u B, %u CTAs/SM, %d staged buffers, %d read from global\n",
-                   tp.stages, tp.stage_bytes, at - (size_t)stages * tp.stage_bytes, tp.dyn_smem, tp.ctas_per_sm, staged, unstaged);
-    }
-  }
+  const size_t sb = stage_bytes();
+  tp.cols_off = (uint32_t)(sb + t_cols);
+  tp.cnt_off = (uint32_t)(sb + t_cnt);
+  tp.pre_off = (uint32_t)(sb + t_pre);
+  tp.tot_off = (uint32_t)(sb + t_tot);
+  tp.bits_off = (uint32_t)(sb + t_bits);
+  tp.ltab_off = (uint32_t)(sb + t_ltab);
+  tp.pext_off = (uint32_t)(sb + t_pext);
+  tp.params_off = (uint32_t)(sb + t_params);
+  tp.dyn_smem = (uint32_t)(sb + tables);
+  return std::max(1, ctas_for(tp.dyn_smem));
 }
 
 namespace {
@@ -146,23 +114,17 @@ cudaError_t grant_smem(const void* kern) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemPerCtaMax - fa.sharedSizeBytes));
   if (e != cudaSuccess) return e;
-  // The plan counts on the whole 228 KB of the SM being shared memory (two CTAs of ~114 KB each): without this the
-  // driver may pick a smaller carve-out, one CTA per SM becomes resident and the launch takes twice as long.
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
   ok = true;
   return cudaSuccess;
 }
 }  // namespace
 
-cudaError_t launch_stream_kernel(const void* kernel, const KernelParams& p, const TilePlan& tp, int sm_count, cudaStream_t stream) {
+cudaError_t launch_stream_kernel(const void* kernel, const KernelParams& p, const TilePlan& tp, unsigned grid, cudaStream_t stream) {
   cudaError_t e = grant_smem(kernel);
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<KernelParams*>(&p), const_cast<TilePlan*>(&tp)};
   cudaLaunchConfig_t cfg = {};
-  // persistent: every CTA is resident (tickets hand the tiles to whoever runs); never more CTAs than tiles
-  const unsigned resident = (unsigned)std::max(1, sm_count) * std::max(1u, tp.ctas_per_sm);
-  cfg.gridDim = dim3(std::max(1u, std::min(resident, (unsigned)std::max(p.total_tiles, 1))));
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = tp.dyn_smem;
   cfg.stream = stream;
@@ -174,11 +136,11 @@ cudaError_t launch_stream_kernel(const void* kernel, const KernelParams& p, cons
   return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
-cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, int sm_count, cudaStream_t stream) {
+cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, unsigned grid, cudaStream_t stream) {
   const bool many = p.many != nullptr;
   const void* kern = has64 ? (many ? (const void*)stream_kernel<uint64_t, true> : (const void*)stream_kernel<uint64_t, false>)
                            : (many ? (const void*)stream_kernel<uint32_t, true> : (const void*)stream_kernel<uint32_t, false>);
-  return launch_stream_kernel(kern, p, tp, sm_count, stream);
+  return launch_stream_kernel(kern, p, tp, grid, stream);
 }
 
 cudaError_t launch_zero(void* p, size_t bytes, cudaStream_t stream) {

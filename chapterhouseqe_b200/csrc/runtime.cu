@@ -41,6 +41,7 @@ struct CtxCore {
   cudaStream_t stream = nullptr;
   std::atomic<int64_t> launches{0};
   std::atomic<int64_t> jit_launches{0};   // launches that ran an NVRTC-specialised kernel
+  std::atomic<int64_t> alloc_misses{0};   // device allocations that went to cudaMallocAsync (block cache misses)
   int sm_count = 148;                     // persistent grid = CTAs per SM x SMs
   std::mutex mu;
   std::vector<void*> pinned_free;   // small pinned blocks for count read-back
@@ -167,6 +168,7 @@ static Buf dev_alloc(const Core& core, size_t bytes) {
       return b;
     }
   }
+  core->alloc_misses++;
   CUDA_CHECK(cudaMallocAsync(&b->ptr, b->bytes, core->stream));
   return b;
 }
@@ -824,12 +826,12 @@ static void prepare(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in
   }
 }
 
-// Bytes of the zeroed per-batch workspace: counts | error word (| done, tickets) || look-back descriptors || bit-packed outputs
+// Bytes of the zeroed per-batch workspace: counts | error word | done || look-back descriptors || bit-packed outputs
 static size_t workspace_layout(Prepared& P, size_t* ws_counts_out, size_t* ws_desc_out) {
   const int64_t num_tiles = (P.n + kTileRows - 1) / kTileRows;
   const int nq = 1 + P.n_utf8;
   const size_t ws_counts = round_up((size_t)(P.n_counts + 2) * 8, 128);
-  const size_t ws_desc = P.compact ? round_up((size_t)desc_groups(nq) * (size_t)num_tiles * 8, 128) : 0;
+  const size_t ws_desc = P.compact ? round_up((size_t)nq * (size_t)num_tiles * 8, 128) : 0;
   size_t total = ws_counts + ws_desc;
   for (auto& z : P.zero_reqs) { z.at = total; total += round_up(z.bytes, 128); }
   *ws_counts_out = ws_counts;
@@ -857,6 +859,7 @@ static void bind_workspace(Prepared& P, const std::shared_ptr<LaunchShared>& ls,
   bh.num_rows = P.n;
   bh.counts = (uint64_t*)ws;
   bh.error_word = (uint64_t*)ws + P.n_counts;
+  bh.done = (uint32_t*)((uint64_t*)ws + P.n_counts + 1);
   bh.desc = (uint64_t*)(ws + ws_counts);
   bh.host_counts = host_counts;
   bh.num_tiles = (int32_t)((P.n + kTileRows - 1) / kTileRows);
@@ -870,7 +873,7 @@ static void bind_workspace(Prepared& P, const std::shared_ptr<LaunchShared>& ls,
 }
 
 // The program part of the kernel parameters + the plan, from the first batch of a launch.
-static void fill_program_params(const Program& p, const Prepared& P, KernelParams& kp, TilePlan& tp, bool many) {
+static int fill_program_params(const Program& p, const Prepared& P, KernelParams& kp, TilePlan& tp, bool many) {
   kp.n_in = (int)p.slot_to_col.size();
   kp.n_out = P.ko;
   kp.n_utf8 = P.n_utf8;
@@ -906,23 +909,25 @@ static void fill_program_params(const Program& p, const Prepared& P, KernelParam
     }
   };
   mark_instrs(kp.pred_begin, kp.pred_end);
+  for (int i = kp.pred_begin; i < kp.pred_end; i++)
+    if (kp.instrs[i].op == OP_CMP_UTF8) tp.pred_reads_utf8 = 1;
   for (int k = 0; k < P.ko; k++) {
     const OutDesc& od = kp.out[k];
     if (od.kind == OUT_EXPR) mark_instrs(od.begin, od.end);
     else tp.use[od.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
   }
-  plan_tile(kp, tp, slot_avg, many);
+  return plan_tile(kp, tp, slot_avg, many);
 }
 
 // Zero kernel + stream kernel.  Long scans run the same device code specialised for this program by NVRTC
 // (jit.cpp); short ones, or boxes without NVRTC, run the bytecode interpreter kernels.
-static void launch_set(const Core& core, const Program& p, const KernelParams& kp_in, const TilePlan& tp, void* ws, size_t ws_bytes,
-                       int64_t rows, const std::shared_ptr<LaunchShared>& ls) {
+static void launch_set(const Core& core, const Program& p, const KernelParams& kp_in, const TilePlan& tp, int ctas_per_sm, unsigned grid,
+                       void* ws, size_t ws_bytes, int64_t rows, const std::shared_ptr<LaunchShared>& ls) {
   KernelParams kp_traced;
   const KernelParams* kpp = &kp_in;
   Buf trace_buf;
-  const char* trace_path = std::getenv("CHDB_TRACE");   // debugging aid: per-CTA pipeline time stamps of this launch -> file
-  const size_t trace_bytes = (size_t)core->sm_count * 4 * kTraceIters * 8 * 8;
+  const char* trace_path = std::getenv("CHDB_TRACE");   // debugging aid: per-tile phase time stamps of this launch -> file
+  const size_t trace_bytes = (size_t)8192 * 8 * 8;
   if (trace_path && *trace_path) {
     trace_buf = dev_alloc(core, trace_bytes);
     CUDA_CHECK(cudaMemsetAsync(trace_buf->ptr, 0, trace_bytes, core->stream));
@@ -937,10 +942,9 @@ static void launch_set(const Core& core, const Program& p, const KernelParams& k
   const JitMode jm = jit_mode();
   if (jm == JitMode::Always || (jm == JitMode::Auto && rows >= kJitAutoRows)) {
     std::string why;
-    jk = jit_get(kp, p.has64, (int)tp.ctas_per_sm, &why);
+    jk = jit_get(kp, p.has64, std::min(ctas_per_sm, 8), &why);
   }
-  const cudaError_t le = jk ? jit_launch_stream(jk, kp, tp, core->sm_count, core->stream)
-                            : launch_stream(kp, tp, p.has64, core->sm_count, core->stream);
+  const cudaError_t le = jk ? jit_launch_stream(jk, kp, tp, grid, core->stream) : launch_stream(kp, tp, p.has64, grid, core->stream);
   core->launches++;
   if (jk) core->jit_launches++;
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
@@ -966,12 +970,44 @@ static void after_launch(Prepared& P) {
   }
 }
 
+// CHDB_HOST_TIMING=1: where the host spends its time inside execute() (debugging aid): calls that take longer than
+// 300 us report their phases on stderr.
+struct HostClock {
+  bool on;
+  std::chrono::steady_clock::time_point t0, t;
+  double ph[5] = {0, 0, 0, 0, 0};
+  int64_t misses0 = 0;
+  const CtxCore* core = nullptr;
+  HostClock() {
+    static const bool enabled = [] { const char* e = std::getenv("CHDB_HOST_TIMING"); return e && *e == '1'; }();
+    on = enabled;
+    if (on) t0 = t = std::chrono::steady_clock::now();
+  }
+  void lap(int i) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    ph[i] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  ~HostClock() {
+    if (!on) return;
+    const double total = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    if (total > 300)
+      std::fprintf(stderr, "[chdb host] execute %.0f us: prepare %.0f, workspace %.0f, params+plan %.0f, launches %.0f, after %.0f; %lld block cache misses\n",
+                   total, ph[0], ph[1], ph[2], ph[3], ph[4], core ? (long long)(core->alloc_misses.load() - misses0) : -1ll);
+  }
+};
+
 static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in_orig) {
+  HostClock hc;
   const Core& core = ctx->core;
+  hc.core = core.get();
+  hc.misses0 = core->alloc_misses.load();
   CUDA_CHECK(cudaSetDevice(core->device));
   Prepared P;
   prepare(ctx, p, in_orig, nullptr, P);
   if (!P.launch) return std::move(P.out);
+  hc.lap(0);
 
   size_t ws_counts, ws_desc;
   const size_t ws_total = workspace_layout(P, &ws_counts, &ws_desc);
@@ -984,13 +1020,14 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   KernelParams kp;
   std::memset(&kp, 0, sizeof(kp));
   bind_workspace(P, ls, ws, ws_counts, kp.b, (uint64_t*)ls->host, 0);
-  kp.done = (uint32_t*)((uint64_t*)ws + P.n_counts + 1);
-  kp.tickets = kp.done + 1;
-  kp.total_tiles = kp.b.num_tiles;
+  hc.lap(1);
   TilePlan tp;
-  fill_program_params(p, P, kp, tp, false);
-  launch_set(core, p, kp, tp, ws, ws_total, P.n, ls);
+  const int ctas = fill_program_params(p, P, kp, tp, false);
+  hc.lap(2);
+  launch_set(core, p, kp, tp, ctas, (unsigned)kp.b.num_tiles, ws, ws_total, P.n, ls);
+  hc.lap(3);
   after_launch(P);
+  hc.lap(4);
   return std::move(P.out);
 }
 
@@ -1035,9 +1072,9 @@ static void execute_many(chdb_ctx* ctx, const Program& p, const chdb_device_batc
     const Prepared& P0 = preps[(size_t)group[0]];
     const int n_in = (int)p.slot_to_col.size(), n_out = P0.ko, per = P0.n_counts + 1;
     const size_t stride = sizeof(BatchHeader) + (size_t)n_in * sizeof(ColumnDesc) + (size_t)n_out * sizeof(OutDesc);
-    // workspace: done, tickets | per batch: counts, descriptors, bit-packed outputs
+    // workspace, per batch: counts, done, descriptors, bit-packed outputs
     std::vector<size_t> ws_at((size_t)nb), ws_counts((size_t)nb);
-    size_t ws_total = 128;
+    size_t ws_total = 0;
     int64_t tiles = 0;
     for (int g = 0; g < nb; g++) {
       Prepared& P = preps[(size_t)group[(size_t)g]];
@@ -1074,17 +1111,14 @@ static void execute_many(chdb_ctx* ctx, const Program& p, const chdb_device_batc
     KernelParams kp;
     std::memset(&kp, 0, sizeof(kp));
     std::memcpy(&kp.b, stage, sizeof(BatchHeader));   // (batch 0's; the kernel reads every batch's own from its record)
-    kp.done = (uint32_t*)ws;
-    kp.tickets = kp.done + 1;
-    kp.total_tiles = (int32_t)tiles;
     kp.many = (const uint8_t*)ls->params->ptr;
     kp.many_tile_batch = (const int32_t*)((const uint8_t*)ls->params->ptr + rec_bytes);
     kp.many_batches = nb;
     kp.many_stride = (int32_t)stride;
     TilePlan tp;
     Prepared& F = preps[(size_t)group[0]];
-    fill_program_params(p, F, kp, tp, true);
-    launch_set(core, p, kp, tp, ws, ws_total, total_rows, ls);
+    const int ctas = fill_program_params(p, F, kp, tp, true);
+    launch_set(core, p, kp, tp, ctas, (unsigned)tiles, ws, ws_total, total_rows, ls);
     for (int g = 0; g < nb; g++) done[(size_t)group[(size_t)g]] = std::move(preps[(size_t)group[(size_t)g]].out);
   }
   for (int32_t i = 0; i < count; i++) outs[i] = done[(size_t)i].release();
@@ -1191,6 +1225,7 @@ int32_t chdb_ctx_synchronize(chdb_ctx* ctx, chdb_status* st) {
 }
 int64_t chdb_ctx_launch_count(chdb_ctx* ctx) { return ctx ? ctx->core->launches.load() : 0; }
 int64_t chdb_ctx_jit_launch_count(chdb_ctx* ctx) { return ctx ? ctx->core->jit_launches.load() : 0; }
+int64_t chdb_ctx_alloc_miss_count(chdb_ctx* ctx) { return ctx ? ctx->core->alloc_misses.load() : 0; }
 
 int32_t chdb_jit_available(char* why, size_t cap) {
   std::string reason;

@@ -126,6 +126,8 @@ int32_t chdb_ctx_synchronize(chdb_ctx* ctx, chdb_status* st);
 int64_t chdb_ctx_launch_count(chdb_ctx* ctx);
 /* ...and how many of them ran a kernel specialised for the program at run time (see below). */
 int64_t chdb_ctx_jit_launch_count(chdb_ctx* ctx);
+/* Device allocations that missed the ctx's block cache and went to cudaMallocAsync (0 in a warmed-up steady state). */
+int64_t chdb_ctx_alloc_miss_count(chdb_ctx* ctx);
 
 /* ---- run-time specialisation ----
  * Long scans run the kernels' own source compiled by NVRTC with the program's bytecode baked

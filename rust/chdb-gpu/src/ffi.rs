@@ -38,6 +38,7 @@ extern "C" {
     pub fn chdb_ctx_synchronize(ctx: *mut ChdbCtx, st: *mut ChdbStatus) -> i32;
     pub fn chdb_ctx_launch_count(ctx: *mut ChdbCtx) -> i64;
     pub fn chdb_ctx_jit_launch_count(ctx: *mut ChdbCtx) -> i64;
+    pub fn chdb_ctx_alloc_miss_count(ctx: *mut ChdbCtx) -> i64;
     pub fn chdb_jit_available(why: *mut c_char, cap: usize) -> i32;
 
     // ---- programs ----
