@@ -407,7 +407,7 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cfg):
@@ -460,13 +460,11 @@ def run_ours(args, cfg, rank, world, local_rank):
             dist.barrier()
 
     if many:
-        groups = [dev_batches[i:i + many] for i in range(0, len(dev_batches), many)]
+        # handle arrays built once: a launch set is one C call over a slice of pointers (what a Rust caller passes)
+        groups = [C.DeviceBatchList.from_batches(dev_batches[i:i + many]) for i in range(0, len(dev_batches), many)]
 
         def one_pass():
-            out = []
-            for g in groups:
-                out.extend(C.DeviceBatch.run_many(prog, g))
-            return out
+            return [C.DeviceBatch.run_many(prog, g) for g in groups]
     else:
         def one_pass():
             return [b.run(prog) for b in dev_batches]
@@ -488,11 +486,15 @@ def run_ours(args, cfg, rank, world, local_rank):
     outs = run_passes(max(args.warmup, 3))
     ctx.synchronize()
     torch.cuda.synchronize(device)
-    rows_out = sum(o.num_rows for o in outs)
-    bytes_out = sum(o.nbytes for o in outs)
-    for o in outs:
+    def flat(results):
+        return [o for r in results for o in r] if many else results
+
+    rows_out = bytes_out = 0
+    for o in flat(outs):
         o.check()
-    del o   # (the loop variable would keep the last batch -- and its blocks -- out of the cache)
+        rows_out += o.num_rows
+        bytes_out += o.nbytes
+    o = None   # (the loop variable would keep the last batch -- and its blocks -- out of the cache)
 
     # ---- the benchmarked configuration against the oracle: first, middle and last record of this rank ----
     parity = None
@@ -501,13 +503,15 @@ def run_ours(args, cfg, rank, world, local_rank):
         O.lib()
         fn = oracle_step_fn(sel)
         checked = []
+        flat_outs = flat(outs)
         for i in sorted({0, len(dev_batches) // 2, len(dev_batches) - 1}):
-            got = O.batch_from_arrow(outs[i].download())
+            got = O.batch_from_arrow(flat_outs[i].download())
             want = fn(O.batch_from_arrow(to_host_batch(cfg, tensors[i], pin=False)[0]))
             ok, why = O.batches_equal(got, want)
             if not ok:
                 raise SystemExit(f"bench.py: record {i} of the benchmarked run differs from the oracle: {why}")
             checked.append(i)
+        flat_outs = None
         parity = {"parity_checked_batches": len(checked), "records": checked, "rows_each": [sizes[i][1] for i in checked],
                   "against": "oracle (bit-exact: values, validity, offsets, schema)"}
     outs = None
@@ -536,10 +540,12 @@ def run_ours(args, cfg, rank, world, local_rank):
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
     jit_launches = ctx.jit_launch_count - jit0
-    for o in prev:   # the LAST timed pass's outputs: device error word + row counts must match the warm-up's
+    rows_timed = 0
+    for o in flat(prev):   # the LAST timed pass's outputs: device error word + row counts must match the warm-up's
         o.check()
-    del o
-    assert sum(o.num_rows for o in prev) == rows_out, "timed pass produced a different row count than the warm-up"
+        rows_timed += o.num_rows
+    o = None
+    assert rows_timed == rows_out, "timed pass produced a different row count than the warm-up"
     prev = None
 
     # whole-job numbers: MAX over ranks of the device time, SUM of rows / launches (no data-path collective)
@@ -587,11 +593,12 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     # ---- materialize-side gather (N > 1): every rank's compacted batches travel to rank 0 over NVLink ----
     if world > 1 and not args.no_gather:
-        def gather_step():
+        def gather_step(verify=False):
             outs_ = one_pass()
             torch.cuda.current_stream(device).wait_stream(stream)
-            got = multigpu.gather_batches(outs_, dst=0)
+            got = multigpu.gather_batches(flat(outs_), dst=0, verify=verify)
             return outs_, got
+        gather_step(verify=True)   # (checksums of every slab compared across the link once, outside the timed steps)
         gather_step()
         barrier()
         torch.cuda.synchronize(device)
@@ -655,11 +662,30 @@ def run_ours(args, cfg, rank, world, local_rank):
         line["cpu_baseline"] = cpu_baselines(args, cfg, sel, host)
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's real stdout (see main())."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # stdout carries exactly one JSON line: everything else a library may print there (NCCL's version banner, ...)
+    # is sent to stderr by pointing file descriptor 1 at stderr for the whole run
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -115,8 +115,10 @@ def load_library():
         ctypes.POINTER(i64), stp)
     sig("chdb_download", i32, vp, vp, vp, vp, stp)
     sig("chdb_peer_copy", i32, vp, vp, vp, pvp, stp)
+    sig("chdb_device_batches_pack", i32, vp, pvp, i32, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64), stp)
     sig("chdb_device_batch_retain", None, vp)
     sig("chdb_device_batch_release", None, vp)
+    sig("chdb_device_batch_release_many", None, pvp, i32)
     sig("chdb_record_pool_create", i32, vp, i64, pvp, stp)
     sig("chdb_record_pool_destroy", None, vp)
     sig("chdb_record_pool_add", i32, vp, ctypes.c_uint64, vp, i32, stp)
@@ -138,8 +140,8 @@ EXPORTED_SYMBOLS = [
     "chdb_filter_record_async", "chdb_project_record_async", "chdb_poll", "chdb_pending_result", "chdb_pending_release",
     "chdb_device_batch_status", "chdb_device_batch_num_rows",
     "chdb_device_batch_num_columns", "chdb_device_batch_column", "chdb_device_batch_nbytes", "chdb_download",
-    "chdb_peer_copy", "chdb_device_batch_retain",
-    "chdb_device_batch_release", "chdb_record_pool_create", "chdb_record_pool_destroy", "chdb_record_pool_add",
+    "chdb_peer_copy", "chdb_device_batches_pack", "chdb_device_batch_retain",
+    "chdb_device_batch_release", "chdb_device_batch_release_many", "chdb_record_pool_create", "chdb_record_pool_destroy", "chdb_record_pool_add",
     "chdb_record_pool_get", "chdb_record_pool_complete", "chdb_record_pool_stats",
 ]
 
@@ -446,19 +448,20 @@ class DeviceBatch:
         return DeviceBatch(h, self.ctx, (self, self._keepalive))
 
     @staticmethod
-    def run_many(prog: Program, batches: list["DeviceBatch"]) -> list["DeviceBatch"]:
-        """ONE launch set over many batches of one schema (chdb_run_device_many); one output batch per input."""
-        if not batches:
-            return []
-        L = load_library()
-        ctx = batches[0].ctx
+    def run_many(prog: Program, batches) -> "DeviceBatchList":
+        """ONE launch set over many batches of one schema (chdb_run_device_many); one output batch per input.
+        `batches`: a list of DeviceBatch, or a DeviceBatchList (its handle array is passed as is: no per-record work
+        on the Python side, like a Rust caller handing over a slice of pointers)."""
+        if not isinstance(batches, DeviceBatchList):
+            batches = DeviceBatchList.from_batches(batches)
         n = len(batches)
-        arr = ctypes.c_void_p * n
-        ins = arr(*[b._h for b in batches])
-        outs = arr()
+        if n == 0:
+            return DeviceBatchList((ctypes.c_void_p * 0)(), 0, batches.ctx, None)
+        L = load_library()
+        outs = (ctypes.c_void_p * n)()
         st = _Status()
-        _check(L.chdb_run_device_many(ctx._h, prog._h, ins, n, outs, ctypes.byref(st)), st)
-        return [DeviceBatch(ctypes.c_void_p(outs[i]), ctx, batches[i]) for i in range(n)]
+        _check(L.chdb_run_device_many(batches.ctx._h, prog._h, batches._arr, n, outs, ctypes.byref(st)), st)
+        return DeviceBatchList(outs, n, batches.ctx, batches)
 
     @property
     def ready(self) -> bool:
@@ -516,6 +519,61 @@ class DeviceBatch:
         if getattr(self, "_h", None):
             load_library().chdb_device_batch_release(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class DeviceBatchList:
+    """n device batches behind one ctypes array of handles; a DeviceBatch wrapper is only made for the ones asked for."""
+
+    def __init__(self, arr, n: int, ctx: Context, keepalive=None):
+        self._arr, self._n, self.ctx, self._keepalive = arr, n, ctx, keepalive
+
+    @staticmethod
+    def from_batches(batches) -> "DeviceBatchList":
+        batches = list(batches)
+        ctx = batches[0].ctx if batches else default_context()
+        L = load_library()
+        arr = (ctypes.c_void_p * len(batches))(*[b._h for b in batches])
+        for b in batches:
+            L.chdb_device_batch_retain(b._h)
+        return DeviceBatchList(arr, len(batches), ctx, batches)
+
+    def __len__(self) -> int:
+        return self._n
+
+    def __getitem__(self, i: int) -> DeviceBatch:
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        h = ctypes.c_void_p(self._arr[i])
+        load_library().chdb_device_batch_retain(h)
+        return DeviceBatch(h, self.ctx, self._keepalive)
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+    def pack(self, dst_ptr: int = 0, capacity: int = 0):
+        """chdb_device_batches_pack: every buffer of every batch into one contiguous device buffer (asynchronous on
+        the ctx stream).  Returns (total bytes, sizes) -- sizes: int64[n * columns * 3]; dst_ptr == 0 only sizes them."""
+        L = load_library()
+        ncols = int(L.chdb_device_batch_num_columns(ctypes.c_void_p(self._arr[0]))) if self._n else 0
+        sizes = (ctypes.c_int64 * max(self._n * ncols * 3, 1))()
+        total, st = ctypes.c_int64(0), _Status()
+        _check(L.chdb_device_batches_pack(self.ctx._h, self._arr, self._n, ctypes.c_void_p(dst_ptr or None), capacity, sizes,
+                                          ctypes.byref(total), ctypes.byref(st)), st)
+        return int(total.value), sizes
+
+    def close(self):
+        if getattr(self, "_arr", None) is not None:
+            load_library().chdb_device_batch_release_many(self._arr, self._n)
+            self._arr = None
+            self._n = 0
 
     def __del__(self):
         try:

@@ -703,8 +703,8 @@ static void prepare(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in
   for (auto& o : p.outputs) any_kernel_out |= o.kind == OutputColumn::EXPR || (o.kind == OutputColumn::PASS && compact);
   const bool launch = P.launch = n > 0 && (any_kernel_out || compact);
 
-  std::memset(P.in_desc, 0, sizeof(P.in_desc));
-  std::memset(P.out_desc, 0, sizeof(P.out_desc));
+  std::memset(P.in_desc, 0, p.slot_to_col.size() * sizeof(ColumnDesc));
+  std::memset(P.out_desc, 0, p.outputs.size() * sizeof(OutDesc));
   int n_utf8 = 0, n_counts = 1;
   if (launch) {
     for (size_t s = 0; s < p.slot_to_col.size(); s++) {
@@ -880,8 +880,8 @@ static int fill_program_params(const Program& p, const Prepared& P, KernelParams
   kp.n_counts = P.n_counts;
   kp.pred_begin = P.compact ? p.pred_begin : 0;
   kp.pred_end = P.compact ? p.pred_end : 0;
-  std::memcpy(kp.in, P.in_desc, sizeof(kp.in));
-  std::memcpy(kp.out, P.out_desc, sizeof(kp.out));
+  std::memcpy(kp.in, P.in_desc, p.slot_to_col.size() * sizeof(ColumnDesc));
+  std::memcpy(kp.out, P.out_desc, (size_t)P.ko * sizeof(OutDesc));
   std::memcpy(kp.instrs, p.instrs.data(), p.instrs.size() * sizeof(Instr));
   std::memcpy(kp.strpool, p.strpool.data(), p.strpool.size());
   // bit-packed outputs assembled in shared memory: Boolean values and validity bitmaps
@@ -1443,6 +1443,10 @@ void chdb_device_batch_retain(chdb_device_batch* b) {
 void chdb_device_batch_release(chdb_device_batch* b) {
   if (b && b->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) delete b;
 }
+void chdb_device_batch_release_many(chdb_device_batch* const* batches, int32_t count) {
+  if (!batches) return;
+  for (int32_t i = 0; i < count; i++) chdb_device_batch_release(batches[i]);
+}
 
 // ---- device-resident record pool ---------------------------------------------------------------
 // What a GPU-aware exchange keeps instead of `RecordPool.records: HashMap<u64, Arc<RecordBatch>>`
@@ -1591,6 +1595,46 @@ void chdb_record_pool_stats(chdb_record_pool* pool, int64_t* records, int64_t* d
   if (device_bytes) *device_bytes = pool->device_bytes;
   if (spilled_records) *spilled_records = pool->spilled_records;
   if (spilled_bytes) *spilled_bytes = pool->spilled_bytes;
+}
+
+int32_t chdb_device_batches_pack(chdb_ctx* ctx, const chdb_device_batch* const* batches, int32_t count, void* dst, int64_t capacity,
+                                 int64_t* sizes_out, int64_t* total_bytes, chdb_status* st) {
+  return guarded(st, [&] {
+    if (!ctx || (count > 0 && !batches) || count < 0) throw Error(CHDB_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_CHECK(cudaSetDevice(ctx->core->device));
+    int64_t at = 0, si = 0;
+    auto piece = [&](const void* p, int64_t bytes) {
+      if (sizes_out) sizes_out[si] = bytes;
+      si++;
+      if (bytes <= 0) return;
+      if (dst) {
+        if (at + bytes > capacity) throw Error(CHDB_ERR_INVALID_ARGUMENT, "pack: destination too small");
+        CUDA_CHECK(cudaMemcpyAsync((uint8_t*)dst + at, p, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx->core->stream));
+      }
+      at += (bytes + 255) / 256 * 256;
+    };
+    for (int32_t i = 0; i < count; i++) {
+      chdb_device_batch* b = const_cast<chdb_device_batch*>(batches[i]);
+      if (!b) throw Error(CHDB_ERR_INVALID_ARGUMENT, "null batch");
+      if (b->core->device != ctx->core->device) throw Error(CHDB_ERR_INVALID_ARGUMENT, "batch lives on another device than the ctx");
+      check_run_error(b);
+      resolve(b);
+      const int64_t n = b->num_rows;
+      for (auto& c : b->cols) {
+        const bool has_validity = c.validity != nullptr && c.null_count != 0;
+        piece(c.validity, has_validity ? (int64_t)bitmap_bytes(n) : 0);
+        if (c.meta.type == T_UTF8) {
+          if (utf8_value_bytes(c, n) < 0 || c.first_offset < 0) throw Error(CHDB_ERR_NOT_IMPLEMENTED, "pack of a sliced Utf8 view");
+          piece(c.offsets, (n + 1) * 4);
+          piece((const uint8_t*)c.values + c.first_offset, c.value_bytes);
+        } else {
+          piece(nullptr, 0);
+          piece(c.values, c.meta.type == T_BOOL ? (int64_t)bitmap_bytes(n) : n * c.meta.width);
+        }
+      }
+    }
+    if (total_bytes) *total_bytes = at;
+  });
 }
 
 int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_batch* src, chdb_device_batch** out,

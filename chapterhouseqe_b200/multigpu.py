@@ -35,10 +35,6 @@ def reduce_step(elapsed_ms: float, sums: Sequence[float], device=None):
     return float(t.item()), [float(x) for x in s.tolist()]
 
 
-GATHER_TRANSPORT = ("one ncclGroupStart/End per step (torch.distributed.batch_isend_irecv): every result buffer of every "
-                    "rank is one grouped NCCL send/recv over NVLink, received into one slab per source rank")
-
-
 def gather_buffers(buffers: Sequence, dst: int = 0, packed: bool | None = None):
     """Variable-size gather of byte buffers (1-D uint8 tensors, one list per rank) onto rank `dst`.
 
@@ -98,19 +94,92 @@ def gather_buffers(buffers: Sequence, dst: int = 0, packed: bool | None = None):
     return out
 
 
-def gather_batches(batches: Sequence, dst: int = 0):
-    """The materialize-side gather: every buffer of every result DeviceBatch of every rank onto rank `dst`."""
-    bufs = [t for b in batches for t in device_batch_buffers(b)]
-    return gather_buffers(bufs, dst=dst)
+_SLABS: dict = {}
+
+
+def _slab(key, nbytes: int, device):
+    """A reusable device buffer (grown, never shrunk): gather traffic lands in / leaves from the same allocation every step."""
+    import torch
+    t = _SLABS.get(key)
+    if t is None or t.numel() < nbytes or t.device != device:
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _SLABS[key] = t
+    return t
+
+
+def gather_batches(batches, dst: int = 0, verify: bool = False):
+    """The materialize-side gather: every result batch of every rank onto rank `dst`.
+
+    Each rank packs all buffers of its batches into ONE slab (chdb_device_batches_pack: device-to-device copies on
+    the ctx stream) and sends it as ONE NCCL message; rank `dst` posts one receive per source rank, all inside one
+    ncclGroupStart/End.  The pieces' sizes travel next to the payload, so `dst` can take the slab apart again
+    (order: batch, column, {validity, offsets, values}; pieces 256-byte aligned).  Returns on dst a list per source
+    rank of (slab[:total] tensor, sizes tensor); elsewhere None.  verify: also compares a checksum of every slab
+    across the link."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from .api import DeviceBatchList
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bl = batches if isinstance(batches, DeviceBatchList) else DeviceBatchList.from_batches(list(batches))
+    device = torch.device("cuda", bl.ctx.device)
+    total, sizes = bl.pack()                      # waits for the batches' counts, sizes the slab
+    out_slab = _slab(("send",), total, device)
+    if total:
+        bl.pack(out_slab.data_ptr(), out_slab.numel())
+    # NCCL runs on torch's stream: order it behind the copies the library enqueued on the ctx stream
+    torch.cuda.current_stream(device).wait_stream(torch.cuda.ExternalStream(bl.ctx.stream, device=device))
+    sizes_t = torch.from_numpy(np.frombuffer(sizes, dtype=np.int64).copy()).to(device)
+    meta = torch.tensor([total, sizes_t.numel()], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    ops, out = [], None
+    if rank == dst:
+        out = []
+        for src in range(world):
+            if src == dst:
+                out.append((out_slab[:total], sizes_t))
+                continue
+            n, m = (int(x) for x in metas[src].tolist())
+            slab = _slab(("recv", src), n, device)
+            st = torch.empty(m, dtype=torch.int64, device=device)
+            if n:
+                ops.append(dist.P2POp(dist.irecv, slab[:n], src))
+            if m:
+                ops.append(dist.P2POp(dist.irecv, st, src))
+            out.append((slab[:n], st))
+    else:
+        if total:
+            ops.append(dist.P2POp(dist.isend, out_slab[:total], dst))
+        if sizes_t.numel():
+            ops.append(dist.P2POp(dist.isend, sizes_t, dst))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    if verify:
+        mine = out_slab[:total].to(torch.int64).sum().reshape(1) if total else torch.zeros(1, dtype=torch.int64, device=device)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == dst:
+            for src, (slab, _) in enumerate(out):
+                got = int(slab.to(torch.int64).sum()) if slab.numel() else 0
+                if got != int(sums[src]):
+                    raise AssertionError(f"gather: slab of rank {src} arrived with checksum {got}, sent {int(sums[src])}")
+    return out
+
+
+GATHER_TRANSPORT = ("per rank ONE packed slab (chdb_device_batches_pack, device-to-device) sent as ONE NCCL message; rank 0 posts one "
+                    "receive per source inside one ncclGroupStart/End (torch.distributed.batch_isend_irecv) over NVLink")
 
 
 def gathered_bytes(got) -> int:
-    """Bytes rank `dst` received from the other ranks (its own buffers are not counted)."""
+    """Bytes rank `dst` received from the other ranks (its own slab is not counted)."""
     import torch.distributed as dist
     if got is None:
         return 0
     rank = dist.get_rank()
-    return sum(int(t.numel()) for src, bufs in enumerate(got) if src != rank for t in bufs)
+    return sum(int(slab.numel()) for src, (slab, _) in enumerate(got) if src != rank)
 
 
 class _CudaView:

@@ -234,6 +234,13 @@ int32_t chdb_device_batch_column(chdb_ctx* ctx, const chdb_device_batch* b, int3
 int64_t chdb_device_batch_nbytes(chdb_ctx* ctx, const chdb_device_batch* b, chdb_status* st);
 int32_t chdb_download(chdb_ctx* ctx, const chdb_device_batch* b, struct ArrowArray* out,
                       struct ArrowSchema* out_schema, chdb_status* st);
+/* Packs every buffer of `count` finished batches into ONE contiguous device buffer (pieces 256-byte aligned; order:
+ * batch, column, {validity, offsets, values}) with device-to-device copies on the ctx stream: the unit a
+ * materialize-side gather between processes sends over NVLink -- one message per GPU instead of one per buffer.
+ * sizes_out: int64[count * num_columns * 3] byte sizes of the pieces (0 = absent), or NULL.  dst == NULL: only the
+ * sizes and *total_bytes are computed (to size the destination). */
+int32_t chdb_device_batches_pack(chdb_ctx* ctx, const chdb_device_batch* const* batches, int32_t count, void* dst,
+                                 int64_t capacity, int64_t* sizes_out, int64_t* total_bytes, chdb_status* st);
 /* Copy a finished batch's buffers to another ctx's GPU (cudaMemcpyPeerAsync over NVLink; peer access is
  * enabled on first use): the materialize-side gather of per-GPU results.  Asynchronous on the destination
  * ctx's stream, ordered after the source ctx's stream; the source may be released right after the call. */
@@ -243,6 +250,7 @@ int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_b
  * (the buffers go back to the ctx's block cache with the last one). */
 void chdb_device_batch_retain(chdb_device_batch* b);
 void chdb_device_batch_release(chdb_device_batch* b);
+void chdb_device_batch_release_many(chdb_device_batch* const* batches, int32_t count);
 
 /* ---- device-resident record pool: the GPU-aware exchange's RecordPool ----
  * The reference's exchange keeps `records: HashMap<u64, Arc<RecordBatch>>` with a per-consumer-operator queue

@@ -208,6 +208,16 @@ extern "C" {
         out_schema: *mut FFI_ArrowSchema,
         st: *mut ChdbStatus,
     ) -> i32;
+    pub fn chdb_device_batches_pack(
+        ctx: *mut ChdbCtx,
+        batches: *const *const ChdbDeviceBatch,
+        count: i32,
+        dst: *mut c_void,
+        capacity: i64,
+        sizes_out: *mut i64,
+        total_bytes: *mut i64,
+        st: *mut ChdbStatus,
+    ) -> i32;
     pub fn chdb_peer_copy(
         dst_ctx: *mut ChdbCtx,
         src_ctx: *mut ChdbCtx,
@@ -217,6 +227,7 @@ extern "C" {
     ) -> i32;
     pub fn chdb_device_batch_retain(b: *mut ChdbDeviceBatch);
     pub fn chdb_device_batch_release(b: *mut ChdbDeviceBatch);
+    pub fn chdb_device_batch_release_many(batches: *const *mut ChdbDeviceBatch, count: i32);
 
     // ---- device-resident record pool (what a GPU-aware exchange keeps instead of Arc<RecordBatch>) ----
     pub fn chdb_record_pool_create(ctx: *mut ChdbCtx, budget_bytes: i64, out: *mut *mut ChdbRecordPool, st: *mut ChdbStatus) -> i32;
