@@ -51,6 +51,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 #define CHDB_OUT_META(P, k) chdb_jit::kOutMeta[k]
 #define CHDB_LONG_STRINGS(P) (chdb_jit::kLongStrings != 0)
 #define CHDB_OUT_HAS_VALIDITY(P, k) (chdb_jit::kOutHasValidity[k] != 0)
+#define CHDB_EARLY_COUNTS(P) (chdb_jit::kEarlyCounts != 0)
 #else
 #define CHDB_STATIC_UNROLL _Pragma("unroll 1")
 #define CHDB_N_IN P.n_in
@@ -64,6 +65,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 #define CHDB_OUT_META(P, k) (reinterpret_cast<const uint64_t*>(&P.out[k])[3])
 #define CHDB_LONG_STRINGS(P) (P.long_strings != 0)
 #define CHDB_OUT_HAS_VALIDITY(P, k) (P.out[k].validity != nullptr)
+#define CHDB_EARLY_COUNTS(P) (P.early_counts != 0)
 #endif
 
 template <typename V> struct Cont;
@@ -902,6 +904,18 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// [sel4 << 4 | bits4] -> the bits of bits4 at the set positions of sel4, packed (a 4-bit pext), four entries per word;
+// every CTA with bit-packed outputs copies it into shared memory.
+__device__ const uint32_t kPext4Words[64] = {
+    0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x01000100u, 0x01000100u, 0x01000100u, 0x01000100u,
+    0x01010000u, 0x01010000u, 0x01010000u, 0x01010000u, 0x03020100u, 0x03020100u, 0x03020100u, 0x03020100u,
+    0x00000000u, 0x01010101u, 0x00000000u, 0x01010101u, 0x01000100u, 0x03020302u, 0x01000100u, 0x03020302u,
+    0x01010000u, 0x03030202u, 0x01010000u, 0x03030202u, 0x03020100u, 0x07060504u, 0x03020100u, 0x07060504u,
+    0x00000000u, 0x00000000u, 0x01010101u, 0x01010101u, 0x01000100u, 0x01000100u, 0x03020302u, 0x03020302u,
+    0x01010000u, 0x01010000u, 0x03030202u, 0x03030202u, 0x03020100u, 0x03020100u, 0x07060504u, 0x07060504u,
+    0x00000000u, 0x01010101u, 0x02020202u, 0x03030303u, 0x01000100u, 0x03020302u, 0x05040504u, 0x07060706u,
+    0x01010000u, 0x03030202u, 0x05050404u, 0x07070606u, 0x03020100u, 0x07060504u, 0x0b0a0908u, 0x0f0e0d0cu};
+
 // What the output code needs from the CTA's shared memory besides the tile itself.
 struct TileShared {
   const uint8_t* pool;      // string literals (kernel parameter space)
@@ -988,11 +1002,12 @@ __device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan&
 // What a lane knows about its rows of the current slice.
 struct LaneCtx {
   int64_t row_base;       // absolute row of the lane's first row
+  uint32_t row32;         // the same in 32 bits (Arrow arrays hold < 2^31 rows): one IMAD.WIDE per address
   uint32_t inrange;       // rows that exist (tail tile), 4 bits
   uint32_t sel;           // selected rows, 4 bits
   uint32_t rank;          // slice-local rank of the lane's first selected row
   uint32_t count;         // selected rows of the slice
-  uint64_t obase;         // output row of the slice's first selected row
+  uint32_t obase;         // output row of the slice's first selected row (< 2^31, like every position below)
   const uint64_t* prefix; // the tile's slice prefixes [quantity][kTileSlices], or nullptr without a predicate
   int lane, slice;
   int wid;                // compute warp index in the CTA (its private bit stage / long-string tables)
@@ -1004,13 +1019,13 @@ __device__ __forceinline__ void put_bits(uint32_t bits, const LaneCtx& L, uint32
   const uint32_t s4 = L.sel, b4 = bits & 0xFu & s4;
   if (b4) {
     const uint32_t c = pext4[(s4 << 4) | b4];
-    const uint32_t p = ((uint32_t)L.obase & 31u) + L.rank, sh = p & 31u;
+    const uint32_t p = (L.obase & 31u) + L.rank, sh = p & 31u;
     atomicOr(&sb[p >> 5], c << sh);
     if (sh > 28u && (c >> (32u - sh))) atomicOr(&sb[(p >> 5) + 1], c >> (32u - sh));
   }
 }
 
-__device__ __forceinline__ uint32_t load_bits4(const uint8_t* __restrict__ bits, int64_t r, uint32_t need) {
+__device__ __forceinline__ uint32_t load_bits4(const uint8_t* __restrict__ bits, uint32_t r, uint32_t need) {
   if (bits == nullptr) return FULL;
   if (!need) return 0;
   return ((uint32_t)bits[r >> 3] >> (uint32_t)(r & 4)) & 0xFu;
@@ -1018,12 +1033,12 @@ __device__ __forceinline__ uint32_t load_bits4(const uint8_t* __restrict__ bits,
 
 // Stores the selected elements of one quad at consecutive output positions.
 template <typename E>
-__device__ __forceinline__ void store_sel(E* d, uint32_t s4, const E& e0, const E& e1, const E& e2, const E& e3) {
-  const uint32_t i1 = s4 & 1u, i2 = i1 + ((s4 >> 1) & 1u), i3 = i2 + ((s4 >> 2) & 1u);
-  if (s4 & 1u) d[0] = e0;
-  if (s4 & 2u) d[i1] = e1;
-  if (s4 & 4u) d[i2] = e2;
-  if (s4 & 8u) d[i3] = e3;
+__device__ __forceinline__ void store_sel(E* base, uint32_t o, uint32_t s4, const E& e0, const E& e1, const E& e2, const E& e3) {
+  const uint32_t i1 = o + (s4 & 1u), i2 = i1 + ((s4 >> 1) & 1u), i3 = i2 + ((s4 >> 2) & 1u);
+  if (s4 & 1u) base[o] = e0;
+  if (s4 & 2u) base[i1] = e1;
+  if (s4 & 4u) base[i2] = e2;
+  if (s4 & 8u) base[i3] = e3;
 }
 
 // 16 / 4 bytes from an arbitrarily aligned address (buffers are padded, so the aligned words around
@@ -1048,11 +1063,12 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* p) {
   return __funnelshift_r(w0, w[1], sh);
 }
 
-// One short value: by one thread, in the widest unit source, destination and length allow.
-__device__ __forceinline__ void copy_value(uint8_t* dst, const uint8_t* src, uint32_t n) {
+// One short value: by one thread, in the widest unit source, destination and length allow.  Only the common
+// case (one aligned 8-byte unit) is inlined at the call sites: eight inlined copies of the loops below were a
+// quarter of the kernel's code.
+__device__ __noinline__ void copy_value_slow(uint8_t* dst, const uint8_t* src, uint32_t n) {
   const uint32_t a = (uint32_t)(uintptr_t)dst | (uint32_t)(uintptr_t)src | n;
   if ((a & 7u) == 0) {
-    if (n == 8) { *(uint2*)dst = *(const uint2*)src; return; }
 #pragma unroll 1
     for (uint32_t i = 0; i < n; i += 8) *(uint2*)(dst + i) = *(const uint2*)(src + i);
   } else if ((a & 3u) == 0) {
@@ -1062,6 +1078,11 @@ __device__ __forceinline__ void copy_value(uint8_t* dst, const uint8_t* src, uin
 #pragma unroll 1
     for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
   }
+}
+__device__ __forceinline__ void copy_value(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  const uint32_t a = (uint32_t)(uintptr_t)dst | (uint32_t)(uintptr_t)src;
+  if (n == 8 && (a & 7u) == 0) *(uint2*)dst = *(const uint2*)src;
+  else copy_value_slow(dst, src, n);
 }
 
 // Long strings: the warp's output byte range is produced chunk-centric -- each lane builds aligned
@@ -1133,23 +1154,23 @@ __device__ __forceinline__ void load_output(const KernelParams& P, const ColumnD
   if (o_kind != OUT_PASS) return;
   const ColumnDesc& c = cols[o_slot];
   const uint32_t sel = L.sel;
-  const int64_t r = L.row_base;
+  const uint32_t r = L.row32;
   if (CHDB_OUT_HAS_VALIDITY(P, k)) R.vbits = load_bits4(c.validity, r, sel);
   if (!L.inrange) return;   // (a tail tile's missing rows: nothing to read, nothing will be stored)
   const uint8_t* src = (const uint8_t*)c.values;
   if (o_type == T_BOOL) {
     R.z = load_bits4(src, r, sel);
   } else if (o_type == T_UTF8) {
-    const int4 a = *(const int4*)(c.offsets + r);
+    const int4 a = *(const int4*)(c.offsets + (size_t)r);
     R.x = make_uint4((uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w);
-    R.z = (uint32_t)c.offsets[r + 4];
+    R.z = (uint32_t)c.offsets[(size_t)r + 4];
   } else if (o_width == 4) {
-    R.x = *(const uint4*)(src + r * 4);
+    R.x = *(const uint4*)(src + (size_t)r * 4);
   } else if (o_width == 8) {
-    R.x = *(const uint4*)(src + r * 8);
-    R.y = *(const uint4*)(src + r * 8 + 16);
+    R.x = *(const uint4*)(src + (size_t)r * 8);
+    R.y = *(const uint4*)(src + (size_t)r * 8 + 16);
   } else if (o_width == 2) {
-    const uint2 t = *(const uint2*)(src + r * 2);
+    const uint2 t = *(const uint2*)(src + (size_t)r * 2);
     R.x.x = t.x; R.x.y = t.y;
   } else if (o_width == 1) {
     R.x.x = *(const uint32_t*)(src + r);
@@ -1169,7 +1190,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const Column
   const bool o_has_validity = CHDB_OUT_HAS_VALIDITY(P, k);
   const uint32_t sel = L.sel;
   const int lane = L.lane;
-  const uint64_t o = L.obase + L.rank;   // output row of the lane's first selected row
+  const uint32_t o = L.obase + L.rank;   // output row of the lane's first selected row
   uint32_t vbits = R.vbits;  // validity of this output for the lane's rows
   if (o_kind == OUT_EXPR) {
     uint32_t accm = 0;
@@ -1180,10 +1201,10 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const Column
       // `sel` as the active mask: checked arithmetic only sees rows that survived the filter
       run_program<V, 1, BEGIN, END>(P, cols, (int)o_begin, (int)o_end, qb, L.inrange, sel, sh.pool, a4, accm, vbits);
       if (o_type == T_BOOL) {}
-      else if (o_width == 4) store_sel<uint32_t>((uint32_t*)o_values + o, sel, (uint32_t)a4[0], (uint32_t)a4[1], (uint32_t)a4[2], (uint32_t)a4[3]);
-      else if (o_width == 8) store_sel<uint64_t>((uint64_t*)o_values + o, sel, (uint64_t)a4[0], (uint64_t)a4[1], (uint64_t)a4[2], (uint64_t)a4[3]);
-      else if (o_width == 2) store_sel<uint16_t>((uint16_t*)o_values + o, sel, (uint16_t)a4[0], (uint16_t)a4[1], (uint16_t)a4[2], (uint16_t)a4[3]);
-      else store_sel<uint8_t>((uint8_t*)o_values + o, sel, (uint8_t)a4[0], (uint8_t)a4[1], (uint8_t)a4[2], (uint8_t)a4[3]);
+      else if (o_width == 4) store_sel<uint32_t>((uint32_t*)o_values, o, sel, (uint32_t)a4[0], (uint32_t)a4[1], (uint32_t)a4[2], (uint32_t)a4[3]);
+      else if (o_width == 8) store_sel<uint64_t>((uint64_t*)o_values, o, sel, (uint64_t)a4[0], (uint64_t)a4[1], (uint64_t)a4[2], (uint64_t)a4[3]);
+      else if (o_width == 2) store_sel<uint16_t>((uint16_t*)o_values, o, sel, (uint16_t)a4[0], (uint16_t)a4[1], (uint16_t)a4[2], (uint16_t)a4[3]);
+      else store_sel<uint8_t>((uint8_t*)o_values, o, sel, (uint8_t)a4[0], (uint8_t)a4[1], (uint8_t)a4[2], (uint8_t)a4[3]);
     }
     if (o_type == T_BOOL) { put_bits(accm, L, bitstage + kb * kBitWords, sh.pext4); kb++; }
   } else {
@@ -1194,7 +1215,7 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const Column
     } else if (o_type == T_UTF8) {
       // offsets: running sum of the selected lengths, restarted at 0 for the output
       const uint8_t* sv = (const uint8_t*)c.values;
-      const uint64_t byte_base = L.prefix[(1 + o_utf8) * kTileSlices + L.slice];   // output byte offset of this slice's first value
+      const uint32_t byte_base = (uint32_t)L.prefix[(1 + o_utf8) * kTileSlices + L.slice];   // output byte offset of this slice's first value
       int32_t* const o_off = P.out[k].offsets;
       const int32_t o5[5] = {(int32_t)R.x.x, (int32_t)R.x.y, (int32_t)R.x.z, (int32_t)R.x.w, (int32_t)R.z};
       uint32_t len[4];
@@ -1206,42 +1227,42 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const Column
       const bool chunked = CHDB_LONG_STRINGS(P) && slice_bytes > 24u * L.count;
       uint32_t* s_oo = ltab + L.wid * (2 * (kWarpRows + 4));
       int32_t* s_src = (int32_t*)(s_oo + kWarpRows + 4);
-      int32_t* d = o_off + o;
+      uint32_t oi = o;
       uint32_t wr = L.rank;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         if ((sel >> i) & 1u) {
-          *d = (int32_t)(uint32_t)(byte_base + bo);
-          d++;
+          o_off[oi] = (int32_t)(byte_base + bo);
+          oi++;
           if (chunked) { s_oo[wr] = bo; s_src[wr] = o5[i]; wr++; }
-          else if (len[i]) copy_value(o_values + byte_base + bo, sv + o5[i], len[i]);
+          else if (len[i]) copy_value(o_values + (byte_base + bo), sv + (uint32_t)o5[i], len[i]);
           bo += len[i];
         }
       }
       if (chunked) {
         if (lane == 0) s_oo[L.count] = slice_bytes;
         __syncwarp();
-        const uint32_t mis = (uint32_t)(byte_base & 15u);
+        const uint32_t mis = byte_base & 15u;
         copy_long_strings(sv, o_values + (byte_base - mis), mis, slice_bytes, L.count, s_oo, s_src, lane);
         __syncwarp();
       }
     } else if (sel) {
       if (o_width == 4) {
-        store_sel<uint32_t>((uint32_t*)o_values + o, sel, R.x.x, R.x.y, R.x.z, R.x.w);
+        store_sel<uint32_t>((uint32_t*)o_values, o, sel, R.x.x, R.x.y, R.x.z, R.x.w);
       } else if (o_width == 8) {
-        store_sel<uint2>((uint2*)o_values + o, sel, make_uint2(R.x.x, R.x.y), make_uint2(R.x.z, R.x.w), make_uint2(R.y.x, R.y.y),
+        store_sel<uint2>((uint2*)o_values, o, sel, make_uint2(R.x.x, R.x.y), make_uint2(R.x.z, R.x.w), make_uint2(R.y.x, R.y.y),
                          make_uint2(R.y.z, R.y.w));
       } else if (o_width == 16) {
-        const uint4* s16 = (const uint4*)c.values + L.row_base;
+        const uint4* s16 = (const uint4*)c.values + L.row32;
         uint4* d = (uint4*)o_values + o;
 #pragma unroll
         for (int i = 0; i < 4; i++)
           if ((sel >> i) & 1u) { *d = s16[i]; d++; }
       } else if (o_width == 2) {
-        store_sel<uint16_t>((uint16_t*)o_values + o, sel, (uint16_t)R.x.x, (uint16_t)(R.x.x >> 16), (uint16_t)R.x.y, (uint16_t)(R.x.y >> 16));
+        store_sel<uint16_t>((uint16_t*)o_values, o, sel, (uint16_t)R.x.x, (uint16_t)(R.x.x >> 16), (uint16_t)R.x.y, (uint16_t)(R.x.y >> 16));
       } else {
         const uint32_t x = R.x.x;
-        store_sel<uint8_t>(o_values + o, sel, (uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24));
+        store_sel<uint8_t>(o_values, o, sel, (uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24));
       }
     }
   }
@@ -1249,8 +1270,10 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const Column
     // nulls are the rare case: the stage collects the NULL bits (most lanes have nothing to add)
     const uint32_t nulls = sel & ~vbits & 0xFu;
     if (nulls) put_bits(nulls, L, bitstage + kb * kBitWords, sh.pext4);
-    const uint32_t slice_nulls = __reduce_add_sync(FULL, (uint32_t)__popc(nulls));
-    if (lane == 0 && slice_nulls) atomicAdd(&sh.nulls[k], slice_nulls);
+    if (!CHDB_EARLY_COUNTS(P)) {   // (two-launch form with pass-through outputs only: the select kernel has counted them)
+      const uint32_t slice_nulls = __reduce_add_sync(FULL, (uint32_t)__popc(nulls));
+      if (lane == 0 && slice_nulls) atomicAdd(&sh.nulls[k], slice_nulls);
+    }
     kb++;
   }
 }
@@ -1277,10 +1300,10 @@ __device__ __forceinline__ void store_outputs_range(const KernelParams& P, const
 // The warp's bit stage -> global bitmaps.  Stage bit (obase & 31) + r belongs to output row obase + r;
 // whole words are stored, the (at most two) words shared with neighbouring slices are merged with
 // atomicOr (the bitmaps are zero-initialised).  The stage is left zeroed for the warp's next slice.
-__device__ __forceinline__ void flush_bits(const KernelParams& P, uint32_t* bitstage, uint64_t obase, uint32_t count, int lane) {
-  const uint32_t o = (uint32_t)obase & 31u, end = o + count;
+__device__ __forceinline__ void flush_bits(const KernelParams& P, uint32_t* bitstage, uint32_t obase, uint32_t count, int lane) {
+  const uint32_t o = obase & 31u, end = o + count;
   const uint32_t nwords = (end + 31u) >> 5;
-  const uint64_t g0 = obase >> 5;
+  const uint32_t g0 = obase >> 5;
   int kb = 0;
   CHDB_STATIC_UNROLL
   for (int k = 0; k < CHDB_N_OUT; k++) {
@@ -1329,14 +1352,26 @@ __device__ __forceinline__ void trace_event(const KernelParams& P, int ev) {
   if (P.trace != nullptr && blockIdx.x < 8192) P.trace[(size_t)blockIdx.x * 8 + ev] = (uint64_t)clock64();
 }
 
-template <typename V, bool MANY>
+// MODE: kFused -- everything in one launch (steps 1-4 above);
+//       kSelect / kGather -- the same work as two launches without any CTA waiting on another while it holds a tile:
+//         select: no staging (every predicate byte is read once, by one thread: plain 128-bit global loads), steps 2-3:
+//                 selection bits -> P.b.selbits, tile aggregates -> look-back -> every descriptor ends up as the tile's
+//                 inclusive prefix; the CTAs that wait in the look-back hold registers only, and nothing follows the wait;
+//         gather: steps 1 and 4 with the selection bits read back (128 B per tile) and the tile's exclusive prefix taken
+//                 from its predecessor's descriptor.  Tiles are visited last-to-first: what select read last is still
+//                 in L2 when gather starts.
+enum StreamMode : int { kFused = 0, kSelect = 1, kGather = 2 };
+
+template <typename V, bool MANY, int MODE>
 __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePlan& TP) {
+  static_assert(MODE == kFused || !MANY, "many-batch launches run the fused kernel");
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_full, s_full_values;
   __shared__ uint32_t s_nulls[kMaxOutCols];
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int64_t tile = blockIdx.x;
+  if (MODE == kGather) tile = (int64_t)gridDim.x - 1 - (int64_t)blockIdx.x;
   if (MANY) {
     // this tile's parameter block: the program part from the launch parameters, the batch part from its record
     KernelParams* mine = (KernelParams*)(smem + TP.params_off);
@@ -1361,7 +1396,9 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
   const bool has_pred = CHDB_PRED_END > CHDB_PRED_BEGIN;
   const int nq = 1 + CHDB_N_UTF8;
   uint8_t* const stage = smem;
-  ColumnDesc* const cols = (ColumnDesc*)(smem + TP.cols_off);
+  // (select reads the columns where they are: the descriptors come straight from the kernel parameters)
+  ColumnDesc* const cols_s = (ColumnDesc*)(smem + TP.cols_off);
+  const ColumnDesc* const cols = MODE == kSelect ? P.in : cols_s;
   uint32_t* const s_cnt = (uint32_t*)(smem + TP.cnt_off);
   uint64_t* const s_pre = (uint64_t*)(smem + TP.pre_off);
   uint64_t* const s_tot = (uint64_t*)(smem + TP.tot_off);
@@ -1369,20 +1406,15 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
   uint32_t* const ltab = (uint32_t*)(smem + TP.ltab_off);
   uint8_t* const pext4 = smem + TP.pext_off;
   const uint32_t full = smem_u32(&s_full), full_values = smem_u32(&s_full_values);
-  if (tid == 0) {
+  if (MODE != kSelect && tid == 0) {
     mbar_init(full, 1);
     mbar_init(full_values, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (P.n_bits > 0) {
-    for (int i = tid; i < 256; i += kThreads) {
-      const uint32_t s = (uint32_t)i >> 4, v = (uint32_t)i & 15u;
-      uint32_t out = 0, n = 0;
-      for (int j = 0; j < 4; j++)
-        if ((s >> j) & 1u) { out |= ((v >> j) & 1u) << n; n++; }
-      pext4[i] = (uint8_t)out;
-    }
+  if (MODE != kSelect && P.n_bits > 0) {
+    for (int i = tid; i < 64; i += kThreads) ((uint32_t*)pext4)[i] = kPext4Words[i];
+#pragma unroll 1
     for (int i = tid; i < kWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
   }
   if (tid < kMaxOutCols) s_nulls[tid] = 0;
@@ -1391,20 +1423,189 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
   const bool last_tile = tile == (int64_t)P.b.num_tiles - 1;
   __syncthreads();
   grid_launch_dependents();
+  // gather: the tile's loads do not depend on the select kernel (the launch chain starts with a kernel that is NOT a
+  // programmatic dependent, so everything older on the stream -- whatever produced the inputs -- has completed)
+  if (MODE == kGather && warp == 0) load_tile(P, TP, cols_s, stage, full, full_values, row0, (uint32_t)tile_rows, lane);
   grid_dependency_wait();     // the zeroed workspace; inputs an earlier kernel on this stream may still be writing
   if (tid == 0) {
     trace_event(P, 0);
     if (P.trace != nullptr && blockIdx.x < 8192) { uint32_t smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); P.trace[(size_t)blockIdx.x * 8 + 7] = smid; }
   }
-  if (warp == 0) load_tile(P, TP, cols, stage, full, full_values, row0, (uint32_t)tile_rows, lane);
-  mbar_wait(full, 0);
-  if (TP.pred_reads_utf8) mbar_wait(full_values, 0);
+  if (MODE == kFused && warp == 0) load_tile(P, TP, cols_s, stage, full, full_values, row0, (uint32_t)tile_rows, lane);
+  // gather: the lane's selection bits of each of its slices (written by the select kernel; served by L2)
+  uint32_t selq[kSpw];
+  if (MODE == kGather && has_pred) {
+#pragma unroll
+    for (int j = 0; j < kSpw; j++) {
+      const int64_t r = row0 + (warp * kSpw + j) * kWarpRows + lane * 4;
+      selq[j] = ((uint32_t)__ldcg((const uint8_t*)P.b.selbits + (r >> 3)) >> (uint32_t)(r & 4)) & 0xFu;
+    }
+  }
+  if (MODE == kGather && CHDB_EARLY_COUNTS(P) && blockIdx.x == 0 && warp == kWarps - 1) {
+    // The select kernel has completed: batch totals = the sums of its group totals; the closing Utf8 offset
+    // (offsets[total_rows] = total_bytes, also covers an empty result); counts, NULL counts and the error word go to
+    // the pinned host mirror.  One warp of one CTA, while its tile lands.
+    const size_t nt = (size_t)P.b.num_tiles, ng = (nt + kGroupTiles - 1) / kGroupTiles;
+    uint64_t rows = 0;
+#pragma unroll 1
+    for (int q = 0; q < nq; q++) {
+      const uint64_t* gt = P.b.desc + (size_t)nq * nt + (size_t)q * ng;
+      uint64_t part = 0;
+#pragma unroll 1
+      for (size_t i = lane; i < ng; i += 32) part += load_descriptor(gt + i);
+      part = warp_sum64(part);   // (every lane holds the total)
+      if (q == 0) rows = part;
+      if (lane == 0) { P.b.counts[q] = part; P.b.host_counts[q] = part; }
+      if (q > 0 && lane < CHDB_N_OUT) {
+        const OutDesc& o = P.out[lane];
+        if (o.utf8_index == (uint8_t)(q - 1)) o.offsets[rows] = (int32_t)part;
+      }
+    }
+#pragma unroll 1
+    for (int i = nq + lane; i <= P.n_counts; i += 32) P.b.host_counts[i] = load_descriptor((const uint64_t*)P.b.counts + i);
+    __syncwarp();
+  }
+  if (MODE == kGather && has_pred) {
+    // the tile's exclusive prefixes: the totals of the tile groups before its own + of the tiles before it inside its
+    // group (left by the select kernel); the loads are in flight while the tile lands
+    for (int q = warp; q < nq; q += kWarps) {
+      const size_t nt = (size_t)P.b.num_tiles, ng = (nt + kGroupTiles - 1) / kGroupTiles;
+      const int64_t g = tile / kGroupTiles;
+      const uint64_t* tt = P.b.desc + (size_t)q * nt;
+      const uint64_t* gt = P.b.desc + (size_t)nq * nt + (size_t)q * ng;
+      uint64_t part = 0;
+#pragma unroll 2
+      for (int64_t i = lane; i < g; i += 32) part += load_descriptor(gt + i);
+#pragma unroll 2
+      for (int64_t i = g * kGroupTiles + lane; i < tile; i += 32) part += load_descriptor(tt + i);
+      part = warp_sum64(part);
+      if (lane == 0) s_tot[q] = part;
+    }
+  }
+  if (MODE != kSelect) {
+    mbar_wait(full, 0);
+    if (TP.pred_reads_utf8 && MODE == kFused) mbar_wait(full_values, 0);
+  }
   if (tid == 0) trace_event(P, 1);
 
   TileShared sh;
   sh.pool = (const uint8_t*)P.strpool;
   sh.pext4 = pext4;
   sh.nulls = s_nulls;
+
+  // ---- 2 (select). every load of the warp's kSpw slices is issued before anything waits for one of them: the predicate
+  //      runs on all of the lane's quads at once, the Utf8 offsets are requested alongside its columns ----
+  if constexpr (MODE == kSelect) {
+    int64_t qb[kSpw];
+    uint32_t in_all = 0;
+#pragma unroll
+    for (int j = 0; j < kSpw; j++) {
+      const int slice = warp * kSpw + j;
+      qb[j] = row0 + slice * kWarpRows + lane * 4;
+      const int left = tile_rows - (slice * kWarpRows + lane * 4);
+      in_all |= (left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u)) << (4 * j);
+    }
+#ifdef CHDB_JIT
+    int4 oa[chdb_jit::kNumUtf8 > 0 ? chdb_jit::kNumUtf8 : 1][kSpw];
+    int ob[chdb_jit::kNumUtf8 > 0 ? chdb_jit::kNumUtf8 : 1][kSpw];
+#pragma unroll
+    for (int k = 0; k < chdb_jit::kNumOut; k++) {
+      const uint64_t meta = chdb_jit::kOutMeta[k];
+      const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu, o_slot = (uint32_t)(meta >> 24) & 0xFFu;
+      if (o_utf8 == 0xFFu) continue;
+      const int32_t* off = cols[o_slot].offsets;
+#pragma unroll
+      for (int j = 0; j < kSpw; j++) {
+        oa[o_utf8][j] = make_int4(0, 0, 0, 0);
+        ob[o_utf8][j] = 0;
+        if ((in_all >> (4 * j)) & 0xFu) { oa[o_utf8][j] = *(const int4*)(off + qb[j]); ob[o_utf8][j] = off[qb[j] + 4]; }
+      }
+    }
+#endif
+    V acc[4 * kSpw];
+    uint32_t accm, accv;
+#ifdef CHDB_JIT
+    run_program<V, kSpw, chdb_jit::kPredBegin, chdb_jit::kPredEnd>(P, cols, 0, 0, qb, in_all, in_all, sh.pool, acc, accm, accv);
+#else
+    run_program<V, kSpw>(P, cols, P.pred_begin, P.pred_end, qb, in_all, in_all, sh.pool, acc, accm, accv);
+#endif
+    const uint32_t sel_all = accm & accv & in_all;   // NULL predicate rows are dropped (arrow-select filter)
+#pragma unroll
+    for (int j = 0; j < kSpw; j++) {
+      const int slice = warp * kSpw + j;
+      const uint32_t sel4 = (sel_all >> (4 * j)) & 0xFu;
+      const uint32_t wrows = __reduce_add_sync(FULL, (uint32_t)__popc(sel4));
+      if (lane == 0) s_cnt[slice] = wrows;
+      // selected value bytes per Utf8 output
+      CHDB_STATIC_UNROLL
+      for (int k = 0; k < CHDB_N_OUT; k++) {
+        const uint64_t meta = CHDB_OUT_META(P, k);
+        const uint32_t o_utf8 = (uint32_t)(meta >> 48) & 0xFFu;
+        if (o_utf8 == 0xFFu) continue;   // uniform branch
+        uint32_t bytes = 0;
+#ifdef CHDB_JIT
+        const int4 a = oa[o_utf8][j];
+        const int a4 = ob[o_utf8][j];
+#else
+        int4 a = make_int4(0, 0, 0, 0);
+        int a4 = 0;
+        if (sel4) {
+          const int32_t* off = cols[(uint32_t)(meta >> 24) & 0xFFu].offsets;
+          a = *(const int4*)(off + qb[j]);
+          a4 = off[qb[j] + 4];
+        }
+#endif
+        if (sel4 & 1u) bytes += (uint32_t)(a.y - a.x);
+        if (sel4 & 2u) bytes += (uint32_t)(a.z - a.y);
+        if (sel4 & 4u) bytes += (uint32_t)(a.w - a.z);
+        if (sel4 & 8u) bytes += (uint32_t)(a4 - a.w);
+        const uint32_t wbytes = __reduce_add_sync(FULL, bytes);
+        if (lane == 0) s_cnt[(1 + o_utf8) * kTileSlices + slice] = wbytes;
+      }
+      // the selection bits of the slice, LSB-first, one 32-bit word per 8 lanes
+      uint32_t w = sel4;
+      w |= __shfl_down_sync(FULL, w, 1) << 4;
+      w |= __shfl_down_sync(FULL, w, 2) << 8;
+      w |= __shfl_down_sync(FULL, w, 4) << 16;
+      if ((lane & 7) == 0) P.b.selbits[tile * (kTileRows / 32) + slice * (kWarpRows / 32) + (lane >> 3)] = w;
+    }
+    // With pass-through outputs only, everything the host wants to know is known here: the NULLs among the selected
+    // rows of every nullable output are counted now, and the first gather CTA publishes the batch totals before it
+    // starts on its tile -- the gather kernel otherwise moves data and nothing else (no counting, no fence, no
+    // last-CTA protocol at its end).
+    if (CHDB_EARLY_COUNTS(P)) {
+      CHDB_STATIC_UNROLL
+      for (int k = 0; k < CHDB_N_OUT; k++) {
+        if (!CHDB_OUT_HAS_VALIDITY(P, k)) continue;
+        const uint64_t meta = CHDB_OUT_META(P, k);
+        const uint8_t* vb = cols[(uint32_t)(meta >> 24) & 0xFFu].validity;
+        uint32_t nulls = 0;
+#pragma unroll
+        for (int j = 0; j < kSpw; j++) {
+          const uint32_t sel4 = (sel_all >> (4 * j)) & 0xFu;
+          nulls += (uint32_t)__popc(sel4 & ~load_bits4(vb, (uint32_t)qb[j], sel4) & 0xFu);
+        }
+        nulls = __reduce_add_sync(FULL, nulls);
+        if (lane == 0 && nulls) atomicAdd(&s_nulls[k], nulls);
+      }
+    }
+    // tile totals: plain counts for the gather kernel's prefix sums, and the tile group's running totals
+    __syncthreads();
+    const size_t nt = (size_t)P.b.num_tiles, ng = (nt + kGroupTiles - 1) / kGroupTiles;
+    for (int q = warp; q < nq; q += kWarps) {
+      const uint32_t c = lane < kTileSlices ? s_cnt[q * kTileSlices + lane] : 0u;
+      const uint32_t agg = __reduce_add_sync(FULL, c);
+      if (lane == 0) {
+        P.b.desc[(size_t)q * nt + (size_t)tile] = agg;
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(P.b.desc + (size_t)nq * nt + (size_t)q * ng + (size_t)(tile / kGroupTiles)), "l"((uint64_t)agg) : "memory");
+      }
+    }
+    // (fire-and-forget: the gather kernel only starts once this kernel has completed, and its first CTA publishes
+    //  the batch totals -- no fence, no last-CTA protocol here)
+    if (CHDB_EARLY_COUNTS(P) && warp == 0 && lane < CHDB_N_OUT && P.out[lane].validity != nullptr && s_nulls[lane] != 0)
+      asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(P.b.counts + P.out[lane].count_index), "l"((uint64_t)s_nulls[lane]) : "memory");
+    return;
+  }
 
   // ---- 2. predicate -> selection bits, ranks, slice counts ----
   uint32_t sels = 0;        // 4 selection bits per slice of this warp
@@ -1416,7 +1617,9 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
     const int left = tile_rows - (slice * kWarpRows + lane * 4);
     const uint32_t in4 = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
     uint32_t sel4 = in4;
-    if (has_pred) {
+    if (MODE == kGather) {
+      if (has_pred) sel4 = selq[j] & in4;
+    } else if (has_pred) {
       V acc[4];
       uint32_t accm, accv;
 #ifdef CHDB_JIT
@@ -1462,6 +1665,13 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
       uint32_t agg;
       const uint32_t before = warp_excl_scan(c, lane, agg);
       uint64_t* desc = P.b.desc + (size_t)q * (size_t)P.b.num_tiles;
+      if (MODE == kGather) {
+        const uint64_t excl = s_tot[q];   // (summed by this warp before the tile landed)
+        __syncwarp();
+        if (lane < kTileSlices) s_pre[q * kTileSlices + lane] = excl + before;
+        if (lane == 0) s_tot[q] = excl + agg;
+        continue;
+      }
       if (lane == 0) publish_descriptor(desc + tile, tile == 0 ? kFlagPrefix : kFlagAgg, agg);
       const uint64_t excl = lookback(desc, (uint32_t)tile, agg, lane);
       if (lane < kTileSlices) s_pre[q * kTileSlices + lane] = excl + before;
@@ -1469,7 +1679,7 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
       if (q == 0 && lane == 0) trace_event(P, 3);
     }
     __syncthreads();
-    if (last_tile) {
+    if (last_tile && !(MODE == kGather && CHDB_EARLY_COUNTS(P))) {
       // batch totals, and the closing Utf8 offset: offsets[total_rows] = total_bytes (also covers an empty result)
       if (tid < nq) P.b.counts[tid] = s_tot[tid];
       if (tid < CHDB_N_OUT) {
@@ -1480,7 +1690,7 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
   }
 
   // ---- 4. the selected rows, to their final positions ----
-  if (!TP.pred_reads_utf8) mbar_wait(full_values, 0);
+  if (!TP.pred_reads_utf8 || MODE == kGather) mbar_wait(full_values, 0);
   if (tid == 0) trace_event(P, 4);
   uint32_t* const bitstage = bitstages + warp * P.n_bits * kBitWords;
 #pragma unroll
@@ -1492,6 +1702,7 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
     L.slice = slice;
     L.wid = warp;
     L.row_base = row0 + slice * kWarpRows + lane * 4;
+    L.row32 = (uint32_t)L.row_base;
     {
       const int left = tile_rows - (slice * kWarpRows + lane * 4);
       L.inrange = left >= 4 ? 0xFu : left <= 0 ? 0u : ((1u << left) - 1u);
@@ -1501,10 +1712,10 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
     L.count = s_cnt[slice];
     if (has_pred) {
       L.prefix = s_pre;
-      L.obase = s_pre[slice];
+      L.obase = (uint32_t)s_pre[slice];
     } else {
       L.prefix = nullptr;
-      L.obase = (uint64_t)(row0 + slice * kWarpRows);
+      L.obase = (uint32_t)(row0 + slice * kWarpRows);
     }
     int kb = 0;
 #ifdef CHDB_JIT
@@ -1529,6 +1740,8 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
     }
   }
 
+  if (MODE == kGather && CHDB_EARLY_COUNTS(P)) return;   // (the select kernel did the bookkeeping)
+
   // ---- null counts; the last CTA to finish mirrors the counts into pinned host memory (warp 0 only: the other warps
   //      are done once their rows are stored) ----
   __syncthreads();
@@ -1545,6 +1758,7 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
   last = __shfl_sync(FULL, last, 0);
   if (last) {
     __threadfence();
+#pragma unroll 1
     for (int i = lane; i <= P.n_counts; i += 32) P.b.host_counts[i] = __ldcg((const unsigned long long*)P.b.counts + i);
   }
   if (tid == 0) trace_event(P, 6);
@@ -1560,9 +1774,9 @@ __device__ __forceinline__ void zero_body(uint4* p, size_t n16) {
 }
 
 #ifndef CHDB_JIT
-template <typename V, bool MANY>
+template <typename V, bool MANY, int MODE>
 __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) stream_kernel(const __grid_constant__ KernelParams P, const __grid_constant__ TilePlan TP) {
-  stream_body<V, MANY>(P, TP);
+  stream_body<V, MANY, MODE>(P, TP);
 }
 __global__ void __launch_bounds__(kZeroThreads) zero_kernel(uint4* p, size_t n16) { zero_body(p, n16); }
 #endif
@@ -1572,9 +1786,18 @@ __global__ void __launch_bounds__(kZeroThreads) zero_kernel(uint4* p, size_t n16
 #ifdef CHDB_JIT
 // the specialised kernels of one NVRTC module, found by their unmangled names
 extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_stream(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::TilePlan TP) {
-  chdb::stream_body<chdb_jit::Container, false>(P, TP);
+  chdb::stream_body<chdb_jit::Container, false, chdb::kFused>(P, TP);
+}
+#ifndef CHDB_JIT_SELECT_MIN_BLOCKS
+#define CHDB_JIT_SELECT_MIN_BLOCKS 8
+#endif
+extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_SELECT_MIN_BLOCKS) chdb_jit_select(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::TilePlan TP) {
+  chdb::stream_body<chdb_jit::Container, false, chdb::kSelect>(P, TP);
+}
+extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_gather(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::TilePlan TP) {
+  chdb::stream_body<chdb_jit::Container, false, chdb::kGather>(P, TP);
 }
 extern "C" __global__ void __launch_bounds__(chdb::kThreads, CHDB_JIT_MIN_BLOCKS) chdb_jit_stream_many(const __grid_constant__ chdb::KernelParams P, const __grid_constant__ chdb::TilePlan TP) {
-  chdb::stream_body<chdb_jit::Container, true>(P, TP);
+  chdb::stream_body<chdb_jit::Container, true, chdb::kFused>(P, TP);
 }
 #endif

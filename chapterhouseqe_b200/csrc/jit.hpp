@@ -19,14 +19,15 @@ constexpr int64_t kJitAutoRows = 1 << 18;
 struct JitKernel {   // one NVRTC module: the stream kernel (single-batch and many-batch entry points) specialised for one program
   std::vector<char> cubin;
   cudaLibrary_t library = nullptr;
-  cudaKernel_t stream = nullptr, stream_many = nullptr;
+  cudaKernel_t stream = nullptr, stream_many = nullptr, select = nullptr, gather = nullptr;
 };
 
 bool jit_available(std::string* why);
 std::string jit_prologue(const KernelParams& kp, bool has64, int min_blocks);
 // Cached; returns nullptr (and the reason) when specialisation is impossible -> use the interpreter.
 const JitKernel* jit_get(const KernelParams& kp, bool has64, int min_blocks, std::string* err);
-cudaError_t jit_launch_stream(const JitKernel* k, const KernelParams& p, const TilePlan& tp, unsigned grid, cudaStream_t stream);
+// mode: StreamMode (0 fused, 1 select, 2 gather)
+cudaError_t jit_launch_stream(const JitKernel* k, const KernelParams& p, const TilePlan& tp, int mode, unsigned grid, cudaStream_t stream);
 void jit_stats(int64_t* compiles, double* seconds);
 std::vector<char> jit_compile_offline(const KernelParams& kp, bool has64, std::string* log);
 

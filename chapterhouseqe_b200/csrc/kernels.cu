@@ -31,11 +31,12 @@ inline size_t up128(size_t x) { return (x + 127) & ~(size_t)127; }
 // would leave room for fewer than kWantCtas CTAs per SM, the largest buffers are read from global memory instead
 // (the loading warp then prefetches their slices into L2).  Utf8 value bytes are staged only when the values
 // are short (long values are copied global -> global by whole warps).
-int plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many) {
+int plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many, bool stage) {
   struct Buf { int slot; int kind; size_t bytes; };   // kind 0: validity, 1: offsets, 2: values
   std::vector<Buf> bufs;
   for (int s = 0; s < kp.n_in; s++) {
     tp.slot[s] = StageSlot{kNotStaged, kNotStaged, kNotStaged, 0};
+    if (!stage) continue;
     const ColumnDesc& c = kp.in[s];
     const uint8_t use = tp.use[s];
     if ((use & USE_VALIDITY) && c.validity != nullptr) bufs.push_back({s, 0, (size_t)kTileRows / 8});
@@ -136,10 +137,13 @@ cudaError_t launch_stream_kernel(const void* kernel, const KernelParams& p, cons
   return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
-cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, unsigned grid, cudaStream_t stream) {
+cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, int mode, unsigned grid, cudaStream_t stream) {
   const bool many = p.many != nullptr;
-  const void* kern = has64 ? (many ? (const void*)stream_kernel<uint64_t, true> : (const void*)stream_kernel<uint64_t, false>)
-                           : (many ? (const void*)stream_kernel<uint32_t, true> : (const void*)stream_kernel<uint32_t, false>);
+  const void* kern;
+  if (mode == kSelect) kern = has64 ? (const void*)stream_kernel<uint64_t, false, kSelect> : (const void*)stream_kernel<uint32_t, false, kSelect>;
+  else if (mode == kGather) kern = has64 ? (const void*)stream_kernel<uint64_t, false, kGather> : (const void*)stream_kernel<uint32_t, false, kGather>;
+  else kern = has64 ? (many ? (const void*)stream_kernel<uint64_t, true, kFused> : (const void*)stream_kernel<uint64_t, false, kFused>)
+                    : (many ? (const void*)stream_kernel<uint32_t, true, kFused> : (const void*)stream_kernel<uint32_t, false, kFused>);
   return launch_stream_kernel(kern, p, tp, grid, stream);
 }
 

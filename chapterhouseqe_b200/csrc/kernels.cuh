@@ -30,6 +30,7 @@ constexpr int kMaxQuantities = 1 + kMaxOutCols;       // scanned quantities: row
 constexpr int kBitWords = kWarpRows / 32 + 2;         // words of one slice's bit-packed output stage
 constexpr uint32_t kNotStaged = 0xFFFFFFFFu;
 constexpr int kZeroThreads = 256;
+constexpr int kGroupTiles = 64;                       // two-launch form: tile totals are also summed per group of tiles
 static_assert(kTileSlices <= 32, "a warp scans the tile's slice counts in one go");
 
 struct ColumnDesc {          // one input column slot (32 bytes)
@@ -89,11 +90,13 @@ struct OutDesc {             // one output column that goes through the kernel (
 // these per batch from global memory (packed: header, then n_in ColumnDesc, then n_out OutDesc).
 struct BatchHeader {
   int64_t num_rows;
-  uint64_t* desc;            // [quantity][num_tiles] decoupled look-back descriptors (zeroed)
+  uint64_t* desc;            // [quantity][num_tiles] decoupled look-back descriptors (zeroed); two-launch form: plain tile
+                             // totals, followed by [quantity][ceil(num_tiles / kGroupTiles)] group totals
   uint64_t* counts;          // see below (zeroed)
   uint64_t* error_word;      // zeroed; atomicMax(~packed)
   uint64_t* host_counts;     // pinned host mirror of counts[] + error word, written by the last CTA to finish
   uint32_t* done;            // zeroed; CTAs that have finished
+  uint32_t* selbits;         // select -> gather: one selection bit per row, LSB-first, whole tiles (two-launch form only)
   int32_t num_tiles;
   int32_t first_tile;        // MANY: blockIdx.x of this batch's tile 0
 };
@@ -107,6 +110,7 @@ struct KernelParams {
   int32_t n_bits;                // bit-packed outputs (Boolean values + validity bitmaps)
   int32_t long_strings;          // 1: per-warp row tables for the chunk-centric long-string copy are allocated
   int32_t n_counts;              // entries of counts[] before the error word
+  int32_t early_counts;          // two-launch form, pass-through outputs only: the select kernel counts NULLs and publishes the totals
   // MANY (one launch over several batches of one schema and shape): packed per-batch records in global memory
   uint64_t* trace;               // debugging aid (CHDB_TRACE): [tile][8] clock64() stamps of the CTA's phases, or nullptr
   const uint8_t* many;           // nullptr: single batch (everything is in this block)
@@ -123,9 +127,10 @@ static_assert(sizeof(KernelParams) + sizeof(TilePlan) <= 4096, "kernel parameter
 // Fills `tp` (tp.use[] set by the caller; needs kp.in[], kp.n_*): decides which buffers are staged in
 // shared memory.  avg_utf8[s]: mean value length of Utf8 slot s (or < 0).  Returns the CTAs per SM the
 // plan leaves room for.
-int plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many);
-// has64: the program touches 64-bit types (selects the 64-bit accumulator container).
-cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, unsigned grid, cudaStream_t stream);
+// stage = false: the plan of the select kernel (nothing staged, only the small tables).
+int plan_tile(const KernelParams& kp, TilePlan& tp, const int64_t* avg_utf8, bool many, bool stage = true);
+// has64: the program touches 64-bit types (selects the 64-bit accumulator container).  mode: StreamMode (0 fused, 1 select, 2 gather).
+cudaError_t launch_stream(const KernelParams& p, const TilePlan& tp, bool has64, int mode, unsigned grid, cudaStream_t stream);
 // Zeroes `bytes` (a multiple of 16) at p; the stream kernel that follows is launched as its programmatic dependent.
 cudaError_t launch_zero(void* p, size_t bytes, cudaStream_t stream);
 // shared by the ahead-of-time and the run-time compiled kernels

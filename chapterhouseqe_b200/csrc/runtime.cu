@@ -831,7 +831,8 @@ static size_t workspace_layout(Prepared& P, size_t* ws_counts_out, size_t* ws_de
   const int64_t num_tiles = (P.n + kTileRows - 1) / kTileRows;
   const int nq = 1 + P.n_utf8;
   const size_t ws_counts = round_up((size_t)(P.n_counts + 2) * 8, 128);
-  const size_t ws_desc = P.compact ? round_up((size_t)nq * (size_t)num_tiles * 8, 128) : 0;
+  const size_t num_groups = (size_t)(num_tiles + kGroupTiles - 1) / kGroupTiles;   // (two-launch form: group totals behind the tile totals)
+  const size_t ws_desc = P.compact ? round_up((size_t)nq * ((size_t)num_tiles + num_groups) * 8, 128) : 0;
   size_t total = ws_counts + ws_desc;
   for (auto& z : P.zero_reqs) { z.at = total; total += round_up(z.bytes, 128); }
   *ws_counts_out = ws_counts;
@@ -916,11 +917,26 @@ static int fill_program_params(const Program& p, const Prepared& P, KernelParams
     if (od.kind == OUT_EXPR) mark_instrs(od.begin, od.end);
     else tp.use[od.slot] |= USE_VALUES | USE_VALIDITY | USE_OFFSETS;
   }
-  return plan_tile(kp, tp, slot_avg, many);
+  // CHDB_STAGE=0 (experiment): nothing is staged, the lanes read their rows from global memory (the loading warp
+  // still prefetches the tile into L2)
+  static const bool stage = [] { const char* e = std::getenv("CHDB_STAGE"); return !(e && *e == '0'); }();
+  return plan_tile(kp, tp, slot_avg, many, stage);
 }
 
 // Zero kernel + stream kernel.  Long scans run the same device code specialised for this program by NVRTC
 // (jit.cpp); short ones, or boxes without NVRTC, run the bytecode interpreter kernels.
+// Single-batch launches with a predicate run as two kernels (select, then gather: device_code.cuh StreamMode) -- no CTA
+// holds a staged tile while it waits for another CTA.  Small batches keep the single fused launch (one launch less on
+// a latency-bound call).  CHDB_SPLIT = 0 | never : always fused;  always : two kernels whatever the size (tests);
+// unset | auto : two kernels from kSplitAutoRows rows on.
+constexpr int64_t kSplitAutoRows = 1 << 16;
+static bool split_wanted(int64_t rows) {
+  const char* e = std::getenv("CHDB_SPLIT");
+  if (e && (*e == '0' || !std::strcmp(e, "never"))) return false;
+  if (e && !std::strcmp(e, "always")) return true;
+  return rows >= kSplitAutoRows;
+}
+
 static void launch_set(const Core& core, const Program& p, const KernelParams& kp_in, const TilePlan& tp, int ctas_per_sm, unsigned grid,
                        void* ws, size_t ws_bytes, int64_t rows, const std::shared_ptr<LaunchShared>& ls) {
   KernelParams kp_traced;
@@ -944,7 +960,18 @@ static void launch_set(const Core& core, const Program& p, const KernelParams& k
     std::string why;
     jk = jit_get(kp, p.has64, std::min(ctas_per_sm, 8), &why);
   }
-  const cudaError_t le = jk ? jit_launch_stream(jk, kp, tp, grid, core->stream) : launch_stream(kp, tp, p.has64, grid, core->stream);
+  const bool split = kp.b.selbits != nullptr;
+  if (split) {
+    // select: nothing staged, only the small tables in shared memory
+    TilePlan tps = tp;
+    plan_tile(kp, tps, nullptr, false, false);
+    const cudaError_t se = jk ? jit_launch_stream(jk, kp, tps, 1, grid, core->stream) : launch_stream(kp, tps, p.has64, 1, grid, core->stream);
+    core->launches++;
+    if (jk) core->jit_launches++;
+    if (se != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(se));
+  }
+  const int mode = split ? 2 : 0;
+  const cudaError_t le = jk ? jit_launch_stream(jk, kp, tp, mode, grid, core->stream) : launch_stream(kp, tp, p.has64, mode, grid, core->stream);
   core->launches++;
   if (jk) core->jit_launches++;
   if (le != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(le));
@@ -1011,18 +1038,27 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
 
   size_t ws_counts, ws_desc;
   const size_t ws_total = workspace_layout(P, &ws_counts, &ws_desc);
+  // two-launch form: the selection bitmap (whole tiles, every word written by the select kernel) sits behind the zeroed part
+  const bool split = P.compact && split_wanted(P.n);
+  const size_t sel_bytes = split ? (size_t)((P.n + kTileRows - 1) / kTileRows) * (kTileRows / 8) : 0;
   auto ls = std::make_shared<LaunchShared>();
   ls->core = core;
-  ls->workspace = dev_alloc(core, ws_total);
+  ls->workspace = dev_alloc(core, ws_total + sel_bytes);
   ls->host = core->host_get((size_t)(P.n_counts + 1) * 8, &ls->host_cls);
   ls->done = core->event_get();
   uint8_t* ws = (uint8_t*)ls->workspace->ptr;
   KernelParams kp;
   std::memset(&kp, 0, sizeof(kp));
   bind_workspace(P, ls, ws, ws_counts, kp.b, (uint64_t*)ls->host, 0);
+  if (split) kp.b.selbits = (uint32_t*)(ws + ws_total);
   hc.lap(1);
   TilePlan tp;
   const int ctas = fill_program_params(p, P, kp, tp, false);
+  if (split) {
+    kp.early_counts = 1;
+    for (int k = 0; k < P.ko; k++)
+      if (kp.out[k].kind != OUT_PASS) kp.early_counts = 0;
+  }
   hc.lap(2);
   launch_set(core, p, kp, tp, ctas, (unsigned)kp.b.num_tiles, ws, ws_total, P.n, ls);
   hc.lap(3);

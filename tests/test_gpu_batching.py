@@ -162,7 +162,7 @@ def test_benchmarked_c2_batch_against_oracle():
     out = bench.wrap_device_batch(C, cfg, t, ctx).run(prog)
     got = O.batch_from_arrow(out.download())
     if C.jit_available()[0]:
-        assert ctx.jit_launch_count == before + 1, "the benchmarked batch size must run the specialised kernel"
+        assert ctx.jit_launch_count >= before + 1, "the benchmarked batch size must run the specialised kernel"
     rb, _keep = bench.to_host_batch(cfg, t, pin=False)
     ok, why = O.batches_equal(got, _oracle(rb, sel))
     assert ok, why

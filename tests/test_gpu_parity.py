@@ -44,7 +44,7 @@ def test_native_library_is_what_runs():
     rb = H.make_batch([("id", "int32", False)], [[1, 2, 3, 4]])
     out = C.filter_record(rb, [[]], sp.parse_expr("id % 2 = 0"))
     assert out.column(0).to_pylist() == [2, 4]
-    assert ctx.launch_count == before + 2   # workspace zeroing + the stream kernel
+    assert ctx.launch_count == before + 2   # workspace zeroing + the (fused, at this size) stream kernel
 
 
 @pytest.mark.parametrize("case", refcases.GOLDEN, ids=[c[0] for c in refcases.GOLDEN])
