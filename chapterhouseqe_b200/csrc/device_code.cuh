@@ -52,6 +52,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 #define CHDB_LONG_STRINGS(P) (chdb_jit::kLongStrings != 0)
 #define CHDB_OUT_HAS_VALIDITY(P, k) (chdb_jit::kOutHasValidity[k] != 0)
 #define CHDB_EARLY_COUNTS(P) (chdb_jit::kEarlyCounts != 0)
+#define CHDB_IN_HAS_VALIDITY(P, s, ptr) (chdb_jit::kInHasValidity[s] != 0)
 #else
 #define CHDB_STATIC_UNROLL _Pragma("unroll 1")
 #define CHDB_N_IN P.n_in
@@ -66,6 +67,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 #define CHDB_LONG_STRINGS(P) (P.long_strings != 0)
 #define CHDB_OUT_HAS_VALIDITY(P, k) (P.out[k].validity != nullptr)
 #define CHDB_EARLY_COUNTS(P) (P.early_counts != 0)
+#define CHDB_IN_HAS_VALIDITY(P, s, ptr) ((ptr) != nullptr)
 #endif
 
 template <typename V> struct Cont;
@@ -100,8 +102,7 @@ __device__ __forceinline__ void report_rows(const KernelParams& P, const Instr& 
 // ------------------------------------------------------------------------------------------
 
 template <int QPT>
-__device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ bits, const int64_t (&qbase)[QPT], uint32_t need) {
-  if (bits == nullptr) return FULL;
+__device__ __forceinline__ uint32_t load_bits_nn(const uint8_t* __restrict__ bits, const int64_t (&qbase)[QPT], uint32_t need) {
   uint32_t m = 0;
 #pragma unroll
   for (int q = 0; q < QPT; q++) {
@@ -111,6 +112,11 @@ __device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ bits, 
     }
   }
   return m;
+}
+template <int QPT>
+__device__ __forceinline__ uint32_t load_bits(const uint8_t* __restrict__ bits, const int64_t (&qbase)[QPT], uint32_t need) {
+  if (bits == nullptr) return FULL;
+  return load_bits_nn<QPT>(bits, qbase, need);
 }
 
 // Column values of the thread's rows in accumulator form (see the convention above).
@@ -620,7 +626,8 @@ __device__ __forceinline__ void fetch_operand(const KernelParams& P, const Colum
   constexpr int R = 4 * QI;
   if (in.src == SRC_COL) {
     const ColumnDesc& c = cols[in.slot];
-    bv = load_bits<QI>(c.validity, qbase, inrange);
+    // (known at compile time in the specialised kernels: no branch between this load and the ones before it)
+    bv = CHDB_IN_HAS_VALIDITY(P, in.slot, c.validity) ? load_bits_nn<QI>(c.validity, qbase, inrange) : FULL;
     if (CHDB_COL_TYPE(P, in.slot) == T_BOOL) {
       bm = load_bits<QI>((const uint8_t*)c.values, qbase, inrange);
 #pragma unroll
@@ -930,8 +937,14 @@ struct TileShared {
 // bulk L2 prefetch.  Utf8 value bytes start at offsets[row0]: those copies are issued in a second
 // step (the two bounds are a global load away), after the fixed-size ones are already in flight.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan& TP, ColumnDesc* cols, uint8_t* stage, uint32_t full,
-                                          uint32_t full_values, int64_t row0, uint32_t tile_rows, int lane) {
+// What load_tile's second step (the Utf8 value bytes) needs from its first.
+struct TileValues {
+  const uint8_t* values;   // the lane's Utf8 column values (nullptr: the lane has none to load)
+  uint32_t o0, o1;         // offsets[row0], offsets[row0 + tile_rows]: requested in step 1, first used in step 2
+  uint32_t cap, vso;
+};
+__device__ __forceinline__ TileValues load_tile(const KernelParams& P, const TilePlan& TP, ColumnDesc* cols, uint8_t* stage, uint32_t full,
+                                                int64_t row0, uint32_t tile_rows, int lane, int warp) {
   const uint32_t ss = smem_u32(stage);
   const uint32_t bits_bytes = (((tile_rows + 7u) >> 3) + 15u) & ~15u;
   uint32_t nb[3] = {0, 0, 0}, so[3] = {0, 0, 0}, pf[3] = {0, 0, 0};   // 0: validity, 1: offsets, 2: values
@@ -940,7 +953,9 @@ __device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan&
   uint32_t cap = 0, vso = 0;
   ColumnDesc c;
   c.values = nullptr; c.validity = nullptr; c.offsets = nullptr; c.type = 0; c.width = 0;
-  if (lane < CHDB_N_IN) {
+  // (every warp of the CTA issues the copies of its share of the slots -- one bulk copy costs the issuing warp
+  //  ~100 cycles, and nothing else can start before the last one is on its way; each warp arrives once on `full`)
+  if (lane < CHDB_N_IN && (lane % kWarps) == warp) {
     c = P.in[lane];
     const StageSlot sl = TP.slot[lane];
     const uint32_t use = TP.use[lane];
@@ -980,12 +995,22 @@ __device__ __forceinline__ void load_tile(const KernelParams& P, const TilePlan&
     if (nb[i]) tma_load(ss + so[i], src[i], nb[i], full);
     if (pf[i]) tma_prefetch_l2(src[i], pf[i]);
   }
+  TileValues tv;
+  tv.values = utf8_values ? (const uint8_t*)c.values : nullptr;
+  tv.o0 = o0; tv.o1 = o1; tv.cap = cap; tv.vso = vso;
+  return tv;
+}
+// Step 2 (the same warp; the rest of the CTA need not wait for it): the Utf8 value bytes, whose bounds were a global
+// round trip away.  The value pointers it puts into the column table are published by the arrival on `full_values`.
+__device__ __forceinline__ void load_tile_values(const TileValues& tv, ColumnDesc* cols, uint8_t* stage, uint32_t full_values, int lane) {
+  const uint32_t ss = smem_u32(stage);
   uint32_t vbytes = 0;
   const uint8_t* vsrc = nullptr;
-  if (utf8_values) {
-    const uint32_t lo = o0 & ~15u, len = (o1 - lo + 15u) & ~15u;
-    vsrc = (const uint8_t*)c.values + lo;
-    if (cap != 0 && len <= cap) { vbytes = len; cols[lane].values = stage + vso - lo; }
+  const uint32_t vso = tv.vso;
+  if (tv.values != nullptr) {
+    const uint32_t lo = tv.o0 & ~15u, len = (tv.o1 - lo + 15u) & ~15u;
+    vsrc = tv.values + lo;
+    if (tv.cap != 0 && len <= tv.cap) { vbytes = len; cols[lane].values = stage + vso - lo; }
     else if (len) tma_prefetch_l2(vsrc, len);
   }
   // The Utf8 value bytes (their bounds were a global load away) complete a second barrier: the predicate does not
@@ -1247,10 +1272,12 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const Column
         __syncwarp();
       }
     } else if (sel) {
+      uint8_t* const vb = o_values;
+      const uint32_t vo = o;
       if (o_width == 4) {
-        store_sel<uint32_t>((uint32_t*)o_values, o, sel, R.x.x, R.x.y, R.x.z, R.x.w);
+        store_sel<uint32_t>((uint32_t*)vb, vo, sel, R.x.x, R.x.y, R.x.z, R.x.w);
       } else if (o_width == 8) {
-        store_sel<uint2>((uint2*)o_values, o, sel, make_uint2(R.x.x, R.x.y), make_uint2(R.x.z, R.x.w), make_uint2(R.y.x, R.y.y),
+        store_sel<uint2>((uint2*)vb, vo, sel, make_uint2(R.x.x, R.x.y), make_uint2(R.x.z, R.x.w), make_uint2(R.y.x, R.y.y),
                          make_uint2(R.y.z, R.y.w));
       } else if (o_width == 16) {
         const uint4* s16 = (const uint4*)c.values + L.row32;
@@ -1259,10 +1286,10 @@ __device__ __forceinline__ void store_output(const KernelParams& P, const Column
         for (int i = 0; i < 4; i++)
           if ((sel >> i) & 1u) { *d = s16[i]; d++; }
       } else if (o_width == 2) {
-        store_sel<uint16_t>((uint16_t*)o_values, o, sel, (uint16_t)R.x.x, (uint16_t)(R.x.x >> 16), (uint16_t)R.x.y, (uint16_t)(R.x.y >> 16));
+        store_sel<uint16_t>((uint16_t*)vb, vo, sel, (uint16_t)R.x.x, (uint16_t)(R.x.x >> 16), (uint16_t)R.x.y, (uint16_t)(R.x.y >> 16));
       } else {
         const uint32_t x = R.x.x;
-        store_sel<uint8_t>(o_values, o, sel, (uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24));
+        store_sel<uint8_t>(vb, vo, sel, (uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24));
       }
     }
   }
@@ -1406,41 +1433,59 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
   uint32_t* const ltab = (uint32_t*)(smem + TP.ltab_off);
   uint8_t* const pext4 = smem + TP.pext_off;
   const uint32_t full = smem_u32(&s_full), full_values = smem_u32(&s_full_values);
+  static_assert(kThreads >= 64, "one thread per word of the bit-compaction table");
+  const int64_t row0 = tile * kTileRows;
+  const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.b.num_rows ? kTileRows : P.b.num_rows - row0);
+  const bool last_tile = tile == (int64_t)P.b.num_tiles - 1;
+  const uint64_t t_entry = (MODE == kGather && P.trace != nullptr) ? (uint64_t)clock64() : 0;
+  // the bit-compaction table: requested now, stored to shared memory once its load has had time to complete
+  // (nothing on the way to the tile's loads waits for a global round trip)
+  uint32_t pext_word = 0;
+  const bool pext_mine = MODE != kSelect && P.n_bits > 0 && tid < 64;
+  if (pext_mine) pext_word = kPext4Words[tid];
   if (MODE != kSelect && tid == 0) {
-    mbar_init(full, 1);
-    mbar_init(full_values, 1);
+    mbar_init(full, kWarps);          // (one arrival per warp: load_tile)
+    mbar_init(full_values, kWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  // gather: the tile's loads are the first thing the CTA does.  They do not depend on the select kernel (the launch
+  // chain starts with a kernel that is NOT a programmatic dependent, so everything older on the stream -- whatever
+  // produced the inputs -- has completed).
+  TileValues tv;
+  if (MODE == kGather) {
+    __syncthreads();   // (the barriers are initialised)
+    tv = load_tile(P, TP, cols_s, stage, full, row0, (uint32_t)tile_rows, lane, warp);
+  }
   if (MODE != kSelect && P.n_bits > 0) {
-    for (int i = tid; i < 64; i += kThreads) ((uint32_t*)pext4)[i] = kPext4Words[i];
+    if (MODE != kGather && pext_mine) ((uint32_t*)pext4)[tid] = pext_word;
 #pragma unroll 1
     for (int i = tid; i < kWarps * P.n_bits * kBitWords; i += kThreads) bitstages[i] = 0;
   }
   if (tid < kMaxOutCols) s_nulls[tid] = 0;
-  const int64_t row0 = tile * kTileRows;
-  const int32_t tile_rows = (int32_t)(row0 + kTileRows < P.b.num_rows ? kTileRows : P.b.num_rows - row0);
-  const bool last_tile = tile == (int64_t)P.b.num_tiles - 1;
   __syncthreads();
   grid_launch_dependents();
-  // gather: the tile's loads do not depend on the select kernel (the launch chain starts with a kernel that is NOT a
-  // programmatic dependent, so everything older on the stream -- whatever produced the inputs -- has completed)
-  if (MODE == kGather && warp == 0) load_tile(P, TP, cols_s, stage, full, full_values, row0, (uint32_t)tile_rows, lane);
   grid_dependency_wait();     // the zeroed workspace; inputs an earlier kernel on this stream may still be writing
   if (tid == 0) {
     trace_event(P, 0);
-    if (P.trace != nullptr && blockIdx.x < 8192) { uint32_t smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); P.trace[(size_t)blockIdx.x * 8 + 7] = smid; }
+    if (P.trace != nullptr && blockIdx.x < 8192) {
+      uint32_t smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      P.trace[(size_t)blockIdx.x * 8 + 7] = MODE == kGather ? t_entry : (uint64_t)smid;
+    }
   }
-  if (MODE == kFused && warp == 0) load_tile(P, TP, cols_s, stage, full, full_values, row0, (uint32_t)tile_rows, lane);
-  // gather: the lane's selection bits of each of its slices (written by the select kernel; served by L2)
+  if (MODE == kFused) tv = load_tile(P, TP, cols_s, stage, full, row0, (uint32_t)tile_rows, lane, warp);
+  // gather: the lane's selection bits of each of its slices (written by the select kernel; served by L2) -- requested
+  // here, looked at after the prefix sums below have been requested too (one round trip, not two)
   uint32_t selq[kSpw];
   if (MODE == kGather && has_pred) {
 #pragma unroll
     for (int j = 0; j < kSpw; j++) {
       const int64_t r = row0 + (warp * kSpw + j) * kWarpRows + lane * 4;
-      selq[j] = ((uint32_t)__ldcg((const uint8_t*)P.b.selbits + (r >> 3)) >> (uint32_t)(r & 4)) & 0xFu;
+      selq[j] = (uint32_t)__ldcg((const uint8_t*)P.b.selbits + (r >> 3));
     }
   }
+  // (the Utf8 bounds have had a barrier's worth of time to arrive; only this warp waits for them)
+  if (MODE != kSelect) load_tile_values(tv, cols_s, stage, full_values, lane);
   if (MODE == kGather && CHDB_EARLY_COUNTS(P) && blockIdx.x == 0 && warp == kWarps - 1) {
     // The select kernel has completed: batch totals = the sums of its group totals; the closing Utf8 offset
     // (offsets[total_rows] = total_bytes, also covers an empty result); counts, NULL counts and the error word go to
@@ -1480,6 +1525,14 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
       for (int64_t i = g * kGroupTiles + lane; i < tile; i += 32) part += load_descriptor(tt + i);
       part = warp_sum64(part);
       if (lane == 0) s_tot[q] = part;
+    }
+  }
+  if (MODE == kGather && pext_mine) ((uint32_t*)pext4)[tid] = pext_word;   // (visible after the barrier of step 3)
+  if (MODE == kGather && has_pred) {
+#pragma unroll
+    for (int j = 0; j < kSpw; j++) {
+      const int64_t r = row0 + (warp * kSpw + j) * kWarpRows + lane * 4;
+      selq[j] = (selq[j] >> (uint32_t)(r & 4)) & 0xFu;
     }
   }
   if (MODE != kSelect) {
@@ -1740,7 +1793,10 @@ __device__ __forceinline__ void stream_body(const KernelParams& PP, const TilePl
     }
   }
 
-  if (MODE == kGather && CHDB_EARLY_COUNTS(P)) return;   // (the select kernel did the bookkeeping)
+  if (MODE == kGather && CHDB_EARLY_COUNTS(P)) {   // (the select kernel did the bookkeeping)
+    if (P.trace != nullptr) { __syncthreads(); if (tid == 0) { trace_event(P, 3); trace_event(P, 5); trace_event(P, 6); } }
+    return;
+  }
 
   // ---- null counts; the last CTA to finish mirrors the counts into pinned host memory (warp 0 only: the other warps
   //      are done once their rows are stored) ----

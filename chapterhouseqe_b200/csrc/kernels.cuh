@@ -12,19 +12,20 @@ namespace chdb {
 // One CTA works on one tile.  A tile is kTileSlices slices of 128 rows; a slice is the unit one warp
 // works on at a time (4 consecutive rows per lane, so every column access is a 128-bit load); warp w
 // owns slices [w * kSpw, (w + 1) * kSpw) of its tile.  Many small CTAs (instead of one persistent CTA
-// per SM) let the hardware hide one tile's load and look-back latency behind its neighbours' work:
-// 5-6 tiles are resident per SM, each with its input landing in (or being read from) shared memory.
+// per SM) let the hardware hide one tile's load latency behind its neighbours' work.  Measured on C2
+// (4 warps x 2 slices = 1024-row tiles: 83.9 us per 4M-row batch; 4 x 1 = 512-row tiles: 77.7 us; 8 x 1:
+// 78.9 us): the default is 512-row tiles, 8-10 of them resident per SM.
 #ifndef CHDB_WARPS
 #define CHDB_WARPS 4
 #endif
 #ifndef CHDB_SPW
-#define CHDB_SPW 2
+#define CHDB_SPW 1
 #endif
 constexpr int kWarps = CHDB_WARPS;
 constexpr int kSpw = CHDB_SPW;                        // slices per warp
 constexpr int kTileSlices = kWarps * kSpw;
 constexpr int kWarpRows = 128;                        // rows of one slice
-constexpr int kTileRows = kTileSlices * kWarpRows;    // 1024 rows per tile
+constexpr int kTileRows = kTileSlices * kWarpRows;    // 512 rows per tile
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxQuantities = 1 + kMaxOutCols;       // scanned quantities: rows + bytes per Utf8 output
 constexpr int kBitWords = kWarpRows / 32 + 2;         // words of one slice's bit-packed output stage

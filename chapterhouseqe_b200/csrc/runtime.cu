@@ -937,6 +937,13 @@ static bool split_wanted(int64_t rows) {
   return rows >= kSplitAutoRows;
 }
 
+// Two-launch form: what the select kernel can take over from the gather kernel (kernels.cuh KernelParams).
+static void set_split_flags(KernelParams& kp) {
+  kp.early_counts = 1;
+  for (int k = 0; k < kp.n_out; k++)
+    if (kp.out[k].kind != OUT_PASS) kp.early_counts = 0;
+}
+
 static void launch_set(const Core& core, const Program& p, const KernelParams& kp_in, const TilePlan& tp, int ctas_per_sm, unsigned grid,
                        void* ws, size_t ws_bytes, int64_t rows, const std::shared_ptr<LaunchShared>& ls) {
   KernelParams kp_traced;
@@ -1054,11 +1061,7 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   hc.lap(1);
   TilePlan tp;
   const int ctas = fill_program_params(p, P, kp, tp, false);
-  if (split) {
-    kp.early_counts = 1;
-    for (int k = 0; k < P.ko; k++)
-      if (kp.out[k].kind != OUT_PASS) kp.early_counts = 0;
-  }
+  if (split) set_split_flags(kp);
   hc.lap(2);
   launch_set(core, p, kp, tp, ctas, (unsigned)kp.b.num_tiles, ws, ws_total, P.n, ls);
   hc.lap(3);
@@ -1199,6 +1202,7 @@ static void shape_params(const Program& p, KernelParams& kp) {
   kp.pred_end = compact ? p.pred_end : 0;
   std::memcpy(kp.instrs, p.instrs.data(), p.instrs.size() * sizeof(Instr));
   std::memcpy(kp.strpool, p.strpool.data(), p.strpool.size());
+  if (compact) set_split_flags(kp);   // (the shape large batches run with)
 }
 
 static_assert(kErrArithmeticOverflow == CHDB_ERR_ARITHMETIC_OVERFLOW && kErrDivideByZero == CHDB_ERR_DIVIDE_BY_ZERO,
