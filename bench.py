@@ -272,6 +272,18 @@ def measured_traffic(config: str, batch_rows: int):
     return None
 
 
+def kernel_description(many, jit: bool, split: bool) -> str:
+    how = "device_code.cuh specialised for the program by NVRTC" if jit else "bytecode interpreter"
+    if many:
+        return (f"chdb_jit_stream_many ({how}): the fused single-pass kernel, one launch per {many} records, preceded by "
+                "zero_kernel")
+    if split:
+        return (f"chdb_jit_select + chdb_jit_gather ({how}): per record one zero_kernel, one select launch (predicate -> "
+                "selection bitmap + tile totals) and one gather launch (TMA-staged tiles -> compacted columns); the gather "
+                "kernel is the dominant one (about three quarters of the launch set)")
+    return f"chdb_jit_stream ({how}): the fused single-pass kernel, one launch per record, preceded by zero_kernel"
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -563,6 +575,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     per_gpu_gbs = total_rows * n_passes * bytes_per_row / secs / 1e9
     peak, peak_src = measured_peak()
     stream_launches_per_pass = len(groups) if many else records
+    # (zero + select + gather = 3 launches per record in the two-launch form, zero + stream = 2 in the fused form)
+    split_launches = (not many) and launches >= 3 * records * (args.steps * args.passes)
     avg_launch_us = elapsed_ms * 1e3 / max(stream_launches_per_pass * n_passes, 1)
     algo_bytes_per_launch = total_rows * bytes_per_row / stream_launches_per_pass
 
@@ -576,17 +590,18 @@ def run_ours(args, cfg, rank, world, local_rank):
         "clocks": clocks, "gpu_launches": int(all_launches), "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
         "specialised_launches": int(jit_launches), "block_cache_misses_in_timed_region": ctx.alloc_misses - misses0,
         "roofline": {"bound": "hbm",
-                     "kernel": ("chdb_jit_stream" + ("_many" if many else "") + " (device_code.cuh specialised for the program by "
-                                "NVRTC), one launch per " + (f"{many} records" if many else "record") + ", preceded by zero_kernel"
-                                if jit_launches else "stream_kernel (bytecode interpreter) preceded by zero_kernel"),
+                     "kernel": kernel_description(many, bool(jit_launches), split_launches),
                      "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
                      "traffic": measured_traffic(args.config, args.batch_rows),
-                     "traffic_note": "DRAM read+write bytes of one stream-kernel launch under ncu (cold L2; part of the output is "
-                                     "still dirty in L2 when the kernel ends, so it can read below the algorithmic bytes)",
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ALL kernels of one record's launch set "
+                                     "(select + gather, or the fused stream kernel) under ncu, cold L2 and serialised: the "
+                                     "gather kernel's re-read of the predicate columns counts in full there, and part of the "
+                                     "output is still dirty in L2 when the last kernel ends",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                      "avg_launch_us": avg_launch_us, "stream_launches_per_pass": stream_launches_per_pass,
-                     "timing": "CUDA events on the ctx stream around all timed passes (zero_kernel + stream kernel per launch)"},
+                     "timing": "CUDA events on the ctx stream around all timed passes (every kernel of every launch set: "
+                               "zero_kernel + select + gather, or zero_kernel + the fused stream kernel)"},
     }
     if parity:
         line.update(parity)
