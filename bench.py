@@ -280,7 +280,8 @@ def kernel_description(many, jit: bool, split: bool) -> str:
     if split:
         return (f"chdb_jit_select + chdb_jit_gather ({how}): per record one zero_kernel, one select launch (predicate -> "
                 "selection bitmap + tile totals) and one gather launch (TMA-staged tiles -> compacted columns); the gather "
-                "kernel is the dominant one (about three quarters of the launch set)")
+                "kernel is the dominant one (about three quarters of the launch set); zero + select of record k run on the "
+                "ctx's second stream next to the gather of record k-1 (overlapped_launch_sets)")
     return f"chdb_jit_stream ({how}): the fused single-pass kernel, one launch per record, preceded by zero_kernel"
 
 
@@ -529,7 +530,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     outs = None
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0, jit0 = ctx.launch_count, ctx.jit_launch_count
+    launches0, jit0, overlapped0 = ctx.launch_count, ctx.jit_launch_count, ctx.overlapped_launch_sets
     barrier()
     torch.cuda.synchronize(device)
     # a cyclic-GC pause in the middle of the enqueue loop (tens of ms with torch / pyarrow loaded) starves the GPU,
@@ -589,6 +590,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         "hbm_gbs_per_gpu": per_gpu_gbs, "pct_of_8TBs": per_gpu_gbs / 8000.0 * 100.0,
         "clocks": clocks, "gpu_launches": int(all_launches), "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
         "specialised_launches": int(jit_launches), "block_cache_misses_in_timed_region": ctx.alloc_misses - misses0,
+        "overlapped_launch_sets": ctx.overlapped_launch_sets - overlapped0,
         "roofline": {"bound": "hbm",
                      "kernel": kernel_description(many, bool(jit_launches), split_launches),
                      "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,

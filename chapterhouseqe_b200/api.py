@@ -83,6 +83,7 @@ def load_library():
     sig("chdb_ctx_launch_count", i64, vp)
     sig("chdb_ctx_jit_launch_count", i64, vp)
     sig("chdb_ctx_alloc_miss_count", i64, vp)
+    sig("chdb_ctx_overlapped_count", i64, vp)
     sig("chdb_jit_available", i32, ctypes.c_char_p, ctypes.c_size_t)
     sig("chdb_program_jit_source", ctypes.c_size_t, vp, ctypes.c_char_p, ctypes.c_size_t)
     sig("chdb_program_jit_check", i32, vp, ctypes.POINTER(i64), ctypes.c_char_p, ctypes.c_size_t, stp)
@@ -132,6 +133,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "chdb_code_name", "chdb_version", "chdb_compiled_arch", "chdb_ctx_create", "chdb_ctx_destroy", "chdb_ctx_stream",
     "chdb_ctx_device", "chdb_ctx_synchronize", "chdb_ctx_launch_count", "chdb_ctx_jit_launch_count", "chdb_ctx_alloc_miss_count",
+    "chdb_ctx_overlapped_count",
     "chdb_jit_available", "chdb_program_jit_source", "chdb_program_jit_check", "chdb_program_compile_filter",
     "chdb_program_compile_project", "chdb_program_compile_filter_project", "chdb_program_release",
     "chdb_program_disassemble", "chdb_program_num_instructions", "chdb_filter_record", "chdb_project_record",
@@ -229,6 +231,11 @@ class Context:
     def alloc_misses(self) -> int:
         """Device allocations that missed the block cache (cudaMallocAsync calls)."""
         return int(load_library().chdb_ctx_alloc_miss_count(self._h))
+
+    @property
+    def overlapped_launch_sets(self) -> int:
+        """Launch sets whose select kernel ran on the second stream, next to the previous set's gather kernel."""
+        return int(load_library().chdb_ctx_overlapped_count(self._h))
 
     def synchronize(self):
         st = _Status()

@@ -53,16 +53,30 @@ struct CtxCore {
   // without going back to cudaMallocAsync / cudaFreeAsync (which cost a dozen driver calls per batch and
   // now and then take the allocator's millisecond slow path).  Reuse is safe because everything this
   // library does with a block is ordered on the ctx's one stream.
-  std::map<size_t, std::vector<void*>> dev_free;
+  // Each cached block remembers how many launch sets had been enqueued when it was released (see launch_set: a
+  // select kernel that runs on the second stream may only touch blocks released before the previous launch set).
+  std::map<size_t, std::vector<std::pair<void*, int64_t>>> dev_free;
   size_t dev_cached = 0;
   std::vector<cudaEvent_t> events_free;   // recycled: creating / destroying an event is a driver resource call
+  // Select / gather overlap (launch_set): launch sets are numbered; before_last[k & 3] fires when everything enqueued on
+  // `stream` before launch set k's LAST kernel has completed; select_done[k & 3] when its select kernel (second stream) has.
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t select_done[4] = {nullptr, nullptr, nullptr, nullptr}, before_last[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::atomic<int64_t> launch_seq{0};
+  std::atomic<int64_t> overlapped{0};     // launch sets whose select kernel ran on aux_stream
   static constexpr size_t kDevCacheCap = (size_t)24 << 30;   // beyond this, released blocks go back to the pool
 
   ~CtxCore() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    if (aux_stream) cudaStreamSynchronize(aux_stream);
     for (auto& kv : dev_free)
-      for (void* p : kv.second) cudaFreeAsync(p, stream);
+      for (auto& p : kv.second) cudaFreeAsync(p.first, stream);
+    for (int i = 0; i < 4; i++) {
+      if (select_done[i]) cudaEventDestroy(select_done[i]);
+      if (before_last[i]) cudaEventDestroy(before_last[i]);
+    }
+    if (aux_stream) cudaStreamDestroy(aux_stream);
     for (cudaEvent_t e : events_free) cudaEventDestroy(e);
     if (stream) cudaStreamSynchronize(stream);
     for (void* p : pinned_free) cudaFreeHost(p);
@@ -143,7 +157,7 @@ struct DevBuf {
     {
       std::lock_guard<std::mutex> g(core->mu);
       if (core->dev_cached + bytes <= CtxCore::kDevCacheCap) {
-        core->dev_free[bytes].push_back(ptr);
+        core->dev_free[bytes].push_back({ptr, core->launch_seq.load()});
         core->dev_cached += bytes;
         return;
       }
@@ -162,7 +176,7 @@ static Buf dev_alloc(const Core& core, size_t bytes) {
     std::lock_guard<std::mutex> g(core->mu);
     auto it = core->dev_free.find(b->bytes);
     if (it != core->dev_free.end() && !it->second.empty()) {
-      b->ptr = it->second.back();
+      b->ptr = it->second.back().first;
       it->second.pop_back();
       core->dev_cached -= b->bytes;
       return b;
@@ -171,6 +185,27 @@ static Buf dev_alloc(const Core& core, size_t bytes) {
   core->alloc_misses++;
   CUDA_CHECK(cudaMallocAsync(&b->ptr, b->bytes, core->stream));
   return b;
+}
+
+// A cached block that was released before launch set `max_seq + 1` was enqueued: everything that ever touched it was
+// enqueued before that launch set.  Null when the cache holds none (the caller then stays on the one stream).
+static Buf dev_alloc_released_by(const Core& core, size_t bytes, int64_t max_seq) {
+  const size_t want = round_up(bytes + kPad, 256);
+  std::lock_guard<std::mutex> g(core->mu);
+  auto it = core->dev_free.find(want);
+  if (it == core->dev_free.end()) return nullptr;
+  auto& v = it->second;
+  for (size_t i = 0; i < v.size(); i++) {   // (oldest first)
+    if (v[i].second > max_seq) continue;
+    auto b = std::make_shared<DevBuf>();
+    b->core = core;
+    b->bytes = want;
+    b->ptr = v[i].first;
+    v.erase(v.begin() + (std::ptrdiff_t)i);
+    core->dev_cached -= want;
+    return b;
+  }
+  return nullptr;
 }
 
 // One launch set (zero kernel + stream kernel): what its output batches share.  The counts of the run are mirrored
@@ -241,6 +276,9 @@ struct chdb_device_batch {
   int64_t num_rows = 0;              // -1: result->host[0]
   std::vector<chdb::DeviceColumn> cols;
   std::shared_ptr<chdb::RunResult> result;
+  // core->launch_seq when the batch was created: whatever fills its buffers was enqueued on the ctx stream before the
+  // launch set of that number (-1: unknown; such a batch is never read from the second stream)
+  int64_t born = -1;
 };
 
 namespace chdb {
@@ -307,6 +345,7 @@ static std::unique_ptr<chdb_device_batch> upload_batch(const Core& core, const :
   CUDA_CHECK(cudaSetDevice(core->device));
   std::unique_ptr<chdb_device_batch> b(new chdb_device_batch);
   b->core = core;
+  b->born = core->launch_seq.load();
   b->num_rows = in->length;
   const int64_t n = in->length;
   for (size_t ci = 0; ci < cols.size(); ci++) {
@@ -563,6 +602,7 @@ namespace chdb {
 static std::unique_ptr<chdb_device_batch> view_rows(const chdb_device_batch* in, int64_t n) {
   std::unique_ptr<chdb_device_batch> v(new chdb_device_batch);
   v->core = in->core;
+  v->born = in->born;
   v->num_rows = n;
   v->cols = in->cols;
   for (auto& c : v->cols) {
@@ -686,6 +726,7 @@ static void prepare(chdb_ctx* ctx, const Program& p, const chdb_device_batch* in
   P.out.reset(new chdb_device_batch);
   chdb_device_batch* out = P.out.get();
   out->core = core;
+  out->born = core->launch_seq.load();   // (outputs of a launch set: renumbered after it, see execute)
 
   // len-1 constant outputs (record_projection.rs:73: RecordBatch::try_new checks equal lengths)
   P.any_const = false;
@@ -930,6 +971,11 @@ static int fill_program_params(const Program& p, const Prepared& P, KernelParams
 // a latency-bound call).  CHDB_SPLIT = 0 | never : always fused;  always : two kernels whatever the size (tests);
 // unset | auto : two kernels from kSplitAutoRows rows on.
 constexpr int64_t kSplitAutoRows = 1 << 16;
+// CHDB_OVERLAP=0: every kernel on the ctx's one stream
+static bool overlap_enabled() {
+  static const bool on = [] { const char* e = std::getenv("CHDB_OVERLAP"); return !(e && *e == '0'); }();
+  return on;
+}
 static bool split_wanted(int64_t rows) {
   const char* e = std::getenv("CHDB_SPLIT");
   if (e && (*e == '0' || !std::strcmp(e, "never"))) return false;
@@ -945,7 +991,7 @@ static void set_split_flags(KernelParams& kp) {
 }
 
 static void launch_set(const Core& core, const Program& p, const KernelParams& kp_in, const TilePlan& tp, int ctas_per_sm, unsigned grid,
-                       void* ws, size_t ws_bytes, int64_t rows, const std::shared_ptr<LaunchShared>& ls) {
+                       void* ws, size_t ws_bytes, int64_t rows, const std::shared_ptr<LaunchShared>& ls, bool overlap = false) {
   KernelParams kp_traced;
   const KernelParams* kpp = &kp_in;
   Buf trace_buf;
@@ -959,7 +1005,25 @@ static void launch_set(const Core& core, const Program& p, const KernelParams& k
     kpp = &kp_traced;
   }
   const KernelParams& kp = *kpp;
-  CUDA_CHECK(launch_zero(ws, ws_bytes, core->stream));
+  // Launch set k.  With `overlap`, its zero and select kernels go to the ctx's second stream, where they wait for
+  // before_last[k-1] only: they run next to launch set k-1's gather kernel (both are bandwidth-hungry but neither
+  // saturates HBM alone), and the gather kernel of this set waits for them on the ctx stream.  execute() grants
+  // `overlap` only when nothing those two kernels touch can still be in use by launch set k-1's last kernel.
+  if (!core->before_last[0]) {
+    for (int i = 0; i < 4; i++) CUDA_CHECK(cudaEventCreateWithFlags(&core->before_last[i], cudaEventDisableTiming));
+  }
+  const int64_t seq = core->launch_seq.load();
+  cudaStream_t sel_stream = core->stream;
+  if (overlap) {
+    if (!core->aux_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&core->aux_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 4; i++) CUDA_CHECK(cudaEventCreateWithFlags(&core->select_done[i], cudaEventDisableTiming));
+    }
+    sel_stream = core->aux_stream;
+    core->overlapped++;
+    CUDA_CHECK(cudaStreamWaitEvent(sel_stream, core->before_last[(seq - 1) & 3], 0));
+  }
+  CUDA_CHECK(launch_zero(ws, ws_bytes, sel_stream));
   core->launches++;
   const JitKernel* jk = nullptr;
   const JitMode jm = jit_mode();
@@ -972,11 +1036,17 @@ static void launch_set(const Core& core, const Program& p, const KernelParams& k
     // select: nothing staged, only the small tables in shared memory
     TilePlan tps = tp;
     plan_tile(kp, tps, nullptr, false, false);
-    const cudaError_t se = jk ? jit_launch_stream(jk, kp, tps, 1, grid, core->stream) : launch_stream(kp, tps, p.has64, 1, grid, core->stream);
+    const cudaError_t se = jk ? jit_launch_stream(jk, kp, tps, 1, grid, sel_stream) : launch_stream(kp, tps, p.has64, 1, grid, sel_stream);
     core->launches++;
     if (jk) core->jit_launches++;
     if (se != cudaSuccess) throw Error(CHDB_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(se));
+    if (overlap) {
+      CUDA_CHECK(cudaEventRecord(core->select_done[seq & 3], sel_stream));
+      CUDA_CHECK(cudaStreamWaitEvent(core->stream, core->select_done[seq & 3], 0));
+    }
   }
+  CUDA_CHECK(cudaEventRecord(core->before_last[seq & 3], core->stream));
+  core->launch_seq++;
   const int mode = split ? 2 : 0;
   const cudaError_t le = jk ? jit_launch_stream(jk, kp, tp, mode, grid, core->stream) : launch_stream(kp, tp, p.has64, mode, grid, core->stream);
   core->launches++;
@@ -1050,7 +1120,15 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   const size_t sel_bytes = split ? (size_t)((P.n + kTileRows - 1) / kTileRows) * (kTileRows / 8) : 0;
   auto ls = std::make_shared<LaunchShared>();
   ls->core = core;
-  ls->workspace = dev_alloc(core, ws_total + sel_bytes);
+  // select next to the previous launch set's gather (launch_set): only when the input was complete, in ctx-stream
+  // order, before that launch set was enqueued, and with a workspace block nothing younger has touched
+  const int64_t seq = core->launch_seq.load();
+  bool overlap = false;
+  if (split && overlap_enabled() && seq >= 1 && in_orig->born >= 0 && in_orig->born <= seq - 1) {
+    ls->workspace = dev_alloc_released_by(core, ws_total + sel_bytes, seq - 1);
+    overlap = ls->workspace != nullptr;
+  }
+  if (!ls->workspace) ls->workspace = dev_alloc(core, ws_total + sel_bytes);
   ls->host = core->host_get((size_t)(P.n_counts + 1) * 8, &ls->host_cls);
   ls->done = core->event_get();
   uint8_t* ws = (uint8_t*)ls->workspace->ptr;
@@ -1063,7 +1141,8 @@ static std::unique_ptr<chdb_device_batch> execute(chdb_ctx* ctx, const Program& 
   const int ctas = fill_program_params(p, P, kp, tp, false);
   if (split) set_split_flags(kp);
   hc.lap(2);
-  launch_set(core, p, kp, tp, ctas, (unsigned)kp.b.num_tiles, ws, ws_total, P.n, ls);
+  launch_set(core, p, kp, tp, ctas, (unsigned)kp.b.num_tiles, ws, ws_total, P.n, ls, overlap);
+  P.out->born = core->launch_seq.load();   // complete once this launch set's last kernel is
   hc.lap(3);
   after_launch(P);
   hc.lap(4);
@@ -1160,7 +1239,10 @@ static void execute_many(chdb_ctx* ctx, const Program& p, const chdb_device_batc
     launch_set(core, p, kp, tp, ctas, (unsigned)tiles, ws, ws_total, total_rows, ls);
     for (int g = 0; g < nb; g++) done[(size_t)group[(size_t)g]] = std::move(preps[(size_t)group[(size_t)g]].out);
   }
-  for (int32_t i = 0; i < count; i++) outs[i] = done[(size_t)i].release();
+  for (int32_t i = 0; i < count; i++) {
+    done[(size_t)i]->born = core->launch_seq.load();
+    outs[i] = done[(size_t)i].release();
+  }
 }
 
 // Kernel parameter block with the *shape* execute() would produce for a batch whose nullable
@@ -1266,6 +1348,7 @@ int32_t chdb_ctx_synchronize(chdb_ctx* ctx, chdb_status* st) {
 int64_t chdb_ctx_launch_count(chdb_ctx* ctx) { return ctx ? ctx->core->launches.load() : 0; }
 int64_t chdb_ctx_jit_launch_count(chdb_ctx* ctx) { return ctx ? ctx->core->jit_launches.load() : 0; }
 int64_t chdb_ctx_alloc_miss_count(chdb_ctx* ctx) { return ctx ? ctx->core->alloc_misses.load() : 0; }
+int64_t chdb_ctx_overlapped_count(chdb_ctx* ctx) { return ctx ? ctx->core->overlapped.load() : 0; }
 
 int32_t chdb_jit_available(char* why, size_t cap) {
   std::string reason;
@@ -1356,6 +1439,7 @@ int32_t chdb_device_batch_wrap(chdb_ctx* ctx, const struct ArrowSchema* schema, 
     std::vector<InputColumn> cols = parse_schema(schema);
     std::unique_ptr<chdb_device_batch> b(new chdb_device_batch);
     b->core = ctx->core;
+    b->born = ctx->core->launch_seq.load();   // (the caller's buffers are ready in ctx-stream order)
     b->num_rows = num_rows;
     for (size_t i = 0; i < cols.size(); i++) {
       DeviceColumn dc;
@@ -1709,6 +1793,7 @@ int32_t chdb_peer_copy(chdb_ctx* dst_ctx, chdb_ctx* src_ctx, const chdb_device_b
     const int64_t n = src->num_rows;
     std::unique_ptr<chdb_device_batch> b(new chdb_device_batch);
     b->core = dc;
+    b->born = dc->launch_seq.load();
     b->num_rows = n;
     auto copy = [&](const void* p, size_t bytes) {
       Buf buf = dev_alloc(dc, bytes);

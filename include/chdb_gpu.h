@@ -128,6 +128,9 @@ int64_t chdb_ctx_launch_count(chdb_ctx* ctx);
 int64_t chdb_ctx_jit_launch_count(chdb_ctx* ctx);
 /* Device allocations that missed the ctx's block cache and went to cudaMallocAsync (0 in a warmed-up steady state). */
 int64_t chdb_ctx_alloc_miss_count(chdb_ctx* ctx);
+/* Launch sets whose select kernel ran on the ctx's second stream, next to the previous launch set's gather kernel
+ * (device-resident batches created at least one launch set earlier; CHDB_OVERLAP=0 turns it off). */
+int64_t chdb_ctx_overlapped_count(chdb_ctx* ctx);
 
 /* ---- run-time specialisation ----
  * Long scans run the kernels' own source compiled by NVRTC with the program's bytecode baked
@@ -201,7 +204,9 @@ int32_t chdb_upload(chdb_ctx* ctx, const struct ArrowArray* in, const struct Arr
                     chdb_device_batch** out, chdb_status* st);
 /* Wrap device buffers the caller already owns (no copy; they must outlive the batch).
  * Per column c: values[c] (Utf8: value bytes), validity[c] or NULL, offsets[c] (Utf8 only, int32[n+1]).
- * Every buffer must be 16-byte aligned and readable for 32 bytes past its logical end. */
+ * Every buffer must be 16-byte aligned and readable for 32 bytes past its logical end.
+ * Their contents must be complete in ctx-stream order at the time of this call (filled on the ctx stream, on a stream
+ * the ctx stream has waited for, or before a synchronisation), and must not change while the batch lives. */
 int32_t chdb_device_batch_wrap(chdb_ctx* ctx, const struct ArrowSchema* schema, int64_t num_rows,
                                const void* const* values, const void* const* validity,
                                const void* const* offsets, chdb_device_batch** out, chdb_status* st);

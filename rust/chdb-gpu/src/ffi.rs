@@ -39,6 +39,7 @@ extern "C" {
     pub fn chdb_ctx_launch_count(ctx: *mut ChdbCtx) -> i64;
     pub fn chdb_ctx_jit_launch_count(ctx: *mut ChdbCtx) -> i64;
     pub fn chdb_ctx_alloc_miss_count(ctx: *mut ChdbCtx) -> i64;
+    pub fn chdb_ctx_overlapped_count(ctx: *mut ChdbCtx) -> i64;
     pub fn chdb_jit_available(why: *mut c_char, cap: usize) -> i32;
 
     // ---- programs ----

@@ -108,3 +108,41 @@ def test_split_many_tile_groups():
     got = O.batch_from_arrow(C.filter_record(rb, al, expr))
     ok, why = O.batches_equal(got, want)
     assert ok, why
+
+
+def test_select_overlaps_previous_gather_and_stays_exact():
+    """Device-resident batches of different contents run back to back: from the second launch set on, the select
+    kernel runs on the ctx's second stream next to the previous set's gather kernel (runtime.cu launch_set).  Outputs
+    are released in an irregular pattern so that workspace blocks come back to the cache at every distance; every
+    result is compared with the oracle."""
+    ctx = C.Context(0)
+    al = None
+    expr = sp.parse_expr("(id % 3 = 0 and value2 > 10.0) or d < 0.5")
+    sizes = [70000, 70000, 131072, 70000, 99999, 70000, 70000, 131072, 70000, 70000, 99999, 70000]
+    rbs = [make_mixed_batch(n, seed=9100 + i) for i, n in enumerate(sizes)]
+    al = [[] for _ in rbs[0].schema]
+    prog = C.Program.compile_filter(expr, rbs[0].schema)
+    wants = [O.filter_record(O.batch_from_arrow(rb), al, expr) for rb in rbs]
+    devs = [C.DeviceBatch.upload(rb, ctx) for rb in rbs]
+    before = ctx.overlapped_launch_sets
+    for rounds in range(3):
+        outs = []
+        for i, d in enumerate(devs):
+            outs.append(d.run(prog))
+            if i % 3 == 2:      # drop some outputs right away, keep others until the end of the round
+                outs[i - 1] = None
+        for i, o in enumerate(outs):
+            if o is None:
+                continue
+            ok, why = O.batches_equal(O.batch_from_arrow(o.download()), wants[i])
+            assert ok, f"round {rounds} batch {i}: {why}"
+        outs = None
+    if os.environ.get("CHDB_OVERLAP") != "0":
+        assert ctx.overlapped_launch_sets > before, "no launch set used the second stream"
+    # a batch consumed right after it was produced must NOT overlap (its producer is the previous launch set)
+    chained = devs[2].run(prog)
+    n0 = ctx.overlapped_launch_sets
+    again = chained.run(prog)
+    assert ctx.overlapped_launch_sets == n0
+    ok, why = O.batches_equal(O.batch_from_arrow(again.download()), wants[2])   # (filtering twice = filtering once)
+    assert ok, why
