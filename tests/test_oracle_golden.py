@@ -172,3 +172,18 @@ def test_get_record_table_aliases():
     with pytest.raises(O.OracleError) as ei:
         O.get_record_table_aliases({"Producer": {"task": {"Filter": {"expr": {}}}}}, b)
     assert ei.value.kind == "OperatorTaskTypeDoesNotHaveAnAliasField"
+
+
+def test_golden_fixture_file_matches_refcases():
+    """tests/golden/reference_vectors.json is the serialised form of refcases.py (made by make_reference_vectors.py)."""
+    import json
+    import os
+    import refcases
+    doc = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    by_name = {c["name"]: c for c in doc["cases"]}
+    assert len(by_name) == len(refcases.GOLDEN) + 1
+    for name, cite, schema, cols, aliases, kind, query, expected in refcases.GOLDEN:
+        c = by_name[name]
+        assert c["reference"] == cite and c["query"] == query and c["kind"] == kind and c["columns"] == cols
+        want = {"dtype": expected[0], "values": expected[1]} if kind == "value" else expected
+        assert c["expected"] == want
