@@ -126,6 +126,15 @@ def load_library():
     sig("chdb_record_pool_get", i32, vp, ctypes.c_uint64, pvp, stp)
     sig("chdb_record_pool_complete", i32, vp, ctypes.c_uint64, stp)
     sig("chdb_record_pool_stats", None, vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64))
+    sig("chdb_parquet_open", i32, vp, i64, pvp, stp)
+    sig("chdb_parquet_close", None, vp)
+    sig("chdb_parquet_num_row_groups", i32, vp)
+    sig("chdb_parquet_num_columns", i32, vp)
+    sig("chdb_parquet_num_rows", i64, vp)
+    sig("chdb_parquet_row_group_num_rows", i64, vp, i32)
+    sig("chdb_parquet_column", i32, vp, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(i32))
+    sig("chdb_parquet_decode_row_group", i32, vp, vp, i32, pvp, stp)
+    sig("chdb_parquet_check_row_group", i32, vp, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), stp)
     _LIB = L
     return L
 
@@ -133,7 +142,9 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "chdb_code_name", "chdb_version", "chdb_compiled_arch", "chdb_ctx_create", "chdb_ctx_destroy", "chdb_ctx_stream",
     "chdb_ctx_device", "chdb_ctx_synchronize", "chdb_ctx_launch_count", "chdb_ctx_jit_launch_count", "chdb_ctx_alloc_miss_count",
-    "chdb_ctx_overlapped_count",
+    "chdb_ctx_overlapped_count", "chdb_parquet_open", "chdb_parquet_close", "chdb_parquet_num_row_groups",
+    "chdb_parquet_num_columns", "chdb_parquet_num_rows", "chdb_parquet_row_group_num_rows", "chdb_parquet_column",
+    "chdb_parquet_decode_row_group", "chdb_parquet_check_row_group",
     "chdb_jit_available", "chdb_program_jit_source", "chdb_program_jit_check", "chdb_program_compile_filter",
     "chdb_program_compile_project", "chdb_program_compile_filter_project", "chdb_program_release",
     "chdb_program_disassemble", "chdb_program_num_instructions", "chdb_filter_record", "chdb_project_record",
@@ -396,6 +407,69 @@ class Pending:
                 self._a.release(ctypes.byref(self._a))
             _release_schema(self._s)
             self._keep = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class ParquetFile:
+    """A Parquet file's bytes, decoded row group by row group ON THE DEVICE (chdb_parquet_*): the GPU build's
+    read_files (table_func_tasks/read_files_task.rs:233-282).  Opening parses the footer on the host and never
+    touches the GPU; `data` (bytes / bytearray / memoryview / numpy uint8 array) stays borrowed."""
+
+    _FORMATS = {"b": pa.bool_(), "c": pa.int8(), "s": pa.int16(), "i": pa.int32(), "l": pa.int64(), "C": pa.uint8(),
+                "S": pa.uint16(), "I": pa.uint32(), "L": pa.uint64(), "f": pa.float32(), "g": pa.float64(), "u": pa.utf8()}
+
+    def __init__(self, data):
+        L = load_library()
+        self._view = memoryview(data).cast("B")
+        self._buf = (ctypes.c_char * len(self._view)).from_buffer_copy(self._view) if self._view.readonly else \
+            (ctypes.c_char * len(self._view)).from_buffer(self._view)
+        h, st = ctypes.c_void_p(), _Status()
+        _check(L.chdb_parquet_open(ctypes.addressof(self._buf), len(self._view), ctypes.byref(h), ctypes.byref(st)), st)
+        self._h = h
+
+    @property
+    def num_row_groups(self) -> int:
+        return int(load_library().chdb_parquet_num_row_groups(self._h))
+
+    @property
+    def num_rows(self) -> int:
+        return int(load_library().chdb_parquet_num_rows(self._h))
+
+    def row_group_num_rows(self, i: int) -> int:
+        return int(load_library().chdb_parquet_row_group_num_rows(self._h, i))
+
+    @property
+    def schema(self) -> pa.Schema:
+        L = load_library()
+        fields = []
+        for c in range(int(L.chdb_parquet_num_columns(self._h))):
+            name, fmt, nullable = ctypes.c_char_p(), ctypes.c_char_p(), ctypes.c_int32()
+            L.chdb_parquet_column(self._h, c, ctypes.byref(name), ctypes.byref(fmt), ctypes.byref(nullable))
+            fields.append(pa.field(name.value.decode(), self._FORMATS[fmt.value.decode()], bool(nullable.value)))
+        return pa.schema(fields)
+
+    def check_row_group(self, i: int) -> tuple[int, int]:
+        """Host-only: (data pages, hybrid runs) of row group i; raises if the decoder does not support it."""
+        pages, runs, st = ctypes.c_int64(), ctypes.c_int64(), _Status()
+        _check(load_library().chdb_parquet_check_row_group(self._h, i, ctypes.byref(pages), ctypes.byref(runs), ctypes.byref(st)), st)
+        return int(pages.value), int(runs.value)
+
+    def decode_row_group(self, i: int, ctx: "Context | None" = None) -> "DeviceBatch":
+        L = load_library()
+        ctx = ctx or default_context()
+        h, st = ctypes.c_void_p(), _Status()
+        _check(L.chdb_parquet_decode_row_group(ctx._h, self._h, i, ctypes.byref(h), ctypes.byref(st)), st)
+        return DeviceBatch(h, ctx)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().chdb_parquet_close(self._h)
+            self._h = None
 
     def __del__(self):
         try:

@@ -1967,3 +1967,5 @@ int32_t chdb_compute_value(chdb_ctx* ctx, const struct ArrowArray* in, const str
 }
 
 }  // extern "C"
+
+#include "parquet.inc"

@@ -277,6 +277,35 @@ int32_t chdb_record_pool_complete(chdb_record_pool* pool, uint64_t record_id, ch
 void chdb_record_pool_stats(chdb_record_pool* pool, int64_t* records, int64_t* device_bytes, int64_t* spilled_records,
                             int64_t* spilled_bytes);
 
+/* ---- Parquet -> device decode: the step immediately upstream of the filter ----
+ * Replaces the CPU decode of read_files (table_func_tasks/read_files_task.rs:233-282: ParquetRecordBatchStreamBuilder
+ * with_batch_size(max_rows_per_batch)) for the files the reference writes (parquet-rs default writer properties,
+ * src/bin/create_sample_data.rs:221-224: uncompressed, data page v1, dictionary encoding with PLAIN fallback).  The host
+ * reads the footer, the page headers and the RLE run headers; a row group's column chunks cross PCIe as stored and are
+ * decoded by kernels into a device batch (one batch per row group; the filter runs on it in place).
+ * Supported: flat schemas; BOOLEAN, INT32 (+ INT_8/16, UINT_8/16/32), INT64 (+ UINT_64), FLOAT, DOUBLE, BYTE_ARRAY/UTF8;
+ * PLAIN, PLAIN_DICTIONARY / RLE_DICTIONARY, RLE booleans; data pages v1 and v2; REQUIRED / OPTIONAL; UNCOMPRESSED.
+ * Anything else: CHDB_ERR_NOT_IMPLEMENTED.  `file` (the whole file's bytes; pinned memory makes the copy asynchronous)
+ * stays borrowed until chdb_parquet_close.  chdb_parquet_open never touches the GPU. */
+typedef struct chdb_parquet chdb_parquet;
+int32_t chdb_parquet_open(const void* file, int64_t len, chdb_parquet** out, chdb_status* st);
+void chdb_parquet_close(chdb_parquet* f);
+int32_t chdb_parquet_num_row_groups(const chdb_parquet* f);
+int32_t chdb_parquet_num_columns(const chdb_parquet* f);
+int64_t chdb_parquet_num_rows(const chdb_parquet* f);
+int64_t chdb_parquet_row_group_num_rows(const chdb_parquet* f, int32_t row_group);
+/* name / Arrow C format string / nullability of column `col` (pointers valid until close). */
+int32_t chdb_parquet_column(const chdb_parquet* f, int32_t col, const char** name, const char** arrow_format,
+                            int32_t* nullable);
+/* Host-only walk of a row group's page and run headers: CHDB_OK if chdb_parquet_decode_row_group supports every page
+ * of it (else the reason, e.g. a compression codec); *pages / *runs = data pages / hybrid runs found. */
+int32_t chdb_parquet_check_row_group(const chdb_parquet* f, int32_t row_group, int64_t* pages, int64_t* runs,
+                                     chdb_status* st);
+/* Decodes one row group on the ctx stream and returns when the batch is complete (one synchronise: the string
+ * buffers are sized from the decoded lengths). */
+int32_t chdb_parquet_decode_row_group(chdb_ctx* ctx, const chdb_parquet* f, int32_t row_group,
+                                      chdb_device_batch** out, chdb_status* st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ opaque!(ChdbProgram);
 opaque!(ChdbDeviceBatch);
 opaque!(ChdbPending);
 opaque!(ChdbRecordPool);
+opaque!(ChdbParquet);
 
 extern "C" {
     // ---- status ----
@@ -40,6 +41,20 @@ extern "C" {
     pub fn chdb_ctx_jit_launch_count(ctx: *mut ChdbCtx) -> i64;
     pub fn chdb_ctx_alloc_miss_count(ctx: *mut ChdbCtx) -> i64;
     pub fn chdb_ctx_overlapped_count(ctx: *mut ChdbCtx) -> i64;
+
+    // ---- Parquet -> device decode (read_files_task.rs:233-282) ----
+    pub fn chdb_parquet_open(file: *const c_void, len: i64, out: *mut *mut ChdbParquet, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_parquet_close(f: *mut ChdbParquet);
+    pub fn chdb_parquet_num_row_groups(f: *const ChdbParquet) -> i32;
+    pub fn chdb_parquet_num_columns(f: *const ChdbParquet) -> i32;
+    pub fn chdb_parquet_num_rows(f: *const ChdbParquet) -> i64;
+    pub fn chdb_parquet_row_group_num_rows(f: *const ChdbParquet, row_group: i32) -> i64;
+    pub fn chdb_parquet_column(f: *const ChdbParquet, col: i32, name: *mut *const c_char, arrow_format: *mut *const c_char,
+                               nullable: *mut i32) -> i32;
+    pub fn chdb_parquet_check_row_group(f: *const ChdbParquet, row_group: i32, pages: *mut i64, runs: *mut i64,
+                                        st: *mut ChdbStatus) -> i32;
+    pub fn chdb_parquet_decode_row_group(ctx: *mut ChdbCtx, f: *const ChdbParquet, row_group: i32,
+                                         out: *mut *mut ChdbDeviceBatch, st: *mut ChdbStatus) -> i32;
     pub fn chdb_jit_available(why: *mut c_char, cap: usize) -> i32;
 
     // ---- programs ----
