@@ -82,6 +82,9 @@ def parse_args():
     ap.add_argument("--gather-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of three benchmarked batches")
+    ap.add_argument("--parquet", action="store_true",
+                    help="SURVEY 8f row f1 instead of the filter: Parquet -> device decode of the reference's sample schema")
+    ap.add_argument("--parquet-plain", action="store_true", help="--parquet: write the file without dictionary encoding")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     a.rows = a.rows or cfg["rows"]
@@ -695,6 +698,98 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+# ---------------------------------------------------------------------------------------------
+# f1: Parquet -> device decode (read_files_task.rs:233-282), the step upstream of the filter
+# ---------------------------------------------------------------------------------------------
+def run_parquet(args):
+    """One step = decoding every row group of one in-memory Parquet file of the reference's sample schema
+    (create_sample_data.rs: id Int32, value1 Utf8, value2 Float32; uncompressed, dictionary + v1 pages like parquet-rs's
+    defaults) from PINNED host memory into device batches.  The file bytes start on the host, so the H2D copy is inside
+    every timed step: value == e2e.  cpu_baseline: pyarrow's reader (Arrow C++) on one thread over the same bytes."""
+    import io
+
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    import torch
+
+    import chapterhouseqe_b200 as C
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; chapterhouseqe_b200 has no CPU fallback")
+    C.load_library()
+    torch.cuda.set_device(0)
+    ctx = C.Context(0)
+    n = args.rows or 16_000_000
+    rg_rows = args.batch_rows or (1 << 20)     # parquet-rs DEFAULT_MAX_ROW_GROUP_SIZE
+    rng = np.random.default_rng(0xF1)
+    table = pa.table({"id": pa.array(np.arange(n, dtype=np.int32)),
+                      "value1": pa.array(np.char.add("v", rng.integers(0, 10**7, n).astype(str)) if args.parquet_plain
+                                         else np.char.add("word", rng.integers(0, 1000, n).astype(str))),
+                      "value2": pa.array(rng.uniform(0, 100, n).astype(np.float32))})
+    buf = io.BytesIO()
+    pq.write_table(table, buf, compression="NONE", row_group_size=rg_rows, use_dictionary=not args.parquet_plain)
+    raw = buf.getvalue()
+    pinned = torch.empty(len(raw), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = np.frombuffer(raw, dtype=np.uint8)
+    f = C.ParquetFile(pinned.numpy())
+    arrow_bytes = sum(c.nbytes for c in table.columns)
+
+    def step():
+        outs = [f.decode_row_group(i, ctx) for i in range(f.num_row_groups)]
+        return outs
+
+    outs = None
+    for _ in range(max(args.warmup, 3)):
+        outs = step()
+    # parity of what is timed: first and last row group against pyarrow's reader
+    pf = pq.ParquetFile(io.BytesIO(raw))
+    for i in sorted({0, f.num_row_groups - 1}):
+        want = pf.read_row_group(i).combine_chunks()
+        got = outs[i].download()
+        for name in want.schema.names:
+            if not got.column(name).equals(want.column(name).chunk(0)):
+                raise SystemExit(f"bench.py --parquet: row group {i} column {name} differs from pyarrow's reader")
+    outs = None
+    launches0 = ctx.launch_count
+    ctx.synchronize()
+    sampler = ClockSampler(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        outs = step()
+    ctx.synchronize()
+    secs = time.perf_counter() - t0
+    sampler.sample_while(lambda: False)
+    launches = ctx.launch_count - launches0
+    # CPU baseline: pyarrow reader, one thread, bounded sample
+    t1 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t1 < min(args.cpu_seconds, 10.0) or reps == 0:
+        pq.read_table(io.BytesIO(raw), use_threads=False)
+        reps += 1
+    cpu_secs = (time.perf_counter() - t1) / reps
+    peak, peak_src = measured_peak()
+    value = n * args.steps / secs
+    moved = (len(raw) + arrow_bytes) * args.steps / secs / 1e9
+    e2e = {"value": value, "unit": "rows/s", "h2d_bytes_per_step": len(raw), "d2h_bytes_per_step": 16 * 3 * f.num_row_groups,
+           "path": "ParquetFile.decode_row_group -> chdb_parquet_decode_row_group from pinned host memory (result stays in HBM; "
+                   "per row group the null counts and string totals are read back)"}
+    emit({"metric": "parquet_decode_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+          "warmup": max(args.warmup, 3), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
+          "config": {"workload": f"f1 Parquet -> device decode, reference sample schema, {n} rows in {f.num_row_groups} row groups, "
+                                 f"{'PLAIN' if args.parquet_plain else 'dictionary'} value1, uncompressed, v1 pages (pyarrow writer)",
+                     "file_bytes": len(raw), "arrow_bytes": arrow_bytes,
+                     "l2": "every step streams the whole file (larger than L2) from host memory"},
+          "timing": "host wall clock around all steps (each row group's decode ends in a stream synchronise), H2D inside",
+          "e2e": e2e, "gpu_launches": int(launches), "parity_checked_row_groups": 2, "clocks": sampler.result(),
+          "roofline": {"bound": "hbm", "kernel": "pq_decode_rows / pq_walk_byte_arrays / pq_scan_* / pq_copy_utf8 + the H2D copy",
+                       "achieved": moved, "peak": peak, "unit": "GB/s", "frac": moved / peak, "traffic": None, "peak_source": peak_src,
+                       "note": "file bytes in + Arrow bytes out per second of the WHOLE call (PCIe copy and per-row-group "
+                               "synchronise included): far from the HBM bound by construction; the PCIe link bounds it first"},
+          "cpu_baseline": {"value": n / cpu_secs, "unit": "rows/s", "cores": 1, "kind": "port",
+                           "sample": f"pyarrow {pa.__version__} parquet.read_table(use_threads=False) of the same bytes, {reps} run(s)"}})
+
+
 def main():
     global _REAL_STDOUT
     args = parse_args()
@@ -707,6 +802,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.parquet:
+        if rank == 0:
+            run_parquet(args)
+        return
     if args.impl == "reference":
         run_reference(args, cfg, rank, world)
         return

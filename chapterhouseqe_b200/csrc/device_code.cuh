@@ -1110,50 +1110,99 @@ __device__ __forceinline__ void copy_value(uint8_t* dst, const uint8_t* src, uin
   else copy_value_slow(dst, src, n);
 }
 
-// Long strings: the warp's output byte range is produced chunk-centric -- each lane builds aligned
-// 16-byte output chunks, finding the source row of a byte by binary search over the warp's
-// selected rows (s_oo: warp-local output byte offsets, s_src: source byte offsets).
+// Long strings: the warp's output byte range is produced chunk-centric -- each lane builds aligned 16-byte output
+// chunks (s_oo: warp-local output byte offsets of the slice's selected rows, s_src: their source byte offsets).
+// A chunk is assembled from PIECES, one per source row it touches: for each piece the 16 source bytes that would line
+// up with the whole chunk are fetched with one unaligned 16-byte read and merged under a byte mask -- a chunk inside
+// one row is one read and one store, a chunk that straddles two rows is two reads and one store (the first version
+// built straddling chunks byte by byte: 42 % of the C4 gather kernel's stall samples).  The row of a lane's next
+// chunk is found by walking on from the previous one when rows are long (a lane's chunks are 512 bytes apart), by
+// binary search otherwise.
+__device__ __forceinline__ uint32_t low_bytes_mask32(uint32_t n) {   // n in [0, 4]: the n low bytes set
+  return (uint32_t)((1ull << (8u * n)) - 1ull);
+}
+__device__ __forceinline__ uint4 byte_range_mask(uint32_t a, uint32_t z) {   // bytes [a, z) of a 16-byte chunk, a < z <= 16
+  uint32_t m[4];
+#pragma unroll
+  for (uint32_t i = 0; i < 4; i++) {
+    const uint32_t lo = a > 4u * i ? (a - 4u * i < 4u ? a - 4u * i : 4u) : 0u;
+    const uint32_t hi = z > 4u * i ? (z - 4u * i < 4u ? z - 4u * i : 4u) : 0u;
+    m[i] = low_bytes_mask32(hi) & ~low_bytes_mask32(lo);
+  }
+  return make_uint4(m[0], m[1], m[2], m[3]);
+}
+// the first version's assembly of one chunk, byte / word at a time: kept for the one case the piece reads cannot
+// serve (a piece whose lined-up source address would lie before the start of the value buffer)
+__device__ __noinline__ uint4 assemble_chunk_bytes(const uint8_t* __restrict__ sv, uint32_t mis, uint32_t lo, uint32_t s, uint32_t t,
+                                                   uint32_t r, const uint32_t* s_oo, const int32_t* s_src) {
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll 1
+  for (uint32_t b = s; b < t;) {
+    const uint32_t xb = b - mis;
+    while (xb >= s_oo[r + 1]) r++;
+    const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
+    uint32_t piece, step;
+    if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) { piece = load4_unaligned(sp); step = 4; }
+    else { piece = (uint32_t)*sp << (8u * (b & 3u)); step = 1; }
+    const uint32_t wi = (b - lo) >> 2;
+    if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
+    b += step;
+  }
+  return make_uint4(w0, w1, w2, w3);
+}
 __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, uint8_t* gal, uint32_t mis, uint32_t nbytes, uint32_t nrows,
                                                const uint32_t* s_oo, const int32_t* s_src, int lane) {
   const uint32_t end = mis + nbytes;
   const uint32_t nchunks = (end + 15u) >> 4;
+  const bool walk = nbytes >= 64u * nrows;   // (uniform) long rows: the next chunk's row is a few rows on
+  uint32_t r = 0;
+  bool first = true;
 #pragma unroll 1
   for (uint32_t ch = lane; ch < nchunks; ch += 32) {
     const uint32_t lo = ch << 4, hi = lo + 16;
     const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
     if (s >= t) continue;
     const uint32_t x = s - mis;  // warp-local output byte index of the first byte produced
-    uint32_t lo_r = 0, hi_r = nrows;  // first r in (0, nrows] with s_oo[r] > x
-    while (lo_r < hi_r) {
-      const uint32_t mid = (lo_r + hi_r) >> 1;
-      if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
-    }
-    uint32_t r = lo_r - 1;  // row holding byte x (empty strings are skipped by the search)
-    const bool full = (t - s) == 16u;
-    if (full && x + 16u <= s_oo[r + 1]) {
-      *(uint4*)(gal + lo) = load16_unaligned(sv + s_src[r] + (x - s_oo[r]));
-      continue;
-    }
-    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-#pragma unroll 1
-    for (uint32_t b = s; b < t;) {
-      const uint32_t xb = b - mis;
-      while (xb >= s_oo[r + 1]) r++;
-      const uint8_t* sp = sv + s_src[r] + (xb - s_oo[r]);
-      uint32_t piece, step;
-      if (((b & 3u) == 0) && b + 4 <= t && xb + 4 <= s_oo[r + 1]) { piece = load4_unaligned(sp); step = 4; }
-      else { piece = (uint32_t)*sp << (8u * (b & 3u)); step = 1; }
-      const uint32_t wi = (b - lo) >> 2;
-      if (wi == 0) w0 |= piece; else if (wi == 1) w1 |= piece; else if (wi == 2) w2 |= piece; else w3 |= piece;
-      b += step;
-    }
-    if (full) {
-      *(uint4*)(gal + lo) = make_uint4(w0, w1, w2, w3);
+    if (walk && !first) {
+      while (s_oo[r + 1] <= x) r++;
     } else {
-      for (uint32_t b = s; b < t; b++) {
-        const uint32_t wi = (b - lo) >> 2;
-        const uint32_t word = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
-        gal[b] = (uint8_t)(word >> (8u * (b & 3u)));
+      uint32_t lo_r = 0, hi_r = nrows;  // first r in (0, nrows] with s_oo[r] > x
+      while (lo_r < hi_r) {
+        const uint32_t mid = (lo_r + hi_r) >> 1;
+        if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
+      }
+      r = lo_r - 1;  // row holding byte x (empty strings are skipped by the search)
+    }
+    first = false;
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t b = s, rr = r;
+    bool fallback = false;
+#pragma unroll 1
+    while (true) {
+      const uint32_t row_lo = s_oo[rr] + mis, row_hi = s_oo[rr + 1] + mis;   // the row's output byte range
+      const uint32_t e = t < row_hi ? t : row_hi;
+      // the source address that lines up with output byte `lo`
+      const int64_t vsrc = (int64_t)s_src[rr] + (int64_t)lo - (int64_t)row_lo;
+      if (vsrc < 0) { fallback = true; break; }
+      const uint4 v = load16_unaligned(sv + vsrc);
+      if (b == lo && e == hi) {
+        acc = v;
+      } else {
+        const uint4 m = byte_range_mask(b - lo, e - lo);
+        acc.x |= v.x & m.x; acc.y |= v.y & m.y; acc.z |= v.z & m.z; acc.w |= v.w & m.w;
+      }
+      b = e;
+      if (b >= t) break;
+      do { rr++; } while (s_oo[rr + 1] + mis <= b);   // (skips empty strings)
+    }
+    if (fallback) acc = assemble_chunk_bytes(sv, mis, lo, s, t, r, s_oo, s_src);
+    if ((t - s) == 16u) {
+      *(uint4*)(gal + lo) = acc;
+    } else {
+      for (uint32_t bb = s; bb < t; bb++) {
+        const uint32_t wi = (bb - lo) >> 2;
+        const uint32_t word = wi == 0 ? acc.x : wi == 1 ? acc.y : wi == 2 ? acc.z : acc.w;
+        gal[bb] = (uint8_t)(word >> (8u * (bb & 3u)));
       }
     }
   }
