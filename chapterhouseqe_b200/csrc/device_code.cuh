@@ -1150,6 +1150,10 @@ __device__ __noinline__ uint4 assemble_chunk_bytes(const uint8_t* __restrict__ s
   }
   return make_uint4(w0, w1, w2, w3);
 }
+// (kChunksInFlight chunks per lane and iteration: the first piece's reads of all of them are issued before any is
+// looked at.  Measured on C4 / C4H (100-byte strings, 100 % / 50 % selected): 1 chunk 169.2 / 123.0 us per 2M-row batch,
+// 2 chunks 164.2 / 102.3 us, 4 chunks 219.4 / 134.8 us)
+constexpr int kChunksInFlight = 2;
 __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, uint8_t* gal, uint32_t mis, uint32_t nbytes, uint32_t nrows,
                                                const uint32_t* s_oo, const int32_t* s_src, int lane) {
   const uint32_t end = mis + nbytes;
@@ -1158,51 +1162,85 @@ __device__ __noinline__ void copy_long_strings(const uint8_t* __restrict__ sv, u
   uint32_t r = 0;
   bool first = true;
 #pragma unroll 1
-  for (uint32_t ch = lane; ch < nchunks; ch += 32) {
-    const uint32_t lo = ch << 4, hi = lo + 16;
-    const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
-    if (s >= t) continue;
-    const uint32_t x = s - mis;  // warp-local output byte index of the first byte produced
-    if (walk && !first) {
-      while (s_oo[r + 1] <= x) r++;
-    } else {
-      uint32_t lo_r = 0, hi_r = nrows;  // first r in (0, nrows] with s_oo[r] > x
-      while (lo_r < hi_r) {
-        const uint32_t mid = (lo_r + hi_r) >> 1;
-        if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
-      }
-      r = lo_r - 1;  // row holding byte x (empty strings are skipped by the search)
-    }
-    first = false;
-    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t b = s, rr = r;
-    bool fallback = false;
-#pragma unroll 1
-    while (true) {
-      const uint32_t row_lo = s_oo[rr] + mis, row_hi = s_oo[rr + 1] + mis;   // the row's output byte range
-      const uint32_t e = t < row_hi ? t : row_hi;
-      // the source address that lines up with output byte `lo`
-      const int64_t vsrc = (int64_t)s_src[rr] + (int64_t)lo - (int64_t)row_lo;
-      if (vsrc < 0) { fallback = true; break; }
-      const uint4 v = load16_unaligned(sv + vsrc);
-      if (b == lo && e == hi) {
-        acc = v;
+  for (uint32_t ch0 = lane; ch0 < nchunks; ch0 += 32 * kChunksInFlight) {
+    uint32_t rs[kChunksInFlight], w[kChunksInFlight][5], shv[kChunksInFlight];
+    uint32_t live = 0, fb = 0;   // bit u: chunk u produces bytes / needs the byte-wise fallback
+    // ---- 1. the row of each chunk's first byte, and the reads of its first piece ----
+#pragma unroll
+    for (int u = 0; u < kChunksInFlight; u++) {
+      const uint32_t ch = ch0 + 32u * u;
+      const uint32_t lo = ch << 4, hi = lo + 16;
+      const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
+      rs[u] = r;
+      shv[u] = 0;
+#pragma unroll
+      for (int i = 0; i < 5; i++) w[u][i] = 0;
+      if (ch >= nchunks || s >= t) continue;
+      const uint32_t x = s - mis;  // warp-local output byte index of the first byte produced
+      if (walk && !first) {
+        while (s_oo[r + 1] <= x) r++;
       } else {
-        const uint4 m = byte_range_mask(b - lo, e - lo);
-        acc.x |= v.x & m.x; acc.y |= v.y & m.y; acc.z |= v.z & m.z; acc.w |= v.w & m.w;
+        uint32_t lo_r = 0, hi_r = nrows;  // first r in (0, nrows] with s_oo[r] > x
+        while (lo_r < hi_r) {
+          const uint32_t mid = (lo_r + hi_r) >> 1;
+          if (s_oo[mid] > x) hi_r = mid; else lo_r = mid + 1;
+        }
+        r = lo_r - 1;  // row holding byte x (empty strings are skipped by the search)
       }
-      b = e;
-      if (b >= t) break;
-      do { rr++; } while (s_oo[rr + 1] + mis <= b);   // (skips empty strings)
+      first = false;
+      rs[u] = r;
+      live |= 1u << u;
+      // the source address that lines up with output byte `lo`
+      const int64_t vsrc = (int64_t)s_src[r] + (int64_t)lo - (int64_t)(s_oo[r] + mis);
+      if (vsrc < 0) { fb |= 1u << u; continue; }
+      const uintptr_t a = (uintptr_t)(sv + vsrc);
+      const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+      shv[u] = (uint32_t)(a & 3u) * 8u;
+#pragma unroll
+      for (int i = 0; i < 5; i++) w[u][i] = q[i];   // (buffers are padded: the fifth word is always readable)
     }
-    if (fallback) acc = assemble_chunk_bytes(sv, mis, lo, s, t, r, s_oo, s_src);
-    if ((t - s) == 16u) {
-      *(uint4*)(gal + lo) = acc;
-    } else {
-      for (uint32_t bb = s; bb < t; bb++) {
-        const uint32_t wi = (bb - lo) >> 2;
-        const uint32_t word = wi == 0 ? acc.x : wi == 1 ? acc.y : wi == 2 ? acc.z : acc.w;
-        gal[bb] = (uint8_t)(word >> (8u * (bb & 3u)));
+    // ---- 2. merge the pieces, store ----
+#pragma unroll
+    for (int u = 0; u < kChunksInFlight; u++) {
+      if (!((live >> u) & 1u)) continue;
+      const uint32_t ch = ch0 + 32u * u;
+      const uint32_t lo = ch << 4, hi = lo + 16;
+      const uint32_t s = lo > mis ? lo : mis, t = hi < end ? hi : end;
+      uint4 acc;
+      if ((fb >> u) & 1u) {
+        acc = assemble_chunk_bytes(sv, mis, lo, s, t, rs[u], s_oo, s_src);
+      } else {
+        uint32_t rr = rs[u];
+        const uint32_t row_hi = s_oo[rr + 1] + mis;
+        uint32_t e = t < row_hi ? t : row_hi;
+        acc = make_uint4(__funnelshift_r(w[u][0], w[u][1], shv[u]), __funnelshift_r(w[u][1], w[u][2], shv[u]),
+                         __funnelshift_r(w[u][2], w[u][3], shv[u]), __funnelshift_r(w[u][3], w[u][4], shv[u]));
+        if (!(s == lo && e == hi)) {
+          const uint4 m = byte_range_mask(s - lo, e - lo);
+          acc.x &= m.x; acc.y &= m.y; acc.z &= m.z; acc.w &= m.w;
+          uint32_t b = e;
+#pragma unroll 1
+          while (b < t) {   // further pieces: the rows that follow inside this chunk
+            do { rr++; } while (s_oo[rr + 1] + mis <= b);   // (skips empty strings)
+            const uint32_t row_lo2 = s_oo[rr] + mis, row_hi2 = s_oo[rr + 1] + mis;
+            e = t < row_hi2 ? t : row_hi2;
+            const int64_t vsrc = (int64_t)s_src[rr] + (int64_t)lo - (int64_t)row_lo2;
+            if (vsrc < 0) { acc = assemble_chunk_bytes(sv, mis, lo, s, t, rs[u], s_oo, s_src); break; }
+            const uint4 v = load16_unaligned(sv + vsrc);
+            const uint4 m2 = byte_range_mask(b - lo, e - lo);
+            acc.x |= v.x & m2.x; acc.y |= v.y & m2.y; acc.z |= v.z & m2.z; acc.w |= v.w & m2.w;
+            b = e;
+          }
+        }
+      }
+      if ((t - s) == 16u) {
+        *(uint4*)(gal + lo) = acc;
+      } else {
+        for (uint32_t bb = s; bb < t; bb++) {
+          const uint32_t wi = (bb - lo) >> 2;
+          const uint32_t word = wi == 0 ? acc.x : wi == 1 ? acc.y : wi == 2 ? acc.z : acc.w;
+          gal[bb] = (uint8_t)(word >> (8u * (bb & 3u)));
+        }
       }
     }
   }
