@@ -134,6 +134,7 @@ def load_library():
     sig("chdb_parquet_row_group_num_rows", i64, vp, i32)
     sig("chdb_parquet_column", i32, vp, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(i32))
     sig("chdb_parquet_decode_row_group", i32, vp, vp, i32, pvp, stp)
+    sig("chdb_parquet_decode_row_groups", i32, vp, vp, i32, i32, pvp, stp)
     sig("chdb_parquet_check_row_group", i32, vp, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), stp)
     _LIB = L
     return L
@@ -145,6 +146,7 @@ EXPORTED_SYMBOLS = [
     "chdb_ctx_overlapped_count", "chdb_parquet_open", "chdb_parquet_close", "chdb_parquet_num_row_groups",
     "chdb_parquet_num_columns", "chdb_parquet_num_rows", "chdb_parquet_row_group_num_rows", "chdb_parquet_column",
     "chdb_parquet_decode_row_group", "chdb_parquet_check_row_group",
+    "chdb_parquet_decode_row_groups",
     "chdb_jit_available", "chdb_program_jit_source", "chdb_program_jit_check", "chdb_program_compile_filter",
     "chdb_program_compile_project", "chdb_program_compile_filter_project", "chdb_program_release",
     "chdb_program_disassemble", "chdb_program_num_instructions", "chdb_filter_record", "chdb_project_record",
@@ -465,6 +467,16 @@ class ParquetFile:
         h, st = ctypes.c_void_p(), _Status()
         _check(L.chdb_parquet_decode_row_group(ctx._h, self._h, i, ctypes.byref(h), ctypes.byref(st)), st)
         return DeviceBatch(h, ctx)
+
+    def decode_row_groups(self, first: int = 0, count: "int | None" = None, ctx: "Context | None" = None) -> "list[DeviceBatch]":
+        """Row groups [first, first + count): the next row group's bytes cross PCIe while this one's kernels run."""
+        L = load_library()
+        ctx = ctx or default_context()
+        count = self.num_row_groups - first if count is None else count
+        outs = (ctypes.c_void_p * max(count, 1))()
+        st = _Status()
+        _check(L.chdb_parquet_decode_row_groups(ctx._h, self._h, first, count, outs, ctypes.byref(st)), st)
+        return [DeviceBatch(ctypes.c_void_p(outs[i]), ctx) for i in range(count)]
 
     def close(self):
         if getattr(self, "_h", None):

@@ -61,6 +61,7 @@ struct CtxCore {
   // Select / gather overlap (launch_set): launch sets are numbered; before_last[k & 3] fires when everything enqueued on
   // `stream` before launch set k's LAST kernel has completed; select_done[k & 3] when its select kernel (second stream) has.
   cudaStream_t aux_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // Parquet decode of several row groups: the next row group's H2D copy (parquet.inc)
   cudaEvent_t select_done[4] = {nullptr, nullptr, nullptr, nullptr}, before_last[4] = {nullptr, nullptr, nullptr, nullptr};
   std::atomic<int64_t> launch_seq{0};
   std::atomic<int64_t> overlapped{0};     // launch sets whose select kernel ran on aux_stream
@@ -77,6 +78,7 @@ struct CtxCore {
       if (before_last[i]) cudaEventDestroy(before_last[i]);
     }
     if (aux_stream) cudaStreamDestroy(aux_stream);
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
     for (cudaEvent_t e : events_free) cudaEventDestroy(e);
     if (stream) cudaStreamSynchronize(stream);
     for (void* p : pinned_free) cudaFreeHost(p);

@@ -306,6 +306,11 @@ int32_t chdb_parquet_check_row_group(const chdb_parquet* f, int32_t row_group, i
 int32_t chdb_parquet_decode_row_group(chdb_ctx* ctx, const chdb_parquet* f, int32_t row_group,
                                       chdb_device_batch** out, chdb_status* st);
 
+/* Row groups [first, first + count) into out[0 .. count): the same results, with row group i+1's bytes crossing PCIe
+ * (on a second stream of the ctx, when `file` is pinned) while row group i's kernels run. */
+int32_t chdb_parquet_decode_row_groups(chdb_ctx* ctx, const chdb_parquet* f, int32_t first, int32_t count,
+                                       chdb_device_batch** out, chdb_status* st);
+
 #ifdef __cplusplus
 }
 #endif

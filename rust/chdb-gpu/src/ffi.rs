@@ -53,6 +53,8 @@ extern "C" {
                                nullable: *mut i32) -> i32;
     pub fn chdb_parquet_check_row_group(f: *const ChdbParquet, row_group: i32, pages: *mut i64, runs: *mut i64,
                                         st: *mut ChdbStatus) -> i32;
+    pub fn chdb_parquet_decode_row_groups(ctx: *mut ChdbCtx, f: *const ChdbParquet, first: i32, count: i32,
+                                          out: *mut *mut ChdbDeviceBatch, st: *mut ChdbStatus) -> i32;
     pub fn chdb_parquet_decode_row_group(ctx: *mut ChdbCtx, f: *const ChdbParquet, row_group: i32,
                                          out: *mut *mut ChdbDeviceBatch, st: *mut ChdbStatus) -> i32;
     pub fn chdb_jit_available(why: *mut c_char, cap: usize) -> i32;

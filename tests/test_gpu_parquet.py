@@ -76,6 +76,37 @@ def test_decoded_batch_feeds_the_filter():
         assert ok, f"row group {i}: {why}"
 
 
+def test_pipelined_decode_of_all_row_groups_matches_one_by_one():
+    t = PC.sample_table(90000, seed=21)
+    data = PC.write(t, row_group_size=11000)
+    f = C.ParquetFile(data)
+    outs = f.decode_row_groups()
+    assert len(outs) == f.num_row_groups == 9
+    for i, dev in enumerate(outs):
+        want = as_batch(PC.read_row_group(data, i))
+        got = dev.download()
+        for name in want.schema.names:
+            assert got.column(name).equals(want.column(name)), f"row group {i} column {name}"
+    part = f.decode_row_groups(3, 2)
+    assert [p.num_rows for p in part] == [11000, 11000]
+    assert f.decode_row_groups(4, 0) == []
+    with pytest.raises(C.ChdbError):
+        f.decode_row_groups(7, 5)
+
+
+def test_big_pages_with_nulls_are_cut_into_segments():
+    """Pages far larger than one segment (4096 rows), with nulls: the per-segment ranks come from the host's popcount of
+    the definition levels."""
+    n = 300_000
+    rng = np.random.default_rng(8)
+    t = pa.table({"a": pa.array(rng.integers(0, 1 << 30, n).astype(np.int32), mask=rng.random(n) < 0.3),
+                  "s": pa.array(np.char.add("k", rng.integers(0, 50, n).astype(str)), mask=rng.random(n) < 0.5),
+                  "b": pa.array(rng.random(n) < 0.5, mask=rng.random(n) < 0.01),
+                  "runs": pa.array(np.repeat(np.arange(n // 1000, dtype=np.int64), 1000), mask=np.repeat(rng.random(n // 1000) < 0.3, 1000))})
+    for kw in (dict(), dict(use_dictionary=False), dict(data_page_version="2.0")):
+        check_file(PC.write(t, data_page_size=8 << 20, **kw), t)
+
+
 def test_truncated_page_does_not_crash():
     t = PC.sample_table(3000, seed=2).select(["id", "value1"])
     data = bytearray(PC.write(t, use_dictionary=False))
