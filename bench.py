@@ -36,7 +36,7 @@ UNIT = "rows/s"
 
 BASE_COLS = lambda L: [("id", "i32", "seq", 0.0), ("value1", "utf8", L, 0.0), ("value2", "f32", "u100", 0.0)]  # noqa: E731
 CONFIGS = {
-    "C2": dict(seed=0xC4DB0002, rows=100_000_000, batch_rows=1 << 22, passes=24,
+    "C2": dict(seed=0xC4DB0002, rows=100_000_000, batch_rows=1 << 22, passes=30,
                cols=[("id", "i32", "seq", 0.0), ("k", "i64", "u31", 0.0), ("value2", "f32", "u100", 0.10),
                      ("d", "f64", "normal", 0.05), ("value1", "utf8", 8, 0.0)],
                sql="select * from read_files('large_simple/*.parquet') where (id % 2 = 0 and value2 > 10.0) or d < 0.5",
@@ -85,6 +85,8 @@ def parse_args():
     ap.add_argument("--parquet", action="store_true",
                     help="SURVEY 8f row f1 instead of the filter: Parquet -> device decode of the reference's sample schema")
     ap.add_argument("--parquet-plain", action="store_true", help="--parquet: write the file without dictionary encoding")
+    ap.add_argument("--parquet-filter", action="store_true",
+                    help="--parquet: read_files -> filter (id %% 2 = 0) -> download of the result, the decoded batches never leave HBM")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     a.rows = a.rows or cfg["rows"]
@@ -734,17 +736,29 @@ def run_parquet(args):
     f = C.ParquetFile(pinned.numpy())
     arrow_bytes = sum(c.nbytes for c in table.columns)
 
+    prog = None
+    if args.parquet_filter:
+        from chapterhouseqe_b200 import sqlparser_lite as sp
+        prog = C.Program.compile_filter(sp.parse_expr("id % 2 = 0"), f.schema)
+
     def step():
-        return f.decode_row_groups(0, None, ctx)   # (row group i+1's H2D copy runs next to row group i's kernels)
+        decoded = f.decode_row_groups(0, None, ctx)   # (row group i+1's H2D copy runs next to row group i's kernels)
+        if prog is None:
+            return decoded
+        results = [b.run(prog) for b in decoded]      # filter on the decoded device batches, in place
+        return [r.download() for r in results]        # only the filtered rows cross PCIe back
 
     outs = None
     for _ in range(max(args.warmup, 3)):
         outs = step()
     # parity of what is timed: first and last row group against pyarrow's reader
     pf = pq.ParquetFile(io.BytesIO(raw))
+    import pyarrow.compute as pc
     for i in sorted({0, f.num_row_groups - 1}):
         want = pf.read_row_group(i).combine_chunks()
-        got = outs[i].download()
+        if prog is not None:   # (ids are non-negative: id % 2 = 0 <=> the low bit is clear)
+            want = want.filter(pc.equal(pc.bit_wise_and(want.column("id"), 1), 0)).combine_chunks()
+        got = outs[i] if prog is not None else outs[i].download()
         for name in want.schema.names:
             if not got.column(name).equals(want.column(name).chunk(0)):
                 raise SystemExit(f"bench.py --parquet: row group {i} column {name} differs from pyarrow's reader")
@@ -760,19 +774,24 @@ def run_parquet(args):
     sampler.sample_while(lambda: False)
     launches = ctx.launch_count - launches0
     # CPU baseline: pyarrow reader, one thread, bounded sample
+    d2h = 16 * 3 * f.num_row_groups + (sum(rb.nbytes for rb in outs) if prog is not None else 0)
+    outs = None
     t1 = time.perf_counter()
     reps = 0
     while time.perf_counter() - t1 < min(args.cpu_seconds, 10.0) or reps == 0:
-        pq.read_table(io.BytesIO(raw), use_threads=False)
+        tb = pq.read_table(io.BytesIO(raw), use_threads=False)
+        if prog is not None:
+            tb = tb.filter(pc.equal(pc.bit_wise_and(tb.column("id"), 1), 0))
         reps += 1
     cpu_secs = (time.perf_counter() - t1) / reps
     peak, peak_src = measured_peak()
     value = n * args.steps / secs
     moved = (len(raw) + arrow_bytes) * args.steps / secs / 1e9
-    e2e = {"value": value, "unit": "rows/s", "h2d_bytes_per_step": len(raw), "d2h_bytes_per_step": 16 * 3 * f.num_row_groups,
-           "path": "ParquetFile.decode_row_groups -> chdb_parquet_decode_row_groups from pinned host memory (result stays in HBM; "
-                   "per row group the null counts and string totals are read back)"}
-    emit({"metric": "parquet_decode_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+    e2e = {"value": value, "unit": "rows/s", "h2d_bytes_per_step": len(raw), "d2h_bytes_per_step": d2h,
+           "path": "ParquetFile.decode_row_groups -> chdb_parquet_decode_row_groups from pinned host memory"
+                   + (" -> DeviceBatch.run (chdb_run_device, filter id % 2 = 0) -> download of the filtered batches" if prog is not None
+                      else " (result stays in HBM; per row group the null counts and string totals are read back)")}
+    emit({"metric": "parquet_decode_filter_rows_per_s" if prog is not None else "parquet_decode_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
           "warmup": max(args.warmup, 3), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
           "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
           "config": {"workload": f"f1 Parquet -> device decode, reference sample schema, {n} rows in {f.num_row_groups} row groups, "
@@ -786,7 +805,8 @@ def run_parquet(args):
                        "note": "file bytes in + Arrow bytes out per second of the WHOLE call (PCIe copy and per-row-group "
                                "synchronise included): far from the HBM bound by construction; the PCIe link bounds it first"},
           "cpu_baseline": {"value": n / cpu_secs, "unit": "rows/s", "cores": 1, "kind": "port",
-                           "sample": f"pyarrow {pa.__version__} parquet.read_table(use_threads=False) of the same bytes, {reps} run(s)"}})
+                           "sample": f"pyarrow {pa.__version__} parquet.read_table(use_threads=False) of the same bytes"
+                                     + (" + Table.filter(id & 1 == 0)" if prog is not None else "") + f", {reps} run(s)"}})
 
 
 def main():

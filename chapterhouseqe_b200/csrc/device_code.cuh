@@ -1118,18 +1118,29 @@ __device__ __forceinline__ void copy_value(uint8_t* dst, const uint8_t* src, uin
 // built straddling chunks byte by byte: 42 % of the C4 gather kernel's stall samples).  The row of a lane's next
 // chunk is found by walking on from the previous one when rows are long (a lane's chunks are 512 bytes apart), by
 // binary search otherwise.
-__device__ __forceinline__ uint32_t low_bytes_mask32(uint32_t n) {   // n in [0, 4]: the n low bytes set
-  return (uint32_t)((1ull << (8u * n)) - 1ull);
-}
+// kLowBytes16[n]: the n low bytes of a 16-byte chunk set (n in [0, 16]).  A table in constant memory: computing the
+// masks with shifts was 29 % of the C4 gather kernel's instructions (profiles/r2g_c4_gather_ncu_summary.txt).
+__constant__ uint4 kLowBytes16[17] = {
+  {0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+  {0x000000FFu, 0x00000000u, 0x00000000u, 0x00000000u},
+  {0x0000FFFFu, 0x00000000u, 0x00000000u, 0x00000000u},
+  {0x00FFFFFFu, 0x00000000u, 0x00000000u, 0x00000000u},
+  {0xFFFFFFFFu, 0x00000000u, 0x00000000u, 0x00000000u},
+  {0xFFFFFFFFu, 0x000000FFu, 0x00000000u, 0x00000000u},
+  {0xFFFFFFFFu, 0x0000FFFFu, 0x00000000u, 0x00000000u},
+  {0xFFFFFFFFu, 0x00FFFFFFu, 0x00000000u, 0x00000000u},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0x00000000u},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0x000000FFu, 0x00000000u},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu, 0x00000000u},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu, 0x00000000u},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x000000FFu},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu},
+  {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}};
 __device__ __forceinline__ uint4 byte_range_mask(uint32_t a, uint32_t z) {   // bytes [a, z) of a 16-byte chunk, a < z <= 16
-  uint32_t m[4];
-#pragma unroll
-  for (uint32_t i = 0; i < 4; i++) {
-    const uint32_t lo = a > 4u * i ? (a - 4u * i < 4u ? a - 4u * i : 4u) : 0u;
-    const uint32_t hi = z > 4u * i ? (z - 4u * i < 4u ? z - 4u * i : 4u) : 0u;
-    m[i] = low_bytes_mask32(hi) & ~low_bytes_mask32(lo);
-  }
-  return make_uint4(m[0], m[1], m[2], m[3]);
+  const uint4 lo = kLowBytes16[a], hi = kLowBytes16[z];
+  return make_uint4(hi.x & ~lo.x, hi.y & ~lo.y, hi.z & ~lo.z, hi.w & ~lo.w);
 }
 // the first version's assembly of one chunk, byte / word at a time: kept for the one case the piece reads cannot
 // serve (a piece whose lined-up source address would lie before the start of the value buffer)
