@@ -9,7 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FULL_BATCH = {"C2": 1 << 22, "C3": 1 << 22, "C4": 1 << 21, "C5": 1 << 22}
 out = {}
 for cfg, rows in FULL_BATCH.items():
-    path = os.path.join(HERE, f"r2f_{cfg}_launches.csv")
+    path = os.path.join(HERE, f"r2g_{cfg}_launches.csv")   # (re-captured after the last change to that config's kernels)
+    if not os.path.exists(path):
+        path = os.path.join(HERE, f"r2f_{cfg}_launches.csv")
     if not os.path.exists(path):
         continue
     lines = [l for l in open(path) if l.startswith('"')]
@@ -32,7 +34,7 @@ for cfg, rows in FULL_BATCH.items():
                 "duration_us_under_ncu": round(sum(k["us"] for k in kern.values()), 2),
                 "capture": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
                            "(serialised, cold L2), the last full-batch launch set (zero_kernel + chdb_jit_select + chdb_jit_gather) "
-                           f"of profiles/r2f_{cfg}_launches.csv; the gather kernel's re-read of the predicate columns counts in "
+                           f"of profiles/{os.path.basename(path)}; the gather kernel's re-read of the predicate columns counts in "
                            "full here, and part of the output is still dirty in L2 when the last kernel ends"}
 json.dump(out, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
 for c, v in out.items():
