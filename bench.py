@@ -85,6 +85,9 @@ def parse_args():
     ap.add_argument("--parquet", action="store_true",
                     help="SURVEY 8f row f1 instead of the filter: Parquet -> device decode of the reference's sample schema")
     ap.add_argument("--parquet-plain", action="store_true", help="--parquet: write the file without dictionary encoding")
+    ap.add_argument("--parquet-encode", action="store_true",
+                    help="f3: device batches -> Parquet file image in pinned host memory (chdb_parquet_encode), records of --batch-rows rows "
+                         "coalesced into 1 Mi-row row groups, against pyarrow's writer on one thread")
     ap.add_argument("--parquet-filter", action="store_true",
                     help="--parquet: read_files -> filter (id %% 2 = 0) -> download of the result, the decoded batches never leave HBM")
     a = ap.parse_args()
@@ -808,6 +811,88 @@ def run_parquet(args):
                            "sample": f"pyarrow {pa.__version__} parquet.read_table(use_threads=False) of the same bytes"
                                      + (" + Table.filter(id & 1 == 0)" if prog is not None else "") + f", {reps} run(s)"}})
 
+# ---------------------------------------------------------------------------------------------
+# f3: device batches -> Parquet with record coalescing (materialize_files_task.rs:116-141, DEV_NOTES.md:117-122)
+# ---------------------------------------------------------------------------------------------
+def run_parquet_encode(args):
+    """One step = encoding device-resident records of the reference's sample schema (id Int32, value1 Utf8 with 5 % nulls,
+    value2 Float32) into ONE Parquet file image in pinned host memory: records of --batch-rows rows (default 10 000, the
+    reference's record size) coalesced into row groups of at most 1 Mi rows.  The image crosses PCIe inside every timed
+    step: value == e2e.  cpu_baseline: pyarrow's writer (Arrow C++), one thread, PLAIN, uncompressed, same row groups."""
+    import io
+
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    import torch
+
+    import chapterhouseqe_b200 as C
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; chapterhouseqe_b200 has no CPU fallback")
+    C.load_library()
+    torch.cuda.set_device(0)
+    ctx = C.Context(0)
+    n = args.rows or 16_000_000
+    rec_rows = args.batch_rows or 10_000
+    rng = np.random.default_rng(0xF3)
+    table = pa.table({"id": pa.array(np.arange(n, dtype=np.int32)),
+                      "value1": pa.array(np.char.add("v", rng.integers(0, 10**7, n).astype(str)), mask=rng.random(n) < 0.05),
+                      "value2": pa.array(rng.uniform(0, 100, n).astype(np.float32))})
+    recs = table.to_batches(max_chunksize=rec_rows)
+    devs = C.DeviceBatchList.from_batches([C.DeviceBatch.upload(rb, ctx) for rb in recs])
+    arrow_bytes = sum(c.nbytes for c in table.columns)
+    img = None
+    for _ in range(max(args.warmup, 3)):
+        if img is not None:
+            img.close()
+        img = C.encode_parquet(devs, 1 << 20, 0, ctx)
+    # parity of what is timed: the whole image through pyarrow's reader
+    back = pq.read_table(io.BytesIO(img.to_bytes()), use_threads=True)
+    for name in table.schema.names:
+        if not back.column(name).combine_chunks().equals(table.column(name).combine_chunks()):
+            raise SystemExit(f"bench.py --parquet-encode: column {name} read back by pyarrow differs from the records encoded")
+    file_bytes, row_groups = img.nbytes, img.row_groups
+    launches0 = ctx.launch_count
+    ctx.synchronize()
+    sampler = ClockSampler(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        img.close()
+        img = C.encode_parquet(devs, 1 << 20, 0, ctx)
+    ctx.synchronize()
+    secs = time.perf_counter() - t0
+    sampler.sample_while(lambda: False)
+    launches = ctx.launch_count - launches0
+    img.close()
+    t1 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t1 < min(args.cpu_seconds, 10.0) or reps == 0:
+        sink = io.BytesIO()
+        pq.write_table(table, sink, compression="NONE", use_dictionary=False, row_group_size=1 << 20, write_statistics=False)
+        reps += 1
+    cpu_secs = (time.perf_counter() - t1) / reps
+    peak, peak_src = measured_peak()
+    value = n * args.steps / secs
+    moved = (arrow_bytes + file_bytes) * args.steps / secs / 1e9
+    emit({"metric": "parquet_encode_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+          "warmup": max(args.warmup, 3), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
+          "config": {"workload": f"f3 device batches -> Parquet, reference sample schema (value1 5 % nulls), {n} rows in {len(recs)} records of "
+                                 f"<= {rec_rows} rows coalesced into {row_groups} row groups, PLAIN, uncompressed, v1 pages",
+                     "file_bytes": file_bytes, "arrow_bytes": arrow_bytes,
+                     "l2": "every step streams all records (larger than L2) and writes the whole image to host memory"},
+          "timing": "host wall clock around all steps (each encode ends in a stream synchronise), D2H of the image inside",
+          "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": file_bytes,
+                  "path": "encode_parquet -> chdb_parquet_encode: device-resident records -> file image in pinned host memory"},
+          "gpu_launches": int(launches), "parity_checked": "whole image read back by pyarrow", "clocks": sampler.result(),
+          "roofline": {"bound": "hbm", "kernel": "pqe_sizes / pqe_scan / pqe_write + device-to-device copies + the D2H copy",
+                       "achieved": moved, "peak": peak, "unit": "GB/s", "frac": moved / peak, "traffic": None, "peak_source": peak_src,
+                       "note": "Arrow bytes in + file bytes out per second of the WHOLE call (D2H copy and two synchronises included): "
+                               "the PCIe link bounds it first"},
+          "cpu_baseline": {"value": n / cpu_secs, "unit": "rows/s", "cores": 1, "kind": "port",
+                           "sample": f"pyarrow {pa.__version__} parquet.write_table(use_dictionary=False, compression=NONE) of the same table, "
+                                     f"{reps} run(s)"}})
+
 
 def main():
     global _REAL_STDOUT
@@ -821,6 +906,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.parquet_encode:
+        if rank == 0:
+            run_parquet_encode(args)
+        return
     if args.parquet:
         if rank == 0:
             run_parquet(args)

@@ -136,6 +136,8 @@ def load_library():
     sig("chdb_parquet_decode_row_group", i32, vp, vp, i32, pvp, stp)
     sig("chdb_parquet_decode_row_groups", i32, vp, vp, i32, i32, pvp, stp)
     sig("chdb_parquet_check_row_group", i32, vp, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), stp)
+    sig("chdb_parquet_encode", i32, vp, vp, i32, i64, i32, pvp, ctypes.POINTER(i64), ctypes.POINTER(i32), ctypes.POINTER(i32), stp)
+    sig("chdb_parquet_image_free", None, vp)
     _LIB = L
     return L
 
@@ -145,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "chdb_ctx_device", "chdb_ctx_synchronize", "chdb_ctx_launch_count", "chdb_ctx_jit_launch_count", "chdb_ctx_alloc_miss_count",
     "chdb_ctx_overlapped_count", "chdb_parquet_open", "chdb_parquet_close", "chdb_parquet_num_row_groups",
     "chdb_parquet_num_columns", "chdb_parquet_num_rows", "chdb_parquet_row_group_num_rows", "chdb_parquet_column",
-    "chdb_parquet_decode_row_group", "chdb_parquet_check_row_group",
+    "chdb_parquet_decode_row_group", "chdb_parquet_check_row_group", "chdb_parquet_encode", "chdb_parquet_image_free",
     "chdb_parquet_decode_row_groups",
     "chdb_jit_available", "chdb_program_jit_source", "chdb_program_jit_check", "chdb_program_compile_filter",
     "chdb_program_compile_project", "chdb_program_compile_filter_project", "chdb_program_release",
@@ -673,6 +675,50 @@ class DeviceBatchList:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+class ParquetImage:
+    """A Parquet file image in pinned host memory, written by the device encoder (chdb_parquet_encode): the GPU build's
+    materialize (materialize_files_task.rs:116-141) with the record compaction of DEV_NOTES.md:117-122.
+    `view` is a zero-copy numpy uint8 view valid until close(); `consumed` = batches that went into this file."""
+
+    def __init__(self, ptr: int, nbytes: int, consumed: int, row_groups: int):
+        self._ptr, self.nbytes, self.consumed, self.row_groups = ptr, nbytes, consumed, row_groups
+
+    @property
+    def view(self):
+        import numpy as np
+        return np.ctypeslib.as_array((ctypes.c_uint8 * self.nbytes).from_address(self._ptr))
+
+    def to_bytes(self) -> bytes:
+        return ctypes.string_at(self._ptr, self.nbytes)
+
+    def close(self):
+        if getattr(self, "_ptr", None):
+            load_library().chdb_parquet_image_free(ctypes.c_void_p(self._ptr))
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def encode_parquet(batches, max_rows_per_row_group: int = 0, max_row_groups: int = 0, ctx: "Context | None" = None) -> ParquetImage:
+    """Device batches of one schema -> one Parquet file image; consecutive batches are coalesced into row groups of at most
+    `max_rows_per_row_group` rows (0: 1 Mi), at most `max_row_groups` of them (0: no limit; see `.consumed`)."""
+    L = load_library()
+    if isinstance(batches, DeviceBatchList):
+        arr, n, ctx = batches._arr, len(batches), ctx or batches.ctx
+    else:
+        batches = list(batches)
+        arr, n = (ctypes.c_void_p * max(len(batches), 1))(*[b._h for b in batches]), len(batches)
+        ctx = ctx or (batches[0].ctx if batches else default_context())
+    ptr, nbytes, consumed, groups, st = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int32(), _Status()
+    _check(L.chdb_parquet_encode(ctx._h, arr, n, max_rows_per_row_group, max_row_groups, ctypes.byref(ptr), ctypes.byref(nbytes),
+                                 ctypes.byref(consumed), ctypes.byref(groups), ctypes.byref(st)), st)
+    return ParquetImage(ptr.value, int(nbytes.value), int(consumed.value), int(groups.value))
 
 
 class RecordPool:

@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "jit.hpp"
@@ -1971,3 +1972,4 @@ int32_t chdb_compute_value(chdb_ctx* ctx, const struct ArrowArray* in, const str
 }  // extern "C"
 
 #include "parquet.inc"
+#include "parquet_encode.inc"

@@ -311,6 +311,21 @@ int32_t chdb_parquet_decode_row_group(chdb_ctx* ctx, const chdb_parquet* f, int3
 int32_t chdb_parquet_decode_row_groups(chdb_ctx* ctx, const chdb_parquet* f, int32_t first, int32_t count,
                                        chdb_device_batch** out, chdb_status* st);
 
+/* ---- device batches -> Parquet, with batch coalescing: the step immediately downstream of the projection ----
+ * Replaces the write half of materialize_files_task.rs:116-141 (AsyncArrowWriter over one <= 10 000-row record per file)
+ * and implements the compaction DEV_NOTES.md:117-122 lists as a TODO: the first `*consumed` of `count` finished device
+ * batches of one schema become ONE Parquet file image in pinned host memory; consecutive batches are coalesced into row
+ * groups of at most max_rows_per_row_group rows (<= 0: 1 Mi, parquet-rs's default; a batch is never split), at most
+ * max_row_groups of them (<= 0: no limit; the caller encodes the remaining batches into the next file).  Every batch is
+ * one data page per column.  Written: data page v1, PLAIN, RLE / bit-packed definition levels (the Arrow validity bitmap
+ * as one bit-packed run), UNCOMPRESSED; the decoder's types; nullable columns OPTIONAL.  Kernels squeeze null slots out,
+ * widen narrow integers, re-pack booleans and interleave BYTE_ARRAY length prefixes; the host writes page headers and
+ * footer.  *file_out (length *len_out) is freed with chdb_parquet_image_free. */
+int32_t chdb_parquet_encode(chdb_ctx* ctx, const chdb_device_batch* const* batches, int32_t count,
+                            int64_t max_rows_per_row_group, int32_t max_row_groups, void** file_out, int64_t* len_out,
+                            int32_t* consumed, int32_t* row_groups, chdb_status* st);
+void chdb_parquet_image_free(void* file);
+
 #ifdef __cplusplus
 }
 #endif
