@@ -11,12 +11,13 @@ Everything goes through the C ABI declared in include/chdb_gpu.h (libchdb_gpu.so
 sm_100a CUDA kernels).  There is no CPU fallback: without the built library or without a CUDA
 device these calls raise.
 """
-from .api import (ArrayDatum, ChdbError, Context, DeviceBatch, DeviceBatchList, ParquetFile, ParquetImage, Pending, Program, RecordPool,  # noqa: F401
+from .api import (EXT_KLEENE, EXT_OPERATORS, sql_extensions,  # noqa: F401
+                  ArrayDatum, ChdbError, Context, DeviceBatch, DeviceBatchList, ParquetFile, ParquetImage, Pending, Program, RecordPool,  # noqa: F401
                   compute_value,
                   default_context, encode_parquet, filter_project_record, filter_record, get_record_table_aliases, jit_available,
                   lib_path, load_library, project_record)
 from . import sqlparser_lite  # noqa: F401
 
-__all__ = ["ArrayDatum", "ChdbError", "Context", "DeviceBatch", "DeviceBatchList", "ParquetFile", "ParquetImage", "Pending", "Program", "RecordPool", "compute_value",
+__all__ = ["EXT_KLEENE", "EXT_OPERATORS", "sql_extensions", "ArrayDatum", "ChdbError", "Context", "DeviceBatch", "DeviceBatchList", "ParquetFile", "ParquetImage", "Pending", "Program", "RecordPool", "compute_value",
            "default_context", "encode_parquet", "filter_project_record", "filter_record", "get_record_table_aliases", "jit_available",
            "lib_path", "load_library", "project_record", "sqlparser_lite"]

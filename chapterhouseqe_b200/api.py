@@ -75,6 +75,8 @@ def load_library():
     sig("chdb_code_name", cp, i32)
     sig("chdb_version", cp)
     sig("chdb_compiled_arch", cp)
+    sig("chdb_set_sql_extensions", ctypes.c_uint32, ctypes.c_uint32)
+    sig("chdb_get_sql_extensions", ctypes.c_uint32)
     sig("chdb_ctx_create", i32, i32, pvp, stp)
     sig("chdb_ctx_destroy", None, vp)
     sig("chdb_ctx_stream", vp, vp)
@@ -143,7 +145,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "chdb_code_name", "chdb_version", "chdb_compiled_arch", "chdb_ctx_create", "chdb_ctx_destroy", "chdb_ctx_stream",
+    "chdb_set_sql_extensions", "chdb_get_sql_extensions", "chdb_code_name", "chdb_version", "chdb_compiled_arch", "chdb_ctx_create", "chdb_ctx_destroy", "chdb_ctx_stream",
     "chdb_ctx_device", "chdb_ctx_synchronize", "chdb_ctx_launch_count", "chdb_ctx_jit_launch_count", "chdb_ctx_alloc_miss_count",
     "chdb_ctx_overlapped_count", "chdb_parquet_open", "chdb_parquet_close", "chdb_parquet_num_row_groups",
     "chdb_parquet_num_columns", "chdb_parquet_num_rows", "chdb_parquet_row_group_num_rows", "chdb_parquet_column",
@@ -258,6 +260,25 @@ class Context:
 
 
 _DEFAULT_CTX: dict[int, Context] = {}
+
+
+EXT_OPERATORS, EXT_KLEENE = 1, 2
+
+
+class sql_extensions:
+    """`with sql_extensions(EXT_OPERATORS | EXT_KLEENE): prog = Program.compile_filter(...)` -- nodes beyond the reference's
+    compute_value (chdb_set_sql_extensions); the mask is read when a program is compiled and restored on exit."""
+
+    def __init__(self, mask: int):
+        self.mask = mask
+
+    def __enter__(self):
+        self.prev = int(load_library().chdb_set_sql_extensions(self.mask))
+        return self
+
+    def __exit__(self, *exc):
+        load_library().chdb_set_sql_extensions(self.prev)
+        return False
 
 
 def default_context(device: int = 0) -> Context:

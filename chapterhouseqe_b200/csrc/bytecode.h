@@ -79,12 +79,16 @@ enum Opcode : uint8_t {
   OP_OR = 10,
   OP_PUSH = 11,   // spill[slot] = acc
   OP_CMP_UTF8 = 12,  // acc(bool) = utf8 operand A <cmp> utf8 operand B (columns / pool strings)
-  OP_END = 13
+  OP_END = 13,
+  // SQL extensions (chdb_set_sql_extensions; the reference rejects these nodes, so none is emitted by default)
+  OP_NEG = 14,    // acc = -acc for floats (sign flip; integers lower to checked 0 - x)
+  OP_NOT = 15,    // acc(bool) = !acc, validity kept (arrow compute::not)
+  OP_ISNULL = 16  // acc(bool) = validity of acc / of the column operand is clear (OPF_NEGATE: IS NOT NULL); never null
 };
 
 enum CmpKind : uint8_t { CMP_EQ = 0, CMP_NE = 1, CMP_LT = 2, CMP_LE = 3, CMP_GT = 4, CMP_GE = 5 };
 enum SrcKind : uint8_t { SRC_NONE = 0, SRC_COL = 1, SRC_IMM = 2, SRC_STK = 3 };
-enum InstrFlags : uint8_t { OPF_SWAP = 1 };
+enum InstrFlags : uint8_t { OPF_SWAP = 1, OPF_KLEENE = 2 /* OP_AND / OP_OR: SQL three-valued logic */, OPF_NEGATE = 4 };
 
 // 16 bytes; lives in kernel parameter (constant) space, read with uniform loads.
 struct Instr {

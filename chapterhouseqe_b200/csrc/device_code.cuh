@@ -703,8 +703,26 @@ __device__ __forceinline__ void exec_instr(const KernelParams& P, const ColumnDe
         V b[R];
         fetch_operand<V, QI>(P, cols, in, qbase, inrange, stk, b, bm, bv);
       }
-      accm = in.op == OP_AND ? (accm & bm) : (accm | bm);
-      accv &= bv;
+      if (in.flags & OPF_KLEENE) {   // and_kleene / or_kleene: a false (true) side decides an AND (OR) whatever the other is
+        const uint32_t at = accm & accv, bt = bm & bv, af = ~accm & accv, bf = ~bm & bv;
+        if (in.op == OP_AND) { accm = at & bt; accv = (accv & bv) | af | bf; }
+        else { accm = at | bt; accv = (accv & bv) | at | bt; }
+      } else {
+        accm = in.op == OP_AND ? (accm & bm) : (accm | bm);
+        accv &= bv;
+      }
+      break;
+    }
+    case OP_NEG:
+#pragma unroll
+      for (int j = 0; j < R; j++) acc[j] ^= in.type == T_F32 ? (V)0x80000000u : (V)(1ull << (Cont<V>::k64 ? 63 : 31));
+      break;
+    case OP_NOT: accm = ~accm; break;
+    case OP_ISNULL: {
+      uint32_t v = accv;
+      if (in.src == SRC_COL) v = load_bits<QI>(cols[in.slot].validity, qbase, inrange);
+      accm = (in.flags & OPF_NEGATE) ? v : ~v;
+      accv = FULL;
       break;
     }
     case OP_PUSH:

@@ -7,6 +7,7 @@
 // but instead of materialising an array per node it emits accumulator-machine code that
 // one fused kernel interprets.  Scalar-only subtrees are folded here with the same
 // arithmetic the kernels use (checked integers, IEEE floats, totalOrder compares).
+#include <atomic>
 #include <cerrno>
 #include <climits>
 #include <cmath>
@@ -229,21 +230,28 @@ static bool fold_tobool(uint8_t t, uint64_t v) {
 // typed IR
 // ------------------------------------------------------------------------------------------
 struct TNode {
-  enum K { CONST, COL, CAST, TOBOOL, ARITH, CMP, AND, OR } k = CONST;
+  enum K { CONST, COL, CAST, TOBOOL, ARITH, CMP, AND, OR, NEG, NOT, ISNULL } k = CONST;
   uint8_t type = T_NONE;   // result type
   bool is_scalar = false;  // ArrayDatum.is_scalar
   bool len1 = false;       // array of length 1 whatever the batch length
   uint64_t imm = 0;
   std::string str;
   int col = -1;
-  uint8_t op = 0;          // ARITH: Opcode; CMP: CmpKind
+  uint8_t op = 0;          // ARITH: Opcode; CMP: CmpKind; AND / OR: 1 = Kleene; ISNULL: 1 = IS NOT NULL
   uint8_t order = 0;
   std::unique_ptr<TNode> l, r;
 };
 using TP = std::unique_ptr<TNode>;
 
+// SQL nodes beyond what the reference's compute_value accepts; off unless the host asks for them
+// (chdb_set_sql_extensions), so by default every such node returns the reference's own error.
+std::atomic<uint32_t> g_sql_extensions{0};
+constexpr uint32_t kExtOperators = 1;   // binary -, unary - / +, NOT, IS [NOT] NULL
+constexpr uint32_t kExtKleene = 2;      // AND / OR in SQL three-valued logic (arrow and_kleene / or_kleene)
+
 struct Lowering {
   Program& prog;
+  const uint32_t ext = g_sql_extensions.load();
   std::vector<std::vector<std::string>> aliases;
   bool aliases_given = false;
   int next_order = 0;
@@ -474,7 +482,74 @@ struct Lowering {
       std::string op = oj->kind == Json::String ? oj->str : (oj->kind == Json::Object && !oj->obj.empty() ? oj->obj[0].first : "?");
       return binary(op, std::move(l), std::move(r));
     }
+    if ((ext & kExtOperators) && tag == "UnaryOp") {
+      const Json *xj = body->get("expr"), *oj = body->get("op");
+      if (!xj || !oj || oj->kind != Json::String) throw Error(CHDB_ERR_BAD_JSON, "UnaryOp needs op, expr");
+      return unary(oj->str, check(*xj));
+    }
+    if ((ext & kExtOperators) && (tag == "IsNull" || tag == "IsNotNull")) return is_null(check(*body), tag == "IsNotNull");
     throw Error(CHDB_ERR_EXPRESSION_TYPE_NOT_IMPLEMENTED, "expression type not implemented: " + tag);
+  }
+
+  // ---- extension nodes: arrow-rs semantics of the kernels a Rust implementation would call ----
+  TP unary(const std::string& op, TP x) {
+    if (op == "Plus") return x;
+    if (op == "Not") {   // compute::not over the Boolean cast, validity kept
+      x = to_bool(std::move(x));
+      if (x->k == TNode::CONST) { x->imm ^= 1; return x; }
+      TP n(new TNode);
+      n->k = TNode::NOT;
+      n->type = T_BOOL;
+      n->is_scalar = x->is_scalar;
+      n->len1 = x->len1;
+      n->l = std::move(x);
+      return n;
+    }
+    if (op != "Minus") throw Error(CHDB_ERR_EXPRESSION_TYPE_NOT_IMPLEMENTED, "expression type not implemented: UnaryOp " + op);
+    const uint8_t t = x->type;   // numeric::neg: checked on signed integers, sign flip on floats, no unsigned form
+    if (!(is_signed_int(t) || t == T_F32 || t == T_F64))
+      throw Error(CHDB_ERR_INVALID_ARGUMENT, std::string("Invalid argument error: Invalid arithmetic operation: -") + type_arrow_name(t));
+    if (is_signed_int(t)) {
+      const uint8_t order = (uint8_t)std::min(next_order++, 254);
+      if (x->k == TNode::CONST) {
+        TP c = make_const(t, fold_arith(OP_SUB, t, 0, x->imm));
+        c->is_scalar = x->is_scalar;
+        return c;
+      }
+      TP n(new TNode);
+      n->k = TNode::ARITH;
+      n->type = t;
+      n->op = OP_SUB;
+      n->order = order;
+      n->is_scalar = x->is_scalar;
+      n->len1 = x->len1;
+      n->l = make_const(t, 0);
+      n->r = std::move(x);
+      return n;
+    }
+    if (x->k == TNode::CONST) { x->imm ^= t == T_F32 ? 0x80000000ull : (1ull << 63); return x; }
+    TP n(new TNode);
+    n->k = TNode::NEG;
+    n->type = t;
+    n->is_scalar = x->is_scalar;
+    n->len1 = x->len1;
+    n->l = std::move(x);
+    return n;
+  }
+  TP is_null(TP x, bool negate) {   // arrow is_null / is_not_null: never null itself
+    if (x->k == TNode::CONST) {     // literals are never null
+      TP c = make_const(T_BOOL, negate ? 1 : 0);
+      c->is_scalar = x->is_scalar;
+      return c;
+    }
+    TP n(new TNode);
+    n->k = TNode::ISNULL;
+    n->type = T_BOOL;
+    n->op = negate ? 1 : 0;
+    n->is_scalar = x->is_scalar;
+    n->len1 = x->len1;
+    n->l = std::move(x);
+    return n;
   }
 
   TP binary(const std::string& op, TP l, TP r) {
@@ -486,6 +561,7 @@ struct Lowering {
         length_mismatch(CHDB_ERR_COMPUTE_ERROR, "Compute error: Cannot perform bitwise operation on arrays of different length");
       TP n(new TNode);
       n->k = op == "And" ? TNode::AND : TNode::OR;
+      n->op = (ext & kExtKleene) ? 1 : 0;
       n->type = T_BOOL;
       n->is_scalar = false;  // new_binary_op over bare BooleanArrays (compute_value.rs:81-85)
       n->len1 = l->len1 && r->len1;
@@ -498,7 +574,8 @@ struct Lowering {
       n->r = std::move(r);
       return n;
     }
-    uint8_t arith = op == "Plus" ? OP_ADD : op == "Multiply" ? OP_MUL : op == "Divide" ? OP_DIV : op == "Modulo" ? OP_REM : 0xFF;
+    uint8_t arith = op == "Plus" ? OP_ADD : op == "Multiply" ? OP_MUL : op == "Divide" ? OP_DIV : op == "Modulo" ? OP_REM
+                    : (op == "Minus" && (ext & kExtOperators)) ? OP_SUB : 0xFF;
     int cmp = op == "Eq" ? CMP_EQ : op == "NotEq" ? CMP_NE : op == "Lt" ? CMP_LT : op == "LtEq" ? CMP_LE
               : op == "Gt" ? CMP_GT : op == "GtEq" ? CMP_GE : -1;
     if (arith == 0xFF && cmp < 0)
@@ -577,7 +654,8 @@ struct Lowering {
   int need(const TNode* n) {
     Operand o;
     if (as_operand(n, o)) return 0;
-    if (n->k == TNode::CAST || n->k == TNode::TOBOOL) return need(n->l.get());
+    if (n->k == TNode::CAST || n->k == TNode::TOBOOL || n->k == TNode::NEG || n->k == TNode::NOT) return need(n->l.get());
+    if (n->k == TNode::ISNULL) return n->l->k == TNode::COL ? 0 : need(n->l.get());
     if (n->k == TNode::CMP && n->l->type == T_UTF8) return 0;
     int a = need(n->l.get()), b = need(n->r.get());
     Operand ol, orr;
@@ -643,6 +721,27 @@ struct Lowering {
         push(mk(OP_TOBOOL, n->l->type));
         return;
       }
+      case TNode::NEG:
+        emit(n->l.get(), spill);
+        push(mk(OP_NEG, n->type));
+        return;
+      case TNode::NOT:
+        emit(n->l.get(), spill);
+        push(mk(OP_NOT, T_BOOL));
+        return;
+      case TNode::ISNULL: {
+        Instr in = mk(OP_ISNULL, T_BOOL);
+        if (n->op) in.flags |= OPF_NEGATE;
+        if (n->l->k == TNode::COL) {   // only the column's validity bitmap is read (any type, Utf8 included)
+          in.src = SRC_COL;
+          in.slot = (uint8_t)prog.slot_for(n->l->col);
+          in.from_type = T_BOOL;
+        } else {
+          emit(n->l.get(), spill);
+        }
+        push(in);
+        return;
+      }
       case TNode::CMP:
         if (n->l->type == T_UTF8) {
           Instr in = mk(OP_CMP_UTF8, T_UTF8);
@@ -663,6 +762,7 @@ struct Lowering {
     Instr in = mk(opc, optype);
     in.order = n->order;
     in.aux = n->k == TNode::CMP ? n->op : 0;
+    if ((n->k == TNode::AND || n->k == TNode::OR) && n->op) in.flags |= OPF_KLEENE;
     const TNode *l = n->l.get(), *r = n->r.get();
     Operand ol, orr;
     bool lo = as_operand(l, ol), ro = as_operand(r, orr);
@@ -877,7 +977,7 @@ std::unique_ptr<Program> compile_value(const char* expr_json, const ::ArrowSchem
 // disassembler
 // ------------------------------------------------------------------------------------------
 std::string Program::disassemble() const {
-  static const char* opn[] = {"load", "cast", "add", "mul", "div", "rem", "sub", "cmp", "tobool", "and", "or", "push", "cmp_utf8", "end"};
+  static const char* opn[] = {"load", "cast", "add", "mul", "div", "rem", "sub", "cmp", "tobool", "and", "or", "push", "cmp_utf8", "end", "neg", "not", "isnull"};
   static const char* cmpn[] = {"eq", "ne", "lt", "le", "gt", "ge"};
   std::ostringstream os;
   os << "mode=" << (mode == FILTER ? "filter" : mode == PROJECT ? "project" : "filter_project")
@@ -889,7 +989,7 @@ std::string Program::disassemble() const {
   auto dump = [&](int b, int e) {
     for (int i = b; i < e; i++) {
       const Instr& in = instrs[i];
-      os << "    " << i << ": " << opn[in.op];
+      os << "    " << i << ": " << opn[in.op] << ((in.flags & OPF_KLEENE) ? "_kleene" : "") << ((in.flags & OPF_NEGATE) ? "_not" : "");
       if (in.op == OP_CMP || in.op == OP_CMP_UTF8) os << "." << cmpn[in.aux];
       os << "." << type_arrow_name(in.type);
       if (in.flags & OPF_SWAP) os << " swap";

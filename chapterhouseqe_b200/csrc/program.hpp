@@ -1,5 +1,6 @@
 // Compiled program: the planner's expression tree(s) lowered for one input schema.
 #pragma once
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -61,6 +62,9 @@ std::unique_ptr<Program> compile_program(Program::Mode mode, const char* expr_js
 // compute_value(): one output named "value"; *is_scalar as ArrayDatum.is_scalar.
 std::unique_ptr<Program> compile_value(const char* expr_json, const ::ArrowSchema* schema,
                                        const char* aliases_json, bool* is_scalar);
+
+// chdb_set_sql_extensions: bit 0 = binary -, unary - / +, NOT, IS [NOT] NULL; bit 1 = Kleene AND / OR (read at compile time)
+extern std::atomic<uint32_t> g_sql_extensions;
 
 const char* type_arrow_name(uint8_t t);   // "Int32", "Float32", ...
 const char* type_format(uint8_t t);       // Arrow C format string

@@ -1312,6 +1312,8 @@ const char* chdb_code_name(int32_t code) {
 }
 const char* chdb_version(void) { return "chdb-gpu 0.1.0"; }
 const char* chdb_compiled_arch(void) { return "sm_100a"; }
+uint32_t chdb_set_sql_extensions(uint32_t mask) { return chdb::g_sql_extensions.exchange(mask & 3u); }
+uint32_t chdb_get_sql_extensions(void) { return chdb::g_sql_extensions.load(); }
 
 int32_t chdb_ctx_create(int32_t device, chdb_ctx** out, chdb_status* st) {
   return guarded(st, [&] {

@@ -154,6 +154,17 @@ int32_t chdb_program_compile_filter_project(const char* expr_json, const char* s
                                             const struct ArrowSchema* in_schema,
                                             const char* table_aliases_json, chdb_program** out,
                                             chdb_status* st);
+/* SQL nodes beyond the reference's compute_value (README.md:44-74 lists them as missing).  Off by
+ * default: every such node then returns the reference's own error (BinaryOperatorNotImplemented for `-`,
+ * ExpressionTypeNotImplemented for the others).  The mask is read when a program is compiled; returns the previous mask.
+ *   CHDB_EXT_OPERATORS: binary `-` (numeric::sub: checked integers, IEEE floats), unary `-` (numeric::neg: checked on signed
+ *                       integers, sign flip on floats, error on unsigned) and `+`, NOT (compute::not over the Boolean cast,
+ *                       nulls stay null), IS NULL / IS NOT NULL (never null);
+ *   CHDB_EXT_KLEENE:    AND / OR as SQL three-valued logic (and_kleene / or_kleene) instead of the reference's and / or. */
+#define CHDB_EXT_OPERATORS 1u
+#define CHDB_EXT_KLEENE 2u
+uint32_t chdb_set_sql_extensions(uint32_t mask);
+uint32_t chdb_get_sql_extensions(void);
 void chdb_program_release(chdb_program* prog);
 /* Human-readable bytecode listing; returns the number of bytes needed (excluding NUL). */
 size_t chdb_program_disassemble(const chdb_program* prog, char* buf, size_t cap);

@@ -42,6 +42,27 @@ NP_DTYPE = {"int8": np.int8, "int16": np.int16, "int32": np.int32, "int64": np.i
             "uint8": np.uint8, "uint16": np.uint16, "uint32": np.uint32, "uint64": np.uint64,
             "float32": np.float32, "float64": np.float64}
 ARITH = {"Plus": 0, "Multiply": 1, "Divide": 2, "Modulo": 3}
+# SQL nodes beyond the reference's compute_value, mirroring chdb_set_sql_extensions: off by default, so the
+# oracle raises the reference's errors for them.  Semantics = the arrow-rs kernels a Rust implementation would call
+# (numeric::sub / neg, boolean::not, is_null / is_not_null, and_kleene / or_kleene).  Parity for these is UNPINNED by the
+# reference (it has no such code); the checker beside this restatement is pyarrow.compute in tests/test_gpu_extensions.py.
+EXT_OPERATORS, EXT_KLEENE = 1, 2
+EXTENSIONS = 0
+
+
+class extensions:
+    def __init__(self, mask):
+        self.mask = mask
+
+    def __enter__(self):
+        global EXTENSIONS
+        self.prev, EXTENSIONS = EXTENSIONS, self.mask
+        return self
+
+    def __exit__(self, *exc):
+        global EXTENSIONS
+        EXTENSIONS = self.prev
+        return False
 CMP = {"Eq": 0, "NotEq": 1, "Lt": 2, "LtEq": 3, "Gt": 4, "GtEq": 5}
 # arrow DataType Display names, used in error messages like the reference's
 ARROW_NAME = {"bool": "Boolean", "int8": "Int8", "int16": "Int16", "int32": "Int32", "int64": "Int64",
@@ -465,7 +486,7 @@ def _arith(op: str, l: ArrayDatum, r: ArrayDatum) -> ArrayDatum:
     validity = _union_validity(n, l.array, l.is_scalar, r.array, r.is_scalar)
     out = np.empty(n, dtype=NP_DTYPE[t])
     err_row = ctypes.c_int64(-1)
-    rc = lib().ora_arith(ARITH[op], TYPE_ID[t], n, _p(l.array.values), int(l.is_scalar), _p(r.array.values),
+    rc = lib().ora_arith(ARITH.get(op, 4), TYPE_ID[t], n, _p(l.array.values), int(l.is_scalar), _p(r.array.values),
                          int(r.is_scalar), _p(validity), _p(out), ctypes.byref(err_row))
     if rc == 1:
         raise OracleError("ArithmeticOverflow", f"Overflow happened on row {err_row.value}")
@@ -493,6 +514,50 @@ def _compare(op: str, l: ArrayDatum, r: ArrayDatum) -> ArrayDatum:
     return ArrayDatum(Array("bool", n, out, None, validity), l.is_scalar and r.is_scalar)
 
 
+def _boolean_kernel_kleene(l: ArrayDatum, r: ArrayDatum, is_and: bool) -> ArrayDatum:
+    """arrow-arith boolean.rs and_kleene / or_kleene: a false (true) side decides an AND (OR) whatever the other side is."""
+    lb, rb = _cast_to_bool(l.array), _cast_to_bool(r.array)
+    if lb.length != rb.length:
+        raise OracleError("ComputeError", "Cannot perform bitwise operation on arrays of different length")
+    n = lb.length
+    av, bv = lb.valid_mask(), rb.valid_mask()
+    a, b = unpack_bits(lb.values, n), unpack_bits(rb.values, n)
+    at, bt, af, bf = a & av, b & bv, ~a & av, ~b & bv
+    if is_and:
+        val, valid = at & bt, (av & bv) | af | bf
+    else:
+        val, valid = at | bt, (av & bv) | at | bt
+    validity = None if valid.all() else np.packbits(valid, bitorder="little")
+    return ArrayDatum(Array("bool", n, np.packbits(val, bitorder="little") if n else np.zeros(0, np.uint8), None, validity), False)
+
+
+def _unary(op: str, x: ArrayDatum) -> ArrayDatum:
+    a = x.array
+    if op == "Plus":
+        return x
+    if op == "Not":  # boolean::not: values flipped, validity kept
+        b = _cast_to_bool(a)
+        vals = np.packbits(~unpack_bits(b.values, b.length), bitorder="little") if b.length else np.zeros(0, np.uint8)
+        return ArrayDatum(Array("bool", b.length, vals, None, b.validity), x.is_scalar)
+    if op != "Minus":
+        raise OracleError("ExpressionTypeNotImplemented", "UnaryOp " + op)
+    if a.dtype in ("int8", "int16", "int32", "int64"):  # numeric::neg = neg_checked on valid slots
+        zero = ArrayDatum(Array(a.dtype, 1, np.zeros(1, dtype=NP_DTYPE[a.dtype])), True)
+        return _arith("Minus", zero, x)
+    if a.dtype in ("float32", "float64"):  # neg_wrapping: the sign bit, NaN included
+        u = a.values.view(np.uint32 if a.dtype == "float32" else np.uint64)
+        out = (u ^ (u.dtype.type(1) << u.dtype.type(u.dtype.itemsize * 8 - 1))).view(a.values.dtype)
+        return ArrayDatum(Array(a.dtype, a.length, out, None, a.validity), x.is_scalar)
+    raise OracleError("InvalidArgumentError", f"Invalid arithmetic operation: -{ARROW_NAME[a.dtype]}")
+
+
+def _is_null(x: ArrayDatum, negate: bool) -> ArrayDatum:
+    a = x.array
+    v = a.valid_mask()
+    bits = v if negate else ~v
+    return ArrayDatum(Array("bool", a.length, np.packbits(bits, bitorder="little") if a.length else np.zeros(0, np.uint8)), x.is_scalar)
+
+
 def compute_value(rec: Batch, table_aliases: list[list[str]], expr) -> ArrayDatum:
     if isinstance(expr, dict) and len(expr) == 1:
         (tag, body), = expr.items()
@@ -505,11 +570,9 @@ def compute_value(rec: Batch, table_aliases: list[list[str]], expr) -> ArrayDatu
         left = compute_value(rec, table_aliases, body["left"])
         right = compute_value(rec, table_aliases, body["right"])
         op = body["op"] if isinstance(body["op"], str) else next(iter(body["op"]))
-        if op == "And":
-            return _boolean_kernel(left, right, True)
-        if op == "Or":
-            return _boolean_kernel(left, right, False)
-        if op in ARITH:
+        if op in ("And", "Or"):
+            return (_boolean_kernel_kleene if EXTENSIONS & EXT_KLEENE else _boolean_kernel)(left, right, op == "And")
+        if op in ARITH or (op == "Minus" and EXTENSIONS & EXT_OPERATORS):
             return _arith(op, left, right)
         if op in CMP:
             return _compare(op, left, right)
@@ -537,6 +600,10 @@ def compute_value(rec: Batch, table_aliases: list[list[str]], expr) -> ArrayDatu
                     if alias in table_aliases[idx]:
                         return ArrayDatum(rec.columns[idx], False)
         raise OracleError("IdentifierNotFound", ".".join(i["value"] for i in idents))
+    if EXTENSIONS & EXT_OPERATORS and tag == "UnaryOp":
+        return _unary(body["op"], compute_value(rec, table_aliases, body["expr"]))
+    if EXTENSIONS & EXT_OPERATORS and tag in ("IsNull", "IsNotNull"):
+        return _is_null(compute_value(rec, table_aliases, body), tag == "IsNotNull")
     raise OracleError("ExpressionTypeNotImplemented", tag)  # :338-342
 
 

@@ -57,6 +57,11 @@ extern "C" {
                                           out: *mut *mut ChdbDeviceBatch, st: *mut ChdbStatus) -> i32;
     pub fn chdb_parquet_decode_row_group(ctx: *mut ChdbCtx, f: *const ChdbParquet, row_group: i32,
                                          out: *mut *mut ChdbDeviceBatch, st: *mut ChdbStatus) -> i32;
+    // ---- device batches -> Parquet with record coalescing (materialize_files_task.rs:116-141, DEV_NOTES.md:117-122) ----
+    pub fn chdb_parquet_encode(ctx: *mut ChdbCtx, batches: *const *const ChdbDeviceBatch, count: i32, max_rows_per_row_group: i64,
+                               max_row_groups: i32, file_out: *mut *mut c_void, len_out: *mut i64, consumed: *mut i32,
+                               row_groups: *mut i32, st: *mut ChdbStatus) -> i32;
+    pub fn chdb_parquet_image_free(file: *mut c_void);
     pub fn chdb_jit_available(why: *mut c_char, cap: usize) -> i32;
 
     // ---- programs ----

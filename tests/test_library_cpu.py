@@ -26,7 +26,7 @@ def _has_gpu():
 def test_library_exports_every_header_symbol():
     import ctypes
     hdr = open(os.path.join(ROOT, "include", "chdb_gpu.h")).read()
-    declared = sorted(set(re.findall(r"^(?:const char\*|int32_t|int64_t|size_t|void\*?)\s+(chdb_[a-z0-9_]+)\(", hdr, re.M)))
+    declared = sorted(set(re.findall(r"^(?:const char\*|int32_t|uint32_t|int64_t|size_t|void\*?)\s+(chdb_[a-z0-9_]+)\(", hdr, re.M)))
     assert len(declared) >= 25
     L = ctypes.CDLL(C.lib_path())
     for name in declared:
