@@ -749,11 +749,19 @@ def run_parquet(args):
         if prog is None:
             return decoded
         results = [b.run(prog) for b in decoded]      # filter on the decoded device batches, in place
+        if args.parquet_encode:                       # ... and materialize on the device: only the result FILE crosses PCIe back
+            return C.encode_parquet(results, 1 << 20, 0, ctx)
         return [r.download() for r in results]        # only the filtered rows cross PCIe back
 
+    if args.parquet_encode and prog is None:
+        raise SystemExit("bench.py --parquet --parquet-encode needs --parquet-filter (the whole query: read_files -> filter -> materialize)")
     outs = None
     for _ in range(max(args.warmup, 3)):
+        if args.parquet_encode and outs is not None:
+            outs.close()
         outs = step()
+    if args.parquet_encode:
+        return run_parquet_query_tail(args, ctx, f, raw, n, step, outs, arrow_bytes)
     # parity of what is timed: first and last row group against pyarrow's reader
     pf = pq.ParquetFile(io.BytesIO(raw))
     import pyarrow.compute as pc
@@ -893,6 +901,65 @@ def run_parquet_encode(args):
                            "sample": f"pyarrow {pa.__version__} parquet.write_table(use_dictionary=False, compression=NONE) of the same table, "
                                      f"{reps} run(s)"}})
 
+def run_parquet_query_tail(args, ctx, f, raw, n, step, img, arrow_bytes):
+    """--parquet --parquet-filter --parquet-encode: the whole query `select * from read_files(..) where id % 2 = 0`
+    materialized to Parquet, file bytes in -> file bytes out, everything in between on the device (f1 -> filter -> f3)."""
+    import io
+
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import pyarrow.parquet as pq
+    want = pq.read_table(io.BytesIO(raw))
+    want = want.filter(pc.equal(pc.bit_wise_and(want.column("id"), 1), 0))
+    got = pq.read_table(io.BytesIO(img.to_bytes()))
+    for name in want.schema.names:
+        if not got.column(name).combine_chunks().equals(want.column(name).combine_chunks()):
+            raise SystemExit(f"bench.py --parquet query: column {name} of the written file differs from pyarrow read + filter")
+    out_bytes, out_groups, out_rows = img.nbytes, img.row_groups, got.num_rows
+    launches0 = ctx.launch_count
+    ctx.synchronize()
+    sampler = ClockSampler(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        img.close()
+        img = step()
+    ctx.synchronize()
+    secs = time.perf_counter() - t0
+    sampler.sample_while(lambda: False)
+    launches = ctx.launch_count - launches0
+    img.close()
+    t1 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t1 < min(args.cpu_seconds, 10.0) or reps == 0:
+        tb = pq.read_table(io.BytesIO(raw), use_threads=False)
+        tb = tb.filter(pc.equal(pc.bit_wise_and(tb.column("id"), 1), 0))
+        pq.write_table(tb, io.BytesIO(), compression="NONE", use_dictionary=False, row_group_size=1 << 20, write_statistics=False)
+        reps += 1
+    cpu_secs = (time.perf_counter() - t1) / reps
+    peak, peak_src = measured_peak()
+    value = n * args.steps / secs
+    moved = (len(raw) + 2 * arrow_bytes + out_bytes) * args.steps / secs / 1e9
+    emit({"metric": "parquet_query_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+          "warmup": max(args.warmup, 3), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
+          "config": {"workload": f"select * from read_files(..) where id % 2 = 0 -> Parquet: {n} input rows in {f.num_row_groups} row groups "
+                                 f"(reference sample schema, {'PLAIN' if args.parquet_plain else 'dictionary'} value1) -> {out_rows} rows in "
+                                 f"{out_groups} row groups; decode, filter and encode on the device",
+                     "file_bytes": len(raw), "out_file_bytes": out_bytes,
+                     "l2": "every step streams the whole file (larger than L2) from host memory"},
+          "timing": "host wall clock around all steps, H2D of the input file and D2H of the output file inside",
+          "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": len(raw), "d2h_bytes_per_step": out_bytes,
+                  "path": "ParquetFile.decode_row_groups -> DeviceBatch.run (filter) -> encode_parquet: chdb_parquet_decode_row_groups -> "
+                          "chdb_run_device -> chdb_parquet_encode; only file bytes cross PCIe"},
+          "gpu_launches": int(launches), "parity_checked": "whole output file read back by pyarrow against pyarrow read + filter",
+          "clocks": sampler.result(),
+          "roofline": {"bound": "hbm", "kernel": "pq_* decode + select / gather + pqe_* encode + both PCIe copies",
+                       "achieved": moved, "peak": peak, "unit": "GB/s", "frac": moved / peak, "traffic": None, "peak_source": peak_src,
+                       "note": "bytes of the three stages per second of the WHOLE call: PCIe and per-row-group synchronises bound it"},
+          "cpu_baseline": {"value": n / cpu_secs, "unit": "rows/s", "cores": 1, "kind": "port",
+                           "sample": f"pyarrow {pa.__version__} read_table(use_threads=False) + Table.filter(id & 1 == 0) + write_table "
+                                     f"(PLAIN, uncompressed), {reps} run(s)"}})
+
 
 def main():
     global _REAL_STDOUT
@@ -906,7 +973,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.parquet_encode:
+    if args.parquet_encode and not args.parquet:
         if rank == 0:
             run_parquet_encode(args)
         return

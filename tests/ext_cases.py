@@ -31,7 +31,7 @@ def table(n: int, seed: int = 0) -> pa.RecordBatch:
 
 # (sql, extension mask): 1 = operators, 2 = Kleene AND / OR
 VALUE_CASES = [
-    ("a - 7", 1), ("7 - a", 1), ("k - a", 1), ("f - 1.5", 1), ("d - f", 1), ("u - 5", 1), ("h - h", 1), ("id - a - k", 1),
+    ("a - 7", 1), ("7 - a", 1), ("k - a", 1), ("f - 1.5", 1), ("d - f", 1), ("h - h", 1), ("u - u", 1), ("id - a - k", 1),
     ("-a", 1), ("-k", 1), ("-h", 1), ("-f", 1), ("-d", 1), ("+a", 1), ("-(a + 1) * 2", 1), ("- -a", 1), ("-5", 1), ("-2.5", 1),
     ("not p", 1), ("not (a > 0)", 1), ("not a", 1), ("not (p and q)", 1), ("not true", 1),
     ("a is null", 1), ("a is not null", 1), ("s is null", 1), ("s is not null", 1), ("p is null", 1), ("(a + k) is null", 1),
