@@ -63,6 +63,8 @@ extern "C" {
                                row_groups: *mut i32, st: *mut ChdbStatus) -> i32;
     pub fn chdb_parquet_image_free(file: *mut c_void);
     pub fn chdb_jit_available(why: *mut c_char, cap: usize) -> i32;
+    pub fn chdb_set_sql_extensions(mask: u32) -> u32;
+    pub fn chdb_get_sql_extensions() -> u32;
 
     // ---- programs ----
     pub fn chdb_program_compile_filter(

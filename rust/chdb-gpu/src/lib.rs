@@ -244,3 +244,45 @@ impl DeviceBatch {
         Ok(DeviceBatch { raw, ctx: dst_ctx.0 })
     }
 }
+
+/// A Parquet file image in pinned host memory written by the device encoder (`chdb_parquet_encode`): the GPU build's
+/// materialize step (materialize_files_task.rs:116-141) with the record compaction of DEV_NOTES.md:117-122.
+pub struct ParquetImage {
+    ptr: *mut std::ffi::c_void,
+    len: usize,
+    /// how many of the batches handed to `encode_parquet` went into this file
+    pub consumed: usize,
+    pub row_groups: usize,
+}
+unsafe impl Send for ParquetImage {}
+impl ParquetImage {
+    pub fn as_bytes(&self) -> &[u8] {
+        unsafe { std::slice::from_raw_parts(self.ptr as *const u8, self.len) }
+    }
+}
+impl Drop for ParquetImage {
+    fn drop(&mut self) {
+        unsafe { ffi::chdb_parquet_image_free(self.ptr) }
+    }
+}
+
+/// Device batches of one schema -> one Parquet file image; consecutive batches are coalesced into row groups of at most
+/// `max_rows_per_row_group` rows (<= 0: 1 Mi), at most `max_row_groups` of them (<= 0: no limit; see `consumed`).
+pub fn encode_parquet(ctx: &GpuContext, recs: &[&DeviceBatch], max_rows_per_row_group: i64, max_row_groups: i32) -> Result<ParquetImage> {
+    let ins: Vec<*const ffi::ChdbDeviceBatch> = recs.iter().map(|b| b.raw as *const _).collect();
+    let (mut ptr, mut len, mut consumed, mut groups, mut st) = (std::ptr::null_mut(), 0i64, 0i32, 0i32, new_status());
+    check(
+        unsafe {
+            ffi::chdb_parquet_encode(ctx.0, ins.as_ptr(), ins.len() as i32, max_rows_per_row_group, max_row_groups, &mut ptr,
+                                     &mut len, &mut consumed, &mut groups, &mut st)
+        },
+        &st,
+    )?;
+    Ok(ParquetImage { ptr, len: len as usize, consumed: consumed as usize, row_groups: groups as usize })
+}
+
+/// SQL nodes beyond the reference's compute_value (`-`, unary minus, NOT, IS [NOT] NULL: bit 0; Kleene AND / OR: bit 1); read
+/// when a program is compiled, off by default.  Returns the previous mask.
+pub fn set_sql_extensions(mask: u32) -> u32 {
+    unsafe { ffi::chdb_set_sql_extensions(mask) }
+}

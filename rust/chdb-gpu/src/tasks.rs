@@ -200,6 +200,37 @@ struct GpuMaterializeFilesTask {
 }
 
 impl GpuMaterializeFilesTask {
+    /// The compaction the reference lists as a TODO (DEV_NOTES.md:117-122), on the device: projected records stay in HBM
+    /// until `max_rows_per_row_group * max_row_groups` rows are pending (or the exchange is drained), then ONE call encodes
+    /// them into a `part_<n>.parquet` image in pinned memory (`chdb_parquet_encode`: a page per record and column, records
+    /// coalesced into row groups) and only the image crosses PCIe.  Records are completed after their file is written.
+    async fn write_compacted(
+        &mut self,
+        storage_conn: &opendal::Operator,
+        query_uuid_id: &Uuid,
+        pending: &mut Vec<(crate::DeviceBatch, exchange_handlers::record_handler::ExchangeRecord)>,
+        file_no: &mut u64,
+        rec_handler: &mut exchange_handlers::record_handler::RecordHandler,
+        max_rows_per_row_group: i64,
+        max_row_groups: i32,
+    ) -> Result<()> {
+        while !pending.is_empty() {
+            let image = {
+                let refs: Vec<&crate::DeviceBatch> = pending.iter().map(|(b, _)| b).collect();
+                crate::encode_parquet(&self.ctx, &refs, max_rows_per_row_group, max_row_groups)?
+            };
+            let path = format!("/query_results/{}/part_{}.parquet", query_uuid_id, *file_no);
+            let mut writer = storage_conn.writer_with(&path).chunk(16 * 1024 * 1024).concurrent(4).await?;
+            writer.write(image.as_bytes().to_vec()).await?;
+            writer.close().await?;
+            for (_, rec) in pending.drain(..image.consumed) {
+                rec_handler.complete_record(&mut self.operator_pipe, rec).await?;
+            }
+            *file_no += 1;
+        }
+        Ok(())
+    }
+
     async fn async_main(&mut self, ct: CancellationToken) -> Result<()> {
         let storage_conn = self.conn_reg.get_operator("default")?;
         let query_uuid_id = Uuid::from_u128(self.operator_instance_config.query_id.clone());
