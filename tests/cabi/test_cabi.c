@@ -217,6 +217,41 @@ int main(void) {
   check_output("filter_record_async", &out, &os, &b, N);
   chdb_pending_release(pend);
 
+  /* 4b. materialize on the device: three filtered records -> one Parquet image (a row group per record with a 1-row limit),
+   *     read back through the device decoder and compared with what the filter must have kept */
+  {
+    enum { M = 3 };
+    struct Batch mrecs[M];
+    chdb_device_batch *mins[M], *mouts[M], *back[M];
+    for (int r = 0; r < M; r++) {
+      make_batch(&mrecs[r], N - 77 * r, 500 * r);
+      CHECK(chdb_upload(ctx, &mrecs[r].array, &mrecs[r].schema, &mins[r], &st) == 0, "upload %d: %s", r, st.message);
+    }
+    CHECK(chdb_run_device_many(ctx, prog, (const chdb_device_batch* const*)mins, M, mouts, &st) == 0, "run_device_many: %s", st.message);
+    void* image = NULL;
+    int64_t image_len = 0;
+    int32_t consumed = 0, groups = 0;
+    CHECK(chdb_parquet_encode(ctx, (const chdb_device_batch* const*)mouts, M, 1, 0, &image, &image_len, &consumed, &groups, &st) == 0,
+          "parquet_encode: %s", st.message);
+    CHECK(consumed == M && groups == M && image_len > 12 && memcmp(image, "PAR1", 4) == 0 &&
+              memcmp((const char*)image + image_len - 4, "PAR1", 4) == 0,
+          "parquet image: consumed %d, row groups %d, %lld bytes", consumed, groups, (long long)image_len);
+    chdb_parquet* pf = NULL;
+    CHECK(chdb_parquet_open(image, image_len, &pf, &st) == 0, "parquet_open of the written image: %s", st.message);
+    CHECK(chdb_parquet_num_row_groups(pf) == M && chdb_parquet_num_columns(pf) == 2, "written image: row groups / columns");
+    CHECK(chdb_parquet_decode_row_groups(ctx, pf, 0, M, back, &st) == 0, "decode of the written image: %s", st.message);
+    for (int r = 0; r < M; r++) {
+      CHECK(chdb_download(ctx, back[r], &out, &os, &st) == 0, "download %d: %s", r, st.message);
+      check_output("encode -> decode", &out, &os, &mrecs[r], N - 77 * r);
+      chdb_device_batch_release(back[r]);
+      chdb_device_batch_release(mouts[r]);
+      chdb_device_batch_release(mins[r]);
+      free_batch(&mrecs[r]);
+    }
+    chdb_parquet_close(pf);
+    chdb_parquet_image_free(image);
+  }
+
   /* 5. errors: the reference's kinds */
   chdb_program* bad = NULL;
   rc = chdb_program_compile_filter(kMissing, &b.schema, NULL, &bad, &st);
