@@ -13,7 +13,9 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <condition_variable>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
